@@ -1,0 +1,119 @@
+"""ctypes binding of libb2c.so (include/b2c.h).
+
+The library is loaded lazily (DataLoader workers re-import this package under ``spawn`` and must not
+touch CUDA — reference `_1_embed_with_CLIP.py`:202) and loudly: if ``libb2c.so`` is missing or a call
+fails there is no fallback, a ``B2CError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libb2c.so")
+
+B2C_F32, B2C_F16, B2C_BF16, B2C_U8 = 0, 1, 2, 3
+OUT_NCHW_F32, OUT_PATCH_BF16 = 0, 1
+ACT_QUICK_GELU, ACT_GELU = 0, 1
+EPI_BIAS_BF16, EPI_BIAS_QGELU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
+CMP_FP32, CMP_REF_FP16 = 0, 1
+MLP_MAX_LAYERS = 8
+
+
+class B2CError(RuntimeError):
+    pass
+
+
+class Crop(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("cw", "ch", "dx", "dy", "out_w", "out_h", "off_x", "off_y")]
+
+
+class VitCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("image", "patch", "width", "layers", "heads", "mlp", "embed", "act")]
+
+
+class Pair(C.Structure):
+    _fields_ = [("i", C.c_int32), ("j", C.c_int32), ("sim", C.c_float)]
+
+
+class MlpWeights(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32),
+        ("dims", C.c_int32 * (MLP_MAX_LAYERS + 1)),
+        ("weight", C.c_void_p * MLP_MAX_LAYERS),
+        ("bias", C.c_void_p * MLP_MAX_LAYERS),
+        ("leaky_slope", C.c_float),
+    ]
+
+
+_vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+_u64 = C.c_ulonglong
+
+# name -> (restype, argtypes); every symbol include/b2c.h declares
+SIGNATURES = {
+    "b2c_last_error": (C.c_char_p, []),
+    "b2c_version": (_i, []),
+    "b2c_launch_count": (_u64, []),
+    "b2c_crop_geometry": (_i, [_i, _i, _i, C.POINTER(Crop)]),
+    "b2c_preprocess_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "b2c_preprocess_4crop": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _i, _i,
+                                  C.POINTER(_f), C.POINTER(_f), _i, _vp, _vp, _sz, _vp]),
+    "b2c_vit_create": (_i, [C.POINTER(VitCfg), C.POINTER(_vp)]),
+    "b2c_vit_destroy": (_i, [_vp]),
+    "b2c_vit_set_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i]),
+    "b2c_vit_ready": (_i, [_vp]),
+    "b2c_vit_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
+    "b2c_vit_forward_pixels": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "b2c_vit_forward_patches": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "b2c_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    "b2c_layernorm_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _vp]),
+    "b2c_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "b2c_normalize_rows_f16": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "b2c_dedup_pairs": (_i, [_vp, _i64, _i, _i64, _i64, _f, _i, _vp, _u64, _vp, _vp]),
+    "b2c_mlp_score": (_i, [_vp, _i64, C.POINTER(MlpWeights), _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libb2c.so (once) and attach the prototypes. Raises B2CError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise B2CError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().b2c_last_error().decode("utf-8", "replace")
+        raise B2CError(f"{what or 'libb2c call'} failed (code {rc}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point and raise B2CError on a non-zero status."""
+    check(getattr(load(), name)(*args), name)
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().b2c_launch_count())

@@ -1,0 +1,182 @@
+// b2c_gemm.cu — the ViT tower's dense contractions on tcgen05 tensor cores with fused epilogues.
+//   K1 patch-embed (conv1, stride = kernel, no bias) + positional embedding      -> f32 residual stream
+//   K3 attn.in_proj  (+bias)                                                     -> bf16 qkv
+//   K5 attn.out_proj (+bias, += residual)                                        -> f32 residual stream
+//   K6 mlp.c_fc      (+bias, QuickGELU | erf-GELU)                               -> bf16 hidden
+//   K7 mlp.c_proj    (+bias, += residual)                                        -> f32 residual stream
+// Arithmetic restated from open_clip's VisionTransformer (third-party), which the
+// reference calls at utils/embedder.py:98.  bf16 operands, fp32 accumulation in TMEM.
+#include <cuda_bf16.h>
+
+#include "b2c_launch.h"
+#include "b2c_umma_pipeline.cuh"
+
+namespace b2c {
+
+struct GemmParams {
+  int num_tiles;
+  int k_blocks;
+  int n_blocks;
+  int M, N;
+  const float* bias;
+  void* out;
+  long long ldo;
+  const float* pos;
+  int T, G2;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int MODE>
+struct GemmPolicy {
+  using Params = GemmParams;
+
+  // n-block fastest: the CTAs running concurrently share A tiles (L2 hits) and the weight matrix
+  // (<= 10 MB) stays L2-resident.
+  __device__ static __forceinline__ bool tile(const Params& p, int t, int& a_row, int& b_row) {
+    const int mb = t / p.n_blocks;
+    const int nb = t - mb * p.n_blocks;
+    a_row = mb * kBM;
+    b_row = nb * kBN;
+    return true;
+  }
+
+  __device__ static __forceinline__ void epilogue(const Params& p, int a_row, int b_row, int row_in_tile, int col0,
+                                                  const uint32_t (&acc)[32]) {
+    const int row = a_row + row_in_tile;
+    if (row >= p.M) return;
+    const int col = b_row + col0;
+
+    if constexpr (MODE == kGemmBiasBf16 || MODE == kGemmBiasQGeluBf16 || MODE == kGemmBiasGeluBf16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[j + e]);
+        if (p.bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j + 4));
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        if constexpr (MODE == kGemmBiasQGeluBf16) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
+        } else if constexpr (MODE == kGemmBiasGeluBf16) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+        }
+        uint4 w;
+        w.x = pack_bf16x2(f[0], f[1]);
+        w.y = pack_bf16x2(f[2], f[3]);
+        w.z = pack_bf16x2(f[4], f[5]);
+        w.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(o + j) = w;
+      }
+    } else {
+      size_t orow = static_cast<size_t>(row);
+      const float* addend = p.bias ? p.bias + col : nullptr;  // per-column addend (bias or pos row)
+      if constexpr (MODE == kGemmPatchEmbedF32) {
+        const int crop = row / p.G2;
+        const int pidx = row - crop * p.G2;
+        orow = static_cast<size_t>(crop) * p.T + 1 + pidx;
+        addend = p.pos + static_cast<size_t>(1 + pidx) * p.N + col;
+      }
+      float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 v;
+        v.x = __uint_as_float(acc[j + 0]);
+        v.y = __uint_as_float(acc[j + 1]);
+        v.z = __uint_as_float(acc[j + 2]);
+        v.w = __uint_as_float(acc[j + 3]);
+        if (addend) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(addend + j));
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if constexpr (MODE == kGemmBiasResidF32) {
+          const float4 r = *reinterpret_cast<const float4*>(o + j);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    }
+  }
+};
+
+template <int MODE>
+static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
+  auto kern = umma_tile_kernel<GemmPolicy<MODE>>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  B2C_REQUIRE(sms > 0, "no CUDA device");
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(g.tmap_a, g.tmap_b, p, make_idesc_f16(kBM, kBN, 1));
+  B2C_POST_LAUNCH("umma_tile_kernel<gemm>");
+  return 0;
+}
+
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
+  B2C_REQUIRE(g.M > 0 && g.M < (1ll << 31) - kBM, "gemm: M=%lld out of range", (long long)g.M);
+  B2C_REQUIRE(g.N > 0 && g.N % kBN == 0, "gemm: N=%d must be a positive multiple of %d", g.N, kBN);
+  B2C_REQUIRE(g.K > 0 && g.K % kBK == 0, "gemm: K=%d must be a positive multiple of %d", g.K, kBK);
+  GemmParams p;
+  p.k_blocks = g.K / kBK;
+  p.n_blocks = g.N / kBN;
+  const long long m_blocks = (g.M + kBM - 1) / kBM;
+  B2C_REQUIRE(m_blocks * p.n_blocks < (1ll << 31), "gemm: too many tiles");
+  p.num_tiles = static_cast<int>(m_blocks * p.n_blocks);
+  p.M = static_cast<int>(g.M);
+  p.N = g.N;
+  p.bias = g.bias;
+  p.out = g.out;
+  p.ldo = g.ldo;
+  p.pos = g.pos;
+  p.T = g.T;
+  p.G2 = g.G2;
+  switch (g.mode) {
+    case kGemmBiasBf16: return gemm_launch_mode<kGemmBiasBf16>(g, p, stream);
+    case kGemmBiasQGeluBf16: return gemm_launch_mode<kGemmBiasQGeluBf16>(g, p, stream);
+    case kGemmBiasGeluBf16: return gemm_launch_mode<kGemmBiasGeluBf16>(g, p, stream);
+    case kGemmBiasResidF32: return gemm_launch_mode<kGemmBiasResidF32>(g, p, stream);
+    case kGemmPatchEmbedF32:
+      B2C_REQUIRE(g.pos && g.T > 0 && g.G2 > 0, "gemm: patch-embed mode needs pos/T/G2");
+      return gemm_launch_mode<kGemmPatchEmbedF32>(g, p, stream);
+    default: return set_error(B2C_ERR_ARG, "gemm: unknown epilogue mode %d", g.mode);
+  }
+}
+
+}  // namespace b2c
+
+extern "C" int b2c_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K,
+                             int epilogue, b2c_stream stream) {
+  using namespace b2c;
+  B2C_REQUIRE(A && W && out, "b2c_gemm_bf16: null pointer");
+  B2C_REQUIRE(epilogue >= B2C_EPI_BIAS_BF16 && epilogue <= B2C_EPI_BIAS_RESID_F32, "b2c_gemm_bf16: bad epilogue %d",
+              epilogue);
+  B2C_REQUIRE(M > 0 && N > 0 && K > 0, "b2c_gemm_bf16: empty problem");
+  GemmLaunch g{};
+  B2C_TRY(make_tmap_2d(&g.tmap_a, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
+                       static_cast<uint64_t>(K) * 2, kBM, 1));
+  B2C_TRY(make_tmap_2d(&g.tmap_b, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
+                       static_cast<uint64_t>(K) * 2, kBN, 1));
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.mode = epilogue;
+  g.bias = bias;
+  g.out = out;
+  g.ldo = N;
+  return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,77 @@
+// b2c_host.cu — error plumbing, driver entry points, launch counter.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "b2c_host.h"
+#include "b2c_launch.h"
+
+namespace b2c {
+
+static thread_local char g_err[1024] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                 uint32_t box_rows, int elem) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return set_error(B2C_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  B2C_REQUIRE(row_stride_bytes % 16 == 0, "TMA row stride %llu B is not a multiple of 16",
+              (unsigned long long)row_stride_bytes);
+  B2C_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer is not 16-byte aligned");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, elem == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B2C_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu stride=%llu)",
+                     (int)r, (unsigned long long)rows, (unsigned long long)cols,
+                     (unsigned long long)row_stride_bytes);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+
+}  // namespace b2c
+
+extern "C" const char* b2c_last_error(void) { return b2c::g_err; }
+extern "C" int b2c_version(void) { return 100; }
+extern "C" unsigned long long b2c_launch_count(void) { return b2c::g_launches.load(); }

@@ -1,0 +1,42 @@
+// b2c_host.h — host-side helpers shared by the translation units of libb2c.so:
+// thread-local error string, CUDA error checks that never throw, TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b2c.h"
+
+namespace b2c {
+
+// Sets the thread-local message returned by b2c_last_error() and returns `code`.
+int set_error(int code, const char* fmt, ...);
+
+#define B2C_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ::b2c::set_error(B2C_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,          \
+                              cudaGetErrorString(_e));                                            \
+  } while (0)
+
+#define B2C_REQUIRE(cond, ...)                                                                    \
+  do {                                                                                            \
+    if (!(cond)) return ::b2c::set_error(B2C_ERR_ARG, __VA_ARGS__);                               \
+  } while (0)
+
+#define B2C_TRY(expr)                                                                             \
+  do {                                                                                            \
+    int _r = (expr);                                                                              \
+    if (_r != 0) return _r;                                                                       \
+  } while (0)
+
+// 2-D row-major tensor [rows, cols] of 16-bit elements, box = [box_rows, 64 cols], 128-B swizzle.
+// elem: 0 = fp16, 1 = bf16.  row_stride_bytes must be a multiple of 16.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                 uint32_t box_rows, int elem);
+
+int num_sms();
+
+}  // namespace b2c

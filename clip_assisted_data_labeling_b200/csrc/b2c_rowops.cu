@@ -1,0 +1,386 @@
+// b2c_rowops.cu — the HBM-bound row kernels of the tower (warp-shuffle reductions, 128-bit accesses):
+//   K2  LayerNorm (ln_pre in place f32; ln_1/ln_2 f32 -> bf16), eps 1e-5, fp32 statistics
+//   K1' class token + positional embedding row, pixel -> patch-major re-index (conv1 im2col, stride = kernel)
+//   K8  CLS pool -> ln_post -> @ proj -> L2 normalise            (utils/embedder.py:98-99)
+//   K10 SimpleFC forward                                          (utils/nn_model.py:23-41)
+// plus dtype conversion used when weights are loaded.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "b2c_launch.h"
+
+namespace b2c {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p, size_t i) { return __half2float(p[i]); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
+  return __bfloat162float(p[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the whole row lives in registers (NV float4 per lane, d = 128*NV).
+// Two-pass statistics (mean, then centred sum of squares) in fp32 like torch's LayerNorm kernel.
+// OUT_BF16: y is a separate bf16 tensor; otherwise y aliases x (in-place f32).
+// ------------------------------------------------------------------------------------------------
+template <int NV, bool OUT_BF16>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, void* y,
+                                                        long long M, int d, float eps, int nv_rt) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = NV > 0 ? NV : nv_rt;
+  constexpr int CAP = NV > 0 ? NV : 16;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  float4 v[CAP];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CAP; ++i) {
+    if (i < nv) {
+      v[i] = xr[i * 32 + lane];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < CAP; ++i) {
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < CAP; ++i) {
+    if (i < nv) {
+      const float4 g = __ldg(g4 + i * 32 + lane);
+      const float4 b = __ldg(b4 + i * 32 + lane);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (OUT_BF16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 w;
+        w.x = *reinterpret_cast<uint32_t*>(&lo);
+        w.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * d)[i * 32 + lane] = w;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * d)[i * 32 + lane] = o;
+      }
+    }
+  }
+}
+
+template <bool OUT_BF16>
+static int layernorm_dispatch(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d,
+                              float eps, cudaStream_t stream) {
+  B2C_REQUIRE(d % 128 == 0 && d >= 128 && d <= 2048, "layernorm: d=%d must be a multiple of 128 in [128,2048]", d);
+  B2C_REQUIRE(M > 0, "layernorm: M must be positive");
+  const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  const int nv = d / 128;
+  switch (nv) {
+    case 6: layernorm_kernel<6, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
+    case 8: layernorm_kernel<8, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
+    case 10: layernorm_kernel<10, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
+    default: layernorm_kernel<0, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
+  }
+  B2C_POST_LAUNCH("layernorm_kernel");
+  return 0;
+}
+
+int layernorm_bf16_launch(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d, float eps,
+                          cudaStream_t stream) {
+  return layernorm_dispatch<true>(x, gamma, beta, y, M, d, eps, stream);
+}
+int layernorm_f32_inplace_launch(float* x, const float* gamma, const float* beta, int64_t M, int d, float eps,
+                                 cudaStream_t stream) {
+  return layernorm_dispatch<false>(x, gamma, beta, x, M, d, eps, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// x[crop*T + 0, :] = class_embedding + positional_embedding[0, :]
+// ------------------------------------------------------------------------------------------------
+__global__ void cls_pos_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                               int T, int d) {
+  float* row = x + static_cast<size_t>(blockIdx.x) * T * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) row[i] = cls[i] + pos[i];
+}
+int cls_pos_launch(float* x, const float* cls, const float* pos, int n, int T, int d, cudaStream_t stream) {
+  cls_pos_kernel<<<n, 256, 0, stream>>>(x, cls, pos, T, d);
+  B2C_POST_LAUNCH("cls_pos_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pixels [n,3,R,R] -> patches bf16 [n*g*g, Kp], k = c*p*p + py*p + px (the flattening of conv1.weight
+// [d,3,p,p]); columns k >= 3*p*p are zero.  Only the encode_image(Tensor) surface uses this; the fused
+// u8 path writes patch-major directly from the resize kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ px, __nv_bfloat16* __restrict__ out, int R, int p, int g, int Kp) {
+  const int prow = blockIdx.x;  // crop*g*g + gy*g + gx
+  const int crop = prow / (g * g);
+  const int pi = prow - crop * g * g;
+  const int gy = pi / g, gx = pi - gy * g;
+  const int pp = p * p;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float v = 0.f;
+    if (k < 3 * pp) {
+      const int c = k / pp;
+      const int r = k - c * pp;
+      const int py = r / p, pxx = r - py * p;
+      v = load_as_float<T>(px, ((static_cast<size_t>(crop) * 3 + c) * R + (gy * p + py)) * R + gx * p + pxx);
+    }
+    out[static_cast<size_t>(prow) * Kp + k] = __float2bfloat16_rn(v);
+  }
+}
+int patchify_launch(const void* pixels, int dtype, void* patches, int n, int R, int patch, int Kp,
+                    cudaStream_t stream) {
+  const int g = R / patch;
+  const unsigned grid = static_cast<unsigned>(n) * g * g;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(patches);
+  switch (dtype) {
+    case B2C_F32: patchify_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(pixels), o, R, patch, g, Kp); break;
+    case B2C_F16: patchify_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(pixels), o, R, patch, g, Kp); break;
+    case B2C_BF16: patchify_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(pixels), o, R, patch, g, Kp); break;
+    default: return set_error(B2C_ERR_ARG, "patchify: unsupported pixel dtype %d", dtype);
+  }
+  B2C_POST_LAUNCH("patchify_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head: for CPB crops per block: y = LN(x[crop*T]) ; e = y @ proj[d,E] ; out = e / ||e||_2.
+// proj is read once per block (coalesced over E) and reused for the CPB crops.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadCPB = 4;
+constexpr int kHeadThreads = 256;
+
+__global__ void __launch_bounds__(kHeadThreads) head_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ proj, float* __restrict__ out,
+                                                            int n, int T, int d, int E, float eps) {
+  extern __shared__ float sm[];  // [kHeadCPB][d] normalised CLS rows, then [kHeadCPB][8] partial norms
+  float* ys = sm;
+  float* red = sm + kHeadCPB * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crop0 = blockIdx.x * kHeadCPB;
+  // LN of each CLS row by one warp (warps 0..CPB-1)
+  if (warp < kHeadCPB) {
+    const int crop = crop0 + warp;
+    float* yr = ys + warp * d;
+    if (crop < n) {
+      const float* xr = x + static_cast<size_t>(crop) * T * d;
+      float s = 0.f;
+      for (int i = lane; i < d; i += 32) s += xr[i];
+      const float mean = warp_sum(s) / d;
+      float q = 0.f;
+      for (int i = lane; i < d; i += 32) { const float c = xr[i] - mean; q += c * c; }
+      const float rstd = rsqrtf(warp_sum(q) / d + eps);
+      for (int i = lane; i < d; i += 32) yr[i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
+    } else {
+      for (int i = lane; i < d; i += 32) yr[i] = 0.f;
+    }
+  }
+  __syncthreads();
+  // projection: thread owns columns e = tid, tid+256, ... (<= 4 for E <= 1024)
+  float acc[kHeadCPB][4];
+#pragma unroll
+  for (int c = 0; c < kHeadCPB; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+  for (int k = 0; k < d; ++k) {
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = threadIdx.x + j * kHeadThreads;
+      w[j] = e < E ? __ldg(proj + static_cast<size_t>(k) * E + e) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < kHeadCPB; ++c) {
+      const float yv = ys[c * d + k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[c][j] = fmaf(yv, w[j], acc[c][j]);
+    }
+  }
+  // L2 norm per crop
+#pragma unroll
+  for (int c = 0; c < kHeadCPB; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += acc[c][j] * acc[c][j];
+    s = warp_sum(s);
+    if (lane == 0) red[c * 8 + warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < kHeadCPB; ++c) {
+    const int crop = crop0 + c;
+    if (crop >= n) break;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[c * 8 + w];
+    const float inv = 1.0f / sqrtf(s);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = threadIdx.x + j * kHeadThreads;
+      if (e < E) out[static_cast<size_t>(crop) * E + e] = acc[c][j] * inv;
+    }
+  }
+}
+int head_launch(const float* x, const float* gamma, const float* beta, const float* proj, float* out, int n, int T,
+                int d, int E, float eps, cudaStream_t stream) {
+  B2C_REQUIRE(E <= 4 * kHeadThreads, "head: E=%d exceeds %d", E, 4 * kHeadThreads);
+  const size_t smem = (static_cast<size_t>(kHeadCPB) * d + kHeadCPB * 8) * sizeof(float);
+  B2C_REQUIRE(smem <= 48 * 1024, "head: d=%d too wide", d);
+  head_kernel<<<(n + kHeadCPB - 1) / kHeadCPB, kHeadThreads, smem, stream>>>(x, gamma, beta, proj, out, n, T, d, E, eps);
+  B2C_POST_LAUNCH("head_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dtype conversion / row padding for weights
+// ------------------------------------------------------------------------------------------------
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, long long rows, int cols, int cols_padded) {
+  const long long total = rows * cols_padded;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols_padded;
+    const int c = static_cast<int>(i - r * cols_padded);
+    const float v = c < cols ? load_as_float<S>(src, static_cast<size_t>(r) * cols + c) : 0.f;
+    if constexpr (sizeof(D) == 2) dst[i] = __float2bfloat16_rn(v);
+    else dst[i] = v;
+  }
+}
+template <typename D>
+static int convert_rows(const void* src, int src_dtype, D* dst, int64_t rows, int cols, int cols_padded,
+                        cudaStream_t stream) {
+  const long long total = rows * static_cast<long long>(cols_padded);
+  if (total == 0) return 0;
+  const unsigned grid = static_cast<unsigned>(total / 256 + 1 > 4096 ? 4096 : total / 256 + 1);
+  switch (src_dtype) {
+    case B2C_F32: convert_kernel<float, D><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), dst, rows, cols, cols_padded); break;
+    case B2C_F16: convert_kernel<__half, D><<<grid, 256, 0, stream>>>(static_cast<const __half*>(src), dst, rows, cols, cols_padded); break;
+    case B2C_BF16: convert_kernel<__nv_bfloat16, D><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), dst, rows, cols, cols_padded); break;
+    default: return set_error(B2C_ERR_ARG, "convert: unsupported source dtype %d", src_dtype);
+  }
+  B2C_POST_LAUNCH("convert_kernel");
+  return 0;
+}
+int convert_launch(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, cudaStream_t stream) {
+  if (dst_dtype == B2C_BF16) return convert_rows<__nv_bfloat16>(src, src_dtype, static_cast<__nv_bfloat16*>(dst), 1, (int)count, (int)count, stream);
+  if (dst_dtype == B2C_F32) return convert_rows<float>(src, src_dtype, static_cast<float*>(dst), 1, (int)count, (int)count, stream);
+  return set_error(B2C_ERR_ARG, "convert: unsupported destination dtype %d", dst_dtype);
+}
+int pad_rows_bf16_launch(const void* src, int src_dtype, void* dst, int64_t rows, int cols, int cols_padded,
+                         cudaStream_t stream) {
+  return convert_rows<__nv_bfloat16>(src, src_dtype, static_cast<__nv_bfloat16*>(dst), rows, cols, cols_padded, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: SimpleFC forward.  IPB images per block share every weight read; activations ping-pong in smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMlpIPB = 4;
+constexpr int kMlpThreads = 256;
+
+__global__ void __launch_bounds__(kMlpThreads) mlp_kernel(const float* __restrict__ feats, long long B,
+                                                          const b2c_mlp_weights w, float* __restrict__ out, int max_dim) {
+  extern __shared__ float sm[];  // 2 x [kMlpIPB][max_dim]
+  float* cur = sm;
+  float* nxt = sm + kMlpIPB * max_dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long img0 = static_cast<long long>(blockIdx.x) * kMlpIPB;
+  const int d0 = w.dims[0];
+  for (int c = 0; c < kMlpIPB; ++c) {
+    const long long img = img0 + c;
+    for (int i = threadIdx.x; i < d0; i += kMlpThreads) cur[c * max_dim + i] = img < B ? feats[img * d0 + i] : 0.f;
+  }
+  __syncthreads();
+  for (int l = 0; l < w.n_layers; ++l) {
+    const int din = w.dims[l], dout = w.dims[l + 1];
+    const float* W = w.weight[l];
+    const float* bvec = w.bias[l];
+    const bool last = (l == w.n_layers - 1);
+    for (int j = warp; j < dout; j += kMlpThreads / 32) {
+      float acc[kMlpIPB];
+#pragma unroll
+      for (int c = 0; c < kMlpIPB; ++c) acc[c] = 0.f;
+      const float* wr = W + static_cast<size_t>(j) * din;
+      for (int k = lane; k < din; k += 32) {
+        const float wv = __ldg(wr + k);
+#pragma unroll
+        for (int c = 0; c < kMlpIPB; ++c) acc[c] = fmaf(wv, cur[c * max_dim + k], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < kMlpIPB; ++c) acc[c] = warp_sum(acc[c]);
+      if (lane == 0) {
+        const float b = bvec ? bvec[j] : 0.f;
+#pragma unroll
+        for (int c = 0; c < kMlpIPB; ++c) {
+          float v = acc[c] + b;
+          if (last) {
+            v = 1.0f / (1.0f + expf(-v));
+            const long long img = img0 + c;
+            if (img < B) out[img * dout + j] = v;
+          } else {
+            v = v > 0.f ? v : v * w.leaky_slope;
+            nxt[c * max_dim + j] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+}
+
+}  // namespace b2c
+
+extern "C" int b2c_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d,
+                                  float eps, b2c_stream stream) {
+  using namespace b2c;
+  B2C_REQUIRE(x && gamma && beta && y, "b2c_layernorm_bf16: null pointer");
+  return layernorm_bf16_launch(x, gamma, beta, y, M, d, eps, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2c_mlp_score(const float* feats, int64_t B, const b2c_mlp_weights* w, float* out, b2c_stream stream) {
+  using namespace b2c;
+  B2C_REQUIRE(feats && w && out, "b2c_mlp_score: null pointer");
+  B2C_REQUIRE(w->n_layers >= 1 && w->n_layers <= B2C_MLP_MAX_LAYERS, "b2c_mlp_score: n_layers=%d out of range", w->n_layers);
+  if (B <= 0) return 0;
+  int max_dim = 0;
+  for (int l = 0; l <= w->n_layers; ++l) {
+    B2C_REQUIRE(w->dims[l] > 0, "b2c_mlp_score: dims[%d] must be positive", l);
+    if (w->dims[l] > max_dim) max_dim = w->dims[l];
+  }
+  for (int l = 0; l < w->n_layers; ++l) B2C_REQUIRE(w->weight[l], "b2c_mlp_score: weight[%d] is null", l);
+  const size_t smem = 2ull * kMlpIPB * max_dim * sizeof(float);
+  B2C_REQUIRE(smem <= 200 * 1024, "b2c_mlp_score: layer width %d too large", max_dim);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const unsigned grid = static_cast<unsigned>((B + kMlpIPB - 1) / kMlpIPB);
+  mlp_kernel<<<grid, kMlpThreads, smem, static_cast<cudaStream_t>(stream)>>>(feats, B, *w, out, max_dim);
+  B2C_POST_LAUNCH("mlp_kernel");
+  return 0;
+}

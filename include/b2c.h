@@ -1,0 +1,183 @@
+/* b2c.h — C-ABI of libb2c.so, the B200 (sm_100a) implementation of the one data-parallel hot path of
+ * aiXander/CLIP_assisted_data_labeling: 4-crop CLIP-ViT image embedding and the all-to-all cosine
+ * duplicate search.  All citations are file:line in the reference tree.
+ *
+ * Conventions:
+ *   - plain C types only; every function returns int (0 = ok, <0 = error code below); the message of
+ *     the last failure on the calling thread is b2c_last_error();  no C++ exception crosses this ABI;
+ *   - the CALLER owns every tensor (device pointers, e.g. torch allocations, including workspaces whose
+ *     size is queried first); the library owns only opaque handles (b2c_vit) and their converted weights;
+ *   - every launch takes a stream (a cudaStream_t passed as void*; NULL = legacy default stream), is
+ *     asynchronous and never synchronises the device;
+ *   - there is no CPU fallback: without an sm_100 device the compute entry points fail with B2C_ERR_CUDA.
+ */
+#ifndef B2C_H_
+#define B2C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_OK 0
+#define B2C_ERR_ARG (-1)         /* bad argument / unsupported shape */
+#define B2C_ERR_CUDA (-2)        /* a CUDA runtime or driver call failed (incl. no usable device) */
+#define B2C_ERR_STATE (-3)       /* handle not ready (e.g. missing weights) */
+#define B2C_ERR_WORKSPACE (-4)   /* workspace too small */
+
+typedef void* b2c_stream; /* cudaStream_t */
+
+/* dtype codes used wherever a tensor's element type is passed */
+#define B2C_F32 0
+#define B2C_F16 1
+#define B2C_BF16 2
+#define B2C_U8 3
+
+const char* b2c_last_error(void);
+int b2c_version(void);
+/* Number of kernels this library has launched since load (all threads); bench.py reports the delta
+ * over its timed region as "gpu_launches". */
+unsigned long long b2c_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K0 — 4-crop geometry + PIL-exact bicubic resize + normalise.
+ * Replaces CustomImageDataset.extract_crops (utils/embedder.py:184-251) and the open_clip val
+ * transform applied per crop (utils/embedder.py:90-92,173: Resize(R,BICUBIC) -> CenterCrop(R) ->
+ * ToTensor -> Normalize(mean,std)).
+ * ------------------------------------------------------------------------------------------- */
+
+/* One crop as the reference builds it: a (cw x ch) canvas whose pixel (x,y) is image pixel
+ * (x+dx, y+dy) when that lies inside the W x H image and black otherwise (square_padded_crop,
+ * utils/embedder.py:204-212); the canvas is resized so that its shorter side is R (out_w x out_h,
+ * torchvision Resize semantics) and the centre R x R window starting at (off_x, off_y) is kept. */
+typedef struct {
+  int32_t cw, ch;       /* canvas size before resize; 0,0 = crop dropped as empty (embedder.py:243-247) */
+  int32_t dx, dy;       /* canvas -> image offset */
+  int32_t out_w, out_h; /* size after Resize(R) */
+  int32_t off_x, off_y; /* CenterCrop(R) offset inside the resized canvas */
+} b2c_crop;
+
+/* Host-only, pure integer/double arithmetic: the 4 crops [centre_crop, square_padded_crop, subcrop1,
+ * subcrop2] of a W x H image at model resolution R (utils/embedder.py:196-236 + torchvision
+ * Resize/CenterCrop rounding). */
+int b2c_crop_geometry(int W, int H, int R, b2c_crop out[4]);
+
+/* Bytes of device workspace b2c_preprocess_4crop needs for B images whose sides are <= max_side. */
+int b2c_preprocess_workspace_bytes(int B, int max_side, int R, size_t* bytes);
+
+/* out_layout */
+#define B2C_OUT_NCHW_F32 0   /* f32[B,4,3,R,R]  — bit-identical to torch.stack([preprocess(c)...]) (embedder.py:173) */
+#define B2C_OUT_PATCH_BF16 1 /* bf16[B*4, (R/patch)^2, Kp], Kp = round_up(3*patch*patch, 64), k = c*p*p + py*p + px:
+                                the A operand of the patch-embed GEMM (conv1 with stride = kernel) */
+
+/* img_ptrs: HOST array of B DEVICE pointers to uint8 RGB images, HWC, row pitch pitch[i] bytes.
+ * H, W, pitch: HOST int arrays.  mean/std: HOST float[3].  Crops that the reference would drop
+ * (zero area) are written as zeros. */
+int b2c_preprocess_4crop(const uint8_t* const* img_ptrs, const int* H, const int* W, const int* pitch, int B,
+                         int R, int patch, const float* mean, const float* std, int out_layout, void* out,
+                         void* ws, size_t ws_bytes, b2c_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1..K8 — the open_clip VisionTransformer forward + L2 normalise.
+ * Replaces CLIP_Encoder.encode_image (utils/embedder.py:94-100), i.e. open_clip's
+ * model.encode_image (third-party, un-vendored; architecture restated in SURVEY.md App. A).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b2c_vit b2c_vit;
+
+#define B2C_ACT_QUICK_GELU 0 /* x*sigmoid(1.702x): open_clip tags ending in /openai */
+#define B2C_ACT_GELU 1       /* exact erf GELU: LAION tags (ViT-H-14/laion2b_s32b_b79k) */
+
+typedef struct {
+  int32_t image;  /* R, e.g. 224 / 336 */
+  int32_t patch;  /* 14 / 32 */
+  int32_t width;  /* d */
+  int32_t layers; /* L */
+  int32_t heads;  /* width / heads must be 64 or 80 */
+  int32_t mlp;    /* hidden width of the MLP (4d) */
+  int32_t embed;  /* E */
+  int32_t act;    /* B2C_ACT_* */
+} b2c_vit_cfg;
+
+int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out);
+int b2c_vit_destroy(b2c_vit* vit);
+/* key: open_clip visual state-dict name without the 'visual.' prefix, e.g.
+ * "conv1.weight", "transformer.resblocks.3.attn.in_proj_weight", "proj".  dev_ptr: DEVICE pointer,
+ * contiguous, dtype B2C_F32/F16/BF16.  The handle keeps its own converted copy; the caller may free
+ * the source after the stream work completes (the copy runs on the legacy default stream and is
+ * synchronised before return). */
+int b2c_vit_set_weight(b2c_vit* vit, const char* key, const void* dev_ptr, int dtype, const int64_t* shape,
+                       int ndim);
+/* 0 when every tensor of the architecture has been set, else B2C_ERR_STATE (message names one missing key). */
+int b2c_vit_ready(const b2c_vit* vit);
+int b2c_vit_workspace_bytes(const b2c_vit* vit, int n_crops, size_t* bytes);
+/* pixels: [n,3,R,R] (B2C_F32 / B2C_F16 / B2C_BF16), already normalised — the tensor the reference
+ * feeds encode_image (utils/embedder.py:95-98).  out: f32[n,E], unit-norm rows (embedder.py:99). */
+int b2c_vit_forward_pixels(b2c_vit* vit, const void* pixels, int dtype, int n_crops, float* out, void* ws,
+                           size_t ws_bytes, b2c_stream stream);
+/* patches: bf16[n, g*g, Kp] as written by b2c_preprocess_4crop(B2C_OUT_PATCH_BF16). */
+int b2c_vit_forward_patches(b2c_vit* vit, const void* patches, int n_crops, float* out, void* ws,
+                            size_t ws_bytes, b2c_stream stream);
+
+/* Operator-level entry points (unit parity tests; each is one kernel of the tower). */
+#define B2C_EPI_BIAS_BF16 0      /* out bf16[M,N]  = A·Wᵀ + bias                    (K3 in_proj)          */
+#define B2C_EPI_BIAS_QGELU_BF16 1 /* out bf16[M,N] = quick_gelu(A·Wᵀ + bias)        (K6 c_fc, openai)     */
+#define B2C_EPI_BIAS_GELU_BF16 2 /* out bf16[M,N]  = gelu_erf(A·Wᵀ + bias)          (K6 c_fc, laion)      */
+#define B2C_EPI_BIAS_RESID_F32 3 /* out f32[M,N]  += A·Wᵀ + bias                    (K5 out_proj, K7 c_proj) */
+/* A: bf16[M,K] row-major, W: bf16[N,K] row-major (torch Linear layout), bias: f32[N] or NULL.
+ * K % 64 == 0, N % 256 == 0. */
+int b2c_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K, int epilogue,
+                  b2c_stream stream);
+/* y bf16[M,d] = LayerNorm(x f32[M,d]; gamma,beta f32[d], eps) — ln_1 / ln_2 (K2). d % 128 == 0, d <= 2048. */
+int b2c_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d, float eps,
+                       b2c_stream stream);
+/* qkv: bf16[n*T, 3d] (q | k | v packed like nn.MultiheadAttention.in_proj), out: bf16[n*T, d]. hd in {64,80}. */
+int b2c_attention_bf16(const void* qkv, void* out, int n, int T, int heads, int hd, b2c_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K9 — duplicate search.  Replaces the body of find_near_duplicates (_2_remove_duplicates.py:63-80):
+ * row normalise (67), S = E·Eᵀ (69), where(triu(S,1) > thr) (74), S[i,j] per pair (80) — without
+ * ever materialising S.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t i, j; /* i < j */
+  float sim;    /* fp32 accumulator of the fp16 x fp16 dot product */
+} b2c_pair;
+
+/* out f16[n, E_pad] = in[n,E] / ||in||_2 per row (fp32 math; _2_remove_duplicates.py:67), zero-padded to
+ * E_pad = round_up(E, 64) columns.  in_dtype: B2C_F32 or B2C_F16. */
+int b2c_normalize_rows_f16(const void* in, int in_dtype, int64_t n, int E, void* out_f16, b2c_stream stream);
+
+#define B2C_CMP_FP32 0 /* pair kept iff fp32 accumulator > threshold */
+#define B2C_CMP_REF_FP16 1 /* pair kept iff fp16(acc) > fp16(threshold): the reference's comparison on its
+                              fp16 similarity matrix (_2_remove_duplicates.py:38,69,74) */
+/* emb: f16[n_total, E_pad] unit-norm rows (all ranks' shards gathered), E_pad % 64 == 0.
+ * Emits every pair (i,j), row_begin <= i < row_end, i < j < n_total, whose similarity passes the
+ * comparison.  out/count are DEVICE memory; *count is incremented atomically once per pair and may
+ * exceed capacity (overflow: pairs beyond capacity are dropped, re-run with a larger buffer).
+ * Pair order is unspecified (the host sorts by (i,j) to reproduce torch.where's row-major order). */
+int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, int64_t row_begin, int64_t row_end,
+                    float threshold, int compare_mode, b2c_pair* out, unsigned long long capacity,
+                    unsigned long long* count, b2c_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K10 — SimpleFC regressor forward (utils/nn_model.py:23-41; called at _5_predict_labels.py:135):
+ * Linear -> LeakyReLU(slope) [-> Dropout: identity in eval] per hidden layer, Linear -> Sigmoid.
+ * ------------------------------------------------------------------------------------------- */
+#define B2C_MLP_MAX_LAYERS 8
+typedef struct {
+  int32_t n_layers;                      /* number of Linear layers (hidden + 1) */
+  int32_t dims[B2C_MLP_MAX_LAYERS + 1];  /* dims[0] = input, dims[n_layers] = output (1) */
+  const float* weight[B2C_MLP_MAX_LAYERS]; /* DEVICE f32[dims[l+1], dims[l]] (torch Linear layout) */
+  const float* bias[B2C_MLP_MAX_LAYERS];   /* DEVICE f32[dims[l+1]] */
+  float leaky_slope;                     /* 0.01 (nn.LeakyReLU default, utils/nn_model.py:28) */
+} b2c_mlp_weights;
+
+/* feats: DEVICE f32[B, dims[0]]; out: DEVICE f32[B, dims[n_layers]]. Hidden widths <= 1024. */
+int b2c_mlp_score(const float* feats, int64_t B, const b2c_mlp_weights* w, float* out, b2c_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2C_H_ */

@@ -1,0 +1,324 @@
+// b2c_vit.cu — the open_clip VisionTransformer forward as a sequence of sm_100a kernels behind an
+// opaque handle.  Replaces model.encode_image + the in-place L2 normalise of
+// CLIP_Encoder.encode_image (utils/embedder.py:94-100).  Architecture per SURVEY.md App. A:
+//   conv1 (no bias) -> [cls ; patches] + pos -> ln_pre -> L x { x += out_proj(MHA(ln_1 x)) ;
+//   x += c_proj(act(c_fc(ln_2 x))) } -> ln_post(cls) @ proj -> / ||.||
+// The residual stream and all LayerNorm statistics are fp32; GEMM/attention operands are bf16 with
+// fp32 accumulation.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "b2c_launch.h"
+#include "b2c_umma_pipeline.cuh"
+
+using namespace b2c;
+
+struct b2c_vit_layer {
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+  __nv_bfloat16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
+  float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+  CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;
+};
+
+struct b2c_vit {
+  b2c_vit_cfg cfg;
+  int T, g, G2, Kp, hd;
+  int chunk;  // crops processed per pass over the layers
+  __nv_bfloat16* conv1 = nullptr;  // [d, Kp]
+  float *cls = nullptr, *pos = nullptr, *proj = nullptr;
+  float *ln_pre_w = nullptr, *ln_pre_b = nullptr, *ln_post_w = nullptr, *ln_post_b = nullptr;
+  CUtensorMap tm_conv1;
+  std::vector<b2c_vit_layer> layers;
+  std::map<std::string, bool> have;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t x, h, big, patches, total;
+};
+
+WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
+  const size_t M = static_cast<size_t>(nc) * v->T;
+  const size_t d = v->cfg.width;
+  const size_t wide = std::max<size_t>(3 * d, v->cfg.mlp);
+  WsLayout w;
+  size_t off = 0;
+  w.x = off;
+  off = align_up(off + M * d * sizeof(float), 1024);
+  w.h = off;
+  off = align_up(off + M * d * 2, 1024);
+  w.big = off;
+  off = align_up(off + M * wide * 2, 1024);
+  w.patches = off;
+  if (need_patches) off = align_up(off + static_cast<size_t>(nc) * v->G2 * v->Kp * 2, 1024);
+  w.total = off;
+  return w;
+}
+
+std::vector<std::string> expected_keys(const b2c_vit* v) {
+  std::vector<std::string> k = {"class_embedding", "positional_embedding", "proj",        "conv1.weight",
+                                "ln_pre.weight",   "ln_pre.bias",          "ln_post.weight", "ln_post.bias"};
+  for (int i = 0; i < v->cfg.layers; ++i) {
+    const std::string p = "transformer.resblocks." + std::to_string(i) + ".";
+    for (const char* s : {"ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight",
+                          "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "mlp.c_fc.weight",
+                          "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias"})
+      k.push_back(p + s);
+  }
+  return k;
+}
+
+int alloc_dev(b2c_vit* v, void** p, size_t bytes) {
+  if (*p) return 0;
+  B2C_CHECK_CUDA(cudaMalloc(p, bytes));
+  v->allocs.push_back(*p);
+  return 0;
+}
+
+int store_f32(b2c_vit* v, float** dst, const void* src, int dtype, int64_t count, int64_t expect, const char* key) {
+  B2C_REQUIRE(count == expect, "set_weight(%s): %lld elements, expected %lld", key, (long long)count, (long long)expect);
+  B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(dst), static_cast<size_t>(count) * sizeof(float)));
+  return convert_launch(src, dtype, *dst, B2C_F32, count, nullptr);
+}
+
+int store_bf16(b2c_vit* v, __nv_bfloat16** dst, const void* src, int dtype, int64_t rows, int cols, int cols_padded,
+               int64_t count, const char* key) {
+  B2C_REQUIRE(count == rows * cols, "set_weight(%s): %lld elements, expected %lld", key, (long long)count,
+              (long long)(rows * cols));
+  B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(dst), static_cast<size_t>(rows) * cols_padded * 2));
+  return pad_rows_bf16_launch(src, dtype, *dst, rows, cols, cols_padded, nullptr);
+}
+
+int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* ws, const WsLayout& w,
+                  cudaStream_t stream) {
+  const b2c_vit_cfg& c = v->cfg;
+  const int d = c.width;
+  const int64_t M = static_cast<int64_t>(nc) * v->T;
+  float* x = reinterpret_cast<float*>(ws + w.x);
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(ws + w.h);
+  __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(ws + w.big);
+  const float eps = 1e-5f;
+
+  CUtensorMap tm_patches, tm_h, tm_mlp;
+  B2C_TRY(make_tmap_2d(&tm_patches, patches, static_cast<uint64_t>(nc) * v->G2, v->Kp, static_cast<uint64_t>(v->Kp) * 2,
+                       kBM, 1));
+  B2C_TRY(make_tmap_2d(&tm_h, h, M, d, static_cast<uint64_t>(d) * 2, kBM, 1));
+  B2C_TRY(make_tmap_2d(&tm_mlp, big, M, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBM, 1));
+
+  // K1: conv1 as a GEMM over patch rows, + positional embedding, scattered past the class token
+  {
+    GemmLaunch gl{};
+    gl.tmap_a = tm_patches;
+    gl.tmap_b = v->tm_conv1;
+    gl.M = static_cast<int64_t>(nc) * v->G2;
+    gl.N = d;
+    gl.K = v->Kp;
+    gl.mode = kGemmPatchEmbedF32;
+    gl.out = x;
+    gl.ldo = d;
+    gl.pos = v->pos;
+    gl.T = v->T;
+    gl.G2 = v->G2;
+    B2C_TRY(gemm_launch(gl, stream));
+  }
+  B2C_TRY(cls_pos_launch(x, v->cls, v->pos, nc, v->T, d, stream));
+  B2C_TRY(layernorm_f32_inplace_launch(x, v->ln_pre_w, v->ln_pre_b, M, d, eps, stream));
+
+  for (int li = 0; li < c.layers; ++li) {
+    const b2c_vit_layer& L = v->layers[li];
+    // attention half
+    B2C_TRY(layernorm_bf16_launch(x, L.ln1_w, L.ln1_b, h, M, d, eps, stream));
+    {
+      GemmLaunch gl{};
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
+      gl.mode = kGemmBiasBf16; gl.bias = L.b_qkv; gl.out = big; gl.ldo = 3 * d;
+      B2C_TRY(gemm_launch(gl, stream));
+    }
+    B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
+    {
+      GemmLaunch gl{};
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_out; gl.M = M; gl.N = d; gl.K = d;
+      gl.mode = kGemmBiasResidF32; gl.bias = L.b_out; gl.out = x; gl.ldo = d;
+      B2C_TRY(gemm_launch(gl, stream));
+    }
+    // MLP half
+    B2C_TRY(layernorm_bf16_launch(x, L.ln2_w, L.ln2_b, h, M, d, eps, stream));
+    {
+      GemmLaunch gl{};
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc; gl.M = M; gl.N = c.mlp; gl.K = d;
+      gl.mode = c.act == B2C_ACT_GELU ? kGemmBiasGeluBf16 : kGemmBiasQGeluBf16;
+      gl.bias = L.b_fc; gl.out = big; gl.ldo = c.mlp;
+      B2C_TRY(gemm_launch(gl, stream));
+    }
+    {
+      GemmLaunch gl{};
+      gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj; gl.M = M; gl.N = d; gl.K = c.mlp;
+      gl.mode = kGemmBiasResidF32; gl.bias = L.b_proj; gl.out = x; gl.ldo = d;
+      B2C_TRY(gemm_launch(gl, stream));
+    }
+  }
+  return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, nc, v->T, d, c.embed, eps, stream);
+}
+
+int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches, int n, float* out, void* ws,
+                 size_t ws_bytes, cudaStream_t stream) {
+  B2C_REQUIRE(v && out && ws, "vit_forward: null pointer");
+  B2C_REQUIRE(n > 0, "vit_forward: n_crops must be positive");
+  B2C_TRY(b2c_vit_ready(v));
+  const int nc_max = n < v->chunk ? n : v->chunk;
+  const WsLayout w = ws_layout(v, nc_max, pixels != nullptr);
+  if (ws_bytes < w.total)
+    return set_error(B2C_ERR_WORKSPACE, "vit_forward: workspace %zu B < required %zu B", ws_bytes, w.total);
+  B2C_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "vit_forward: workspace must be 1024-byte aligned");
+  uint8_t* wsb = static_cast<uint8_t*>(ws);
+  const int R = v->cfg.image;
+  const size_t px_elt = dtype == B2C_F32 ? 4 : 2;
+  for (int c0 = 0; c0 < n; c0 += nc_max) {
+    const int nc = (n - c0) < nc_max ? (n - c0) : nc_max;
+    const void* pch;
+    if (pixels) {
+      const uint8_t* px = static_cast<const uint8_t*>(pixels) + static_cast<size_t>(c0) * 3 * R * R * px_elt;
+      B2C_TRY(patchify_launch(px, dtype, wsb + w.patches, nc, R, v->cfg.patch, v->Kp, stream));
+      pch = wsb + w.patches;
+    } else {
+      pch = static_cast<const uint8_t*>(patches) + static_cast<size_t>(c0) * v->G2 * v->Kp * 2;
+    }
+    B2C_TRY(forward_chunk(v, pch, nc, out + static_cast<size_t>(c0) * v->cfg.embed, wsb, w, stream));
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
+  B2C_REQUIRE(cfg && out, "b2c_vit_create: null pointer");
+  B2C_REQUIRE(cfg->patch > 0 && cfg->image > 0 && cfg->image % cfg->patch == 0, "b2c_vit_create: image %d / patch %d",
+              cfg->image, cfg->patch);
+  B2C_REQUIRE(cfg->width > 0 && cfg->width % 256 == 0, "b2c_vit_create: width %d must be a multiple of 256", cfg->width);
+  B2C_REQUIRE(cfg->mlp > 0 && cfg->mlp % 256 == 0, "b2c_vit_create: mlp %d must be a multiple of 256", cfg->mlp);
+  B2C_REQUIRE(cfg->heads > 0 && cfg->width % cfg->heads == 0, "b2c_vit_create: width %d / heads %d", cfg->width,
+              cfg->heads);
+  const int hd = cfg->width / cfg->heads;
+  B2C_REQUIRE(hd == 64 || hd == 80, "b2c_vit_create: head dim %d unsupported (64 or 80)", hd);
+  B2C_REQUIRE(cfg->layers > 0 && cfg->layers <= 64, "b2c_vit_create: layers %d", cfg->layers);
+  B2C_REQUIRE(cfg->embed > 0 && cfg->embed <= 1024, "b2c_vit_create: embed %d out of range", cfg->embed);
+  B2C_REQUIRE(cfg->act == B2C_ACT_QUICK_GELU || cfg->act == B2C_ACT_GELU, "b2c_vit_create: act %d", cfg->act);
+  b2c_vit* v = new b2c_vit();
+  v->cfg = *cfg;
+  v->g = cfg->image / cfg->patch;
+  v->G2 = v->g * v->g;
+  v->T = v->G2 + 1;
+  v->Kp = (3 * cfg->patch * cfg->patch + kBK - 1) / kBK * kBK;
+  v->hd = hd;
+  v->chunk = 512;
+  if (const char* e = getenv("B2C_VIT_CHUNK")) {
+    const int cv = atoi(e);
+    if (cv > 0) v->chunk = cv;
+  }
+  v->layers.resize(cfg->layers);
+  *out = v;
+  return 0;
+}
+
+extern "C" int b2c_vit_destroy(b2c_vit* v) {
+  if (!v) return 0;
+  for (void* p : v->allocs) cudaFree(p);
+  delete v;
+  return 0;
+}
+
+extern "C" int b2c_vit_set_weight(b2c_vit* v, const char* key, const void* dev_ptr, int dtype, const int64_t* shape,
+                                  int ndim) {
+  B2C_REQUIRE(v && key && dev_ptr && shape, "b2c_vit_set_weight: null pointer");
+  B2C_REQUIRE(dtype == B2C_F32 || dtype == B2C_F16 || dtype == B2C_BF16, "b2c_vit_set_weight(%s): dtype %d", key, dtype);
+  int64_t count = 1;
+  for (int i = 0; i < ndim; ++i) count *= shape[i];
+  const b2c_vit_cfg& c = v->cfg;
+  const int64_t d = c.width;
+  const std::string k(key);
+  int rc = B2C_ERR_ARG;
+  const std::string pre = "transformer.resblocks.";
+  if (k == "class_embedding") rc = store_f32(v, &v->cls, dev_ptr, dtype, count, d, key);
+  else if (k == "positional_embedding") rc = store_f32(v, &v->pos, dev_ptr, dtype, count, v->T * d, key);
+  else if (k == "proj") rc = store_f32(v, &v->proj, dev_ptr, dtype, count, d * c.embed, key);
+  else if (k == "ln_pre.weight") rc = store_f32(v, &v->ln_pre_w, dev_ptr, dtype, count, d, key);
+  else if (k == "ln_pre.bias") rc = store_f32(v, &v->ln_pre_b, dev_ptr, dtype, count, d, key);
+  else if (k == "ln_post.weight") rc = store_f32(v, &v->ln_post_w, dev_ptr, dtype, count, d, key);
+  else if (k == "ln_post.bias") rc = store_f32(v, &v->ln_post_b, dev_ptr, dtype, count, d, key);
+  else if (k == "conv1.weight") {
+    rc = store_bf16(v, &v->conv1, dev_ptr, dtype, d, 3 * c.patch * c.patch, v->Kp, count, key);
+    if (rc == 0) rc = make_tmap_2d(&v->tm_conv1, v->conv1, d, v->Kp, static_cast<uint64_t>(v->Kp) * 2, kBN, 1);
+  } else if (k.compare(0, pre.size(), pre) == 0) {
+    const size_t dot = k.find('.', pre.size());
+    B2C_REQUIRE(dot != std::string::npos, "b2c_vit_set_weight: malformed key %s", key);
+    const int li = atoi(k.substr(pre.size(), dot - pre.size()).c_str());
+    B2C_REQUIRE(li >= 0 && li < c.layers, "b2c_vit_set_weight: layer index out of range in %s", key);
+    b2c_vit_layer& L = v->layers[li];
+    const std::string s = k.substr(dot + 1);
+    if (s == "ln_1.weight") rc = store_f32(v, &L.ln1_w, dev_ptr, dtype, count, d, key);
+    else if (s == "ln_1.bias") rc = store_f32(v, &L.ln1_b, dev_ptr, dtype, count, d, key);
+    else if (s == "ln_2.weight") rc = store_f32(v, &L.ln2_w, dev_ptr, dtype, count, d, key);
+    else if (s == "ln_2.bias") rc = store_f32(v, &L.ln2_b, dev_ptr, dtype, count, d, key);
+    else if (s == "attn.in_proj_bias") rc = store_f32(v, &L.b_qkv, dev_ptr, dtype, count, 3 * d, key);
+    else if (s == "attn.out_proj.bias") rc = store_f32(v, &L.b_out, dev_ptr, dtype, count, d, key);
+    else if (s == "mlp.c_fc.bias") rc = store_f32(v, &L.b_fc, dev_ptr, dtype, count, c.mlp, key);
+    else if (s == "mlp.c_proj.bias") rc = store_f32(v, &L.b_proj, dev_ptr, dtype, count, d, key);
+    else if (s == "attn.in_proj_weight") {
+      rc = store_bf16(v, &L.w_qkv, dev_ptr, dtype, 3 * d, d, d, count, key);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_qkv, L.w_qkv, 3 * d, d, d * 2, kBN, 1);
+    } else if (s == "attn.out_proj.weight") {
+      rc = store_bf16(v, &L.w_out, dev_ptr, dtype, d, d, d, count, key);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_out, L.w_out, d, d, d * 2, kBN, 1);
+    } else if (s == "mlp.c_fc.weight") {
+      rc = store_bf16(v, &L.w_fc, dev_ptr, dtype, c.mlp, d, d, count, key);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_fc, L.w_fc, c.mlp, d, d * 2, kBN, 1);
+    } else if (s == "mlp.c_proj.weight") {
+      rc = store_bf16(v, &L.w_proj, dev_ptr, dtype, d, c.mlp, c.mlp, count, key);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_proj, L.w_proj, d, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBN, 1);
+    } else {
+      return set_error(B2C_ERR_ARG, "b2c_vit_set_weight: unknown key %s", key);
+    }
+  } else {
+    return set_error(B2C_ERR_ARG, "b2c_vit_set_weight: unknown key %s", key);
+  }
+  if (rc != 0) return rc;
+  B2C_CHECK_CUDA(cudaStreamSynchronize(nullptr));
+  v->have[k] = true;
+  return 0;
+}
+
+extern "C" int b2c_vit_ready(const b2c_vit* v) {
+  B2C_REQUIRE(v, "b2c_vit_ready: null handle");
+  for (const std::string& k : expected_keys(v))
+    if (!v->have.count(k)) return set_error(B2C_ERR_STATE, "vit: weight '%s' has not been set", k.c_str());
+  return 0;
+}
+
+extern "C" int b2c_vit_workspace_bytes(const b2c_vit* v, int n_crops, size_t* bytes) {
+  B2C_REQUIRE(v && bytes, "b2c_vit_workspace_bytes: null pointer");
+  B2C_REQUIRE(n_crops > 0, "b2c_vit_workspace_bytes: n_crops must be positive");
+  *bytes = ws_layout(v, n_crops < v->chunk ? n_crops : v->chunk, true).total;
+  return 0;
+}
+
+extern "C" int b2c_vit_forward_pixels(b2c_vit* v, const void* pixels, int dtype, int n_crops, float* out, void* ws,
+                                      size_t ws_bytes, b2c_stream stream) {
+  B2C_REQUIRE(pixels, "b2c_vit_forward_pixels: null pixels");
+  B2C_REQUIRE(dtype == B2C_F32 || dtype == B2C_F16 || dtype == B2C_BF16, "b2c_vit_forward_pixels: dtype %d", dtype);
+  return forward_impl(v, pixels, dtype, nullptr, n_crops, out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2c_vit_forward_patches(b2c_vit* v, const void* patches, int n_crops, float* out, void* ws,
+                                       size_t ws_bytes, b2c_stream stream) {
+  B2C_REQUIRE(patches, "b2c_vit_forward_patches: null patches");
+  return forward_impl(v, nullptr, 0, patches, n_crops, out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,203 @@
+"""Drop-in mirror of the reference's embedder call surface (utils/embedder.py) on the B200 path.
+
+Kept from the reference (names, positional order, defaults, attributes):
+  * ``CLIP_Encoder(model_name, model_path=None, device=None)`` with ``device, precision, model_name,
+    model_architecture, pretrained_dataset, model, preprocess, img_resolution`` (utils/embedder.py:59-86),
+    ``get_preprocess_transform()`` (90-92), ``encode_image(Tensor[n,3,R,R]) -> Tensor[n,E]`` unit-norm (94-100);
+  * ``CustomImageDataset(image_paths, crop_names, preprocess_transform)`` with ``__len__``,
+    ``__getitem__ -> (Tensor[k,3,R,R], list[str], str, dict)`` and ``extract_crops(pil)`` (153-251).
+Added (SURVEY.md §8b "additive fast entry"):
+  * ``CLIP_Encoder.encode_images_u8(uint8 [B,H,W,3] | list of ragged HWC) -> f32 [B,4,E]`` — crops,
+    PIL-exact resize, normalise and the tower fused on the device;
+  * ``RawImageDataset`` — decodes to uint8 HWC only, leaving crops/resize to the GPU.
+Deliberate deviations, both documented in DESIGN.md: outputs are float32 (the reference returns fp16 on
+CUDA and every consumer casts with ``.float()``); a failed image is skipped and reported instead of being
+silently replaced by a random other image (utils/embedder.py:176-181).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.utils.data import Dataset
+
+from .vit_arch import ARCHS, CROP_NAMES, OPENAI_MEAN, OPENAI_STD, activation_for, random_state_dict, split_model_name
+
+
+def _open_clip_val_transform(image_size: int):
+    """The open_clip validation transform (third-party): Resize(R, BICUBIC) ->
+    CenterCrop(R) -> RGB -> ToTensor -> Normalize(OPENAI mean/std)."""
+    from torchvision import transforms
+
+    return transforms.Compose([
+        transforms.Resize(image_size, interpolation=transforms.InterpolationMode.BICUBIC),
+        transforms.CenterCrop(image_size),
+        _ConvertRGB(),
+        transforms.ToTensor(),
+        transforms.Normalize(mean=OPENAI_MEAN, std=OPENAI_STD),
+    ])
+
+
+class _ConvertRGB:  # picklable (DataLoader workers use spawn, _1_embed_with_CLIP.py:202)
+    def __call__(self, im):
+        return im.convert("RGB")
+
+
+def _find_checkpoint(model_path: str, arch: str, pretrained: str):
+    if model_path is None:
+        return None
+    if os.path.isfile(model_path):
+        return model_path
+    if os.path.isdir(model_path):
+        want = [f"{arch}_{pretrained}", f"{arch}-{pretrained}", arch]
+        files = sorted(os.listdir(model_path))
+        for w in want:
+            for f in files:
+                if f.startswith(w) and f.endswith((".pt", ".pth", ".bin", ".safetensors")):
+                    return os.path.join(model_path, f)
+    return None
+
+
+def _load_checkpoint(path: str) -> dict:
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    if isinstance(sd, dict) and "state_dict" in sd:
+        sd = sd["state_dict"]
+    return sd
+
+
+class CLIP_Encoder:
+    """utils/embedder.py:58-100 on sm_100a kernels."""
+
+    def __init__(self, model_name, model_path=None, device=None, state_dict=None, seed=0):
+        from .vit import VisionTower
+
+        self.device = device if device else "cuda"
+        if not str(self.device).startswith("cuda"):
+            raise RuntimeError("CLIP_Encoder (B200 path) runs on CUDA only; there is no CPU fallback")
+        # the reference runs fp16 on CUDA (utils/embedder.py:61); this path runs bf16 tensor-core GEMMs with an
+        # fp32 residual stream and returns fp32
+        self.precision = "bf16"
+        self.model_name = model_name
+        self.model_architecture, self.pretrained_dataset = split_model_name(model_name)
+        if self.model_architecture not in ARCHS:
+            raise ValueError(f"unknown architecture {self.model_architecture}; known: {sorted(ARCHS)}")
+        cfg = ARCHS[self.model_architecture]
+        print(f"Loading CLIP model {self.model_name}...")
+        self.model = VisionTower(cfg, activation_for(self.pretrained_dataset), self.device)
+        self.weights_source = "state_dict"
+        if state_dict is None:
+            ckpt = _find_checkpoint(model_path, self.model_architecture, self.pretrained_dataset)
+            if ckpt is not None:
+                state_dict = _load_checkpoint(ckpt)
+                self.weights_source = ckpt
+            else:
+                # no network / no open_clip in this image: seeded random init of the named architecture
+                state_dict = random_state_dict(cfg, seed=seed)
+                self.weights_source = f"random-init(seed={seed})"
+                print(f"WARNING: no checkpoint found for {model_name} under {model_path!r}; using {self.weights_source}")
+        self.model.load_state_dict(state_dict)
+        self.preprocess = _open_clip_val_transform(cfg["image"])
+        self.img_resolution = cfg["image"]
+        print(f"CLIP model {self.model_name} with img_resolution {self.img_resolution} loaded on {self.device}!")
+
+    def get_preprocess_transform(self):
+        return self.preprocess
+
+    @torch.no_grad()
+    def encode_image(self, preprocessed_images: torch.Tensor) -> torch.Tensor:
+        """[n,3,R,R] normalised crops -> [n,E] unit-norm (utils/embedder.py:94-100)."""
+        return self.model.forward_pixels(preprocessed_images)
+
+    @torch.no_grad()
+    def encode_images_u8(self, images) -> torch.Tensor:
+        """uint8 [B,H,W,3] (or a list of ragged HWC uint8 tensors) -> f32 [B,4,E]: the 4 crops in the order
+        [centre_crop, square_padded_crop, subcrop1, subcrop2] (_1_embed_with_CLIP.py:200)."""
+        return self.model.encode_u8(images)
+
+
+class CustomImageDataset(Dataset):
+    """utils/embedder.py:153-251 — host (PIL) implementation kept for the reference-compatible
+    ``encode_image`` path and as the CPU side of parity tests.  ``image_features`` are not computed
+    (ImageFeaturizer is out of scope): the fourth element is an empty dict."""
+
+    def __init__(self, image_paths, crop_names, preprocess_transform):
+        self.image_paths = image_paths
+        self.crop_names = crop_names
+        self.preprocess_transform = preprocess_transform
+
+    def __len__(self):
+        return len(self.image_paths)
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        img_path = self.image_paths[idx]
+        pil_img = Image.open(img_path).convert("RGB")
+        raw_crops, crop_names_list = self.extract_crops(pil_img)
+        processed = torch.stack([self.preprocess_transform(c) for c in raw_crops])
+        return processed, crop_names_list, img_path, {}
+
+    def extract_crops(self, pil_img):
+        """Same crop rectangles as utils/embedder.py:184-251 (centre / black-padded square / 2 sub-crops)."""
+        from PIL import Image
+        W, H = pil_img.width, pil_img.height
+        crops, names = [], []
+        if "centre_crop" in self.crop_names:
+            s = min(W, H)
+            top, left = int(round((H - s) / 2.0)), int(round((W - s) / 2.0))  # torchvision CenterCrop
+            crops.append(pil_img.crop((left, top, left + s, top + s)))
+            names.append("centre_crop")
+        if "square_padded_crop" in self.crop_names:
+            S = max(W, H)
+            canvas = Image.new("RGB", (S, S), (0, 0, 0))
+            canvas.paste(pil_img, ((S - W) // 2, (S - H) // 2))
+            crops.append(canvas)
+            names.append("square_padded_crop")
+        if any("subcrop1" in n for n in self.crop_names) or any("subcrop2" in n for n in self.crop_names):
+            sizes = [int((W * H * 0.15) ** 0.5), int((W * H * 0.1) ** 0.5)]
+            if W >= H:
+                centers = [(W // 4, H // 2), (W // 4 * 3, H // 2)]
+            else:
+                centers = [(W // 2, H // 4), (W // 2, H // 4 * 3)]
+            for name, (cx, cy), sz in zip(["subcrop1", "subcrop2"], centers, sizes):
+                if name not in self.crop_names:
+                    continue
+                left, top = max(0, cx - sz // 2), max(0, cy - sz // 2)
+                right, bottom = min(W, left + sz), min(H, top + sz)
+                if right - left > 0 and bottom - top > 0:
+                    crops.append(pil_img.crop((left, top, right, bottom)))
+                    names.append(name)
+                else:
+                    print(f"Warning: {name} resulted in zero size.")
+        return crops, names
+
+
+class RawImageDataset(Dataset):
+    """Decode only: returns (uint8 HWC tensor | None, path).  Crops, resize and normalisation run on the
+    GPU (b2c_preprocess_4crop).  A file that fails to decode yields ``None`` and is reported by the driver
+    (no silent substitution)."""
+
+    def __init__(self, image_paths):
+        self.image_paths = image_paths
+
+    def __len__(self):
+        return len(self.image_paths)
+
+    def __getitem__(self, idx):
+        import numpy as np
+        from PIL import Image
+        path = self.image_paths[idx]
+        try:
+            with Image.open(path) as im:
+                arr = np.asarray(im.convert("RGB"))
+            return torch.from_numpy(np.ascontiguousarray(arr)), path
+        except Exception as e:  # noqa: BLE001
+            print(f"Error loading image {path}: {e}")
+            return None, path
+
+
+def collate_raw(batch):
+    """Keep ragged images as a list (default_collate would try to stack them)."""
+    return [b[0] for b in batch], [b[1] for b in batch]

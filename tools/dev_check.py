@@ -116,6 +116,126 @@ def case_layernorm():
     return out
 
 
+def case_attention():
+    import torch
+    L = lib()
+    out = []
+    for (n, T, heads, hd) in [(3, 257, 16, 64), (2, 50, 12, 64), (2, 257, 16, 80), (1, 577, 16, 64)]:
+        torch.manual_seed(2)
+        d = heads * hd
+        qkv = (torch.randn(n * T, 3 * d, device="cuda") * 1.0).to(torch.bfloat16)
+        o = torch.zeros(n * T, d, device="cuda", dtype=torch.bfloat16)
+        rc = L.b2c_attention_bf16(C.c_void_p(qkv.data_ptr()), C.c_void_p(o.data_ptr()), n, T, heads, hd,
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, L.b2c_last_error()
+        torch.cuda.synchronize()
+        q, k, v = qkv.float().view(n, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(n * T, d)
+        err = (o.float() - ref).abs().max().item()
+        out.append({"n": n, "T": T, "heads": heads, "hd": hd, "max_abs_err": err, "ok": bool(err < 0.03)})
+    return out
+
+
+def case_preprocess():
+    import numpy as np
+    import torch
+    from clip_assisted_data_labeling_b200.vit import preprocess_u8
+    from oracle.preprocess_oracle import four_crop_preprocess, synthetic_image
+    out = []
+    rng = np.random.default_rng(0)
+    sizes = [(512, 512), (768, 512), (512, 768), (1024, 256), (100, 1000), (64, 64), (513, 512), (333, 517)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (w, h) in sizes]
+    got = preprocess_u8([torch.from_numpy(im).cuda() for im in imgs], 224, 14, "nchw").cpu().numpy()
+    for (w, h), im, g in zip(sizes, imgs, got):
+        ref = four_crop_preprocess(im, 224)
+        out.append({"W": w, "H": h, "bit_exact": bool(np.array_equal(ref, g)), "max_abs": float(np.abs(ref - g).max()),
+                    "n_diff": int((ref != g).sum())})
+    # uniform batch + patch layout
+    batch = np.stack([synthetic_image(k) for k in range(4)])
+    gp = preprocess_u8(torch.from_numpy(batch).cuda(), 224, 14, "patch").float().cpu()
+    gn = preprocess_u8(torch.from_numpy(batch).cuda(), 224, 14, "nchw").cpu()
+    x = gn.view(16, 3, 16, 14, 16, 14).permute(0, 2, 4, 1, 3, 5).reshape(16, 256, 588).to(torch.bfloat16).float()
+    out.append({"patch_layout_equal": bool(torch.equal(gp[:, :, :588], x)), "pad_zero": bool((gp[:, :, 588:] == 0).all().item())})
+    ref0 = four_crop_preprocess(batch[0], 224)
+    out.append({"uniform_bit_exact": bool(np.array_equal(ref0, gn[0].numpy()))})
+    for o in out:
+        o["ok"] = all(v for k, v in o.items() if isinstance(v, bool))
+    return out
+
+
+def _vit_case(arch, n, seed=0):
+    import torch
+    from oracle import vit_oracle
+    from clip_assisted_data_labeling_b200.vit import VisionTower
+    m = vit_oracle.build_visual(arch, "openai" if arch != "ViT-H-14" else "laion2b_s32b_b79k", seed=seed)
+    sd = vit_oracle.visual_state_dict(m)
+    tower = VisionTower(vit_oracle.ARCHS[arch], m.cfg["act"], "cuda")
+    tower.load_state_dict(sd)
+    torch.manual_seed(seed + 1)
+    R = m.cfg["image"]
+    px = torch.randn(n, 3, R, R)
+    t0 = time.time()
+    ref = vit_oracle.encode_image_oracle(m, px)
+    t_cpu = time.time() - t0
+    got = tower.forward_pixels(px.cuda()).cpu()
+    cos = torch.nn.functional.cosine_similarity(ref, got, dim=-1)
+    return {"arch": arch, "n": n, "min_cos": cos.min().item(), "max_abs": (ref - got).abs().max().item(),
+            "cpu_s": round(t_cpu, 2), "ok": bool(cos.min().item() >= 0.9995 and (ref - got).abs().max().item() <= 2e-3)}
+
+
+def case_vit_b32():
+    return [_vit_case("ViT-B-32", 8)]
+
+
+def case_vit_l14():
+    return [_vit_case("ViT-L-14", 4)]
+
+
+def case_vit_h14():
+    return [_vit_case("ViT-H-14", 2)]
+
+
+def case_dedup():
+    import torch
+    L = lib()
+    out = []
+    for (N, E, thr) in [(300, 768, 0.96), (5000, 768, 0.96), (3000, 512, 0.9), (10000, 768, 0.96)]:
+        torch.manual_seed(3)
+        e = torch.nn.functional.normalize(torch.randn(N, E), dim=1)
+        ndup = N // 50
+        src = torch.randint(0, N, (ndup,))
+        dst = torch.randperm(N)[:ndup]
+        c = torch.empty(ndup).uniform_(0.90, 0.999)
+        sigma = (1 / c ** 2 - 1).sqrt()
+        e[dst] = torch.nn.functional.normalize(e[src] + sigma[:, None] * torch.randn(ndup, E) / E ** 0.5, dim=1)
+        e16 = e.to(torch.float16).cuda()
+        # reference semantics (_2_remove_duplicates.py:67-80) on the GPU in fp16
+        nrm = e16 / torch.norm(e16, dim=1, keepdim=True)
+        S = nrm @ nrm.T
+        idx = torch.where(torch.triu(S, diagonal=1) > thr)
+        ref = set(zip(idx[0].tolist(), idx[1].tolist()))
+        S32 = (nrm.float() @ nrm.float().T)
+        E_pad = (E + 63) // 64 * 64
+        buf = torch.zeros(N, E_pad, dtype=torch.float16, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = L.b2c_normalize_rows_f16(C.c_void_p(e16.data_ptr()), 1, C.c_int64(N), E, C.c_void_p(buf.data_ptr()), st)
+        assert rc == 0, L.b2c_last_error()
+        cap = 1 << 20
+        pairs = torch.zeros(cap, 3, dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        rc = L.b2c_dedup_pairs(C.c_void_p(buf.data_ptr()), C.c_int64(N), E_pad, C.c_int64(0), C.c_int64(N), C.c_float(thr), 1,
+                               C.c_void_p(pairs.data_ptr()), C.c_ulonglong(cap), C.c_void_p(cnt.data_ptr()), st)
+        assert rc == 0, L.b2c_last_error()
+        torch.cuda.synchronize()
+        k = int(cnt.item())
+        got = set((int(a), int(b)) for a, b in pairs[:k, :2].tolist())
+        diff = ref ^ got
+        # pairs may differ only where the similarity is within 1e-3 of the threshold
+        bad = [(i, j) for (i, j) in diff if abs(S32[i, j].item() - thr) > 1e-3]
+        out.append({"N": N, "E": E, "ref": len(ref), "got": len(got), "sym_diff": len(diff), "bad": len(bad), "ok": len(bad) == 0 and k > 0})
+    return out
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 

@@ -62,9 +62,16 @@ def get_paths_and_embeddings(args, crop_to_use, shuffle=False):
 # ----------------------------------------------------------------------------------------- device core
 def owned_bands(n_total: int, rank: int = 0, world_size: int = 1, band_rows: int = BAND_ROWS):
     """Row ranges [(begin, end), ...] of the upper-triangle bands this rank computes.  Band b has
-    (n_total - b*band_rows) columns of work, so bands are dealt cyclically for balance."""
+    (n_total - b*band_rows) columns of work — linearly decreasing — so bands are dealt in a snake
+    (0..P-1, P-1..0, ...): every pair of rounds hands each rank the same amount of work."""
     n_bands = (n_total + band_rows - 1) // band_rows
-    return [(b * band_rows, min(n_total, (b + 1) * band_rows)) for b in range(n_bands) if b % world_size == rank]
+    out = []
+    for b in range(n_bands):
+        rnd, pos = divmod(b, world_size)
+        owner = pos if rnd % 2 == 0 else world_size - 1 - pos
+        if owner == rank:
+            out.append((b * band_rows, min(n_total, (b + 1) * band_rows)))
+    return out
 
 
 def sort_pairs(pairs: np.ndarray, sims: np.ndarray):
@@ -99,6 +106,13 @@ def _pairs_for_ranges(emb_n: torch.Tensor, ranges, threshold: float, compare: st
     n_total, E_pad = emb_n.shape
     mode = _lib.CMP_REF_FP16 if compare == "ref_fp16" else _lib.CMP_FP32
     dev = emb_n.device
+    merged = []  # coalesce adjacent ranges: one call covers them (the library iterates the bands itself)
+    for (r0, r1) in ranges:
+        if merged and merged[-1][1] == r0:
+            merged[-1] = (merged[-1][0], r1)
+        else:
+            merged.append((r0, r1))
+    ranges = merged
     while True:
         buf = torch.empty(max(capacity, 1), 3, dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)

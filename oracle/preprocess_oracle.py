@@ -177,8 +177,13 @@ def normalize_f32(u8: np.ndarray, mean=OPENAI_MEAN, std=OPENAI_STD) -> np.ndarra
 
 
 def four_crop_preprocess(img: np.ndarray, R: int, mean=OPENAI_MEAN, std=OPENAI_STD) -> np.ndarray:
-    """f32 [4, 3, R, R] == torch.stack([preprocess(c) for c in raw_crops]) (embedder.py:173)."""
-    return normalize_f32(four_crop_u8(img, R), mean, std)
+    """f32 [4, 3, R, R] == torch.stack([preprocess(c) for c in raw_crops]) (embedder.py:173).
+    A crop the reference cannot produce (zero area: W*H < 10, where embedder.py:247 itself raises) is all zeros."""
+    out = normalize_f32(four_crop_u8(img, R), mean, std)
+    for i, c in enumerate(crop_geometry(img.shape[1], img.shape[0], R)):
+        if c["cw"] == 0:
+            out[i] = 0.0
+    return out
 
 
 def synthetic_image(k: int, H: int = 512, W: int = 512) -> np.ndarray:

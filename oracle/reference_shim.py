@@ -93,8 +93,9 @@ def import_reference(module: str, seed: int = 0):
         sys.path.insert(0, REFERENCE_ROOT)
     # the reference's top-level package is called 'utils'; make sure no other 'utils' shadows it
     m = sys.modules.get("utils")
-    if m is not None and not getattr(m, "__file__", "").startswith(REFERENCE_ROOT) and \
-            not any(str(p).startswith(REFERENCE_ROOT) for p in getattr(m, "__path__", [])):
-        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
-            del sys.modules[k]
+    if m is not None:
+        locs = [str(getattr(m, "__file__", None) or "")] + [str(p) for p in getattr(m, "__path__", [])]
+        if not any(l.startswith(REFERENCE_ROOT) for l in locs):
+            for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+                del sys.modules[k]
     return importlib.import_module(module)

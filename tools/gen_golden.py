@@ -1,0 +1,166 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own code (imported verbatim from
+/root/reference through oracle/reference_shim.py) in the build container.  The reference tree does not
+exist on the GPU box, so these small fixtures are what pins the oracle (and through it the CUDA path)
+there.  Re-run:  python tools/gen_golden.py
+"""
+import hashlib
+import os
+import shutil
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reference_shim as rs  # noqa: E402
+from oracle import vit_oracle  # noqa: E402
+from oracle.dedup_oracle import synthetic_embeddings  # noqa: E402
+from oracle.preprocess_oracle import CROP_NAMES, OPENAI_MEAN, OPENAI_STD, synthetic_image  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def gen_preprocess():
+    """Reference CustomImageDataset.extract_crops + its preprocess transform on synthetic images."""
+    from PIL import Image
+    emb = rs.import_reference("utils.embedder")
+    enc = emb.CLIP_Encoder("ViT-B-32/openai", device="cpu")
+    tf = enc.get_preprocess_transform()
+    ds = emb.CustomImageDataset([], CROP_NAMES, tf)
+    sizes = [(512, 512), (300, 200), (97, 260), (64, 64), (640, 128), (513, 512), (1000, 100)]  # (W, H)
+    in_digests, digests, crop_sizes, full = [], [], [], {}
+    mean = np.asarray(OPENAI_MEAN, np.float32)[:, None, None]
+    std = np.asarray(OPENAI_STD, np.float32)[:, None, None]
+    for k, (W, H) in enumerate(sizes):
+        img = synthetic_image(k, H, W)  # regenerated from the seed by the tests (numpy Generator streams are stable)
+        pil = Image.fromarray(img)
+        raw, names = ds.extract_crops(pil)
+        assert names == CROP_NAMES
+        ref = torch.stack([tf(c) for c in raw]).numpy()  # f32 [4,3,224,224] — utils/embedder.py:173
+        u8 = np.rint((ref * std + mean) * 255.0).astype(np.uint8)
+        back = ((u8.astype(np.float32) / np.float32(255.0)) - mean) / std
+        assert np.array_equal(back, ref), "u8 round trip must reproduce the reference tensor exactly"
+        in_digests.append(hashlib.sha256(img.tobytes()).hexdigest())
+        digests.append(hashlib.sha256(ref.tobytes()).hexdigest())
+        crop_sizes.append([c.size for c in raw])
+        if (W, H) == (97, 260):  # one full example (small input) for debugging a digest mismatch
+            full = {"full_index": np.asarray(k), "full_img": img, "full_crops_u8": u8[2:4]}  # subcrop1, subcrop2
+    np.savez_compressed(os.path.join(OUT, "preprocess_ref.npz"), sizes=np.asarray(sizes), in_sha256=np.asarray(in_digests),
+                        sha256=np.asarray(digests), crop_sizes=np.asarray(crop_sizes), **full)
+    print("preprocess_ref.npz", [os.path.getsize(os.path.join(OUT, "preprocess_ref.npz"))])
+
+
+def gen_geometry():
+    """Crop rectangles of the reference for many sizes (only sizes, cheap)."""
+    from PIL import Image
+    emb = rs.import_reference("utils.embedder")
+    ds = emb.CustomImageDataset([], CROP_NAMES, None)
+    rng = np.random.default_rng(7)
+    sizes = [(512, 512), (768, 512), (512, 768), (1024, 256), (100, 1000), (64, 64), (513, 512), (333, 517), (1000, 100),
+             (20, 20), (1, 50), (7, 3)]  # (W*H >= 10: below that the reference itself raises NameError at embedder.py:247)
+    sizes += [tuple(int(v) for v in rng.integers(8, 1400, 2)) for _ in range(60)]
+    rows = []
+    for (W, H) in sizes:
+        raw, names = ds.extract_crops(Image.new("RGB", (W, H)))
+        got = {n: c.size for n, c in zip(names, raw)}
+        rows.append([W, H] + [v for n in CROP_NAMES for v in got.get(n, (0, 0))])
+    np.savez_compressed(os.path.join(OUT, "crop_geometry_ref.npz"), rows=np.asarray(rows, np.int64))
+    print("crop_geometry_ref.npz", len(rows))
+
+
+def gen_dedup():
+    """Unmodified _2_remove_duplicates.get_paths_and_embeddings + find_near_duplicates core on synthetic .pt dirs."""
+    ref = rs.import_reference("_2_remove_duplicates")
+    cases = {}
+    for name, (n, d, seed, thr) in {"a": (512, 256, 11, 0.96), "b": (1500, 768, 12, 0.96), "c": (700, 512, 13, 0.9)}.items():
+        e = synthetic_embeddings(n, d, seed)
+        tmp = tempfile.mkdtemp()
+        root = os.path.join(tmp, "data")
+        os.makedirs(root)
+        for i in range(n):
+            open(os.path.join(root, f"{i:06d}.jpg"), "wb").close()
+            torch.save({"ViT-L-14/openai": {"square_padded_crop": e[i:i + 1].clone()}}, os.path.join(root, f"{i:06d}.pt"))
+        args = types.SimpleNamespace(root_dir=root, threshold=thr, mode="copy", clip_model_to_use=None, chunk_size=10000, test=True)
+        pairs, vals = [], []
+        # replay of find_near_duplicates' body (:63-80) on what the reference generator yields, with the reference's ops
+        for paths, embs in ref.get_paths_and_embeddings(args, "square_padded_crop"):
+            idx_of = [int(os.path.basename(p)[:6]) for p in paths]
+            E = torch.stack(embs)
+            nE = E / torch.norm(E, dim=1, keepdim=True)
+            S = torch.matmul(nE, nE.T)
+            w = torch.where(torch.triu(S, diagonal=1) > args.threshold)
+            for i, j in zip(w[0].tolist(), w[1].tolist()):
+                pairs.append((idx_of[i], idx_of[j], i, j))
+                vals.append(S[i, j].item())
+        # and the real function end to end (test=True: no file operations) to make sure it runs on this layout
+        ref.find_near_duplicates(args)
+        order = np.asarray([int(os.path.basename(p)[:6]) for p in paths])
+        shutil.rmtree(tmp)
+        cases[f"{name}_meta"] = np.asarray([n, d, seed], np.int64)
+        cases[f"{name}_thr"] = np.asarray(thr)
+        cases[f"{name}_order"] = order  # os.walk order in which the reference stacked the rows
+        cases[f"{name}_pairs"] = np.asarray(pairs, np.int64).reshape(-1, 4)
+        cases[f"{name}_vals"] = np.asarray(vals, np.float32)
+        if name == "a":
+            cases["a_emb_f16"] = e.to(torch.float16).numpy()
+        print("dedup case", name, "pairs", len(pairs))
+    np.savez_compressed(os.path.join(OUT, "dedup_ref.npz"), **cases)
+
+
+def gen_mlp():
+    """Reference utils/nn_model.SimpleFC forward (seeded small instance) + the shipped checkpoint on seeded inputs."""
+    nn_model = rs.import_reference("utils.nn_model")
+    torch.manual_seed(5)
+    m = nn_model.SimpleFC(96, [264, 128, 64], 1, clip_models=["ViT-L-14/openai"], crop_names=["centre_crop"],
+                          dropout_prob=0.5).eval()
+    x = torch.randn(33, 96)
+    with torch.no_grad():
+        y = m(x)
+    lin = [l for l in m.layers if isinstance(l, torch.nn.Linear)]
+    out = {"x": x.numpy(), "y": y.numpy()}
+    for i, l in enumerate(lin):
+        out[f"w{i}"] = l.weight.detach().numpy()
+        out[f"b{i}"] = l.bias.detach().numpy()
+    # shipped checkpoint: outputs only (weights stay in the reference tree)
+    ck = os.path.join(rs.REFERENCE_ROOT, "models", "single_crop_regression_9.4k_imgs_80_epochs.pth")
+    import collections
+    with torch.serialization.safe_globals([nn_model.SimpleFC, torch.nn.ModuleList, torch.nn.Linear, torch.nn.LeakyReLU,
+                                           torch.nn.Sigmoid, torch.nn.Dropout, set, collections.OrderedDict]):
+        shipped = torch.load(ck, map_location="cpu", weights_only=True).eval()
+    g = torch.Generator().manual_seed(9)
+    xs = torch.nn.functional.normalize(torch.randn(16, 768, generator=g), dim=1)
+    with torch.no_grad():
+        ys = shipped(xs)
+    out["shipped_x"] = xs.numpy()
+    out["shipped_y"] = ys.numpy()
+    out["shipped_crop_names"] = np.asarray(shipped.crop_names)
+    out["shipped_clip_models"] = np.asarray(shipped.clip_models)
+    np.savez_compressed(os.path.join(OUT, "mlp_ref.npz"), **out)
+    print("mlp_ref.npz ok", float(ys.mean()))
+
+
+def gen_vit():
+    """Oracle tower outputs (the open_clip architecture restated) cross-checked against transformers' CLIP here."""
+    out = {}
+    for arch, pretrained, n in [("ViT-B-32", "openai", 4)]:
+        m = vit_oracle.build_visual(arch, pretrained, seed=0)
+        g = torch.Generator().manual_seed(1)
+        px = torch.randn(n, 3, m.cfg["image"], m.cfg["image"], generator=g)
+        with torch.no_grad():
+            raw = m(px)
+            hf = vit_oracle.to_hf_clip(m)(pixel_values=px).image_embeds
+        assert (raw - hf).abs().max().item() < 2e-5, "oracle tower disagrees with transformers' CLIP"
+        out[f"{arch}_emb"] = vit_oracle.encode_image_oracle(m, px).numpy()
+        out[f"{arch}_hf_maxabs"] = np.asarray((raw - hf).abs().max().item())
+        print(arch, "oracle vs HF max abs", (raw - hf).abs().max().item())
+    np.savez_compressed(os.path.join(OUT, "vit_ref.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["preprocess", "geometry", "dedup", "mlp", "vit"]
+    for w in which:
+        globals()["gen_" + w]()

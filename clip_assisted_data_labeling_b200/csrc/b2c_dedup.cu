@@ -32,6 +32,8 @@ struct DedupParams {
 
 struct DedupPolicy {
   using Params = DedupParams;
+  static constexpr int kStore = kStoreDirect;  // the epilogue emits pairs itself; nothing is stored as a tile
+  __device__ static __forceinline__ void transform(const Params&, int, float (&)[32]) {}
 
   // consecutive tiles walk down the band's row blocks for one column block: the CTAs running at the
   // same time share B tiles and the band's A tiles.
@@ -175,7 +177,7 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
     p.bj0 = static_cast<int>(bj0);
     p.num_tiles = static_cast<int>(tiles);
     const int grid = tiles < sms ? static_cast<int>(tiles) : sms;
-    kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(tm_a, tm_b, p, make_idesc_f16(kBM, kBN, 0));
+    kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(tm_a, tm_b, tm_a, p, make_idesc_f16(kBM, kBN, 0));
     B2C_POST_LAUNCH("umma_tile_kernel<dedup>");
   }
   return 0;

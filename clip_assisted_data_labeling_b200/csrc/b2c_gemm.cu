@@ -47,66 +47,47 @@ struct GemmPolicy {
     return true;
   }
 
+  static constexpr int kStore = (MODE == kGemmPatchEmbedF32) ? kStoreDirect
+                                : (MODE == kGemmBiasResidF32) ? kStoreTmaAddF32 : kStoreTmaBf16;
+
+  // bias (+ activation) on one 32-column chunk of an accumulator row; the kernel then stages and TMA-stores it
+  __device__ static __forceinline__ void transform(const Params& p, int col, float (&f)[32]) {
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+      }
+    }
+    if constexpr (MODE == kGemmBiasQGeluBf16) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) f[e] = quick_gelu(f[e]);
+    } else if constexpr (MODE == kGemmBiasGeluBf16) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) f[e] = gelu_erf(f[e]);
+    }
+  }
+
+  // patch-embed only: rows are scattered past each crop's class token, so the stores stay per-thread
   __device__ static __forceinline__ void epilogue(const Params& p, int a_row, int b_row, int row_in_tile, int col0,
                                                   const uint32_t (&acc)[32]) {
     const int row = a_row + row_in_tile;
     if (row >= p.M) return;
     const int col = b_row + col0;
-
-    if constexpr (MODE == kGemmBiasBf16 || MODE == kGemmBiasQGeluBf16 || MODE == kGemmBiasGeluBf16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+    const int crop = row / p.G2;
+    const int pidx = row - crop * p.G2;
+    const size_t orow = static_cast<size_t>(crop) * p.T + 1 + pidx;
+    const float* addend = p.pos + static_cast<size_t>(1 + pidx) * p.N + col;
+    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[j + e]);
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j + 4));
-          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-        }
-        if constexpr (MODE == kGemmBiasQGeluBf16) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
-        } else if constexpr (MODE == kGemmBiasGeluBf16) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
-        }
-        uint4 w;
-        w.x = pack_bf16x2(f[0], f[1]);
-        w.y = pack_bf16x2(f[2], f[3]);
-        w.z = pack_bf16x2(f[4], f[5]);
-        w.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(o + j) = w;
-      }
-    } else {
-      size_t orow = static_cast<size_t>(row);
-      const float* addend = p.bias ? p.bias + col : nullptr;  // per-column addend (bias or pos row)
-      if constexpr (MODE == kGemmPatchEmbedF32) {
-        const int crop = row / p.G2;
-        const int pidx = row - crop * p.G2;
-        orow = static_cast<size_t>(crop) * p.T + 1 + pidx;
-        addend = p.pos + static_cast<size_t>(1 + pidx) * p.N + col;
-      }
-      float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 v;
-        v.x = __uint_as_float(acc[j + 0]);
-        v.y = __uint_as_float(acc[j + 1]);
-        v.z = __uint_as_float(acc[j + 2]);
-        v.w = __uint_as_float(acc[j + 3]);
-        if (addend) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(addend + j));
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-        }
-        if constexpr (MODE == kGemmBiasResidF32) {
-          const float4 r = *reinterpret_cast<const float4*>(o + j);
-          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-        }
-        *reinterpret_cast<float4*>(o + j) = v;
-      }
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(addend + j));
+      float4 v;
+      v.x = __uint_as_float(acc[j + 0]) + b.x;
+      v.y = __uint_as_float(acc[j + 1]) + b.y;
+      v.z = __uint_as_float(acc[j + 2]) + b.z;
+      v.w = __uint_as_float(acc[j + 3]) + b.w;
+      *reinterpret_cast<float4*>(o + j) = v;
     }
   }
 };
@@ -122,9 +103,17 @@ static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(g.tmap_a, g.tmap_b, p, make_idesc_f16(kBM, kBN, 1));
+  kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(g.tmap_a, g.tmap_b, g.tmap_out, p, make_idesc_f16(kBM, kBN, 1));
   B2C_POST_LAUNCH("umma_tile_kernel<gemm>");
   return 0;
+}
+
+int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, int mode) {
+  if (mode == kGemmBiasResidF32)
+    return make_tmap_2d_ex(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 4, 32, 32,
+                           B2C_F32);
+  return make_tmap_2d_ex(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 64,
+                         B2C_BF16);
 }
 
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
@@ -178,5 +167,6 @@ extern "C" int b2c_gemm_bf16(const void* A, const void* W, const float* bias, vo
   g.bias = bias;
   g.out = out;
   g.ldo = N;
+  B2C_TRY(make_out_tmap(&g.tmap_out, out, M, N, N, epilogue));
   return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }

@@ -36,6 +36,10 @@ int set_error(int code, const char* fmt, ...);
 // elem: 0 = fp16, 1 = bf16.  row_stride_bytes must be a multiple of 16.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                  uint32_t box_rows, int elem);
+// General form: dtype B2C_F32 / B2C_F16 / B2C_BF16, box = [box_rows, box_cols] with box_cols * elem_size == 128 B
+// (one 128-B swizzle row).  Used for the epilogue's TMA stores.
+int make_tmap_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                    uint32_t box_rows, uint32_t box_cols, int dtype);
 
 int num_sms();
 

@@ -28,6 +28,8 @@ enum GemmMode {
 struct GemmLaunch {
   CUtensorMap tmap_a;  // [M, K] bf16, box 128 x 64
   CUtensorMap tmap_b;  // [N, K] bf16, box 256 x 64
+  CUtensorMap tmap_out;  // epilogue store map over `out`: bf16 modes box 32 rows x 64 cols, f32 residual mode
+                         // box 32 rows x 32 cols (make_out_tmap); unused by the patch-embed mode
   int64_t M;
   int N, K;
   int mode;
@@ -38,6 +40,8 @@ struct GemmLaunch {
   int T, G2;          // patch-embed only: tokens per crop, patches per crop
 };
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
+// store map for a GEMM output [M, N] (row stride ldo elements) matching `mode`
+int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, int mode);
 
 // ---- row-wise kernels (b2c_rowops.cu) ----------------------------------------------------------
 int layernorm_bf16_launch(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d, float eps,

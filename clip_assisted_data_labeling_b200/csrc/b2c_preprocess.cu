@@ -217,13 +217,14 @@ __global__ void __launch_bounds__(kResThreads) resample_kernel(const ResamplePar
         o[(static_cast<size_t>(c) * R + r0 + rem / R) * R + rem % R] = 0.f;
       }
     } else {
-      const int g = R / p.patch, pp = p.patch * p.patch;
+      // zero whole patch rows (including the K padding): the band holding a patch row's first pixel row owns it
+      const int P = p.patch, g = R / P;
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(crop) * g * g * p.Kp;
-      for (int i = tid; i < 3 * nr * R; i += kResThreads) {
-        const int c = i / (nr * R), rem = i - c * nr * R;
-        const int r = r0 + rem / R, x = rem % R;
-        o[static_cast<size_t>((r / p.patch) * g + x / p.patch) * p.Kp + c * pp + (r % p.patch) * p.patch + x % p.patch] =
-            __float2bfloat16_rn(0.f);
+      for (int r = 0; r < nr; ++r) {
+        const int row = r0 + r;
+        if (row % P != 0) continue;
+        __nv_bfloat16* prow = o + static_cast<size_t>(row / P) * g * p.Kp;
+        for (int i = tid; i < g * p.Kp; i += kResThreads) prow[i] = __float2bfloat16_rn(0.f);
       }
     }
     return;

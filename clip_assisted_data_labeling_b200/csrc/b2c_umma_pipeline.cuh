@@ -14,9 +14,16 @@
 //
 // A Policy supplies:  struct Params { int num_tiles; int k_blocks; ... };
 //   __device__ static bool tile(const Params&, int t, int& a_row, int& b_row)   // false = skip tile
-//   __device__ static void epilogue(const Params&, int a_row, int b_row, int row_in_tile, int col0,
-//                                   const uint32_t (&acc)[32])
+//   static constexpr int kStore = kStoreDirect | kStoreTmaBf16 | kStoreTmaAddF32
+//   kStoreDirect   : __device__ static void epilogue(const Params&, int a_row, int b_row, int row_in_tile,
+//                                                    int col0, const uint32_t (&acc)[32])   // policy writes itself
+//   kStoreTma*     : __device__ static void transform(const Params&, int col, float (&v)[32])   // bias / activation
+//                    the kernel stages the 32-row x 128-byte slab of each epilogue warp in 128B-swizzled shared
+//                    memory and hands it to the TMA unit: a plain tiled store (bf16) or a reduce-add performed
+//                    at L2 (f32 residual stream: x += tile without the SM ever loading x).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "b2c_ptx.cuh"
 
 namespace b2c {
@@ -31,17 +38,22 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kBN;  // 512
 constexpr int kUmmaThreads = 192;
-// ring + 1 KB slack for manual 1024-B alignment + barriers
-constexpr int kUmmaSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kStoreDirect = 0, kStoreTmaBf16 = 1, kStoreTmaAddF32 = 2;
+constexpr int kSlabBytes = 32 * 128;          // one epilogue warp's staging slab: 32 rows x 128 B
+constexpr int kSlabsPerWarp = 2;              // double buffered against the TMA unit's reads
+constexpr int kStagingBytes = 4 * kSlabsPerWarp * kSlabBytes;
+// ring + epilogue staging + 1 KB slack for manual 1024-B alignment + barriers
+constexpr int kUmmaSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
 
 template <class Policy>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 umma_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const typename Policy::Params p, const uint32_t idesc) {
+                 const __grid_constant__ CUtensorMap tmap_out, const typename Policy::Params p, const uint32_t idesc) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;  // [4 warps][kSlabsPerWarp][32 rows][128 B], 1024-B aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full_bar = bars;                           // [kStages]
   uint64_t* empty_bar = bars + kStages;                // [kStages]
   uint64_t* acc_full_bar = bars + 2 * kStages;         // [kAccStages]
@@ -54,6 +66,7 @@ umma_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (Policy::kStore != kStoreDirect) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -134,18 +147,81 @@ umma_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&acc_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kBN + (static_cast<uint32_t>(quarter * 32) << 16);
+      if constexpr (Policy::kStore == kStoreDirect) {
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        Policy::epilogue(p, a_row, b_row, row_in_tile, c * 32, v);
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          Policy::epilogue(p, a_row, b_row, row_in_tile, c * 32, v);
+        }
+      } else {
+        // lane = row of the slab; 16-byte chunk j of the row lands at chunk (j ^ (lane & 7)): the layout
+        // CU_TENSOR_MAP_SWIZZLE_128B expects, and conflict-free for the 8 lanes of a store phase.
+        uint8_t* my_slabs = staging + (warp - 2) * (kSlabsPerWarp * kSlabBytes);
+        const int out_row = a_row + quarter * 32;
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+          Policy::transform(p, b_row + c * 32, f);
+          if constexpr (Policy::kStore == kStoreTmaAddF32) {
+            uint8_t* slab = my_slabs + (c & 1) * kSlabBytes;
+            if (lane == 0) tma_store_wait_read<kSlabsPerWarp - 1>();  // the slab's previous store has been read out
+            __syncwarp();
+            uint8_t* rowp = slab + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmap_out, slab, b_row + c * 32, out_row);
+              tma_store_commit();
+            }
+          } else {
+            // bf16: two 32-column chunks fill one 128-byte row (64 columns) before the store is issued
+            uint8_t* slab = my_slabs + ((c >> 1) & 1) * kSlabBytes;
+            if ((c & 1) == 0) {
+              if (lane == 0) tma_store_wait_read<kSlabsPerWarp - 1>();
+              __syncwarp();
+            }
+            uint8_t* rowp = slab + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+              w.x = *reinterpret_cast<uint32_t*>(&t0);
+              w.y = *reinterpret_cast<uint32_t*>(&t1);
+              w.z = *reinterpret_cast<uint32_t*>(&t2);
+              w.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(rowp + ((((c & 1) * 4 + j) ^ (lane & 7)) << 4)) = w;
+            }
+            if (c & 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmap_out, slab, b_row + (c - 1) * 32, out_row);
+                tma_store_commit();
+              }
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    if (Policy::kStore != kStoreDirect && lane == 0) tma_store_wait<0>();  // all bulk stores retired before exit
   }
 
   tc_fence_before();

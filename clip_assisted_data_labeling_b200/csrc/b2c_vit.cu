@@ -113,12 +113,18 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
                        kBM, 1));
   B2C_TRY(make_tmap_2d(&tm_h, h, M, d, static_cast<uint64_t>(d) * 2, kBM, 1));
   B2C_TRY(make_tmap_2d(&tm_mlp, big, M, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBM, 1));
+  // epilogue store maps: qkv / mlp-hidden (bf16 tiled stores), residual stream (f32 reduce-add at L2)
+  CUtensorMap st_qkv, st_mlp, st_x;
+  B2C_TRY(make_out_tmap(&st_qkv, big, M, 3 * d, 3 * d, kGemmBiasBf16));
+  B2C_TRY(make_out_tmap(&st_mlp, big, M, c.mlp, c.mlp, kGemmBiasBf16));
+  B2C_TRY(make_out_tmap(&st_x, x, M, d, d, kGemmBiasResidF32));
 
   // K1: conv1 as a GEMM over patch rows, + positional embedding, scattered past the class token
   {
     GemmLaunch gl{};
     gl.tmap_a = tm_patches;
     gl.tmap_b = v->tm_conv1;
+    gl.tmap_out = tm_patches;  // unused by the patch-embed epilogue (direct scattered stores)
     gl.M = static_cast<int64_t>(nc) * v->G2;
     gl.N = d;
     gl.K = v->Kp;
@@ -139,14 +145,14 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     B2C_TRY(layernorm_bf16_launch(x, L.ln1_w, L.ln1_b, h, M, d, eps, stream));
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv; gl.tmap_out = st_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
       gl.mode = kGemmBiasBf16; gl.bias = L.b_qkv; gl.out = big; gl.ldo = 3 * d;
       B2C_TRY(gemm_launch(gl, stream));
     }
     B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_out; gl.M = M; gl.N = d; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_out; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = d;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_out; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }
@@ -154,14 +160,14 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     B2C_TRY(layernorm_bf16_launch(x, L.ln2_w, L.ln2_b, h, M, d, eps, stream));
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc; gl.M = M; gl.N = c.mlp; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc; gl.tmap_out = st_mlp; gl.M = M; gl.N = c.mlp; gl.K = d;
       gl.mode = c.act == B2C_ACT_GELU ? kGemmBiasGeluBf16 : kGemmBiasQGeluBf16;
       gl.bias = L.b_fc; gl.out = big; gl.ldo = c.mlp;
       B2C_TRY(gemm_launch(gl, stream));
     }
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj; gl.M = M; gl.N = d; gl.K = c.mlp;
+      gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = c.mlp;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_proj; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }

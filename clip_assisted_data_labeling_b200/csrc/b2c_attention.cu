@@ -2,14 +2,29 @@
 // no mask, no dropout (nn.MultiheadAttention inside open_clip's ResidualAttentionBlock; the reference
 // reaches it through utils/embedder.py:98).
 //
-// One CTA per (crop, head).  K and V of that head (T <= 592 tokens) are staged once in shared memory
+// Two implementations:
+//  (1) attention_umma_kernel — the flagship shape (T = 257 = class token + 256 patches, head dim 64: ViT-L/14-224)
+//      on tcgen05: one CTA per (crop, head, 128-query tile), two CTAs per SM.  TMA loads Q[128x64], K[256x64],
+//      V[256x64] (128B swizzle); S = Q·Kᵀ (M128 N256 K64) accumulates in 256 TMEM columns; the 4 softmax warps own
+//      one TMEM lane (= query row) each, fold the class-token KEY in as a rank-1 term (s0 = q·k0 by FMA, p0·v0 in
+//      the epilogue) so the tensor-core problem is exactly 256 keys with no padding, write P (bf16) into the
+//      128B-swizzled K-major layout over the dead Q/K tiles, and O = P·V runs with V as an MN-major B operand
+//      straight from the TMA tile (no transpose), accumulating over the S columns.  The class-token QUERY row
+//      (1 of 257) is a small SIMT kernel (attention_cls_kernel).
+//  (2) attention_kernel — generic (any T <= 592, head dim 64 or 80) on bf16 mma.sync, used for ViT-B/32,
+//      ViT-L/14-336 and ViT-H/14.
+//
+// (2): One CTA per (crop, head).  K and V of that head (T <= 592 tokens) are staged once in shared memory
 // (cp.async, 16-byte chunks, rows padded by 16 B so ldmatrix is bank-conflict-free); each warp owns
 // 16-query tiles and streams the keys in chunks of 64 with an online (running max / running sum)
 // softmax in fp32 registers.  Tensor work is bf16 mma.sync m16n8k16 with fp32 accumulation; this is
 // 4 % of the tower's FLOPs.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "b2c_launch.h"
+#include "b2c_umma_pipeline.cuh"
 
 namespace b2c {
 
@@ -205,6 +220,311 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
   }
 }
 
+
+// ================================================================================================
+// (1) tcgen05 attention for T = 257, head dim 64
+// ================================================================================================
+constexpr int kAuThreads = 192;
+constexpr int kAuKeys = 256;                      // patch tokens = keys handled by the tensor cores
+constexpr int kAuOffK = 0;                        // K tile  [256 keys x 128 B]          (later P k-blocks 0,1)
+constexpr int kAuOffQ = 32 * 1024;                // Q tile  [128 rows x 128 B]          (later P k-block 2)
+constexpr int kAuOffV = 64 * 1024;                // V tile  [256 keys x 128 B]   ([48K,64K) = P k-block 3 only)
+constexpr int kAuOffBar = 96 * 1024;
+constexpr int kAuSmemBytes = 96 * 1024 + 1024 + 128;
+
+__global__ void __launch_bounds__(kAuThreads, 2)
+attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                      const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int heads,
+                      float scale_log2) {
+  extern __shared__ uint8_t smem_au_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_au_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAuOffBar);
+  uint64_t* bar_qk = bars + 0;  // Q and K tiles landed
+  uint64_t* bar_v = bars + 1;   // V tile landed
+  uint64_t* bar_s = bars + 2;   // S = Q·Kᵀ complete in TMEM
+  uint64_t* bar_p = bars + 3;   // P written to smem by the 4 softmax warps
+  uint64_t* bar_o = bars + 4;   // O = P·V complete in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x & 1;
+  const int ch = blockIdx.x >> 1;
+  const int crop = ch / heads;
+  const int head = ch - crop * heads;
+  const int d = heads * 64;
+  const int tok0 = crop * T;  // the crop's class token; patch tokens follow
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_qk, 48 * 1024);
+      tma_load_2d(smem + kAuOffQ, &tm_q, bar_qk, head * 64, tok0 + 1 + qt * 128);
+      tma_load_2d(smem + kAuOffK, &tm_kv, bar_qk, d + head * 64, tok0 + 1);
+      mbar_arrive_expect_tx(bar_v, 32 * 1024);
+      tma_load_2d(smem + kAuOffV, &tm_kv, bar_v, 2 * d + head * 64, tok0 + 1);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sbase = smem_u32(smem);
+      // S[128 x 256] = Q[128 x 64] · K[256 x 64]ᵀ : both K-major
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint64_t q_desc = make_sw128_kmajor_desc(sbase + kAuOffQ);
+      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + kAuOffK);
+      const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16(tmem, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+      umma_commit(bar_s);
+      // O[128 x 64] = P[128 x 256] · V[256 x 64] : P K-major (4 k-blocks of 64 keys, 16 KB each from offset 0),
+      // V MN-major: tile rows are keys (K), 128 swizzled bytes of head dim (N) per row; 8-key groups 1024 B apart.
+      mbar_wait(bar_p, 0);
+      mbar_wait(bar_v, 0);
+      tc_fence_after();
+      const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // b_major = MN
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint64_t p_desc = make_sw128_kmajor_desc(sbase + kb * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t v_desc = make_sw128_kmajor_desc(sbase + kAuOffV + (kb * 64 + k * 16) * 128);
+          umma_f16(tmem, p_desc + 2 * k, v_desc, idesc_o, (kb | k) != 0);
+        }
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                 // query row of the tile = TMEM lane
+    const int token = tok0 + 1 + qt * 128 + r;
+    const size_t row_stride = static_cast<size_t>(3) * d;
+    // ---- class-token key as a rank-1 term: s0 = q_r · k0 (bf16 inputs, fp32 accumulate like the MMA)
+    float s0 = 0.f;
+    {
+      const uint4* qp = reinterpret_cast<const uint4*>(qkv + token * row_stride + head * 64);
+      const uint4* kp = reinterpret_cast<const uint4*>(qkv + tok0 * row_stride + d + head * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 a = __ldg(qp + j), b = __ldg(kp + j);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+          s0 = fmaf(fa.x, fb.x, s0);
+          s0 = fmaf(fa.y, fb.y, s0);
+        }
+      }
+    }
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    // ---- pass 1: row max over the 256 patch keys and the class key
+    float m = s0;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
+    }
+    const float ms = m * scale_log2;
+    const float p0 = exp2f(fmaf(s0, scale_log2, -ms));
+    float l = p0;
+    // ---- pass 2: p = exp2((s - m) * scale), bf16, into the K-major 128B-swizzled P tiles (over the dead K/Q tiles)
+    uint8_t* prow = smem + r * 128;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        f[e] = exp2f(fmaf(__uint_as_float(v[e]), scale_log2, -ms));
+        l += f[e];
+      }
+      uint8_t* blk = prow + (c >> 1) * 16384;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack2(f[8 * j + 0], f[8 * j + 1]);
+        w.y = pack2(f[8 * j + 2], f[8 * j + 3]);
+        w.z = pack2(f[8 * j + 4], f[8 * j + 5]);
+        w.w = pack2(f[8 * j + 6], f[8 * j + 7]);
+        *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + j) ^ (r & 7)) << 4)) = w;
+      }
+    }
+    fence_proxy_async_smem();  // P must be visible to the tensor core's (async proxy) smem reads
+    tc_fence_before();         // and our TMEM reads of S ordered before O overwrites those columns
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+    // ---- epilogue: O row (64 columns) + class-key term, normalised, bf16
+    const float inv = 1.0f / l;
+    float v0[64];
+    {
+      const uint4* vp = reinterpret_cast<const uint4*>(qkv + tok0 * row_stride + 2 * d + head * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 a = __ldg(vp + j);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(a2[e]);
+          v0[8 * j + 2 * e] = fa.x * p0;
+          v0[8 * j + 2 * e + 1] = fa.y * p0;
+        }
+      }
+    }
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack2((__uint_as_float(v[8 * j + 0]) + v0[c * 32 + 8 * j + 0]) * inv, (__uint_as_float(v[8 * j + 1]) + v0[c * 32 + 8 * j + 1]) * inv);
+        w.y = pack2((__uint_as_float(v[8 * j + 2]) + v0[c * 32 + 8 * j + 2]) * inv, (__uint_as_float(v[8 * j + 3]) + v0[c * 32 + 8 * j + 3]) * inv);
+        w.z = pack2((__uint_as_float(v[8 * j + 4]) + v0[c * 32 + 8 * j + 4]) * inv, (__uint_as_float(v[8 * j + 5]) + v0[c * 32 + 8 * j + 5]) * inv);
+        w.w = pack2((__uint_as_float(v[8 * j + 6]) + v0[c * 32 + 8 * j + 6]) * inv, (__uint_as_float(v[8 * j + 7]) + v0[c * 32 + 8 * j + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + c * 32 + 8 * j) = w;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// The class-token query row of every (crop, head): one warp each, SIMT.  1/257 of the attention work.
+__global__ void __launch_bounds__(128) attention_cls_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads,
+                                                            float scale_log2) {
+  const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ch >= n_ch) return;
+  const int lane = threadIdx.x & 31;
+  const int crop = ch / heads, head = ch - crop * heads;
+  const int d = heads * 64;
+  const size_t row_stride = static_cast<size_t>(3) * d;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(crop) * T * row_stride + head * 64;
+  // q0 in registers (every lane holds all 64 values)
+  float q[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(base);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 a = __ldg(qp + j);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(a2[e]);
+        q[8 * j + 2 * e] = f.x;
+        q[8 * j + 2 * e + 1] = f.y;
+      }
+    }
+  }
+  // scores: lane owns keys lane, lane+32, ...
+  constexpr int SLOTS = 19;  // ceil(592 / 32)
+  float s[SLOTS];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < SLOTS; ++i) {
+    const int key = i * 32 + lane;
+    s[i] = -INFINITY;
+    if (key < T) {
+      const uint4* kp = reinterpret_cast<const uint4*>(base + key * row_stride + d);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 a = __ldg(kp + j);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(a2[e]);
+          acc = fmaf(q[8 * j + 2 * e], f.x, acc);
+          acc = fmaf(q[8 * j + 2 * e + 1], f.y, acc);
+        }
+      }
+      s[i] = acc;
+      m = fmaxf(m, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < SLOTS; ++i) {
+    s[i] = exp2f((s[i] - m) * scale_log2);  // -inf slots become 0
+    l += s[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  // output: lane owns columns 2*lane, 2*lane+1; p broadcast from its owner lane
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < SLOTS; ++i) {
+    if (i * 32 >= T) break;
+    for (int src = 0; src < 32; ++src) {
+      const int key = i * 32 + src;
+      const float p = __shfl_sync(0xffffffffu, s[i], src);
+      if (key < T) {
+        const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(base + key * row_stride + 2 * d + 2 * lane);
+        const float2 f = __bfloat1622float2(vv);
+        o0 = fmaf(p, f.x, o0);
+        o1 = fmaf(p, f.y, o1);
+      }
+    }
+  }
+  const float inv = 1.0f / l;
+  *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(crop) * T * d + head * 64 + 2 * lane) = pack2(o0 * inv, o1 * inv);
+}
+
+static int attention_umma_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
+  const int d = heads * 64;
+  CUtensorMap tm_q, tm_kv;
+  const uint64_t rows = static_cast<uint64_t>(n) * T;
+  B2C_TRY(make_tmap_2d(&tm_q, qkv, rows, 3ull * d, 3ull * d * 2, 128, 1));
+  B2C_TRY(make_tmap_2d(&tm_kv, qkv, rows, 3ull * d, 3ull * d * 2, 256, 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAuSmemBytes));
+    attr_set = true;
+  }
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  attention_umma_kernel<<<static_cast<unsigned>(n) * heads * 2, kAuThreads, kAuSmemBytes, stream>>>(tm_q, tm_kv, q, o, T, heads,
+                                                                                                    scale_log2);
+  B2C_POST_LAUNCH("attention_umma_kernel");
+  attention_cls_kernel<<<(n * heads + 3) / 4, 128, 0, stream>>>(q, o, n * heads, T, heads, scale_log2);
+  B2C_POST_LAUNCH("attention_cls_kernel");
+  return 0;
+}
+
 template <int HD>
 static int attention_launch_hd(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
   const int Tp = (T + 15) / 16 * 16;
@@ -225,6 +545,8 @@ static int attention_launch_hd(const void* qkv, void* out, int n, int T, int hea
 
 int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream) {
   B2C_REQUIRE(n > 0 && T > 0 && heads > 0, "attention: empty problem");
+  static const bool legacy = [] { const char* e = getenv("B2C_ATTN"); return e && e[0] == 'l'; }();
+  if (hd == 64 && T == kAuKeys + 1 && !legacy) return attention_umma_launch(qkv, out, n, T, heads, stream);
   if (hd == 64) return attention_launch_hd<64>(qkv, out, n, T, heads, stream);
   if (hd == 80) return attention_launch_hd<80>(qkv, out, n, T, heads, stream);
   return set_error(B2C_ERR_ARG, "attention: head dim %d unsupported (64 or 80)", hd);

@@ -136,6 +136,29 @@ def case_attention():
     return out
 
 
+def case_attention_perf():
+    import torch
+    L = lib()
+    n, T, heads, hd = 512, 257, 16, 64
+    d = heads * hd
+    qkv = torch.randn(n * T, 3 * d, device="cuda").to(torch.bfloat16)
+    o = torch.zeros(n * T, d, device="cuda", dtype=torch.bfloat16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        assert L.b2c_attention_bf16(C.c_void_p(qkv.data_ptr()), C.c_void_p(o.data_ptr()), n, T, heads, hd, st) == 0, L.b2c_last_error()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(10):
+        L.b2c_attention_bf16(C.c_void_p(qkv.data_ptr()), C.c_void_p(o.data_ptr()), n, T, heads, hd, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    q, k, v = qkv[:4 * T].float().view(4, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(4 * T, d)
+    err = (o[:4 * T].float() - ref).abs().max().item()
+    return [{"ms": ms, "tflops": 4.0 * T * T * d * n / ms / 1e9, "max_abs_err": err, "path": os.environ.get("B2C_ATTN", "umma"), "ok": bool(err < 0.02)}]
+
+
 def case_preprocess():
     import numpy as np
     import torch

@@ -215,7 +215,9 @@ def run_b200_arm(args):
     B = args.batch
     cfg = ARCHS["ViT-L-14"]
 
-    enc = CLIP_Encoder(MODEL, device="cuda", seed=0) if rank == 0 or True else None
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
+        enc = CLIP_Encoder(MODEL, device="cuda", seed=0)
     pool_host = [synth_batch(B, 100 * rank + i).pin_memory() for i in range(args.pool)]
     pool_dev = [b.cuda() for b in pool_host]
     torch.cuda.synchronize()

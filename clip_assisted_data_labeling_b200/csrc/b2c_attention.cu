@@ -525,6 +525,378 @@ static int attention_umma_launch(const void* qkv, void* out, int n, int T, int h
   return 0;
 }
 
+
+// ================================================================================================
+// (1b) tcgen05 attention v2 for T = 257, head dim 64: persistent, pipelined, P kept in tensor memory.
+//   CTA (one per SM, 320 threads) loops over (crop, head) pairs:
+//     warp 0      TMA producer: Q (both 128-row tiles), K, V of the NEXT head stream into the other smem stage
+//     warp 1      MMA issuer:   S_w = Q_w·Kᵀ (SS) into TMEM region w;  O_w = P_w·V (A = P from TMEM, V MN-major);
+//                               L_w = P_w·1 (row sums of the ROUNDED probabilities, fp32, from the tensor core)
+//     warps 2-5   softmax group 0 (query tile 0), warps 6-9 softmax group 1 (query tile 1); one TMEM lane =
+//                 one query row per thread: max pass, exp2 pass, P (bf16x2) written back over S with tcgen05.st,
+//                 O and L read back, class-key rank-1 term added, normalised, stored.
+//   The class-token QUERY row of the head is computed by one of the two groups (alternating) with plain FMAs on
+//   the K/V tiles already in shared memory, inside the time it would otherwise wait for the tensor core.
+//   TMEM region w (256 columns): S [0,256) -> P [0,128) | O [128,192) | L [192,208).
+// ================================================================================================
+constexpr int kA2Threads = 320;
+constexpr int kA2StageBytes = 96 * 1024;   // Q [256 x 128 B] | K [256 x 128 B] | V [256 x 128 B]
+constexpr int kA2OffQ = 0, kA2OffK = 32 * 1024, kA2OffV = 64 * 1024;
+constexpr int kA2OffOnes = 2 * kA2StageBytes;          // 8 KB of bf16 1.0: the B operand of the row-sum MMA
+constexpr int kA2OffMisc = kA2OffOnes + 8 * 1024;
+constexpr int kA2SmemBytes = kA2OffMisc + 14 * 1024 + 1024;
+
+struct A2Misc {
+  uint64_t full_qk[2], full_v[2], empty_qk[2], empty_v[2];
+  uint64_t s_full[2], p_full[2], o_full[2], tmem_free[2];
+  uint32_t tmem_slot;
+  uint32_t pad[3];
+  float red[2][8];          // per group: cross-warp max / sum scratch
+  float vec[2][3][64];      // per group: q0, k0, v0 of the current head as fp32
+  float part[2][16][64];    // per group: 16 key-slices of the class-row output
+  float p_cls[2][264];      // per group: class-row probabilities (256 patch keys + class key)
+};
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// dot of 64 bf16 values (8 x uint4) with 64 fp32 values in shared memory
+__device__ __forceinline__ float dot64(const uint4 (&a)[8], const float* __restrict__ q) {
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 qa = *reinterpret_cast<const float4*>(q + 8 * j);
+    const float4 qb = *reinterpret_cast<const float4*>(q + 8 * j + 4);
+    acc0 = fmaf(bf16_lo(a[j].x), qa.x, acc0);
+    acc1 = fmaf(bf16_hi(a[j].x), qa.y, acc1);
+    acc0 = fmaf(bf16_lo(a[j].y), qa.z, acc0);
+    acc1 = fmaf(bf16_hi(a[j].y), qa.w, acc1);
+    acc0 = fmaf(bf16_lo(a[j].z), qb.x, acc0);
+    acc1 = fmaf(bf16_hi(a[j].z), qb.y, acc1);
+    acc0 = fmaf(bf16_lo(a[j].w), qb.z, acc0);
+    acc1 = fmaf(bf16_hi(a[j].w), qb.w, acc1);
+  }
+  return acc0 + acc1;
+}
+
+__device__ __forceinline__ uint32_t tmem_ld_1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* __restrict__ qkv,
+                       __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads, float scale_log2) {
+  extern __shared__ uint8_t smem_a2_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_a2_raw) + 1023) & ~uintptr_t(1023));
+  A2Misc* mb = reinterpret_cast<A2Misc*>(smem + kA2OffMisc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * 64;
+  const size_t row_stride = static_cast<size_t>(3) * d;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&mb->full_qk[s], 1);
+      mbar_init(&mb->full_v[s], 1);
+      mbar_init(&mb->empty_qk[s], 2);  // MMA commit + the group that computed the class row from K
+      mbar_init(&mb->empty_v[s], 2);   // MMA commit + the group that computed the class row from V
+      mbar_init(&mb->s_full[s], 1);
+      mbar_init(&mb->p_full[s], 4);
+      mbar_init(&mb->o_full[s], 1);
+      mbar_init(&mb->tmem_free[s], 4);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 8 * 1024 / 4; i += kA2Threads)
+    reinterpret_cast<uint32_t*>(smem + kA2OffOnes)[i] = 0x3F803F80u;  // bf16 1.0 x2
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc(&mb->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mb->tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int k = 0;
+      for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+        const int s = k & 1;
+        const uint32_t u = (k >> 1) & 1;
+        const int crop = ch / heads, head = ch - crop * heads;
+        const int row0 = crop * T + 1;
+        uint8_t* st = smem + s * kA2StageBytes;
+        mbar_wait(&mb->empty_qk[s], u ^ 1);
+        mbar_arrive_expect_tx(&mb->full_qk[s], 64 * 1024);
+        tma_load_2d(st + kA2OffQ, &tm, &mb->full_qk[s], head * 64, row0);
+        tma_load_2d(st + kA2OffK, &tm, &mb->full_qk[s], d + head * 64, row0);
+        mbar_wait(&mb->empty_v[s], u ^ 1);
+        mbar_arrive_expect_tx(&mb->full_v[s], 32 * 1024);
+        tma_load_2d(st + kA2OffV, &tm, &mb->full_v[s], 2 * d + head * 64, row0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
+      const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
+      const uint32_t idesc_l = make_idesc_f16(128, 16, 1);
+      const uint64_t ones_desc = make_sw128_kmajor_desc(smem_u32(smem + kA2OffOnes));
+      int k = 0;
+      for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+        const int s = k & 1;
+        const uint32_t u = (k >> 1) & 1, kp = k & 1;
+        const uint32_t sbase = smem_u32(smem + s * kA2StageBytes);
+        mbar_wait(&mb->full_qk[s], u);
+        const uint64_t k_desc = make_sw128_kmajor_desc(sbase + kA2OffK);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(&mb->tmem_free[w], kp ^ 1);  // group w has read the previous O out of its region
+          tc_fence_after();
+          const uint64_t q_desc = make_sw128_kmajor_desc(sbase + kA2OffQ + w * 16384);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tmem + w * 256, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk != 0);
+          umma_commit(&mb->s_full[w]);
+        }
+        umma_commit(&mb->empty_qk[s]);
+        mbar_wait(&mb->full_v[s], u);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(&mb->p_full[w], kp);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            const uint64_t v_desc = make_sw128_kmajor_desc(sbase + kA2OffV + kk * 16 * 128);
+            umma_f16_ts(tmem + w * 256 + 128, tmem + w * 256 + kk * 8, v_desc, idesc_o, kk != 0);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk)  // every element of the ones tile is 1.0, so any 16 x 16 slice will do
+            umma_f16_ts(tmem + w * 256 + 192, tmem + w * 256 + kk * 8, ones_desc + 2 * (kk & 3), idesc_l, kk != 0);
+          umma_commit(&mb->o_full[w]);
+        }
+        umma_commit(&mb->empty_v[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    const int w = (warp - 2) >> 2;          // group = query tile
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+    const int r = quarter * 32 + lane;      // query row in the tile = TMEM lane
+    const int gt = (warp - 2 - 4 * w) * 32 + lane;  // thread index inside the group, 0..127
+    const uint32_t taddr = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* red = mb->red[w];
+    float* pcls = mb->p_cls[w];
+    float* q0f = mb->vec[w][0];
+    float* k0f = mb->vec[w][1];
+    float* v0f = mb->vec[w][2];
+    int k = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t u = (k >> 1) & 1, kp = k & 1;
+      const int crop = ch / heads, head = ch - crop * heads;
+      const int tok0 = crop * T;
+      const int token = tok0 + 1 + w * 128 + r;
+      const uint8_t* st = smem + s * kA2StageBytes;
+      const bool cls_owner = ((k & 1) == w);
+      const __nv_bfloat16* cls_row = qkv + tok0 * row_stride + head * 64;
+
+      // ---- the head's class-token q, k, v as fp32 in the group's scratch (one element per thread)
+      if (gt < 64) {
+        q0f[gt] = __bfloat162float(cls_row[gt]);
+        k0f[gt] = __bfloat162float(cls_row[d + gt]);
+      } else {
+        v0f[gt - 64] = __bfloat162float(cls_row[2 * d + gt - 64]);
+      }
+      uint4 qrow[8];
+      {
+        const uint4* qp4 = reinterpret_cast<const uint4*>(qkv + token * row_stride + head * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qrow[j] = __ldg(qp4 + j);
+      }
+      named_bar_sync(1 + w, 128);
+      // class-token KEY for this thread's query row: s0 = q_r·k0
+      const float s0 = dot64(qrow, k0f);
+
+      // ---- class-token QUERY row, part 1 (scores + softmax statistics) from the K tile in smem
+      float cls_l = 0.f;
+      if (cls_owner) {
+        mbar_wait(&mb->full_qk[s], u);
+        float sa, sb, sc = -INFINITY;
+        {
+          uint4 a[8];
+          const int key = gt;
+          const uint8_t* rowp = st + kA2OffK + key * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const uint4*>(rowp + ((j ^ (key & 7)) << 4));
+          sa = dot64(a, q0f);
+          const uint8_t* rowp2 = rowp + 128 * 128;  // key + 128 (same swizzle phase: 128 % 8 == 0)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const uint4*>(rowp2 + ((j ^ (key & 7)) << 4));
+          sb = dot64(a, q0f);
+        }
+        if (gt == 0) {
+          float acc = 0.f;
+          for (int c = 0; c < 64; ++c) acc = fmaf(q0f[c], k0f[c], acc);
+          sc = acc;
+        }
+        float m = fmaxf(fmaxf(sa, sb), sc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) red[gt >> 5] = m;
+        named_bar_sync(1 + w, 128);  // also: every K read of the group is done
+        if (gt == 0) mbar_arrive(&mb->empty_qk[s]);
+        m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * scale_log2;
+        const float pa = ex2_ftz(fmaf(sa, scale_log2, -m)), pb = ex2_ftz(fmaf(sb, scale_log2, -m));
+        float psum = pa + pb;
+        pcls[gt] = pa;
+        pcls[gt + 128] = pb;
+        if (gt == 0) {
+          const float pc = ex2_ftz(fmaf(sc, scale_log2, -m));
+          pcls[256] = pc;
+          psum += pc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        if (lane == 0) red[4 + (gt >> 5)] = psum;
+        named_bar_sync(1 + w, 128);
+        cls_l = (red[4] + red[5]) + (red[6] + red[7]);
+      }
+
+      // ---- own row: S in TMEM -> max -> P (bf16x2 packed) back into TMEM over S
+      mbar_wait(&mb->s_full[w], kp);
+      tc_fence_after();
+      float m = s0;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+      }
+      const float ms = m * scale_log2;
+      const float p0 = ex2_ftz(fmaf(s0, scale_log2, -ms));
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          pk[e] = pack2(ex2_ftz(fmaf(__uint_as_float(v[2 * e]), scale_log2, -ms)),
+                        ex2_ftz(fmaf(__uint_as_float(v[2 * e + 1]), scale_log2, -ms)));
+        tmem_st_32x16(taddr + c * 16, pk);  // columns [16c, 16c+16) <= columns already consumed
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mb->p_full[w]);
+
+      // ---- class-token QUERY row, part 2: O_cls = P_cls·V from the V tile in smem.
+      //      thread = (16-key slice ks, 8-column chunk cc): one 16-byte read per key.
+      if (cls_owner) {
+        mbar_wait(&mb->full_v[s], u);
+        const int cc = gt & 7, ks = gt >> 3;
+        const uint8_t* vb = st + kA2OffV + (ks * 16) * 128;
+        const float* pp = pcls + ks * 16;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int key = 0; key < 16; ++key) {
+          const uint4 a = *reinterpret_cast<const uint4*>(vb + key * 128 + ((cc ^ (key & 7)) << 4));
+          const float pkey = pp[key];
+          acc[0] = fmaf(pkey, bf16_lo(a.x), acc[0]);
+          acc[1] = fmaf(pkey, bf16_hi(a.x), acc[1]);
+          acc[2] = fmaf(pkey, bf16_lo(a.y), acc[2]);
+          acc[3] = fmaf(pkey, bf16_hi(a.y), acc[3]);
+          acc[4] = fmaf(pkey, bf16_lo(a.z), acc[4]);
+          acc[5] = fmaf(pkey, bf16_hi(a.z), acc[5]);
+          acc[6] = fmaf(pkey, bf16_lo(a.w), acc[6]);
+          acc[7] = fmaf(pkey, bf16_hi(a.w), acc[7]);
+        }
+        float* dst = &mb->part[w][ks][cc * 8];
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        named_bar_sync(1 + w, 128);  // also: every V read of the group is done
+        if (gt == 0) mbar_arrive(&mb->empty_v[s]);
+        if (gt < 64) {
+          float o = pcls[256] * v0f[gt];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o += mb->part[w][i][gt];
+          out[static_cast<size_t>(tok0) * d + head * 64 + gt] = __float2bfloat16_rn(o / cls_l);
+        }
+      }
+
+      // ---- own row: (O + p0·v0) / (L + p0) -> bf16
+      mbar_wait(&mb->o_full[w], kp);
+      tc_fence_after();
+      const float lsum = __uint_as_float(tmem_ld_1(taddr + 192));
+      __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + 128 + c * 32, v);
+        tmem_ld_wait();
+        const float inv = 1.0f / (lsum + p0);
+        const float p0i = p0 * inv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 va = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j);
+          const float4 vb4 = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j + 4);
+          uint4 o4;
+          o4.x = pack2(fmaf(__uint_as_float(v[8 * j + 0]), inv, p0i * va.x), fmaf(__uint_as_float(v[8 * j + 1]), inv, p0i * va.y));
+          o4.y = pack2(fmaf(__uint_as_float(v[8 * j + 2]), inv, p0i * va.z), fmaf(__uint_as_float(v[8 * j + 3]), inv, p0i * va.w));
+          o4.z = pack2(fmaf(__uint_as_float(v[8 * j + 4]), inv, p0i * vb4.x), fmaf(__uint_as_float(v[8 * j + 5]), inv, p0i * vb4.y));
+          o4.w = pack2(fmaf(__uint_as_float(v[8 * j + 6]), inv, p0i * vb4.z), fmaf(__uint_as_float(v[8 * j + 7]), inv, p0i * vb4.w));
+          *reinterpret_cast<uint4*>(orow + c * 32 + 8 * j) = o4;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mb->tmem_free[w]);
+      // the group's scratch (q0f/k0f/v0f, p_cls, part) is rewritten next iteration: everyone must be done with it
+      named_bar_sync(1 + w, 128);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int attention_umma2_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
+  const int d = heads * 64;
+  CUtensorMap tm;
+  B2C_TRY(make_tmap_2d(&tm, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes));
+    attr_set = true;
+  }
+  static_assert(sizeof(A2Misc) <= 14 * 1024, "A2Misc must fit its smem slot");
+  const int sms = num_sms();
+  B2C_REQUIRE(sms > 0, "no CUDA device");
+  const int n_ch = n * heads;
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+  attention_umma2_kernel<<<n_ch < sms ? n_ch : sms, kA2Threads, kA2SmemBytes, stream>>>(
+      tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, scale_log2);
+  B2C_POST_LAUNCH("attention_umma2_kernel");
+  return 0;
+}
+
 template <int HD>
 static int attention_launch_hd(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
   const int Tp = (T + 15) / 16 * 16;
@@ -545,8 +917,10 @@ static int attention_launch_hd(const void* qkv, void* out, int n, int T, int hea
 
 int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream) {
   B2C_REQUIRE(n > 0 && T > 0 && heads > 0, "attention: empty problem");
-  static const bool legacy = [] { const char* e = getenv("B2C_ATTN"); return e && e[0] == 'l'; }();
-  if (hd == 64 && T == kAuKeys + 1 && !legacy) return attention_umma_launch(qkv, out, n, T, heads, stream);
+  // B2C_ATTN = v2 (default: persistent, P in TMEM) | v1 (one CTA per query tile, P in smem) | legacy (mma.sync)
+  static const char mode = [] { const char* e = getenv("B2C_ATTN"); return e ? (e[0] == 'l' ? 'l' : (e[1] == '1' ? '1' : '2')) : '2'; }();
+  if (hd == 64 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch(qkv, out, n, T, heads, stream);
+  if (hd == 64 && T == kAuKeys + 1 && mode == '1') return attention_umma_launch(qkv, out, n, T, heads, stream);
   if (hd == 64) return attention_launch_hd<64>(qkv, out, n, T, heads, stream);
   if (hd == 80) return attention_launch_hd<80>(qkv, out, n, T, heads, stream);
   return set_error(B2C_ERR_ARG, "attention: head dim %d unsupported (64 or 80)", hd);

@@ -9,12 +9,16 @@
 #include <cuda_bf16.h>
 
 #include "b2c_launch.h"
+#include <stdlib.h>
+
 #include "b2c_umma_pipeline.cuh"
+#include "b2c_umma_pipeline2.cuh"
 
 namespace b2c {
 
 struct GemmParams {
-  int num_tiles;
+  int num_tiles;   // 128 x 256 tiles (single-CTA kernel)
+  int num_tiles2;  // 256 x 256 tiles (CTA-pair kernel)
   int k_blocks;
   int n_blocks;
   int M, N;
@@ -92,8 +96,33 @@ struct GemmPolicy {
   }
 };
 
+// B2C_GEMM=1cta forces the single-CTA kernel everywhere (A/B testing); default: CTA pairs for the TMA-store epilogues
+static bool use_cta_pairs() {
+  static const bool v = [] { const char* e = getenv("B2C_GEMM"); return !(e && e[0] == '1'); }();
+  return v;
+}
+
+template <int MODE>
+static int gemm_launch_pair(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
+  auto kern = umma2_tile_kernel<GemmPolicy<MODE>>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmma2SmemBytes));
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  B2C_REQUIRE(sms >= 2, "no CUDA device");
+  int grid = 2 * p.num_tiles2 < sms ? 2 * p.num_tiles2 : (sms & ~1);
+  kern<<<grid, kUmmaThreads, kUmma2SmemBytes, stream>>>(g.tmap_a, g.tmap_b_half, g.tmap_out, p, make_idesc_f16(2 * kBM, kBN, 1));
+  B2C_POST_LAUNCH("umma2_tile_kernel<gemm>");
+  return 0;
+}
+
 template <int MODE>
 static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
+  if constexpr (MODE != kGemmPatchEmbedF32) {
+    if (use_cta_pairs()) return gemm_launch_pair<MODE>(g, p, stream);
+  }
   auto kern = umma_tile_kernel<GemmPolicy<MODE>>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -126,6 +155,7 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   const long long m_blocks = (g.M + kBM - 1) / kBM;
   B2C_REQUIRE(m_blocks * p.n_blocks < (1ll << 31), "gemm: too many tiles");
   p.num_tiles = static_cast<int>(m_blocks * p.n_blocks);
+  p.num_tiles2 = static_cast<int>(((m_blocks + 1) / 2) * p.n_blocks);
   p.M = static_cast<int>(g.M);
   p.N = g.N;
   p.bias = g.bias;
@@ -160,6 +190,8 @@ extern "C" int b2c_gemm_bf16(const void* A, const void* W, const float* bias, vo
                        static_cast<uint64_t>(K) * 2, kBM, 1));
   B2C_TRY(make_tmap_2d(&g.tmap_b, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
                        static_cast<uint64_t>(K) * 2, kBN, 1));
+  B2C_TRY(make_tmap_2d(&g.tmap_b_half, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
+                       static_cast<uint64_t>(K) * 2, kBM, 1));
   g.M = M;
   g.N = N;
   g.K = K;

@@ -28,6 +28,7 @@ enum GemmMode {
 struct GemmLaunch {
   CUtensorMap tmap_a;  // [M, K] bf16, box 128 x 64
   CUtensorMap tmap_b;  // [N, K] bf16, box 256 x 64
+  CUtensorMap tmap_b_half;  // same tensor, box 128 x 64: each CTA of a pair loads half of the tile's N
   CUtensorMap tmap_out;  // epilogue store map over `out`: bf16 modes box 32 rows x 64 cols, f32 residual mode
                          // box 32 rows x 32 cols (make_out_tmap); unused by the patch-embed mode
   int64_t M;

@@ -22,7 +22,8 @@ struct b2c_vit_layer {
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
   __nv_bfloat16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
   float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
-  CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;
+  CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;          // box 256 rows (single-CTA kernel)
+  CUtensorMap tm_qkv_h, tm_out_h, tm_fc_h, tm_proj_h;  // box 128 rows (CTA-pair kernel)
 };
 
 struct b2c_vit {
@@ -124,6 +125,7 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     GemmLaunch gl{};
     gl.tmap_a = tm_patches;
     gl.tmap_b = v->tm_conv1;
+    gl.tmap_b_half = v->tm_conv1;  // unused: patch-embed runs on the single-CTA kernel
     gl.tmap_out = tm_patches;  // unused by the patch-embed epilogue (direct scattered stores)
     gl.M = static_cast<int64_t>(nc) * v->G2;
     gl.N = d;
@@ -145,14 +147,14 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     B2C_TRY(layernorm_bf16_launch(x, L.ln1_w, L.ln1_b, h, M, d, eps, stream));
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv; gl.tmap_out = st_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv; gl.tmap_b_half = L.tm_qkv_h; gl.tmap_out = st_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
       gl.mode = kGemmBiasBf16; gl.bias = L.b_qkv; gl.out = big; gl.ldo = 3 * d;
       B2C_TRY(gemm_launch(gl, stream));
     }
     B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_out; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_out; gl.tmap_b_half = L.tm_out_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = d;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_out; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }
@@ -160,14 +162,14 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     B2C_TRY(layernorm_bf16_launch(x, L.ln2_w, L.ln2_b, h, M, d, eps, stream));
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc; gl.tmap_out = st_mlp; gl.M = M; gl.N = c.mlp; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc; gl.tmap_b_half = L.tm_fc_h; gl.tmap_out = st_mlp; gl.M = M; gl.N = c.mlp; gl.K = d;
       gl.mode = c.act == B2C_ACT_GELU ? kGemmBiasGeluBf16 : kGemmBiasQGeluBf16;
       gl.bias = L.b_fc; gl.out = big; gl.ldo = c.mlp;
       B2C_TRY(gemm_launch(gl, stream));
     }
     {
       GemmLaunch gl{};
-      gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = c.mlp;
+      gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj; gl.tmap_b_half = L.tm_proj_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = c.mlp;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_proj; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }
@@ -281,15 +283,19 @@ extern "C" int b2c_vit_set_weight(b2c_vit* v, const char* key, const void* dev_p
     else if (s == "attn.in_proj_weight") {
       rc = store_bf16(v, &L.w_qkv, dev_ptr, dtype, 3 * d, d, d, count, key);
       if (rc == 0) rc = make_tmap_2d(&L.tm_qkv, L.w_qkv, 3 * d, d, d * 2, kBN, 1);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_qkv_h, L.w_qkv, 3 * d, d, d * 2, kBM, 1);
     } else if (s == "attn.out_proj.weight") {
       rc = store_bf16(v, &L.w_out, dev_ptr, dtype, d, d, d, count, key);
       if (rc == 0) rc = make_tmap_2d(&L.tm_out, L.w_out, d, d, d * 2, kBN, 1);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_out_h, L.w_out, d, d, d * 2, kBM, 1);
     } else if (s == "mlp.c_fc.weight") {
       rc = store_bf16(v, &L.w_fc, dev_ptr, dtype, c.mlp, d, d, count, key);
       if (rc == 0) rc = make_tmap_2d(&L.tm_fc, L.w_fc, c.mlp, d, d * 2, kBN, 1);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_fc_h, L.w_fc, c.mlp, d, d * 2, kBM, 1);
     } else if (s == "mlp.c_proj.weight") {
       rc = store_bf16(v, &L.w_proj, dev_ptr, dtype, d, c.mlp, c.mlp, count, key);
       if (rc == 0) rc = make_tmap_2d(&L.tm_proj, L.w_proj, d, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBN, 1);
+      if (rc == 0) rc = make_tmap_2d(&L.tm_proj_h, L.w_proj, d, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBM, 1);
     } else {
       return set_error(B2C_ERR_ARG, "b2c_vit_set_weight: unknown key %s", key);
     }

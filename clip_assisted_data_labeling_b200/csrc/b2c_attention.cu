@@ -698,6 +698,21 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     float* q0f = mb->vec[w][0];
     float* k0f = mb->vec[w][1];
     float* v0f = mb->vec[w][2];
+    // this thread's query row and its element of the head's class-token q/k/v are fetched one iteration ahead,
+    // so their global-memory latency hides behind the previous head's softmax
+    uint4 qnext[8];
+    float cnext = 0.f, cnext2 = 0.f;
+    auto prefetch = [&](int ch) {
+      const int crop = ch / heads, head = ch - crop * heads;
+      const int tok0 = crop * T;
+      const uint4* qp4 = reinterpret_cast<const uint4*>(qkv + (tok0 + 1 + w * 128 + r) * row_stride + head * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qnext[j] = __ldg(qp4 + j);
+      const __nv_bfloat16* cls_row = qkv + tok0 * row_stride + head * 64;
+      cnext = __bfloat162float(gt < 64 ? cls_row[gt] : cls_row[2 * d + gt - 64]);  // q0[gt] | v0[gt-64]
+      cnext2 = __bfloat162float(cls_row[d + (gt & 63)]);                            // k0[gt]
+    };
+    if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
     int k = 0;
     for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
       const int s = k & 1;
@@ -707,21 +722,13 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       const int token = tok0 + 1 + w * 128 + r;
       const uint8_t* st = smem + s * kA2StageBytes;
       const bool cls_owner = ((k & 1) == w);
-      const __nv_bfloat16* cls_row = qkv + tok0 * row_stride + head * 64;
 
-      // ---- the head's class-token q, k, v as fp32 in the group's scratch (one element per thread)
-      if (gt < 64) {
-        q0f[gt] = __bfloat162float(cls_row[gt]);
-        k0f[gt] = __bfloat162float(cls_row[d + gt]);
-      } else {
-        v0f[gt - 64] = __bfloat162float(cls_row[2 * d + gt - 64]);
-      }
       uint4 qrow[8];
-      {
-        const uint4* qp4 = reinterpret_cast<const uint4*>(qkv + token * row_stride + head * 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) qrow[j] = __ldg(qp4 + j);
-      }
+      for (int j = 0; j < 8; ++j) qrow[j] = qnext[j];
+      if (gt < 64) q0f[gt] = cnext; else v0f[gt - 64] = cnext;
+      if (gt < 64) k0f[gt] = cnext2;
+      if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
       named_bar_sync(1 + w, 128);
       // class-token KEY for this thread's query row: s0 = q_r·k0
       const float s0 = dot64(qrow, k0f);

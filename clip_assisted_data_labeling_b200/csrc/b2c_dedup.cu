@@ -9,7 +9,10 @@
 #include <cuda_fp16.h>
 
 #include "b2c_launch.h"
+#include <stdlib.h>
+
 #include "b2c_umma_pipeline.cuh"
+#include "b2c_umma_pipeline2.cuh"
 
 namespace b2c {
 
@@ -17,6 +20,7 @@ constexpr int kDedupBandBlocks = 16;  // 128-row blocks per band (2048 rows, 3 M
 
 struct DedupParams {
   int num_tiles;
+  int num_tiles2;  // CTA-pair kernel: 256 x 256 tiles in this band
   int k_blocks;
   int GI;   // row blocks in this band
   int bi0;  // first row block of the band (units of kBM rows)
@@ -43,6 +47,16 @@ struct DedupPolicy {
     a_row = (p.bi0 + ci) * kBM;
     b_row = (p.bj0 + cj) * kBN;
     return b_row + (kBN - 1) > a_row;  // tile holds at least one j > i
+  }
+
+  // CTA-pair kernel: the band is GI/2 blocks of 256 rows; tile (ci, cj) -> rows (bi0/2 + ci)*256, cols (bj0 + cj)*256
+  __device__ static __forceinline__ bool tile2(const Params& p, int t, int& m_row, int& n_row) {
+    const int g2 = (p.GI + 1) >> 1;
+    const int cj = t / g2;
+    const int ci = t - cj * g2;
+    m_row = p.bi0 * kBM + ci * 2 * kBM;
+    n_row = (p.bj0 + cj) * kBN;
+    return n_row + (kBN - 1) > m_row;
   }
 
   __device__ static __forceinline__ bool passes(const Params& p, float v) {
@@ -163,7 +177,15 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
   p.capacity = capacity;
   p.count = count;
 
-  const long long bi_begin = row_begin / kBM;
+  static const bool pairs = [] { const char* e = getenv("B2C_GEMM"); return !(e && e[0] == '1'); }();
+  auto kern2 = umma2_tile_kernel<DedupPolicy>;
+  static bool attr2_set = false;
+  if (pairs && !attr2_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmma2SmemBytes));
+    attr2_set = true;
+  }
+  // bands start on 256-row boundaries so that both kernels see the same band grid
+  const long long bi_begin = (row_begin / (2 * kBM)) * 2;
   const long long bi_end = (row_end + kBM - 1) / kBM;
   const long long NJ = (n_total + kBN - 1) / kBN;
   for (long long b = bi_begin; b < bi_end; b += kDedupBandBlocks) {
@@ -176,9 +198,16 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
     p.bi0 = static_cast<int>(b);
     p.bj0 = static_cast<int>(bj0);
     p.num_tiles = static_cast<int>(tiles);
-    const int grid = tiles < sms ? static_cast<int>(tiles) : sms;
-    kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(tm_a, tm_b, tm_a, p, make_idesc_f16(kBM, kBN, 0));
-    B2C_POST_LAUNCH("umma_tile_kernel<dedup>");
+    p.num_tiles2 = static_cast<int>(((gi + 1) / 2) * (NJ - bj0));
+    if (pairs) {
+      const int grid = 2 * p.num_tiles2 < sms ? 2 * p.num_tiles2 : (sms & ~1);
+      kern2<<<grid, kUmmaThreads, kUmma2SmemBytes, stream>>>(tm_a, tm_a, tm_a, p, make_idesc_f16(2 * kBM, kBN, 0));
+      B2C_POST_LAUNCH("umma2_tile_kernel<dedup>");
+    } else {
+      const int grid = tiles < sms ? static_cast<int>(tiles) : sms;
+      kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(tm_a, tm_b, tm_a, p, make_idesc_f16(kBM, kBN, 0));
+      B2C_POST_LAUNCH("umma_tile_kernel<dedup>");
+    }
   }
   return 0;
 }

@@ -51,6 +51,15 @@ struct GemmPolicy {
     return true;
   }
 
+  // CTA-pair kernel: 256 x 256 tiles, n-block fastest
+  __device__ static __forceinline__ bool tile2(const Params& p, int t, int& m_row, int& n_row) {
+    const int mb2 = t / p.n_blocks;
+    const int nb = t - mb2 * p.n_blocks;
+    m_row = mb2 * 2 * kBM;
+    n_row = nb * kBN;
+    return true;
+  }
+
   static constexpr int kStore = (MODE == kGemmPatchEmbedF32) ? kStoreDirect
                                 : (MODE == kGemmBiasResidF32) ? kStoreTmaAddF32 : kStoreTmaBf16;
 

@@ -9,8 +9,9 @@
 // multicasts its commits to the barriers of both CTAs; each CTA's epilogue warps drain their own 128 TMEM lanes
 // through the same swizzled-slab TMA store / reduce-add path as the single-CTA kernel.
 //
-// Policy: the kStoreTma* policies of b2c_umma_pipeline.cuh (transform() only).  Params must provide
-// num_tiles2 (256 x 256 tiles), k_blocks, n_blocks.
+// Policy: as in b2c_umma_pipeline.cuh, plus
+//   __device__ static bool tile2(const Params&, int t, int& m_row, int& n_row)   // 256 x 256 tile origin; false = skip
+// Params must provide num_tiles2 and k_blocks.
 #pragma once
 #include "b2c_umma_pipeline.cuh"
 
@@ -24,7 +25,6 @@ template <class Policy>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
 umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const typename Policy::Params p, const uint32_t idesc) {
-  static_assert(Policy::kStore != kStoreDirect, "the CTA-pair kernel only implements the TMA-store epilogues");
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages2 * kStage2Bytes;
@@ -43,7 +43,7 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    tma_prefetch_desc(&tmap_out);
+    if (Policy::kStore != kStoreDirect) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -70,10 +70,10 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cid; t < p.num_tiles2; t += ncl) {
-        const int mb2 = t / p.n_blocks;
-        const int nb = t - mb2 * p.n_blocks;
-        const int a_row = mb2 * 2 * kBM + static_cast<int>(rank) * kBM;
-        const int b_row = nb * kBN + static_cast<int>(rank) * (kBN / 2);
+        int m_row, n_row;
+        if (!Policy::tile2(p, t, m_row, n_row)) continue;
+        const int a_row = m_row + static_cast<int>(rank) * kBM;
+        const int b_row = n_row + static_cast<int>(rank) * (kBN / 2);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStage2Bytes;
@@ -95,6 +95,8 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = cid; t < p.num_tiles2; t += ncl) {
+        int m_row, n_row;
+        if (!Policy::tile2(p, t, m_row, n_row)) continue;
         mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBN;
@@ -121,10 +123,10 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t acc_phase = 0;
     uint8_t* my_slabs = staging + (warp - 2) * (kSlabsPerWarp * kSlabBytes);
     for (int t = cid; t < p.num_tiles2; t += ncl) {
-      const int mb2 = t / p.n_blocks;
-      const int nb = t - mb2 * p.n_blocks;
-      const int b_row = nb * kBN;
-      const int out_row = mb2 * 2 * kBM + static_cast<int>(rank) * kBM + quarter * 32;
+      int m_row, b_row;
+      if (!Policy::tile2(p, t, m_row, b_row)) continue;
+      const int a_row = m_row + static_cast<int>(rank) * kBM;
+      const int out_row = a_row + quarter * 32;
       mbar_wait(&acc_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kBN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -133,6 +135,10 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
+        if constexpr (Policy::kStore == kStoreDirect) {
+          Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c * 32, v);
+          continue;
+        }
         float f[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
@@ -186,7 +192,7 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty_bar[acc]), 0));  // the leader's barrier
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait<0>();
+    if (Policy::kStore != kStoreDirect && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();

@@ -75,7 +75,7 @@ struct DedupPolicy {
     const long long i = static_cast<long long>(a_row) + row_in_tile;
     if (i < p.row_begin || i >= p.row_end) return;
     const long long j0 = static_cast<long long>(b_row) + col0;
-#pragma unroll 1
+#pragma unroll  // static indices keep the accumulator chunk in registers; the body is a rarely-taken branch
     for (int jj = 0; jj < 32; ++jj) {
       const float v = __uint_as_float(acc[jj]);
       const long long j = j0 + jj;

@@ -188,8 +188,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ct
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
   return r;
 }
+// Remote arrive on a peer CTA's mbarrier.  Default (.release.cta) semantics on purpose: the only thing ordered
+// before this arrive is TMEM traffic, which tcgen05.fence::before_thread_sync already covers; spelling
+// .release.cluster makes ptxas emit MEMBAR.ALL.GPU + ERRBAR per arrive (18 % of the dedup kernel's stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair into ITS OWN shared memory, signalling the mbarrier at `bar_cluster_addr`
 // (the leader CTA's barrier).

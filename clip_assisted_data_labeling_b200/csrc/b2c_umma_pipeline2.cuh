@@ -130,15 +130,28 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(&acc_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kBN + (static_cast<uint32_t>(quarter * 32) << 16);
+      if constexpr (Policy::kStore == kStoreDirect) {
+        // four 32-column TMEM loads in flight per wait: the load latency (contended by the running MMAs) is paid
+        // twice per tile instead of eight times
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
+        for (int c4 = 0; c4 < kBN / 128; ++c4) {
+          uint32_t v0[32], v1[32], v2[32], v3[32];
+          tmem_ld_32x32(taddr + c4 * 128, v0);
+          tmem_ld_32x32(taddr + c4 * 128 + 32, v1);
+          tmem_ld_32x32(taddr + c4 * 128 + 64, v2);
+          tmem_ld_32x32(taddr + c4 * 128 + 96, v3);
+          tmem_ld_wait();
+          Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c4 * 128, v0);
+          Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c4 * 128 + 32, v1);
+          Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c4 * 128 + 64, v2);
+          Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c4 * 128 + 96, v3);
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < (Policy::kStore == kStoreDirect ? 0 : kBN / 32); ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        if constexpr (Policy::kStore == kStoreDirect) {
-          Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c * 32, v);
-          continue;
-        }
         float f[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);

@@ -227,7 +227,7 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
   v->T = v->G2 + 1;
   v->Kp = (3 * cfg->patch * cfg->patch + kBK - 1) / kBK * kBK;
   v->hd = hd;
-  v->chunk = 512;
+  v->chunk = 1024;
   if (const char* e = getenv("B2C_VIT_CHUNK")) {
     const int cv = atoi(e);
     if (cv > 0) v->chunk = cv;

@@ -125,3 +125,12 @@ class FCScorer:
 
     def score_embeddings(self, emb: torch.Tensor, emb_crop_names=CROP_NAMES) -> torch.Tensor:
         return self.score(self.assemble(emb, emb_crop_names))
+
+
+@torch.no_grad()
+def embed_and_score(encoder, scorer: "FCScorer", images_u8):
+    """BASELINE config 5 in one pass: 4-crop embeddings (encoder.encode_images_u8) and the regressor score while the
+    [B,4,E] block is still in HBM — the fused form of _1_embed_with_CLIP.py + _5_predict_labels.py:77-82,135.
+    Returns (embeddings f32 [B,4,E], scores f32 [B,1])."""
+    emb = encoder.encode_images_u8(images_u8)
+    return emb, scorer.score_embeddings(emb)

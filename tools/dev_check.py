@@ -159,6 +159,36 @@ def case_attention_perf():
     return [{"ms": ms, "tflops": 4.0 * T * T * d * n / ms / 1e9, "max_abs_err": err, "path": os.environ.get("B2C_ATTN", "umma"), "ok": bool(err < 0.02)}]
 
 
+def case_dedup_perf():
+    import torch
+    L = lib()
+    out = []
+    for N in (200_000, 1_000_000):
+        E = 768
+        e = torch.nn.functional.normalize(torch.randn(N, E, device="cuda"), dim=1).half()
+        cap = 1 << 20
+        pairs = torch.zeros(cap, 3, dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        def run():
+            rc = L.b2c_dedup_pairs(C.c_void_p(e.data_ptr()), C.c_int64(N), E, C.c_int64(0), C.c_int64(N), C.c_float(0.96), 1,
+                                   C.c_void_p(pairs.data_ptr()), C.c_ulonglong(cap), C.c_void_p(cnt.data_ptr()), st)
+            assert rc == 0, L.b2c_last_error()
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        t0 = time.time()
+        e0.record()
+        run()
+        e1.record()
+        t_launch = time.time() - t0
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out.append({"N": N, "kernel_ms": ms, "host_issue_s": t_launch, "pairs_per_s": N * (N - 1) / 2 / (ms / 1e3),
+                    "tflops": N * (N - 1) * E / (ms / 1e3) / 1e12, "ok": True})
+    return out
+
+
 def case_preprocess():
     import numpy as np
     import torch

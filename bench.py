@@ -157,45 +157,48 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
-def gemm_roofline(tower_cfg, n_crops, peaks):
-    """Live CUDA-event timing of the dominant kernel (umma_tile_kernel<GemmPolicy>) on the four GEMM shapes of one
-    ViT-L/14 block at the step's M; FLOP-weighted aggregate."""
+GEMM_STAGES = ("in_proj", "out_proj", "c_fc", "c_proj")
+
+
+def stage_profile(enc, batches, cfg, n_crops, peaks, steps=2):
+    """Per-stage device time of whole steps, measured live with CUDA events on the launching stream by the
+    library's stage timer (include/b2c.h: b2c_prof_enable / b2c_prof_read): every stage of the step is bracketed by
+    an event pair.  The dominant kernel is umma2_tile_kernel<GemmPolicy<mode>> (the four GEMMs of each block);
+    roofline.achieved = their algorithmic FLOPs per step / their summed duration per step."""
     import torch
     from clip_assisted_data_labeling_b200 import _lib
-    lib = _lib.load()
-    d, mlp = tower_cfg["width"], tower_cfg["mlp"]
-    T = (tower_cfg["image"] // tower_cfg["patch"]) ** 2 + 1
+    d, mlp, L = cfg["width"], cfg["mlp"], cfg["layers"]
+    T = (cfg["image"] // cfg["patch"]) ** 2 + 1
     M = n_crops * T
-    st = torch.cuda.current_stream().cuda_stream
-    shapes = [("in_proj", 3 * d, d, _lib.EPI_BIAS_BF16), ("out_proj", d, d, _lib.EPI_BIAS_RESID_F32),
-              ("c_fc", mlp, d, _lib.EPI_BIAS_QGELU_BF16), ("c_proj", d, mlp, _lib.EPI_BIAS_RESID_F32)]
-    per, tot_f, tot_t = {}, 0.0, 0.0
-    for name, N, K, mode in shapes:
-        A = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
-        W = (torch.randn(N, K, device="cuda") * 0.03).to(torch.bfloat16)
-        b = torch.zeros(N, device="cuda")
-        out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if mode == _lib.EPI_BIAS_RESID_F32 else torch.bfloat16)
-        for _ in range(3):
-            _lib.call("b2c_gemm_bf16", A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, mode, st)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            _lib.call("b2c_gemm_bf16", A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, mode, st)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        fl = 2.0 * M * N * K
-        per[name] = {"M": M, "N": N, "K": K, "ms": ms, "tflops": fl / ms / 1e9}
+    torch.cuda.synchronize()
+    _lib.prof_enable(True)
+    for i in range(steps):
+        enc.encode_images_u8(batches[i % len(batches)])
+    torch.cuda.synchronize()
+    rec = _lib.prof_read()
+    _lib.prof_enable(False)
+    shapes = {"in_proj": (3 * d, d), "out_proj": (d, d), "c_fc": (mlp, d), "c_proj": (d, mlp)}
+    per, tot_f, tot_ms = {}, 0.0, 0.0
+    total_ms = sum(ms for ms, _ in rec.values())
+    for name in GEMM_STAGES:
+        ms, n = rec[name]
+        N, K = shapes[name]
+        fl = 2.0 * M * N * K * L * steps  # all launches of this shape in the profiled steps
+        per[name] = {"M_per_step": M, "N": N, "K": K, "launches": n, "ms_per_launch": ms / n, "tflops": fl / ms / 1e9}
         tot_f += fl
-        tot_t += ms
-        del A, W, out
-    ach = tot_f / tot_t / 1e9
-    return {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
-            "traffic": None, "kernel": "umma_tile_kernel<GemmPolicy> (tcgen05 M128 N256 K16, TMA, fused epilogues)",
-            "peak_source": peaks["src"] + ", burst", "per_shape": per,
-            "how": "CUDA events around 5 back-to-back launches per shape on the launching stream, FLOP-weighted over the 4 GEMMs of a block"}
+        tot_ms += ms
+    ach = tot_f / tot_ms / 1e9
+    shares = {k: {"ms_per_step": ms / steps, "share": ms / total_ms, "stages_per_step": n // steps} for k, (ms, n) in rec.items()}
+    return {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+            "traffic": None,
+            "kernel": "umma2_tile_kernel<GemmPolicy<mode>>: tcgen05.mma cta_group::2 (256x256x16 per CTA pair), TMA-fed 6-stage ring, "
+                      "TMEM double-buffered accumulators, fused bias/QuickGELU/residual-reduce epilogues",
+            "peak_source": peaks["src"] + ", sustained (kernel timed inside the step); burst is %.1f" % peaks["tf_burst"],
+            "frac_of_burst": ach / peaks["tf_burst"],
+            "gemm_share_of_step": tot_ms / total_ms,
+            "per_shape": per, "stage_shares": shares,
+            "how": "library stage timer: CUDA event pairs on the launching stream around every stage of %d whole steps; "
+                   "achieved = algorithmic GEMM FLOPs (2*M*N*K, no padding) / summed GEMM stage time" % steps}
 
 
 def run_b200_arm(args):
@@ -249,6 +252,9 @@ def run_b200_arm(args):
     value = world * B * args.steps / (ms_total / 1e3)
     norms_ok = bool(torch.allclose(out.norm(dim=-1), torch.ones_like(out[..., 0]), atol=1e-4))
 
+    # ---------------- stage shares + roofline of the dominant kernel (separate, event-instrumented steps)
+    roof = stage_profile(enc, pool_dev, cfg, 4 * B, peaks) if rank == 0 else None
+
     # ---------------- e2e: host buffers, H2D + D2H inside the timed region
     host_out = torch.empty(B, 4, cfg["embed"], dtype=torch.float32).pin_memory()
     for i in range(min(args.warmup, 3)):
@@ -301,10 +307,11 @@ def run_b200_arm(args):
         return
 
     # ---------------- rank 0: roofline of the dominant kernel, CPU baseline, JSON
-    roof = gemm_roofline(cfg, min(4 * B, 512), peaks)
     prof = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(prof):
-        roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        tr = json.load(open(prof))
+        roof["traffic"] = tr.get("dram_bytes_per_launch")
+        roof["traffic_detail"] = tr
     F = flops_per_crop(cfg) * 4  # FLOPs per image
     step_tf = value / world * F / 1e12
     cpu_v, cpu_parts = (None, None)

@@ -19,6 +19,7 @@ ACT_QUICK_GELU, ACT_GELU = 0, 1
 EPI_BIAS_BF16, EPI_BIAS_QGELU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
 CMP_FP32, CMP_REF_FP16 = 0, 1
 MLP_MAX_LAYERS = 8
+PROF_KINDS = 11
 
 
 class B2CError(RuntimeError):
@@ -55,6 +56,9 @@ SIGNATURES = {
     "b2c_last_error": (C.c_char_p, []),
     "b2c_version": (_i, []),
     "b2c_launch_count": (_u64, []),
+    "b2c_prof_enable": (_i, [_i]),
+    "b2c_prof_read": (_i, [C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "b2c_prof_kind_name": (C.c_char_p, [_i]),
     "b2c_crop_geometry": (_i, [_i, _i, _i, C.POINTER(Crop)]),
     "b2c_preprocess_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "b2c_preprocess_4crop": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _i, _i,
@@ -117,3 +121,17 @@ def current_stream_ptr() -> int:
 
 def launch_count() -> int:
     return int(load().b2c_launch_count())
+
+
+def prof_enable(on: bool) -> None:
+    """Start (and clear) or stop the library's per-stage CUDA-event timer (include/b2c.h: b2c_prof_enable)."""
+    call("b2c_prof_enable", 1 if on else 0)
+
+
+def prof_read() -> dict:
+    """{stage name: (milliseconds, stages)} accumulated since prof_enable(True); synchronises the recorded events."""
+    lib = load()
+    ms = (C.c_double * PROF_KINDS)()
+    cnt = (_u64 * PROF_KINDS)()
+    check(lib.b2c_prof_read(ms, cnt), "b2c_prof_read")
+    return {lib.b2c_prof_kind_name(k).decode(): (ms[k], int(cnt[k])) for k in range(PROF_KINDS) if cnt[k]}

@@ -188,6 +188,7 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
   const long long bi_begin = (row_begin / (2 * kBM)) * 2;
   const long long bi_end = (row_end + kBM - 1) / kBM;
   const long long NJ = (n_total + kBN - 1) / kBN;
+  ProfScope ps(B2C_PROF_DEDUP, stream);
   for (long long b = bi_begin; b < bi_end; b += kDedupBandBlocks) {
     const int gi = static_cast<int>(bi_end - b < kDedupBandBlocks ? bi_end - b : kDedupBandBlocks);
     const long long bj0 = (b * kBM) / kBN;

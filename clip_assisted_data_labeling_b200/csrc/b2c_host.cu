@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "b2c_host.h"
 #include "b2c_launch.h"
@@ -72,6 +73,40 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return make_tmap_2d_ex(out, base, rows, cols, row_stride_bytes, box_rows, 64, elem == 1 ? B2C_BF16 : B2C_F16);
 }
 
+// ---- stage timer ------------------------------------------------------------------------------------
+std::atomic<int> g_prof_on{0};
+namespace {
+struct ProfRec {
+  int kind;
+  cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void prof_begin(int kind, cudaStream_t stream) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  ProfRec r{kind, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, stream);
+  g_prof_recs.push_back(r);
+}
+
+void prof_end(cudaStream_t stream) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, stream);
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -87,3 +122,41 @@ int num_sms() {
 extern "C" const char* b2c_last_error(void) { return b2c::g_err; }
 extern "C" int b2c_version(void) { return 100; }
 extern "C" unsigned long long b2c_launch_count(void) { return b2c::g_launches.load(); }
+
+extern "C" int b2c_prof_enable(int on) {
+  using namespace b2c;
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (on) {
+    for (ProfRec& r : g_prof_recs) {
+      g_prof_pool.push_back(r.e0);
+      g_prof_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+  }
+  g_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+
+extern "C" int b2c_prof_read(double* ms, unsigned long long* stages) {
+  using namespace b2c;
+  B2C_REQUIRE(ms && stages, "b2c_prof_read: null pointer");
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (int k = 0; k < B2C_PROF_KINDS; ++k) {
+    ms[k] = 0.0;
+    stages[k] = 0;
+  }
+  for (const ProfRec& r : g_prof_recs) {
+    B2C_CHECK_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    B2C_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.kind] += t;
+    stages[r.kind] += 1;
+  }
+  return 0;
+}
+
+extern "C" const char* b2c_prof_kind_name(int kind) {
+  static const char* names[B2C_PROF_KINDS] = {"preprocess", "patch_embed", "layernorm", "in_proj", "attention", "out_proj",
+                                              "c_fc",       "c_proj",      "head",      "dedup",   "other"};
+  return kind >= 0 && kind < B2C_PROF_KINDS ? names[kind] : "?";
+}

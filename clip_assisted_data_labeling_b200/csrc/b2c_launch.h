@@ -16,6 +16,21 @@ extern std::atomic<unsigned long long> g_launches;
       return ::b2c::set_error(B2C_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
   } while (0)
 
+// ---- stage timer (b2c_host.cu): records a CUDA-event pair around a stage when b2c_prof_enable(1) is active
+extern std::atomic<int> g_prof_on;
+void prof_begin(int kind, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+struct ProfScope {
+  cudaStream_t s;
+  bool on;
+  ProfScope(int kind, cudaStream_t stream) : s(stream), on(g_prof_on.load(std::memory_order_relaxed) != 0) {
+    if (on) prof_begin(kind, s);
+  }
+  ~ProfScope() {
+    if (on) prof_end(s);
+  }
+};
+
 // ---- tensor-core GEMM family (b2c_gemm.cu) -----------------------------------------------------
 enum GemmMode {
   kGemmBiasBf16 = B2C_EPI_BIAS_BF16,

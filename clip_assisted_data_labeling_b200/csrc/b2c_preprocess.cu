@@ -468,6 +468,7 @@ extern "C" int b2c_preprocess_4crop(const uint8_t* const* img_ptrs, const int* H
   B2C_REQUIRE(smem <= 220 * 1024, "b2c_preprocess_4crop: images too large for the resample tile (need %zu B smem)", smem);
   rp.TR = TR; rp.SR = SR;
 
+  ProfScope ps(B2C_PROF_PREPROCESS, stream);
   resample_plan_kernel<<<dim3(B * 4, 2), R, 0, stream>>>(rp.plans, const_cast<int2*>(rp.bounds),
                                                          const_cast<int32_t*>(rp.coefs), R, KS);
   B2C_POST_LAUNCH("resample_plan_kernel");

@@ -122,6 +122,7 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
 
   // K1: conv1 as a GEMM over patch rows, + positional embedding, scattered past the class token
   {
+    ProfScope ps(B2C_PROF_PATCH_EMBED, stream);
     GemmLaunch gl{};
     gl.tmap_a = tm_patches;
     gl.tmap_b = v->tm_conv1;
@@ -138,29 +139,44 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     gl.G2 = v->G2;
     B2C_TRY(gemm_launch(gl, stream));
   }
-  B2C_TRY(cls_pos_launch(x, v->cls, v->pos, nc, v->T, d, stream));
-  B2C_TRY(layernorm_f32_inplace_launch(x, v->ln_pre_w, v->ln_pre_b, M, d, eps, stream));
+  {
+    ProfScope ps(B2C_PROF_LAYERNORM, stream);
+    B2C_TRY(cls_pos_launch(x, v->cls, v->pos, nc, v->T, d, stream));
+    B2C_TRY(layernorm_f32_inplace_launch(x, v->ln_pre_w, v->ln_pre_b, M, d, eps, stream));
+  }
 
   for (int li = 0; li < c.layers; ++li) {
     const b2c_vit_layer& L = v->layers[li];
     // attention half
-    B2C_TRY(layernorm_bf16_launch(x, L.ln1_w, L.ln1_b, h, M, d, eps, stream));
     {
+      ProfScope ps(B2C_PROF_LAYERNORM, stream);
+      B2C_TRY(layernorm_bf16_launch(x, L.ln1_w, L.ln1_b, h, M, d, eps, stream));
+    }
+    {
+      ProfScope ps(B2C_PROF_IN_PROJ, stream);
       GemmLaunch gl{};
       gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv; gl.tmap_b_half = L.tm_qkv_h; gl.tmap_out = st_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
       gl.mode = kGemmBiasBf16; gl.bias = L.b_qkv; gl.out = big; gl.ldo = 3 * d;
       B2C_TRY(gemm_launch(gl, stream));
     }
-    B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
     {
+      ProfScope ps(B2C_PROF_ATTENTION, stream);
+      B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
+    }
+    {
+      ProfScope ps(B2C_PROF_OUT_PROJ, stream);
       GemmLaunch gl{};
       gl.tmap_a = tm_h; gl.tmap_b = L.tm_out; gl.tmap_b_half = L.tm_out_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = d;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_out; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }
     // MLP half
-    B2C_TRY(layernorm_bf16_launch(x, L.ln2_w, L.ln2_b, h, M, d, eps, stream));
     {
+      ProfScope ps(B2C_PROF_LAYERNORM, stream);
+      B2C_TRY(layernorm_bf16_launch(x, L.ln2_w, L.ln2_b, h, M, d, eps, stream));
+    }
+    {
+      ProfScope ps(B2C_PROF_C_FC, stream);
       GemmLaunch gl{};
       gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc; gl.tmap_b_half = L.tm_fc_h; gl.tmap_out = st_mlp; gl.M = M; gl.N = c.mlp; gl.K = d;
       gl.mode = c.act == B2C_ACT_GELU ? kGemmBiasGeluBf16 : kGemmBiasQGeluBf16;
@@ -168,12 +184,14 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
       B2C_TRY(gemm_launch(gl, stream));
     }
     {
+      ProfScope ps(B2C_PROF_C_PROJ, stream);
       GemmLaunch gl{};
       gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj; gl.tmap_b_half = L.tm_proj_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = c.mlp;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_proj; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }
   }
+  ProfScope ps(B2C_PROF_HEAD, stream);
   return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, nc, v->T, d, c.embed, eps, stream);
 }
 
@@ -195,6 +213,7 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
     const void* pch;
     if (pixels) {
       const uint8_t* px = static_cast<const uint8_t*>(pixels) + static_cast<size_t>(c0) * 3 * R * R * px_elt;
+      ProfScope ps(B2C_PROF_OTHER, stream);
       B2C_TRY(patchify_launch(px, dtype, wsb + w.patches, nc, R, v->cfg.patch, v->Kp, stream));
       pch = wsb + w.patches;
     } else {

@@ -41,6 +41,27 @@ int b2c_version(void);
  * over its timed region as "gpu_launches". */
 unsigned long long b2c_launch_count(void);
 
+/* Stage timer (measurement aid, off by default).  While enabled, every stage of the hot path the library
+ * launches is bracketed by a pair of CUDA events recorded on the launching stream; b2c_prof_read()
+ * synchronises those events and returns, per stage kind, the summed device time in milliseconds and the number
+ * of bracketed stages since b2c_prof_enable(1).  bench.py uses it to report the live duration of the dominant
+ * kernel ("roofline.achieved") and each stage's share of a step next to the ncu launch list. */
+#define B2C_PROF_PREPROCESS 0
+#define B2C_PROF_PATCH_EMBED 1
+#define B2C_PROF_LAYERNORM 2
+#define B2C_PROF_IN_PROJ 3
+#define B2C_PROF_ATTENTION 4
+#define B2C_PROF_OUT_PROJ 5
+#define B2C_PROF_C_FC 6
+#define B2C_PROF_C_PROJ 7
+#define B2C_PROF_HEAD 8
+#define B2C_PROF_DEDUP 9
+#define B2C_PROF_OTHER 10
+#define B2C_PROF_KINDS 11
+int b2c_prof_enable(int on);  /* on != 0: drop earlier records and start recording; 0: stop */
+int b2c_prof_read(double* ms /*[B2C_PROF_KINDS]*/, unsigned long long* stages /*[B2C_PROF_KINDS]*/);
+const char* b2c_prof_kind_name(int kind);
+
 /* ---------------------------------------------------------------------------------------------
  * K0 — 4-crop geometry + PIL-exact bicubic resize + normalise.
  * Replaces CustomImageDataset.extract_crops (utils/embedder.py:184-251) and the open_clip val

@@ -1,0 +1,44 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, bench line, ncu launch list, ncu --set full captures.  Outputs -> gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench launches full
+set -u
+TAG=${1:-run}
+shift || true
+WHAT=${*:-tests bench launches full}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/${TAG}_smi.txt 2>&1
+for w in $WHAT; do
+  case $w in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1
+      echo "tests exit $?" | tee -a $OUT/${TAG}_tests.log; tail -5 $OUT/${TAG}_tests.log ;;
+    smoke)
+      timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; tail -3 $OUT/${TAG}_smoke.log ;;
+    bench)
+      timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+      echo "bench exit $?"; cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err ;;
+    refbench)
+      timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_refbench.json 2> $OUT/${TAG}_refbench.err
+      cat $OUT/${TAG}_refbench.json ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv \
+        --log-file $OUT/${TAG}_launches_embed.csv python tools/profile_step.py embed 256 > $OUT/${TAG}_launches_embed.log 2>&1
+      timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+        --log-file $OUT/${TAG}_launches_dedup.csv python tools/profile_step.py dedup 200000 > $OUT/${TAG}_launches_dedup.log 2>&1
+      echo "launches done" ;;
+    full)
+      # one capture per kernel family: a few launches each (ncu replays ~40x per kernel)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:umma2_tile -s 30 -c 8 \
+        -o $OUT/${TAG}_prof_gemm -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_gemm.log 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention -s 2 -c 1 \
+        -o $OUT/${TAG}_prof_attn -f python tools/profile_attn.py 512 > $OUT/${TAG}_prof_attn.log 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:layernorm -s 4 -c 1 \
+        -o $OUT/${TAG}_prof_ln -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_ln.log 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:resample_kernel -c 1 \
+        -o $OUT/${TAG}_prof_pre -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_pre.log 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:"umma|dedup" -s 1 -c 2 \
+        -o $OUT/${TAG}_prof_dedup -f python tools/profile_step.py dedup 100000 > $OUT/${TAG}_prof_dedup.log 2>&1
+      ls -la $OUT | tail -20 ;;
+  esac
+done

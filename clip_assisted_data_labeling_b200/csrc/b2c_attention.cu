@@ -605,7 +605,9 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     for (int s = 0; s < 2; ++s) {
       mbar_init(&mb->full_qk[s], 1);
       mbar_init(&mb->full_v[s], 1);
-      mbar_init(&mb->empty_qk[s], 2);  // MMA commit + the group that computed the class row from K
+      // MMA commit + the class-row owner group (one arrival after its group barrier: own Q rows and K read) + the four
+      // warps of the other group (one arrival each once the warp has read its Q rows)
+      mbar_init(&mb->empty_qk[s], 6);
       mbar_init(&mb->empty_v[s], 2);   // MMA commit + the group that computed the class row from V
       mbar_init(&mb->s_full[s], 1);
       mbar_init(&mb->p_full[s], 4);
@@ -645,47 +647,55 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
-      const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
-      const uint32_t idesc_l = make_idesc_f16(128, 16, 1);
-      const uint64_t ones_desc = make_sw128_kmajor_desc(smem_u32(smem + kA2OffOnes));
-      int k = 0;
-      for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
-        const int s = k & 1;
-        const uint32_t u = (k >> 1) & 1, kp = k & 1;
-        const uint32_t sbase = smem_u32(smem + s * kA2StageBytes);
-        mbar_wait(&mb->full_qk[s], u);
-        const uint64_t k_desc = make_sw128_kmajor_desc(sbase + kA2OffK);
+    // Warp-uniform control flow (all lanes wait and build the uniform descriptors, one elected lane issues): from inside
+    // a `lane == 0` branch ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall, and the 72 MMAs of a
+    // head then cost more issue time than they take to execute.
+    const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
+    const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
+    const uint32_t idesc_l = make_idesc_f16(128, 16, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t ones_desc = make_sw128_kmajor_desc(smem_base + kA2OffOnes);
+    int k = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t u = (k >> 1) & 1, kp = k & 1;
+      const uint32_t sbase = smem_base + s * kA2StageBytes;
+      mbar_wait(&mb->full_qk[s], u);
+      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + kA2OffK);
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(&mb->tmem_free[w], kp ^ 1);  // group w has read the previous O out of its region
-          tc_fence_after();
-          const uint64_t q_desc = make_sw128_kmajor_desc(sbase + kA2OffQ + w * 16384);
+      for (int w = 0; w < 2; ++w) {
+        mbar_wait(&mb->tmem_free[w], kp ^ 1);  // group w has read the previous O out of its region
+        tc_fence_after();
+        const uint64_t q_desc = make_sw128_kmajor_desc(sbase + kA2OffQ + w * 16384);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_f16(tmem + w * 256, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk != 0);
           umma_commit(&mb->s_full[w]);
         }
-        umma_commit(&mb->empty_qk[s]);
-        mbar_wait(&mb->full_v[s], u);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&mb->empty_qk[s]);
+      __syncwarp();
+      mbar_wait(&mb->full_v[s], u);
+      const uint64_t v_desc0 = make_sw128_kmajor_desc(sbase + kA2OffV);
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(&mb->p_full[w], kp);
-          tc_fence_after();
+      for (int w = 0; w < 2; ++w) {
+        mbar_wait(&mb->p_full[w], kp);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk) {
-            const uint64_t v_desc = make_sw128_kmajor_desc(sbase + kA2OffV + kk * 16 * 128);
-            umma_f16_ts(tmem + w * 256 + 128, tmem + w * 256 + kk * 8, v_desc, idesc_o, kk != 0);
-          }
+          for (int kk = 0; kk < 16; ++kk)  // 16 keys = 16 rows of 128 B further down the V tile: +128 in the addr>>4 field
+            umma_f16_ts(tmem + w * 256 + 128, tmem + w * 256 + kk * 8, v_desc0 + kk * 128, idesc_o, kk != 0);
 #pragma unroll
           for (int kk = 0; kk < 16; ++kk)  // every element of the ones tile is 1.0, so any 16 x 16 slice will do
             umma_f16_ts(tmem + w * 256 + 192, tmem + w * 256 + kk * 8, ones_desc + 2 * (kk & 3), idesc_l, kk != 0);
           umma_commit(&mb->o_full[w]);
         }
-        umma_commit(&mb->empty_v[s]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&mb->empty_v[s]);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ softmax groups
     const int w = (warp - 2) >> 2;          // group = query tile
@@ -698,19 +708,14 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     float* q0f = mb->vec[w][0];
     float* k0f = mb->vec[w][1];
     float* v0f = mb->vec[w][2];
-    // this thread's query row and its element of the head's class-token q/k/v are fetched one iteration ahead,
-    // so their global-memory latency hides behind the previous head's softmax
-    uint4 qnext[8];
-    float cnext = 0.f, cnext2 = 0.f;
+    // this thread's elements of the head's class-token q/k/v are fetched one iteration ahead as RAW bf16 bits (converting
+    // at load time would stall on the load right away); its own query row is read from the Q tile TMA already staged
+    uint32_t cnext = 0, cnext2 = 0;
     auto prefetch = [&](int ch) {
       const int crop = ch / heads, head = ch - crop * heads;
-      const int tok0 = crop * T;
-      const uint4* qp4 = reinterpret_cast<const uint4*>(qkv + (tok0 + 1 + w * 128 + r) * row_stride + head * 64);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) qnext[j] = __ldg(qp4 + j);
-      const __nv_bfloat16* cls_row = qkv + tok0 * row_stride + head * 64;
-      cnext = __bfloat162float(gt < 64 ? cls_row[gt] : cls_row[2 * d + gt - 64]);  // q0[gt] | v0[gt-64]
-      cnext2 = __bfloat162float(cls_row[d + (gt & 63)]);                            // k0[gt]
+      const unsigned short* cls_row = reinterpret_cast<const unsigned short*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * 64);
+      cnext = __ldg(gt < 64 ? cls_row + gt : cls_row + 2 * d + gt - 64);  // q0[gt] | v0[gt-64]
+      cnext2 = __ldg(cls_row + d + (gt & 63));                            // k0[gt]
     };
     if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
     int k = 0;
@@ -723,15 +728,24 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       const uint8_t* st = smem + s * kA2StageBytes;
       const bool cls_owner = ((k & 1) == w);
 
-      uint4 qrow[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) qrow[j] = qnext[j];
-      if (gt < 64) q0f[gt] = cnext; else v0f[gt - 64] = cnext;
-      if (gt < 64) k0f[gt] = cnext2;
+      if (gt < 64) q0f[gt] = __uint_as_float(cnext << 16); else v0f[gt - 64] = __uint_as_float(cnext << 16);
+      if (gt < 64) k0f[gt] = __uint_as_float(cnext2 << 16);
       if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
       named_bar_sync(1 + w, 128);
-      // class-token KEY for this thread's query row: s0 = q_r·k0
-      const float s0 = dot64(qrow, k0f);
+      // class-token KEY for this thread's query row: s0 = q_r·k0, q_r from the (swizzled) Q tile in shared memory
+      mbar_wait(&mb->full_qk[s], u);
+      float s0;
+      {
+        uint4 qrow[8];
+        const uint8_t* qp = st + kA2OffQ + (w * 128 + r) * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qrow[j] = *reinterpret_cast<const uint4*>(qp + ((j ^ (r & 7)) << 4));
+        s0 = dot64(qrow, k0f);
+      }
+      if (!cls_owner) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mb->empty_qk[s]);
+      }
 
       // ---- class-token QUERY row, part 1 (scores + softmax statistics) from the K tile in smem
       float cls_l = 0.f;
@@ -781,28 +795,39 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       // ---- own row: S in TMEM -> max -> P (bf16x2 packed) back into TMEM over S
       mbar_wait(&mb->s_full[w], kp);
       tc_fence_after();
+      // Both passes keep one TMEM load in flight while the previous 32-column chunk is processed (two register buffers).
       float m = s0;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr, va);
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + ((c + 2) & 7) * 32, va);  // last iteration: chunk 0 again, for the second pass
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
       }
       const float ms = m * scale_log2;
       const float p0 = ex2_ftz(fmaf(s0, scale_log2, -ms));
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
+      auto emit_p = [&](const uint32_t (&v)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e)
           pk[e] = pack2(ex2_ftz(fmaf(__uint_as_float(v[2 * e]), scale_log2, -ms)),
                         ex2_ftz(fmaf(__uint_as_float(v[2 * e + 1]), scale_log2, -ms)));
         tmem_st_32x16(taddr + c * 16, pk);  // columns [16c, 16c+16) <= columns already consumed
+      };
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+        emit_p(va, c);
+        tmem_ld_wait();
+        if (c + 2 < 8) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+        emit_p(vb, c + 1);
       }
       tmem_st_wait();
       tc_fence_before();

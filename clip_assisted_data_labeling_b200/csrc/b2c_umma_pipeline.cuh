@@ -105,36 +105,39 @@ umma_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        int a_row, b_row;
-        if (!Policy::tile(p, t, a_row, b_row)) continue;
-        mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+    // warp-uniform control flow, one elected lane issues (see b2c_umma_pipeline2.cuh for why)
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int a_row, b_row;
+      if (!Policy::tile(p, t, a_row, b_row)) continue;
+      mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kBN;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kBN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t a_desc = make_sw128_kmajor_desc(sa);
-          const uint64_t b_desc = make_sw128_kmajor_desc(sa + kABytes);
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        const uint64_t a_desc = make_sw128_kmajor_desc(sa);
+        const uint64_t b_desc = make_sw128_kmajor_desc(sa + kABytes);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the addr>>4 field
             umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&acc_full_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read

@@ -66,34 +66,42 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = cid; t < p.num_tiles2; t += ncl) {
-        int m_row, n_row;
-        if (!Policy::tile2(p, t, m_row, n_row)) continue;
-        const int a_row = m_row + static_cast<int>(rank) * kBM;
-        const int b_row = n_row + static_cast<int>(rank) * (kBN / 2);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // The whole warp runs the loop so that every address / coordinate stays in the uniform datapath; one elected
+    // lane issues the copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t leader_full0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+    for (int t = cid; t < p.num_tiles2; t += ncl) {
+      int m_row, n_row;
+      if (!Policy::tile2(p, t, m_row, n_row)) continue;
+      const int a_row = m_row + static_cast<int>(rank) * kBM;
+      const int b_row = n_row + static_cast<int>(rank) * (kBN / 2);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * kStage2Bytes;
           uint8_t* sb = sa + kABytes;
-          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          const uint32_t leader_full = leader_full0 + stage * 8;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage2Bytes);  // bytes of BOTH CTAs
           tma_load_2d_2sm(sa, &tmap_a, leader_full, kb * kBK, a_row);
           tma_load_2d_2sm(sb, &tmap_b, leader_full, kb * kBK, b_row);
-          if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // Warp-uniform control flow: all 32 lanes wait on the barriers and compute the (uniform) descriptors, one elected
+    // lane issues.  Issuing from inside a `lane == 0` branch makes ptxas treat every operand as divergent and wrap each
+    // tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall (~25 instructions per MMA), which made the issue loop
+    // itself as long as the 4 MMAs of a k-block take to execute.
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (int t = cid; t < p.num_tiles2; t += ncl) {
         int m_row, n_row;
         if (!Policy::tile2(p, t, m_row, n_row)) continue;
@@ -103,19 +111,22 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStage2Bytes);
+          const uint32_t sa = smem_base + stage * kStage2Bytes;
           const uint64_t a_desc = make_sw128_kmajor_desc(sa);
           const uint64_t b_desc = make_sw128_kmajor_desc(sa + kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_2sm(&empty_bar[stage], 3);
+            for (int k = 0; k < kBK / 16; ++k) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2sm(&empty_bar[stage], 3);
+          }
+          __syncwarp();
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&acc_full_bar[acc], 3);
+        if (elect_one()) umma_commit_2sm(&acc_full_bar[acc], 3);
+        __syncwarp();
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue (warps 2..5, both CTAs)
     const int quarter = warp & 3;

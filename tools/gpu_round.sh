@@ -18,6 +18,14 @@ for w in $WHAT; do
     bench)
       timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
       echo "bench exit $?"; cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err ;;
+    multi)
+      N=$(nvidia-smi -L | wc -l)
+      timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > $OUT/${TAG}_multi_tests.log 2>&1; tail -3 $OUT/${TAG}_multi_tests.log
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 \
+        bench.py --gpus $N --steps 6 --warmup 3 > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err
+      echo "bench N=$N exit $?"; cat $OUT/${TAG}_bench_n$N.json; tail -3 $OUT/${TAG}_bench_n$N.err ;;
+    gemmcmp)
+      timeout 300 python tools/gemm_compare.py 1024 > $OUT/${TAG}_gemm_compare.json 2> $OUT/${TAG}_gemm_compare.err; cat $OUT/${TAG}_gemm_compare.json ;;
     refbench)
       timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_refbench.json 2> $OUT/${TAG}_refbench.err
       cat $OUT/${TAG}_refbench.json ;;

@@ -527,7 +527,8 @@ static int attention_umma_launch(const void* qkv, void* out, int n, int T, int h
 
 
 // ================================================================================================
-// (1b) tcgen05 attention v2 for T = 257, head dim 64: persistent, pipelined, P kept in tensor memory.
+// (1b) tcgen05 attention v2 for T = 257, head dim 64 (ViT-L/14) or 80 (ViT-H/14): persistent, pipelined, P kept in
+//      tensor memory.
 //   CTA (one per SM, 320 threads) loops over (crop, head) pairs:
 //     warp 0      TMA producer: Q (both 128-row tiles), K, V of the NEXT head stream into the other smem stage
 //     warp 1      MMA issuer:   S_w = Q_w·Kᵀ (SS) into TMEM region w;  O_w = P_w·V (A = P from TMEM, V MN-major);
@@ -537,25 +538,43 @@ static int attention_umma_launch(const void* qkv, void* out, int n, int T, int h
 //                 O and L read back, class-key rank-1 term added, normalised, stored.
 //   The class-token QUERY row of the head is computed by one of the two groups (alternating) with plain FMAs on
 //   the K/V tiles already in shared memory, inside the time it would otherwise wait for the tensor core.
-//   TMEM region w (256 columns): S [0,256) -> P [0,128) | O [128,192) | L [192,208).
+//   TMEM region w (256 columns): S [0,256) -> P [0,128) | O [128,128+HD) | L [128+HD, +16).
+//   Head dim 80 = one 64-column slab (128-byte rows, 128-B swizzle) + one 16-column slab (32-byte rows, 32-B swizzle)
+//   per operand: the QKᵀ contraction is 4 + 1 K16 steps, P·V is an N=64 plus an N=16 MMA per key step.  Q/K stay
+//   double-buffered; V (needed only after the softmax) is single-buffered for HD = 80 to fit 227 KB.
 // ================================================================================================
 constexpr int kA2Threads = 320;
-constexpr int kA2StageBytes = 96 * 1024;   // Q [256 x 128 B] | K [256 x 128 B] | V [256 x 128 B]
-constexpr int kA2OffQ = 0, kA2OffK = 32 * 1024, kA2OffV = 64 * 1024;
-constexpr int kA2OffOnes = 2 * kA2StageBytes;          // 8 KB of bf16 1.0: the B operand of the row-sum MMA
-constexpr int kA2OffMisc = kA2OffOnes + 8 * 1024;
-constexpr int kA2SmemBytes = kA2OffMisc + 14 * 1024 + 1024;
 
+template <int HD>
+struct A2L {
+  static constexpr int kX = HD - 64;                       // columns in the second slab (0 or 16)
+  static constexpr int kSlab1 = 256 * 128;                 // [256 rows x 128 B]
+  static constexpr int kSlabX = kX ? 256 * 32 : 0;         // [256 rows x 32 B]
+  static constexpr int kOp = kSlab1 + kSlabX;              // one operand tile (Q, K or V)
+  static constexpr int kQKStage = 2 * kOp;                 // Q | K
+  static constexpr int kVStages = kX ? 1 : 2;
+  static constexpr int kOffV = 2 * kQKStage;
+  static constexpr int kOffOnes = kOffV + kVStages * kOp;  // 8 KB of bf16 1.0: the B operand of the row-sum MMA
+  static constexpr int kOffMisc = kOffOnes + 8 * 1024;
+  static constexpr int kColO = 128, kColL = 128 + HD;
+};
+
+template <int HD>
 struct A2Misc {
   uint64_t full_qk[2], full_v[2], empty_qk[2], empty_v[2];
   uint64_t s_full[2], p_full[2], o_full[2], tmem_free[2];
   uint32_t tmem_slot;
   uint32_t pad[3];
   float red[2][8];          // per group: cross-warp max / sum scratch
-  float vec[2][3][64];      // per group: q0, k0, v0 of the current head as fp32
-  float part[2][16][64];    // per group: 16 key-slices of the class-row output
+  float vec[2][3][HD];      // per group: q0, k0, v0 of the current head as fp32
+  float part[2][16][HD];    // per group: 16 key-slices of the class-row output
   float p_cls[2][264];      // per group: class-row probabilities (256 patch keys + class key)
 };
+
+template <int HD>
+constexpr int a2_smem_bytes() {
+  return A2L<HD>::kOffMisc + static_cast<int>((sizeof(A2Misc<HD>) + 1023) / 1024 * 1024) + 1024;
+}
 
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
@@ -565,21 +584,33 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
-// dot of 64 bf16 values (8 x uint4) with 64 fp32 values in shared memory
-__device__ __forceinline__ float dot64(const uint4 (&a)[8], const float* __restrict__ q) {
+// dot of 8 bf16 values (one uint4) with 8 fp32 values in shared memory, accumulated into (acc0, acc1)
+__device__ __forceinline__ void dot8(const uint4& a, const float* __restrict__ q, float& acc0, float& acc1) {
+  const float4 qa = *reinterpret_cast<const float4*>(q);
+  const float4 qb = *reinterpret_cast<const float4*>(q + 4);
+  acc0 = fmaf(bf16_lo(a.x), qa.x, acc0);
+  acc1 = fmaf(bf16_hi(a.x), qa.y, acc1);
+  acc0 = fmaf(bf16_lo(a.y), qa.z, acc0);
+  acc1 = fmaf(bf16_hi(a.y), qa.w, acc1);
+  acc0 = fmaf(bf16_lo(a.z), qb.x, acc0);
+  acc1 = fmaf(bf16_hi(a.z), qb.y, acc1);
+  acc0 = fmaf(bf16_lo(a.w), qb.z, acc0);
+  acc1 = fmaf(bf16_hi(a.w), qb.w, acc1);
+}
+
+// dot over the head dim of row `row` of an operand tile in shared memory (slab 1: 128-B swizzle, slab 2: 32-B swizzle)
+// with an fp32 vector in shared memory.  `tile` points at the operand's slab 1; slab 2 follows at +kSlab1.
+template <int HD>
+__device__ __forceinline__ float dot_row(const uint8_t* tile, int row, const float* __restrict__ q) {
   float acc0 = 0.f, acc1 = 0.f;
+  const uint8_t* rowp = tile + row * 128;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 qa = *reinterpret_cast<const float4*>(q + 8 * j);
-    const float4 qb = *reinterpret_cast<const float4*>(q + 8 * j + 4);
-    acc0 = fmaf(bf16_lo(a[j].x), qa.x, acc0);
-    acc1 = fmaf(bf16_hi(a[j].x), qa.y, acc1);
-    acc0 = fmaf(bf16_lo(a[j].y), qa.z, acc0);
-    acc1 = fmaf(bf16_hi(a[j].y), qa.w, acc1);
-    acc0 = fmaf(bf16_lo(a[j].z), qb.x, acc0);
-    acc1 = fmaf(bf16_hi(a[j].z), qb.y, acc1);
-    acc0 = fmaf(bf16_lo(a[j].w), qb.z, acc0);
-    acc1 = fmaf(bf16_hi(a[j].w), qb.w, acc1);
+  for (int j = 0; j < 8; ++j) dot8(*reinterpret_cast<const uint4*>(rowp + ((j ^ (row & 7)) << 4)), q + 8 * j, acc0, acc1);
+  if constexpr (HD > 64) {
+    const uint8_t* rowx = tile + A2L<HD>::kSlab1 + row * 32;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      dot8(*reinterpret_cast<const uint4*>(rowx + ((j ^ ((row >> 2) & 1)) << 4)), q + 64 + 8 * j, acc0, acc1);
   }
   return acc0 + acc1;
 }
@@ -589,19 +620,46 @@ __device__ __forceinline__ uint32_t tmem_ld_1(uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
   return r;
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 
+// Shared-memory descriptor for a tile of 32-byte rows with the 32-byte swizzle (CU_TENSOR_MAP_SWIZZLE_32B): 8-row groups
+// are 256 B apart (SBO).  Used K-major (Q, K: 16 contraction elements per row) and MN-major (V: 16 head-dim columns
+// per key row); layout code 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
+template <int HD>
 __global__ void __launch_bounds__(kA2Threads, 1)
-attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* __restrict__ qkv,
-                       __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads, float scale_log2) {
+attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmx,
+                       const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads,
+                       float scale_log2) {
+  using L = A2L<HD>;
+  using Misc = A2Misc<HD>;
   extern __shared__ uint8_t smem_a2_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_a2_raw) + 1023) & ~uintptr_t(1023));
-  A2Misc* mb = reinterpret_cast<A2Misc*>(smem + kA2OffMisc);
+  Misc* mb = reinterpret_cast<Misc*>(smem + L::kOffMisc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = heads * 64;
+  const int d = heads * HD;
   const size_t row_stride = static_cast<size_t>(3) * d;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm);
+    if constexpr (HD > 64) tma_prefetch_desc(&tmx);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&mb->full_qk[s], 1);
       mbar_init(&mb->full_v[s], 1);
@@ -617,7 +675,7 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 8 * 1024 / 4; i += kA2Threads)
-    reinterpret_cast<uint32_t*>(smem + kA2OffOnes)[i] = 0x3F803F80u;  // bf16 1.0 x2
+    reinterpret_cast<uint32_t*>(smem + L::kOffOnes)[i] = 0x3F803F80u;  // bf16 1.0 x2
   fence_proxy_async_smem();
   if (warp == 1) tmem_alloc(&mb->tmem_slot, 512);
   tc_fence_before();
@@ -625,6 +683,7 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
   tc_fence_after();
   const uint32_t tmem = mb->tmem_slot;
 
+  // stage / phase of head k:  Q,K: stage k&1, use (k>>1);   V: stage k % kVStages, use k / kVStages
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -632,68 +691,88 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
         const int s = k & 1;
         const uint32_t u = (k >> 1) & 1;
+        const int vs = k % L::kVStages;
+        const uint32_t vu = (k / L::kVStages) & 1;
         const int crop = ch / heads, head = ch - crop * heads;
         const int row0 = crop * T + 1;
-        uint8_t* st = smem + s * kA2StageBytes;
+        uint8_t* st = smem + s * L::kQKStage;
+        uint8_t* sv = smem + L::kOffV + vs * L::kOp;
         mbar_wait(&mb->empty_qk[s], u ^ 1);
-        mbar_arrive_expect_tx(&mb->full_qk[s], 64 * 1024);
-        tma_load_2d(st + kA2OffQ, &tm, &mb->full_qk[s], head * 64, row0);
-        tma_load_2d(st + kA2OffK, &tm, &mb->full_qk[s], d + head * 64, row0);
-        mbar_wait(&mb->empty_v[s], u ^ 1);
-        mbar_arrive_expect_tx(&mb->full_v[s], 32 * 1024);
-        tma_load_2d(st + kA2OffV, &tm, &mb->full_v[s], 2 * d + head * 64, row0);
+        mbar_arrive_expect_tx(&mb->full_qk[s], 2 * L::kOp);
+        tma_load_2d(st, &tm, &mb->full_qk[s], head * HD, row0);
+        tma_load_2d(st + L::kOp, &tm, &mb->full_qk[s], d + head * HD, row0);
+        if constexpr (HD > 64) {
+          tma_load_2d(st + L::kSlab1, &tmx, &mb->full_qk[s], head * HD + 64, row0);
+          tma_load_2d(st + L::kOp + L::kSlab1, &tmx, &mb->full_qk[s], d + head * HD + 64, row0);
+        }
+        mbar_wait(&mb->empty_v[vs], vu ^ 1);
+        mbar_arrive_expect_tx(&mb->full_v[vs], L::kOp);
+        tma_load_2d(sv, &tm, &mb->full_v[vs], 2 * d + head * HD, row0);
+        if constexpr (HD > 64) tma_load_2d(sv + L::kSlab1, &tmx, &mb->full_v[vs], 2 * d + head * HD + 64, row0);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // Warp-uniform control flow (all lanes wait and build the uniform descriptors, one elected lane issues): from inside
-    // a `lane == 0` branch ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall, and the 72 MMAs of a
+    // a `lane == 0` branch ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall, and the MMAs of a
     // head then cost more issue time than they take to execute.
     const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
     const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
+    const uint32_t idesc_ox = make_idesc_f16(128, 16, 1) | (1u << 16);
     const uint32_t idesc_l = make_idesc_f16(128, 16, 1);
     const uint32_t smem_base = smem_u32(smem);
-    const uint64_t ones_desc = make_sw128_kmajor_desc(smem_base + kA2OffOnes);
+    const uint64_t ones_desc = make_sw128_kmajor_desc(smem_base + L::kOffOnes);
     int k = 0;
     for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
       const int s = k & 1;
       const uint32_t u = (k >> 1) & 1, kp = k & 1;
-      const uint32_t sbase = smem_base + s * kA2StageBytes;
+      const int vs = k % L::kVStages;
+      const uint32_t vu = (k / L::kVStages) & 1;
+      const uint32_t sbase = smem_base + s * L::kQKStage;
+      const uint32_t vbase = smem_base + L::kOffV + vs * L::kOp;
       mbar_wait(&mb->full_qk[s], u);
-      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + kA2OffK);
+      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + L::kOp);
+      const uint64_t kx_desc = make_sw32_desc(sbase + L::kOp + L::kSlab1);
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         mbar_wait(&mb->tmem_free[w], kp ^ 1);  // group w has read the previous O out of its region
         tc_fence_after();
-        const uint64_t q_desc = make_sw128_kmajor_desc(sbase + kA2OffQ + w * 16384);
+        const uint64_t q_desc = make_sw128_kmajor_desc(sbase + w * 16384);
+        const uint64_t qx_desc = make_sw32_desc(sbase + L::kSlab1 + w * 4096);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_f16(tmem + w * 256, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk != 0);
+          if constexpr (HD > 64) umma_f16(tmem + w * 256, qx_desc, kx_desc, idesc_s, 1);
           umma_commit(&mb->s_full[w]);
         }
         __syncwarp();
       }
       if (elect_one()) umma_commit(&mb->empty_qk[s]);
       __syncwarp();
-      mbar_wait(&mb->full_v[s], u);
-      const uint64_t v_desc0 = make_sw128_kmajor_desc(sbase + kA2OffV);
+      mbar_wait(&mb->full_v[vs], vu);
+      const uint64_t v_desc0 = make_sw128_kmajor_desc(vbase);
+      const uint64_t vx_desc0 = make_sw32_desc(vbase + L::kSlab1);
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         mbar_wait(&mb->p_full[w], kp);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk)  // 16 keys = 16 rows of 128 B further down the V tile: +128 in the addr>>4 field
-            umma_f16_ts(tmem + w * 256 + 128, tmem + w * 256 + kk * 8, v_desc0 + kk * 128, idesc_o, kk != 0);
+          for (int kk = 0; kk < 16; ++kk) {
+            // 16 keys further down the V tile: 16 rows of 128 B (+128 in the addr>>4 field) / of 32 B (+32)
+            umma_f16_ts(tmem + w * 256 + L::kColO, tmem + w * 256 + kk * 8, v_desc0 + kk * 128, idesc_o, kk != 0);
+            if constexpr (HD > 64)
+              umma_f16_ts(tmem + w * 256 + L::kColO + 64, tmem + w * 256 + kk * 8, vx_desc0 + kk * 32, idesc_ox, kk != 0);
+          }
 #pragma unroll
           for (int kk = 0; kk < 16; ++kk)  // every element of the ones tile is 1.0, so any 16 x 16 slice will do
-            umma_f16_ts(tmem + w * 256 + 192, tmem + w * 256 + kk * 8, ones_desc + 2 * (kk & 3), idesc_l, kk != 0);
+            umma_f16_ts(tmem + w * 256 + L::kColL, tmem + w * 256 + kk * 8, ones_desc + 2 * (kk & 3), idesc_l, kk != 0);
           umma_commit(&mb->o_full[w]);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(&mb->empty_v[s]);
+      if (elect_one()) umma_commit(&mb->empty_v[vs]);
       __syncwarp();
     }
   } else {
@@ -710,38 +789,41 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     float* v0f = mb->vec[w][2];
     // this thread's elements of the head's class-token q/k/v are fetched one iteration ahead as RAW bf16 bits (converting
     // at load time would stall on the load right away); its own query row is read from the Q tile TMA already staged
-    uint32_t cnext = 0, cnext2 = 0;
+    uint32_t cq = 0, ck = 0, cv = 0;
     auto prefetch = [&](int ch) {
-      const int crop = ch / heads, head = ch - crop * heads;
-      const unsigned short* cls_row = reinterpret_cast<const unsigned short*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * 64);
-      cnext = __ldg(gt < 64 ? cls_row + gt : cls_row + 2 * d + gt - 64);  // q0[gt] | v0[gt-64]
-      cnext2 = __ldg(cls_row + d + (gt & 63));                            // k0[gt]
+      if (gt < HD) {
+        const int crop = ch / heads, head = ch - crop * heads;
+        const unsigned short* cls_row =
+            reinterpret_cast<const unsigned short*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * HD);
+        cq = __ldg(cls_row + gt);
+        ck = __ldg(cls_row + d + gt);
+        cv = __ldg(cls_row + 2 * d + gt);
+      }
     };
     if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
     int k = 0;
     for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
       const int s = k & 1;
       const uint32_t u = (k >> 1) & 1, kp = k & 1;
+      const int vs = k % L::kVStages;
+      const uint32_t vu = (k / L::kVStages) & 1;
       const int crop = ch / heads, head = ch - crop * heads;
       const int tok0 = crop * T;
       const int token = tok0 + 1 + w * 128 + r;
-      const uint8_t* st = smem + s * kA2StageBytes;
+      const uint8_t* st = smem + s * L::kQKStage;
+      const uint8_t* sv = smem + L::kOffV + vs * L::kOp;
       const bool cls_owner = ((k & 1) == w);
 
-      if (gt < 64) q0f[gt] = __uint_as_float(cnext << 16); else v0f[gt - 64] = __uint_as_float(cnext << 16);
-      if (gt < 64) k0f[gt] = __uint_as_float(cnext2 << 16);
+      if (gt < HD) {
+        q0f[gt] = __uint_as_float(cq << 16);
+        k0f[gt] = __uint_as_float(ck << 16);
+        v0f[gt] = __uint_as_float(cv << 16);
+      }
       if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
       named_bar_sync(1 + w, 128);
       // class-token KEY for this thread's query row: s0 = q_r·k0, q_r from the (swizzled) Q tile in shared memory
       mbar_wait(&mb->full_qk[s], u);
-      float s0;
-      {
-        uint4 qrow[8];
-        const uint8_t* qp = st + kA2OffQ + (w * 128 + r) * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) qrow[j] = *reinterpret_cast<const uint4*>(qp + ((j ^ (r & 7)) << 4));
-        s0 = dot64(qrow, k0f);
-      }
+      const float s0 = dot_row<HD>(st, w * 128 + r, k0f);
       if (!cls_owner) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&mb->empty_qk[s]);
@@ -750,30 +832,19 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       // ---- class-token QUERY row, part 1 (scores + softmax statistics) from the K tile in smem
       float cls_l = 0.f;
       if (cls_owner) {
-        mbar_wait(&mb->full_qk[s], u);
-        float sa, sb, sc = -INFINITY;
-        {
-          uint4 a[8];
-          const int key = gt;
-          const uint8_t* rowp = st + kA2OffK + key * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const uint4*>(rowp + ((j ^ (key & 7)) << 4));
-          sa = dot64(a, q0f);
-          const uint8_t* rowp2 = rowp + 128 * 128;  // key + 128 (same swizzle phase: 128 % 8 == 0)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const uint4*>(rowp2 + ((j ^ (key & 7)) << 4));
-          sb = dot64(a, q0f);
-        }
+        float sc = -INFINITY;
+        const float sa = dot_row<HD>(st + L::kOp, gt, q0f);
+        const float sb = dot_row<HD>(st + L::kOp, gt + 128, q0f);
         if (gt == 0) {
           float acc = 0.f;
-          for (int c = 0; c < 64; ++c) acc = fmaf(q0f[c], k0f[c], acc);
+          for (int c = 0; c < HD; ++c) acc = fmaf(q0f[c], k0f[c], acc);
           sc = acc;
         }
         float m = fmaxf(fmaxf(sa, sb), sc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) red[gt >> 5] = m;
-        named_bar_sync(1 + w, 128);  // also: every K read of the group is done
+        named_bar_sync(1 + w, 128);  // also: every Q and K read of the group is done
         if (gt == 0) mbar_arrive(&mb->empty_qk[s]);
         m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * scale_log2;
         const float pa = ex2_ftz(fmaf(sa, scale_log2, -m)), pb = ex2_ftz(fmaf(sb, scale_log2, -m));
@@ -835,64 +906,80 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       if (lane == 0) mbar_arrive(&mb->p_full[w]);
 
       // ---- class-token QUERY row, part 2: O_cls = P_cls·V from the V tile in smem.
-      //      thread = (16-key slice ks, 8-column chunk cc): one 16-byte read per key.
+      //      thread = (16-key slice ks, 8-column chunk cc): one 16-byte read per key (two for cc < 2 when HD = 80).
       if (cls_owner) {
-        mbar_wait(&mb->full_v[s], u);
+        mbar_wait(&mb->full_v[vs], vu);
         const int cc = gt & 7, ks = gt >> 3;
-        const uint8_t* vb = st + kA2OffV + (ks * 16) * 128;
         const float* pp = pcls + ks * 16;
-        float acc[8];
+        auto accumulate = [&](const uint8_t* base, int pitch, int chunk_of_key0, int phase_shift, float* dst) {
+          float acc[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-        for (int key = 0; key < 16; ++key) {
-          const uint4 a = *reinterpret_cast<const uint4*>(vb + key * 128 + ((cc ^ (key & 7)) << 4));
-          const float pkey = pp[key];
-          acc[0] = fmaf(pkey, bf16_lo(a.x), acc[0]);
-          acc[1] = fmaf(pkey, bf16_hi(a.x), acc[1]);
-          acc[2] = fmaf(pkey, bf16_lo(a.y), acc[2]);
-          acc[3] = fmaf(pkey, bf16_hi(a.y), acc[3]);
-          acc[4] = fmaf(pkey, bf16_lo(a.z), acc[4]);
-          acc[5] = fmaf(pkey, bf16_hi(a.z), acc[5]);
-          acc[6] = fmaf(pkey, bf16_lo(a.w), acc[6]);
-          acc[7] = fmaf(pkey, bf16_hi(a.w), acc[7]);
+          for (int key = 0; key < 16; ++key) {
+            // ks*16 + key has the same low 4 bits as key, so the swizzle phase depends on `key` only
+            const int phase = phase_shift == 0 ? (key & 7) : ((key >> 2) & 1);
+            const uint4 a = *reinterpret_cast<const uint4*>(base + key * pitch + ((chunk_of_key0 ^ phase) << 4));
+            const float pkey = pp[key];
+            acc[0] = fmaf(pkey, bf16_lo(a.x), acc[0]);
+            acc[1] = fmaf(pkey, bf16_hi(a.x), acc[1]);
+            acc[2] = fmaf(pkey, bf16_lo(a.y), acc[2]);
+            acc[3] = fmaf(pkey, bf16_hi(a.y), acc[3]);
+            acc[4] = fmaf(pkey, bf16_lo(a.z), acc[4]);
+            acc[5] = fmaf(pkey, bf16_hi(a.z), acc[5]);
+            acc[6] = fmaf(pkey, bf16_lo(a.w), acc[6]);
+            acc[7] = fmaf(pkey, bf16_hi(a.w), acc[7]);
+          }
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        };
+        accumulate(sv + (ks * 16) * 128, 128, cc, 0, &mb->part[w][ks][cc * 8]);
+        if constexpr (HD > 64) {
+          if (cc < 2) accumulate(sv + L::kSlab1 + (ks * 16) * 32, 32, cc, 1, &mb->part[w][ks][64 + cc * 8]);
         }
-        float* dst = &mb->part[w][ks][cc * 8];
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         named_bar_sync(1 + w, 128);  // also: every V read of the group is done
-        if (gt == 0) mbar_arrive(&mb->empty_v[s]);
-        if (gt < 64) {
+        if (gt == 0) mbar_arrive(&mb->empty_v[vs]);
+        if (gt < HD) {
           float o = pcls[256] * v0f[gt];
 #pragma unroll
           for (int i = 0; i < 16; ++i) o += mb->part[w][i][gt];
-          out[static_cast<size_t>(tok0) * d + head * 64 + gt] = __float2bfloat16_rn(o / cls_l);
+          out[static_cast<size_t>(tok0) * d + head * HD + gt] = __float2bfloat16_rn(o / cls_l);
         }
       }
 
       // ---- own row: (O + p0·v0) / (L + p0) -> bf16
       mbar_wait(&mb->o_full[w], kp);
       tc_fence_after();
-      const float lsum = __uint_as_float(tmem_ld_1(taddr + 192));
-      __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * 64;
+      const float lsum = __uint_as_float(tmem_ld_1(taddr + L::kColL));
+      __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * HD;
+      auto store8 = [&](const uint32_t* v, const float* v0, __nv_bfloat16* dst, float inv, float p0i) {
+        const float4 va4 = *reinterpret_cast<const float4*>(v0);
+        const float4 vb4 = *reinterpret_cast<const float4*>(v0 + 4);
+        uint4 o4;
+        o4.x = pack2(fmaf(__uint_as_float(v[0]), inv, p0i * va4.x), fmaf(__uint_as_float(v[1]), inv, p0i * va4.y));
+        o4.y = pack2(fmaf(__uint_as_float(v[2]), inv, p0i * va4.z), fmaf(__uint_as_float(v[3]), inv, p0i * va4.w));
+        o4.z = pack2(fmaf(__uint_as_float(v[4]), inv, p0i * vb4.x), fmaf(__uint_as_float(v[5]), inv, p0i * vb4.y));
+        o4.w = pack2(fmaf(__uint_as_float(v[6]), inv, p0i * vb4.z), fmaf(__uint_as_float(v[7]), inv, p0i * vb4.w));
+        *reinterpret_cast<uint4*>(dst) = o4;
+      };
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(taddr + 128 + c * 32, v);
+        tmem_ld_32x32(taddr + L::kColO + c * 32, v);
         tmem_ld_wait();
         const float inv = 1.0f / (lsum + p0);
         const float p0i = p0 * inv;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 va = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j);
-          const float4 vb4 = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j + 4);
-          uint4 o4;
-          o4.x = pack2(fmaf(__uint_as_float(v[8 * j + 0]), inv, p0i * va.x), fmaf(__uint_as_float(v[8 * j + 1]), inv, p0i * va.y));
-          o4.y = pack2(fmaf(__uint_as_float(v[8 * j + 2]), inv, p0i * va.z), fmaf(__uint_as_float(v[8 * j + 3]), inv, p0i * va.w));
-          o4.z = pack2(fmaf(__uint_as_float(v[8 * j + 4]), inv, p0i * vb4.x), fmaf(__uint_as_float(v[8 * j + 5]), inv, p0i * vb4.y));
-          o4.w = pack2(fmaf(__uint_as_float(v[8 * j + 6]), inv, p0i * vb4.z), fmaf(__uint_as_float(v[8 * j + 7]), inv, p0i * vb4.w));
-          *reinterpret_cast<uint4*>(orow + c * 32 + 8 * j) = o4;
-        }
+        for (int j = 0; j < 4; ++j) store8(v + 8 * j, v0f + c * 32 + 8 * j, orow + c * 32 + 8 * j, inv, p0i);
+      }
+      if constexpr (HD > 64) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + L::kColO + 64, v);
+        tmem_ld_wait();
+        const float inv = 1.0f / (lsum + p0);
+        const float p0i = p0 * inv;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) store8(v + 8 * j, v0f + 64 + 8 * j, orow + 64 + 8 * j, inv, p0i);
       }
       tc_fence_before();
       __syncwarp();
@@ -909,22 +996,28 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
   }
 }
 
+template <int HD>
 static int attention_umma2_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
-  const int d = heads * 64;
-  CUtensorMap tm;
+  const int d = heads * HD;
+  CUtensorMap tm, tmx;
   B2C_TRY(make_tmap_2d(&tm, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, 1));
+  tmx = tm;
+  if (HD > 64)
+    B2C_TRY(make_tmap_2d_sw(&tmx, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, HD - 64, B2C_BF16, 32));
+  constexpr int smem_bytes = a2_smem_bytes<HD>();
+  static_assert(smem_bytes <= 227 * 1024, "attention v2 shared memory exceeds 227 KB");
+  auto kern = attention_umma2_kernel<HD>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes));
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
-  static_assert(sizeof(A2Misc) <= 14 * 1024, "A2Misc must fit its smem slot");
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");
   const int n_ch = n * heads;
-  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
-  attention_umma2_kernel<<<n_ch < sms ? n_ch : sms, kA2Threads, kA2SmemBytes, stream>>>(
-      tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, scale_log2);
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));  // log2(e) / sqrt(hd)
+  kern<<<n_ch < sms ? n_ch : sms, kA2Threads, smem_bytes, stream>>>(
+      tm, tmx, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, scale_log2);
   B2C_POST_LAUNCH("attention_umma2_kernel");
   return 0;
 }
@@ -951,7 +1044,8 @@ int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd
   B2C_REQUIRE(n > 0 && T > 0 && heads > 0, "attention: empty problem");
   // B2C_ATTN = v2 (default: persistent, P in TMEM) | v1 (one CTA per query tile, P in smem) | legacy (mma.sync)
   static const char mode = [] { const char* e = getenv("B2C_ATTN"); return e ? (e[0] == 'l' ? 'l' : (e[1] == '1' ? '1' : '2')) : '2'; }();
-  if (hd == 64 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch(qkv, out, n, T, heads, stream);
+  if (hd == 64 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<64>(qkv, out, n, T, heads, stream);
+  if (hd == 80 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
   if (hd == 64 && T == kAuKeys + 1 && mode == '1') return attention_umma_launch(qkv, out, n, T, heads, stream);
   if (hd == 64) return attention_launch_hd<64>(qkv, out, n, T, heads, stream);
   if (hd == 80) return attention_launch_hd<80>(qkv, out, n, T, heads, stream);

@@ -41,6 +41,11 @@ static encode_tiled_fn get_encode_tiled() {
 
 int make_tmap_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                     uint32_t box_rows, uint32_t box_cols, int dtype) {
+  return make_tmap_2d_sw(out, base, rows, cols, row_stride_bytes, box_rows, box_cols, dtype, 128);
+}
+
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                    uint32_t box_rows, uint32_t box_cols, int dtype, int swizzle_bytes) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return set_error(B2C_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   B2C_REQUIRE(row_stride_bytes % 16 == 0, "TMA row stride %llu B is not a multiple of 16",
@@ -54,13 +59,17 @@ int make_tmap_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
     case B2C_BF16: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; esz = 2; break;
     default: return set_error(B2C_ERR_ARG, "make_tmap: unsupported dtype %d", dtype);
   }
-  B2C_REQUIRE(box_cols * esz == 128, "make_tmap: box of %u columns is not one 128-byte swizzle row", box_cols);
+  B2C_REQUIRE(swizzle_bytes == 128 || swizzle_bytes == 64 || swizzle_bytes == 32, "make_tmap: swizzle %d", swizzle_bytes);
+  B2C_REQUIRE(box_cols * esz == static_cast<size_t>(swizzle_bytes), "make_tmap: box of %u columns is not one %d-byte swizzle row",
+              box_cols, swizzle_bytes);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(B2C_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu stride=%llu)",
                      (int)r, (unsigned long long)rows, (unsigned long long)cols,

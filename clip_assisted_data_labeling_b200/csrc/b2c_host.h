@@ -41,6 +41,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 int make_tmap_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                     uint32_t box_rows, uint32_t box_cols, int dtype);
 
+// Same with a 32-, 64- or 128-byte swizzle; box_cols * elem_size must equal the swizzle span.
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                    uint32_t box_rows, uint32_t box_cols, int dtype, int swizzle_bytes);
+
 int num_sms();
 
 }  // namespace b2c

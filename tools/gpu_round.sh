@@ -26,6 +26,15 @@ for w in $WHAT; do
       echo "bench N=$N exit $?"; cat $OUT/${TAG}_bench_n$N.json; tail -3 $OUT/${TAG}_bench_n$N.err ;;
     gemmcmp)
       timeout 300 python tools/gemm_compare.py 1024 > $OUT/${TAG}_gemm_compare.json 2> $OUT/${TAG}_gemm_compare.err; cat $OUT/${TAG}_gemm_compare.json ;;
+    archs)
+      : > $OUT/${TAG}_archs.jsonl
+      timeout 300 python tools/bench_arch.py ViT-H-14/laion2b_s32b_b79k --fc --batch 128 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
+      B2C_ATTN=legacy timeout 300 python tools/bench_arch.py ViT-H-14/laion2b_s32b_b79k --fc --batch 128 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
+      timeout 300 python tools/bench_arch.py ViT-L-14-336/openai --batch 64 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
+      timeout 300 python tools/bench_arch.py ViT-B-32/openai --batch 512 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
+      cat $OUT/${TAG}_archs.jsonl; tail -3 $OUT/${TAG}_archs.err ;;
+    attntest)
+      timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "attention or encode_image" > $OUT/${TAG}_attntest.log 2>&1; tail -15 $OUT/${TAG}_attntest.log ;;
     refbench)
       timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_refbench.json 2> $OUT/${TAG}_refbench.err
       cat $OUT/${TAG}_refbench.json ;;

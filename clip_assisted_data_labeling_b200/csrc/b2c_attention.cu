@@ -1022,6 +1022,352 @@ static int attention_umma2_launch(const void* qkv, void* out, int n, int T, int 
   return 0;
 }
 
+// ================================================================================================
+// (1c) tcgen05 attention v3 for longer sequences (ViT-L/14-336: T = 577 = class token + 576 patches), head dim 64,
+//      patch count a multiple of 96.  Two-pass exact softmax over key blocks of 96:
+//   CTA (one per SM, 320 threads) loops over (crop, head); K and V of the head stay resident in shared memory (2 x 72 KB
+//   for 576 patches), query tiles stream through a 2-stage ring, 256 rows (two 128-row tiles, one per softmax group) per
+//   stage.  Per query tile the key blocks are visited twice: pass A (S_b = Q·K_bᵀ, running row max only) and pass B (S_b
+//   again, p = exp2(s·c − m·c), P_b in bf16 written over S_b in TMEM, O += P_b·V_b on the tensor core, row sums in
+//   registers).  Recomputing S costs tensor time that is idle anyway (the kernel is bound by the exponentials) and keeps
+//   the softmax exact with no rescaling of O.  S is double-buffered per group — TMEM region w (256 columns): S/P buffer 0
+//   [0,96) | S/P buffer 1 [96,192) | O [192,256) — and S tiles are issued two tiles ahead, so the softmax threads never
+//   wait for the tensor core; PV_b and the next S into the same buffer rely on tcgen05.mma executing in issue order.
+//   The class-token KEY is the same rank-1 term as in v2; the class-token QUERY row goes to attention_cls_kernel.
+// ================================================================================================
+constexpr int kA3KB = 96;                       // keys per block
+constexpr int kA3BlockBytes = kA3KB * 128;      // one K or V block: 96 rows x 128 B
+constexpr int kA3QStage = 256 * 128;
+constexpr int kA3MaxNB = 6;
+
+struct A3Misc {
+  uint64_t k_full, k_empty, v_full, v_empty, q_full[2], q_empty[2];
+  uint64_t s_full[2][2], s_free[2][2], p_full[2][2], o_full[2], o_free[2];
+  uint32_t tmem_slot;
+  uint32_t pad[3];
+  float k0[64], v0[64];
+};
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+attention_umma3_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                       const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads,
+                       int NB, float scale_log2) {
+  extern __shared__ uint8_t smem_a3_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_a3_raw) + 1023) & ~uintptr_t(1023));
+  const int off_v = NB * kA3BlockBytes;
+  const int off_q = 2 * NB * kA3BlockBytes;
+  A3Misc* mb = reinterpret_cast<A3Misc*>(smem + off_q + 2 * kA3QStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * 64;
+  const size_t row_stride = static_cast<size_t>(3) * d;
+  const int G2 = NB * kA3KB;
+  const int NQ = (G2 + 255) / 256;  // query-tile pairs per head
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_kv);
+    tma_prefetch_desc(&tm_q);
+    mbar_init(&mb->k_full, 1);
+    mbar_init(&mb->k_empty, 1);
+    mbar_init(&mb->v_full, 1);
+    mbar_init(&mb->v_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&mb->q_full[s], 1);
+      mbar_init(&mb->q_empty[s], 9);  // MMA commit + the eight softmax warps (own Q rows read)
+      mbar_init(&mb->o_full[s], 1);
+      mbar_init(&mb->o_free[s], 4);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&mb->s_full[s][b], 1);
+        mbar_init(&mb->s_free[s][b], 4);
+        mbar_init(&mb->p_full[s][b], 4);
+      }
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&mb->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mb->tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int hk = 0, qk = 0;
+      for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++hk) {
+        const int crop = ch / heads, head = ch - crop * heads;
+        const int row0 = crop * T + 1;
+        auto load_q = [&](int pair) {
+          const int s = qk & 1;
+          mbar_wait(&mb->q_empty[s], ((qk >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&mb->q_full[s], kA3QStage);
+          tma_load_2d(smem + off_q + s * kA3QStage, &tm_q, &mb->q_full[s], head * 64, row0 + pair * 256);
+          ++qk;
+        };
+        mbar_wait(&mb->k_empty, (hk & 1) ^ 1);
+        mbar_arrive_expect_tx(&mb->k_full, NB * kA3BlockBytes);
+        for (int b = 0; b < NB; ++b) tma_load_2d(smem + b * kA3BlockBytes, &tm_kv, &mb->k_full, d + head * 64, row0 + b * kA3KB);
+        load_q(0);
+        mbar_wait(&mb->v_empty, (hk & 1) ^ 1);
+        mbar_arrive_expect_tx(&mb->v_full, NB * kA3BlockBytes);
+        for (int b = 0; b < NB; ++b)
+          tma_load_2d(smem + off_v + b * kA3BlockBytes, &tm_kv, &mb->v_full, 2 * d + head * 64, row0 + b * kA3KB);
+        for (int pair = 1; pair < NQ; ++pair) load_q(pair);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane issues)
+    const uint32_t idesc_s = make_idesc_f16(128, kA3KB, 1);
+    const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
+    const uint32_t smem_base = smem_u32(smem);
+    int hk = 0, qk = 0;
+    uint32_t n_sfree[2][2] = {{0, 0}, {0, 0}}, n_pfull[2][2] = {{0, 0}, {0, 0}}, n_o[2] = {0, 0};
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++hk) {
+      mbar_wait(&mb->k_full, hk & 1);
+      bool v_ready = false;
+      for (int pair = 0; pair < NQ; ++pair, ++qk) {
+        const int s = qk & 1;
+        mbar_wait(&mb->q_full[s], (qk >> 1) & 1);
+        tc_fence_after();
+        const int nact = (pair * 256 + 128 < G2) ? 2 : 1;
+        const uint32_t qbase = smem_base + off_q + s * kA3QStage;
+        // P_b·V_b for tile i (a pass-B tile) of group w, accumulated into O
+        auto issue_pv = [&](int i, int w) {
+          const int b = i - NB, buf = i & 1;
+          mbar_wait(&mb->p_full[w][buf], n_pfull[w][buf] & 1);
+          ++n_pfull[w][buf];
+          if (b == 0) {
+            mbar_wait(&mb->o_free[w], (n_o[w] & 1) ^ 1);  // the group has read the previous O of its region
+            ++n_o[w];
+            if (!v_ready) {
+              mbar_wait(&mb->v_full, hk & 1);
+              v_ready = true;
+            }
+          }
+          tc_fence_after();
+          const uint64_t v_desc0 = make_sw128_kmajor_desc(smem_base + off_v + b * kA3BlockBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < kA3KB / 16; ++kk)
+              umma_f16_ts(tmem + w * 256 + 192, tmem + w * 256 + buf * kA3KB + kk * 8, v_desc0 + kk * 128, idesc_o,
+                          (b | kk) != 0);
+          }
+          __syncwarp();
+        };
+        for (int i = 0; i < 2 * NB; ++i) {
+          const int b = i < NB ? i : i - NB, buf = i & 1;
+          const uint64_t k_desc = make_sw128_kmajor_desc(smem_base + b * kA3BlockBytes);
+          for (int w = 0; w < nact; ++w) {
+            if (i >= 2) {
+              if (i - 2 < NB) {  // the buffer held a pass-A tile: wait until the group has scanned it
+                mbar_wait(&mb->s_free[w][buf], n_sfree[w][buf] & 1);
+                ++n_sfree[w][buf];
+                tc_fence_after();
+              } else {           // it held a pass-B tile: its P·V goes first (same thread, executes in order)
+                issue_pv(i - 2, w);
+              }
+            }
+            const uint64_t q_desc = make_sw128_kmajor_desc(qbase + w * 16384);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(tmem + w * 256 + buf * kA3KB, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk != 0);
+              umma_commit(&mb->s_full[w][buf]);
+            }
+            __syncwarp();
+          }
+        }
+        if (elect_one()) {
+          umma_commit(&mb->q_empty[s]);                       // every S of this pair has been issued
+          if (pair == NQ - 1) umma_commit(&mb->k_empty);      // ... and of this head
+        }
+        __syncwarp();
+        for (int i = 2 * NB - 2; i < 2 * NB; ++i)
+          for (int w = 0; w < nact; ++w) {
+            issue_pv(i, w);
+            if (i == 2 * NB - 1) {
+              if (elect_one()) umma_commit(&mb->o_full[w]);
+              __syncwarp();
+            }
+          }
+      }
+      if (elect_one()) umma_commit(&mb->v_empty);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    const int w = (warp - 2) >> 2;          // group = query tile of the pair
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+    const int r = quarter * 32 + lane;      // query row in the tile = TMEM lane
+    const int t256 = threadIdx.x - 64;      // 0..255 over both groups
+    const uint32_t taddr = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* k0f = mb->k0;
+    float* v0f = mb->v0;
+    uint32_t craw = 0;
+    auto prefetch = [&](int ch) {
+      if (t256 < 128) {
+        const int crop = ch / heads, head = ch - crop * heads;
+        const unsigned short* cls_row =
+            reinterpret_cast<const unsigned short*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * 64);
+        craw = __ldg(t256 < 64 ? cls_row + d + t256 : cls_row + 2 * d + (t256 - 64));  // k0 | v0
+      }
+    };
+    if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
+    int qk = 0;
+    uint32_t n_sfull[2] = {0, 0}, n_ofull = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x) {
+      const int crop = ch / heads, head = ch - crop * heads;
+      const int tok0 = crop * T;
+      named_bar_sync(1, 256);  // everyone is done with the previous head's k0 / v0
+      if (t256 < 64) k0f[t256] = __uint_as_float(craw << 16);
+      else if (t256 < 128) v0f[t256 - 64] = __uint_as_float(craw << 16);
+      if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
+      named_bar_sync(1, 256);
+      for (int pair = 0; pair < NQ; ++pair, ++qk) {
+        const int s = qk & 1;
+        const int qrow = pair * 256 + w * 128 + r;
+        const bool active = pair * 256 + w * 128 < G2;  // group-uniform
+        mbar_wait(&mb->q_full[s], (qk >> 1) & 1);
+        float s0 = 0.f;
+        if (active) s0 = dot_row<64>(smem + off_q + s * kA3QStage, w * 128 + r, k0f);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mb->q_empty[s]);
+        if (!active) continue;
+
+        // ---- pass A: running row max over the key blocks
+        float m = s0;
+        for (int b = 0; b < NB; ++b) {
+          const int buf = b & 1;
+          mbar_wait(&mb->s_full[w][buf], n_sfull[buf] & 1);
+          ++n_sfull[buf];
+          tc_fence_after();
+          uint32_t va[32], vb[32];
+          const uint32_t ta = taddr + buf * kA3KB;
+          tmem_ld_32x32(ta, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(ta + 32, vb);
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
+          tmem_ld_wait();
+          tmem_ld_32x32(ta + 64, va);
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mb->s_free[w][buf]);
+        }
+        const float ms = m * scale_log2;
+        const float p0 = ex2_ftz(fmaf(s0, scale_log2, -ms));
+        float lsum = p0;
+
+        // ---- pass B: probabilities (bf16x2) over S in TMEM, row sum in registers
+        for (int b = 0; b < NB; ++b) {
+          const int buf = (NB + b) & 1;
+          mbar_wait(&mb->s_full[w][buf], n_sfull[buf] & 1);
+          ++n_sfull[buf];
+          tc_fence_after();
+          uint32_t va[32], vb[32];
+          const uint32_t ta = taddr + buf * kA3KB;
+          auto emit_p = [&](const uint32_t (&v)[32], int c) {
+            uint32_t pk[16];
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float pa = ex2_ftz(fmaf(__uint_as_float(v[2 * e]), scale_log2, -ms));
+              const float pb = ex2_ftz(fmaf(__uint_as_float(v[2 * e + 1]), scale_log2, -ms));
+              acc0 += pa;
+              acc1 += pb;
+              pk[e] = pack2(pa, pb);
+            }
+            lsum += acc0 + acc1;
+            tmem_st_32x16(ta + c * 16, pk);  // columns [16c, 16c+16) of the buffer: already consumed
+          };
+          tmem_ld_32x32(ta, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(ta + 32, vb);
+          emit_p(va, 0);
+          tmem_ld_wait();
+          tmem_ld_32x32(ta + 64, va);
+          emit_p(vb, 1);
+          tmem_ld_wait();
+          emit_p(va, 2);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mb->p_full[w][buf]);
+        }
+
+        // ---- (O + p0·v0) / (L + p0) -> bf16   (lsum already includes p0)
+        mbar_wait(&mb->o_full[w], n_ofull & 1);
+        ++n_ofull;
+        tc_fence_after();
+        const float inv = 1.0f / lsum;
+        const float p0i = p0 * inv;
+        __nv_bfloat16* orow = out + (static_cast<size_t>(tok0) + 1 + qrow) * d + head * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + 192 + c * 32, v);
+          tmem_ld_wait();
+          if (qrow < G2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 va4 = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j);
+              const float4 vb4 = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j + 4);
+              uint4 o4;
+              o4.x = pack2(fmaf(__uint_as_float(v[8 * j + 0]), inv, p0i * va4.x), fmaf(__uint_as_float(v[8 * j + 1]), inv, p0i * va4.y));
+              o4.y = pack2(fmaf(__uint_as_float(v[8 * j + 2]), inv, p0i * va4.z), fmaf(__uint_as_float(v[8 * j + 3]), inv, p0i * va4.w));
+              o4.z = pack2(fmaf(__uint_as_float(v[8 * j + 4]), inv, p0i * vb4.x), fmaf(__uint_as_float(v[8 * j + 5]), inv, p0i * vb4.y));
+              o4.w = pack2(fmaf(__uint_as_float(v[8 * j + 6]), inv, p0i * vb4.z), fmaf(__uint_as_float(v[8 * j + 7]), inv, p0i * vb4.w));
+              *reinterpret_cast<uint4*>(orow + c * 32 + 8 * j) = o4;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mb->o_free[w]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int attention_umma3_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
+  const int d = heads * 64;
+  const int NB = (T - 1) / kA3KB;
+  CUtensorMap tm_kv, tm_q;
+  const uint64_t rows = static_cast<uint64_t>(n) * T;
+  B2C_TRY(make_tmap_2d(&tm_kv, qkv, rows, 3ull * d, 3ull * d * 2, kA3KB, 1));
+  B2C_TRY(make_tmap_2d(&tm_q, qkv, rows, 3ull * d, 3ull * d * 2, 256, 1));
+  const int smem_bytes = 2 * NB * kA3BlockBytes + 2 * kA3QStage + static_cast<int>((sizeof(A3Misc) + 1023) / 1024 * 1024) + 1024;
+  B2C_REQUIRE(smem_bytes <= 227 * 1024, "attention v3: T=%d does not fit shared memory", T);
+  static int smem_set = 0;
+  if (smem_bytes > smem_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    smem_set = smem_bytes;
+  }
+  const int sms = num_sms();
+  B2C_REQUIRE(sms > 0, "no CUDA device");
+  const int n_ch = n * heads;
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  attention_umma3_kernel<<<n_ch < sms ? n_ch : sms, kA2Threads, smem_bytes, stream>>>(tm_kv, tm_q, q, o, n_ch, T, heads, NB,
+                                                                                     scale_log2);
+  B2C_POST_LAUNCH("attention_umma3_kernel");
+  attention_cls_kernel<<<(n_ch + 3) / 4, 128, 0, stream>>>(q, o, n_ch, T, heads, scale_log2);
+  B2C_POST_LAUNCH("attention_cls_kernel");
+  return 0;
+}
+
 template <int HD>
 static int attention_launch_hd(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
   const int Tp = (T + 15) / 16 * 16;
@@ -1047,6 +1393,8 @@ int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd
   if (hd == 64 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<64>(qkv, out, n, T, heads, stream);
   if (hd == 80 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
   if (hd == 64 && T == kAuKeys + 1 && mode == '1') return attention_umma_launch(qkv, out, n, T, heads, stream);
+  if (hd == 64 && mode != 'l' && T > kAuKeys + 1 && (T - 1) % kA3KB == 0 && (T - 1) / kA3KB <= kA3MaxNB)
+    return attention_umma3_launch(qkv, out, n, T, heads, stream);
   if (hd == 64) return attention_launch_hd<64>(qkv, out, n, T, heads, stream);
   if (hd == 80) return attention_launch_hd<80>(qkv, out, n, T, heads, stream);
   return set_error(B2C_ERR_ARG, "attention: head dim %d unsupported (64 or 80)", hd);

@@ -207,6 +207,31 @@ def find_near_duplicates(args, sim_type="cosine", crop_to_use="square_padded_cro
     return results
 
 
+def find_near_duplicates_in_store(store, threshold=0.96, crop_to_use="square_padded_crop", per_directory=True,
+                                  compare="ref_fp16"):
+    """The same search fed from a packed store (store.PackedStore) instead of one torch.load per
+    image (_2_remove_duplicates.py:25-46).  ``per_directory=True`` keeps the reference's scope — duplicates are only
+    looked for among the images of one directory (:10) — and compares them in sorted-path order; ``False`` searches the
+    whole store at once.  Embeddings go through fp16 like the reference's loader (:38).  Returns
+    [(near_duplicates [(path_i, path_j)], near_duplicate_values [float])] per group."""
+    emb = store.crop(crop_to_use, torch.float16)
+    usable = store.has_all([crop_to_use])
+    groups = {}
+    for i, p in enumerate(store.paths):
+        if usable[i]:
+            groups.setdefault(os.path.dirname(p) if per_directory else "", []).append(i)
+    results = []
+    for key in sorted(groups):
+        idx = sorted(groups[key], key=lambda i: store.paths[i])
+        if len(idx) < 2:
+            results.append(([], []))
+            continue
+        pairs, sims = duplicate_pairs(emb[idx], threshold, compare)
+        results.append(([(store.paths[idx[i]], store.paths[idx[j]]) for i, j in pairs.tolist()],
+                        [float(np.float16(s)) for s in sims]))
+    return results
+
+
 def fix_duplicate(duplicate_index, img_paths, outdir, sim_value, mode):
     """_2_remove_duplicates.py:102-125: copy both images' companion files, or move only the target's."""
     dirname = os.path.dirname(img_paths[0])

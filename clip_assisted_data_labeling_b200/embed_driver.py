@@ -85,7 +85,8 @@ def already_encoded(path: str, model_name: str) -> bool:
 class Feature_Dataset:
     def __init__(self, root_dir, model_name, batch_size, model_path=None, force_reencode=False, shuffle_filenames=True,
                  num_workers=0, crop_names=("centre_crop", "square_padded_crop", "subcrop1", "subcrop2"),
-                 rank=None, world_size=None, state_dict=None, encoder=None, writer_threads=4):
+                 rank=None, world_size=None, state_dict=None, encoder=None, writer_threads=4, packed_dir=None,
+                 write_pt=True):
         self.device = getattr(encoder, "device", "cuda") if encoder is not None else "cuda"
         self.root_dir = root_dir
         self.model_name = model_name
@@ -121,6 +122,10 @@ class Feature_Dataset:
         self.dataloader = DataLoader(self.img_dataset, **kw)
         self._writer_threads = writer_threads
         self.failed = []
+        # with packed_dir set every rank appends its [B,4,E] blocks to one flat shard
+        # (store.PackedWriter); write_pt=False skips the per-image pickles entirely (store.export_pt writes them later)
+        self.packed_dir = packed_dir
+        self.write_pt = write_pt or packed_dir is None
 
     def __len__(self):
         return len(self.img_filepaths)
@@ -135,29 +140,39 @@ class Feature_Dataset:
         print(f"Embedding dataset of {len(self.img_filepaths)} images using {self.model_name}...")
         pool = concurrent.futures.ThreadPoolExecutor(max_workers=self._writer_threads)
         pending = []
+        packed = None
+        if self.packed_dir is not None:
+            from .store import PackedWriter
+            packed = PackedWriter(self.packed_dir, self.model_name, self.encoder.embed_dim, CROP_NAMES, shard=self.rank)
         for images, img_paths in self.dataloader:
-            todo_imgs, todo_paths = [], []
+            todo_imgs, todo_paths, todo_img_paths = [], [], []
             for im, p in zip(images, img_paths):
                 save_path = os.path.splitext(p)[0] + ".pt"
                 if im is None:
                     self.failed.append(p)
-                elif not self.force_reencode and already_encoded(save_path, self.model_name):
+                elif self.write_pt and not self.force_reencode and already_encoded(save_path, self.model_name):
                     n_skipped += 1
                 else:
                     todo_imgs.append(im)
                     todo_paths.append(save_path)
+                    todo_img_paths.append(p)
             if todo_imgs:
                 if str(self.device).startswith("cuda"):
                     dev_imgs = [im.pin_memory().to(self.device, non_blocking=True) for im in todo_imgs]
                 else:  # only reachable with an injected encoder (host-logic tests)
                     dev_imgs = todo_imgs
                 feats = self.encoder.encode_images_u8(dev_imgs).cpu()  # [B,4,E], one D2H per batch
+                kept_all = []
                 for im, f, sp in zip(todo_imgs, feats, todo_paths):
                     g = (_lib.Crop * 4)()
                     _lib.check(lib.b2c_crop_geometry(int(im.shape[1]), int(im.shape[0]), R, g), "b2c_crop_geometry")
                     kept = [g[i].cw > 0 for i in range(4)]
-                    fd = build_feature_dict(f, self.crop_names, kept)
-                    pending.append(pool.submit(save_feature_file, sp, self.model_name, fd, self.force_reencode))
+                    kept_all.append(kept)
+                    if self.write_pt:
+                        fd = build_feature_dict(f, self.crop_names, kept)
+                        pending.append(pool.submit(save_feature_file, sp, self.model_name, fd, self.force_reencode))
+                if packed is not None:
+                    packed.append(feats, todo_img_paths, kept_all)
                 n_embedded += len(todo_imgs)
             if len(pending) > 4096:
                 for fu in pending:
@@ -166,6 +181,8 @@ class Feature_Dataset:
         for fu in pending:
             fu.result()
         pool.shutdown()
+        if packed is not None:
+            packed.close()
         print("\n--- Feature encoding done! ---\n")
         print(f"Embedded {n_embedded} images ({n_skipped} images were already embedded). "
               f"Features saved with model key '{self.model_name}'.")
@@ -185,6 +202,9 @@ def main(argv=None):
     parser.add_argument("--num_workers", type=int, default=4, help="Number of workers for the dataloader")
     parser.add_argument("--force_reencode", action="store_true", help="Force re-encoding of all images for the specified models")
     parser.add_argument("--model_path", type=str, default=None, help="Path to a local checkpoint file or directory (optional)")
+    parser.add_argument("--packed_dir", type=str, default=None,
+                        help="Also write one packed [N,4,E] shard per rank here (store.py; not a reference flag)")
+    parser.add_argument("--no_pt", action="store_true", help="With --packed_dir: skip the per-image .pt files (export them later)")
     args = parser.parse_args(argv)
     if "LOCAL_RANK" in os.environ:
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -192,7 +212,8 @@ def main(argv=None):
     for model_name in args.models_to_use:
         print(f"\n--- Processing model: {model_name} ---")
         Feature_Dataset(args.root_dir, model_name, args.batch_size, model_path=args.model_path,
-                        force_reencode=args.force_reencode, num_workers=args.num_workers, crop_names=CROP_NAMES).process()
+                        force_reencode=args.force_reencode, num_workers=args.num_workers, crop_names=CROP_NAMES,
+                        packed_dir=args.packed_dir, write_pt=not args.no_pt).process()
 
 
 if __name__ == "__main__":

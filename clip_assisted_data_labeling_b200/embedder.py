@@ -101,6 +101,7 @@ class CLIP_Encoder:
         self.model.load_state_dict(state_dict)
         self.preprocess = _open_clip_val_transform(cfg["image"])
         self.img_resolution = cfg["image"]
+        self.embed_dim = cfg["embed"]
         print(f"CLIP model {self.model_name} with img_resolution {self.img_resolution} loaded on {self.device}!")
 
     def get_preprocess_transform(self):

@@ -134,3 +134,18 @@ def embed_and_score(encoder, scorer: "FCScorer", images_u8):
     Returns (embeddings f32 [B,4,E], scores f32 [B,1])."""
     emb = encoder.encode_images_u8(images_u8)
     return emb, scorer.score_embeddings(emb)
+
+
+@torch.no_grad()
+def score_store(store, scorer: "FCScorer", batch: int = 65536):
+    """Regressor scores for every image of a packed store (store.PackedStore) — the bulk form of the per-image loop of
+    _5_predict_labels.py:69-88,135.  Images missing one of the regressor's crops are skipped like the reference skips
+    unreadable samples (:86-88).  Returns (paths, scores f32 [n] on the host)."""
+    ok = store.has_all(scorer.crop_names)
+    feats = store.features(scorer.crop_names)
+    keep = [i for i in range(len(store)) if ok[i]]
+    out = []
+    for b in range(0, len(keep), batch):
+        sel = keep[b:b + batch]
+        out.append(scorer.score(feats[sel].pin_memory().to(scorer.device, non_blocking=True))[:, 0].cpu())
+    return [store.paths[i] for i in keep], (torch.cat(out) if out else torch.zeros(0))

@@ -1,0 +1,268 @@
+"""Packed embedding store — SURVEY.md §8f row 1.
+
+The reference keeps one ``<img>.pt`` pickle per image (written at _1_embed_with_CLIP.py:146-170, re-read one file
+at a time by _2_remove_duplicates.py:25-46, _4_train_model.py:42-75, _5_predict_labels.py:69-88 and
+tools/find_similar_imgs.py:36-46).  Once the embedding pass runs at >1000 images/s those 14 KB pickles *are* the
+wall time, so the B200 path writes, per rank, one flat shard instead:
+
+    <store_dir>/shard-00000.emb          raw little-endian f32 (or f16) [n, C, E], C = len(crop_names), row-major
+    <store_dir>/shard-00000.json         {"format", "model", "crop_names", "dtype", "embed", "count",
+                                          "paths": [...], "kept": [bitmask per image]}
+
+``kept`` bit c is 0 when the reference would have dropped crop c as empty (utils/embedder.py:243-247); the row is
+all zeros then and the compat exporter omits the key.  Shards are memory-mapped by the readers, so a whole
+directory tree loads as one ``[N, C, E]`` array with no per-image ``torch.load``; ``export_pt`` writes the
+per-image ``.pt`` files lazily, in exactly the layout the reference's consumers read, and
+``import_pt`` is the bulk loader in the other direction (existing ``.pt`` trees -> one shard, thread pool).
+
+Host-side file I/O only: nothing here touches CUDA.
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+from .vit_arch import CROP_NAMES
+
+FORMAT = "b2c-packed-embeddings/1"
+_DTYPES = {"float32": np.float32, "float16": np.float16}
+
+
+def _shard_paths(store_dir: str, shard: int):
+    base = os.path.join(store_dir, f"shard-{shard:05d}")
+    return base + ".emb", base + ".json"
+
+
+class PackedWriter:
+    """Append-only writer of one shard (one per rank).  ``append`` takes the ``[B, 4, E]`` block
+    ``CLIP_Encoder.encode_images_u8`` returns (already on the host), in CROP_NAMES order, and keeps the columns of
+    ``crop_names``.  The index is written on ``close()``; a shard without its ``.json`` is ignored by the reader,
+    so a crashed run never leaves a half-valid shard behind."""
+
+    def __init__(self, store_dir: str, model_name: str, embed: int, crop_names=CROP_NAMES, shard: int = 0,
+                 dtype: str = "float32"):
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        os.makedirs(store_dir, exist_ok=True)
+        self.store_dir, self.model_name, self.embed = store_dir, model_name, int(embed)
+        self.crop_names = list(crop_names)
+        self._cols = [CROP_NAMES.index(c) for c in self.crop_names]
+        self.dtype = dtype
+        self.emb_path, self.idx_path = _shard_paths(store_dir, shard)
+        if os.path.exists(self.idx_path):
+            os.remove(self.idx_path)  # invalidate first, then rewrite the data
+        self._fh = open(self.emb_path, "wb")
+        self.paths: list[str] = []
+        self.kept: list[int] = []
+
+    def append(self, features, paths, kept=None) -> None:
+        """features: [B, 4, E] (torch CPU tensor or numpy) in CROP_NAMES order; paths: B image paths;
+        kept: optional B x 4 booleans (False = crop dropped as empty)."""
+        f = features.detach().cpu().numpy() if isinstance(features, torch.Tensor) else np.asarray(features)
+        if f.ndim != 3 or f.shape[1] != len(CROP_NAMES) or f.shape[2] != self.embed or f.shape[0] != len(paths):
+            raise ValueError(f"expected [{len(paths)},{len(CROP_NAMES)},{self.embed}], got {f.shape}")
+        f = np.ascontiguousarray(f[:, self._cols, :], dtype=_DTYPES[self.dtype])
+        for b in range(len(paths)):
+            mask = 0
+            for ci, c in enumerate(self._cols):
+                if kept is None or kept[b][c]:
+                    mask |= 1 << ci
+                else:
+                    f[b, ci, :] = 0
+            self.kept.append(mask)
+        self._fh.write(f.tobytes())
+        self.paths.extend(os.fspath(p) for p in paths)
+
+    def close(self) -> str:
+        self._fh.flush()
+        os.fsync(self._fh.fileno())
+        self._fh.close()
+        meta = {"format": FORMAT, "model": self.model_name, "crop_names": self.crop_names, "dtype": self.dtype,
+                "embed": self.embed, "count": len(self.paths), "paths": self.paths, "kept": self.kept}
+        tmp = self.idx_path + ".tmp"
+        with open(tmp, "w") as fh:
+            json.dump(meta, fh)
+        os.replace(tmp, self.idx_path)
+        return self.idx_path
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, *_):
+        if exc_type is None:
+            self.close()
+        else:
+            self._fh.close()
+
+
+class PackedStore:
+    """Read side: every complete shard of ``store_dir`` for ``model_name`` (default: the first model found, like
+    _2_remove_duplicates.py:32-34 defaults to the first key), memory-mapped."""
+
+    def __init__(self, store_dir: str, model_name: str | None = None):
+        self.store_dir = store_dir
+        self.shards = []
+        self.model_name = model_name
+        for idx_path in sorted(glob.glob(os.path.join(store_dir, "shard-*.json"))):
+            with open(idx_path) as fh:
+                meta = json.load(fh)
+            if meta.get("format") != FORMAT:
+                raise ValueError(f"{idx_path}: unknown store format {meta.get('format')!r}")
+            if self.model_name is None:
+                self.model_name = meta["model"]
+            if meta["model"] != self.model_name:
+                continue
+            C, E, n = len(meta["crop_names"]), meta["embed"], meta["count"]
+            emb_path = idx_path[:-5] + ".emb"
+            want = n * C * E * np.dtype(_DTYPES[meta["dtype"]]).itemsize
+            have = os.path.getsize(emb_path) if os.path.exists(emb_path) else -1
+            if have != want:
+                raise ValueError(f"{emb_path}: {have} bytes on disk, index says {want}")
+            arr = (np.memmap(emb_path, dtype=_DTYPES[meta["dtype"]], mode="r", shape=(n, C, E)) if n
+                   else np.zeros((0, C, E), _DTYPES[meta["dtype"]]))
+            self.shards.append((meta, arr))
+        if not self.shards:
+            raise FileNotFoundError(f"no packed shards for model {model_name!r} under {store_dir}")
+        first = self.shards[0][0]
+        self.crop_names = list(first["crop_names"])
+        self.embed = first["embed"]
+        for meta, _ in self.shards:
+            if meta["crop_names"] != self.crop_names or meta["embed"] != self.embed:
+                raise ValueError("shards of one model disagree on crop_names / embed")
+        self.paths = [p for meta, _ in self.shards for p in meta["paths"]]
+        self.kept = np.asarray([k for meta, _ in self.shards for k in meta["kept"]], dtype=np.int64)
+
+    def __len__(self):
+        return len(self.paths)
+
+    def array(self) -> np.ndarray:
+        """[N, C, E] over all shards (a view for one shard, one concatenation otherwise)."""
+        if len(self.shards) == 1:
+            return self.shards[0][1]
+        return np.concatenate([a for _, a in self.shards], axis=0)
+
+    def crop(self, crop_name: str, dtype=torch.float32, device=None) -> torch.Tensor:
+        """[N, E] embeddings of one crop, the bulk form of ``d[model][crop].squeeze()`` (_2_remove_duplicates.py:38)."""
+        ci = self.crop_names.index(crop_name)
+        t = torch.from_numpy(np.ascontiguousarray(self.array()[:, ci, :])).to(dtype)
+        return t.to(device) if device is not None else t
+
+    def features(self, crop_names=None, device=None) -> torch.Tensor:
+        """[N, len(crop_names) * E] f32: the regressor's input row per image, crops concatenated in the order given
+        (_4_train_model.py:55, _5_predict_labels.py:78-79)."""
+        names = list(crop_names) if crop_names is not None else self.crop_names
+        idx = [self.crop_names.index(c) for c in names]
+        t = torch.from_numpy(np.ascontiguousarray(self.array()[:, idx, :])).float().reshape(len(self), -1)
+        return t.to(device) if device is not None else t
+
+    def has_all(self, crop_names) -> np.ndarray:
+        """bool [N]: image has every crop of ``crop_names`` (the reference raises/skips on a missing crop, _4:56-58)."""
+        need = 0
+        for c in crop_names:
+            need |= 1 << self.crop_names.index(c)
+        return (self.kept & need) == need
+
+    def feature_dict(self, i: int) -> dict:
+        """{crop_name: f32[1,E]} of image i, the per-model dict of the reference's .pt layout."""
+        row, off = None, i
+        for meta, arr in self.shards:
+            if off < meta["count"]:
+                row = arr[off]
+                break
+            off -= meta["count"]
+        d = {}
+        for ci, name in enumerate(self.crop_names):
+            if (int(self.kept[i]) >> ci) & 1:
+                d[name] = torch.from_numpy(np.array(row[ci], dtype=np.float32)).unsqueeze(0)
+        return d
+
+
+def pt_path_for(img_path: str) -> str:
+    return os.path.splitext(img_path)[0] + ".pt"
+
+
+def _merge_save(pt_path: str, model_name: str, feature_dict: dict, force: bool) -> None:
+    final = {}
+    if os.path.exists(pt_path) and not force:
+        try:
+            final = torch.load(pt_path, map_location="cpu")
+        except Exception as e:  # noqa: BLE001
+            print(f"Warning: Failed to load existing {pt_path} for update: {e}")
+    final[model_name] = feature_dict
+    torch.save(final, pt_path)
+
+
+def export_pt(store: PackedStore, force_reencode: bool = False, threads: int = 8, only=None) -> int:
+    """Compat exporter: write ``<img>.pt`` next to each image in the reference's layout
+    ``{model: {crop: f32[1,E]}}``, merged into an existing file unless ``force_reencode``
+    (_1_embed_with_CLIP.py:138-170).  ``only``: optional iterable of indices.  Returns the number of files written."""
+    idx = list(range(len(store))) if only is None else list(only)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=threads) as ex:
+        futs = [ex.submit(_merge_save, pt_path_for(store.paths[i]), store.model_name, store.feature_dict(i), force_reencode)
+                for i in idx]
+        for f in futs:
+            f.result()
+    return len(idx)
+
+
+def _load_one(img_path: str, model_name, crop_names):
+    try:
+        d = torch.load(pt_path_for(img_path), map_location="cpu")
+        if model_name is None:
+            model_name = list(d.keys())[0]
+        fd = d[model_name]
+        rows, mask, E = [], 0, None
+        for ci, c in enumerate(crop_names):
+            if c in fd:
+                v = fd[c].reshape(-1).float().numpy()
+                E = v.shape[0]
+                rows.append(v)
+                mask |= 1 << ci
+            else:
+                rows.append(None)
+        if E is None:
+            return None
+        return model_name, np.stack([r if r is not None else np.zeros(E, np.float32) for r in rows]), mask
+    except Exception:  # noqa: BLE001  (the reference skips unreadable samples: _2:45-46, _4:72-74)
+        return None
+
+
+def import_pt(root_dir: str, store_dir: str, model_name: str | None = None, crop_names=CROP_NAMES, threads: int = 16,
+              img_extensions=(".jpg",), shard: int = 0) -> PackedStore:
+    """Bulk loader: walk ``root_dir`` for images that have a ``.pt`` companion (the pairing rule of
+    _2_remove_duplicates.py:27), read the pickles on a thread pool and pack them into one shard.  Images are taken
+    in sorted path order so the result is deterministic."""
+    imgs = []
+    for sub, _dirs, files in os.walk(root_dir):
+        names = set(files)
+        for f in sorted(files):
+            stem, ext = os.path.splitext(f)
+            if ext in img_extensions and stem + ".pt" in names:
+                imgs.append(os.path.join(sub, f))
+    imgs.sort()
+    crop_names = list(crop_names)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=threads) as ex:
+        loaded = list(ex.map(lambda p: _load_one(p, model_name, crop_names), imgs))
+    good = [(p, r) for p, r in zip(imgs, loaded) if r is not None]
+    if not good:
+        raise FileNotFoundError(f"no readable .pt embeddings under {root_dir}")
+    model = model_name or good[0][1][0]
+    good = [(p, r) for p, r in good if r[0] == model]
+    E = good[0][1][1].shape[1]
+    full = np.zeros((len(good), len(CROP_NAMES), E), np.float32)
+    kept = []
+    cols = [CROP_NAMES.index(c) for c in crop_names]
+    for b, (_, (_, rows, mask)) in enumerate(good):
+        full[b, cols, :] = rows
+        k = [False] * len(CROP_NAMES)
+        for ci, c in enumerate(cols):
+            k[c] = bool((mask >> ci) & 1)
+        kept.append(k)
+    with PackedWriter(store_dir, model, E, crop_names, shard=shard) as w:
+        w.append(full, [p for p, _ in good], kept)
+    return PackedStore(store_dir, model)

@@ -1,0 +1,138 @@
+"""Packed embedding store: round trip, the compat exporter writes exactly the layout the
+reference's consumers read, the bulk loader inverts it, and — when /root/reference is present — the reference's
+own `_2_remove_duplicates.get_paths_and_embeddings` reads the exported files."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import reference_present
+from test_abi_and_host import _FakeEncoder, _write_images
+
+
+def _fill(tmp_path, n=9, E=8, model="ViT-L-14/openai"):
+    from clip_assisted_data_labeling_b200.store import PackedWriter
+    rng = np.random.default_rng(3)
+    root = tmp_path / "imgs"
+    root.mkdir()
+    feats = rng.standard_normal((n, 4, E)).astype(np.float32)
+    paths = [str(root / f"{i:03d}.jpg") for i in range(n)]
+    for p in paths:
+        open(p, "wb").close()
+    kept = [[True, True, True, i != 4] for i in range(n)]
+    sd = str(tmp_path / "store")
+    with PackedWriter(sd, model, E, shard=0) as w:
+        w.append(feats[:5], paths[:5], kept[:5])
+        w.append(torch.from_numpy(feats[5:]), paths[5:], kept[5:])
+    return sd, feats, paths, kept
+
+
+def test_round_trip_and_views(tmp_path):
+    from clip_assisted_data_labeling_b200.store import PackedStore
+    from clip_assisted_data_labeling_b200.vit_arch import CROP_NAMES
+    sd, feats, paths, kept = _fill(tmp_path)
+    st = PackedStore(sd)
+    assert len(st) == 9 and st.paths == paths and st.model_name == "ViT-L-14/openai" and st.crop_names == CROP_NAMES
+    want = feats.copy()
+    want[4, 3] = 0  # dropped crop is stored as zeros
+    assert np.array_equal(st.array(), want)
+    assert torch.equal(st.crop("square_padded_crop"), torch.from_numpy(want[:, 1]))
+    assert st.crop("subcrop1", torch.float16).dtype == torch.float16
+    f = st.features(["centre_crop", "subcrop2"])
+    assert f.shape == (9, 16) and torch.equal(f[2], torch.from_numpy(np.concatenate([want[2, 0], want[2, 3]])))
+    assert st.has_all(CROP_NAMES).tolist() == [i != 4 for i in range(9)]
+    assert st.has_all(["centre_crop"]).all()
+
+
+def test_incomplete_shard_is_invisible_and_size_is_checked(tmp_path):
+    from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter
+    sd = str(tmp_path / "s")
+    w = PackedWriter(sd, "M/x", 4)
+    w.append(np.ones((2, 4, 4), np.float32), ["a.jpg", "b.jpg"])
+    with pytest.raises(FileNotFoundError):
+        PackedStore(sd)  # no index yet: the shard does not exist as far as readers are concerned
+    w.close()
+    assert len(PackedStore(sd)) == 2
+    with open(os.path.join(sd, "shard-00000.emb"), "ab") as fh:
+        fh.write(b"x")
+    with pytest.raises(ValueError):
+        PackedStore(sd)
+
+
+def test_multi_shard_and_model_filter(tmp_path):
+    from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter
+    sd = str(tmp_path / "s")
+    for r in range(3):
+        with PackedWriter(sd, "M/x", 4, shard=r) as w:
+            w.append(np.full((2, 4, 4), r, np.float32), [f"{r}_{k}.jpg" for k in range(2)])
+    st = PackedStore(sd, "M/x")
+    assert len(st) == 6 and st.array()[:, 0, 0].tolist() == [0, 0, 1, 1, 2, 2]
+    assert st.paths[2] == "1_0.jpg"
+    assert torch.equal(st.feature_dict(3)["centre_crop"], torch.full((1, 4), 1.0))
+    with pytest.raises(FileNotFoundError):
+        PackedStore(sd, "other/model")
+
+
+def test_export_matches_reference_layout_and_import_inverts_it(tmp_path):
+    from clip_assisted_data_labeling_b200.store import PackedStore, export_pt, import_pt
+    from clip_assisted_data_labeling_b200.vit_arch import CROP_NAMES
+    sd, feats, paths, kept = _fill(tmp_path)
+    st = PackedStore(sd)
+    # an older file with another model's entry must be merged, not overwritten (_1_embed_with_CLIP.py:139-143)
+    torch.save({"ViT-B-32/openai": {"centre_crop": torch.zeros(1, 3)}}, paths[0][:-4] + ".pt")
+    assert export_pt(st) == 9
+    d0 = torch.load(paths[0][:-4] + ".pt")
+    assert list(d0.keys()) == ["ViT-B-32/openai", "ViT-L-14/openai"]
+    d4 = torch.load(paths[4][:-4] + ".pt")["ViT-L-14/openai"]
+    assert list(d4.keys()) == CROP_NAMES[:3]  # empty crop omitted (utils/embedder.py:243-247)
+    d2 = torch.load(paths[2][:-4] + ".pt")["ViT-L-14/openai"]
+    for ci, c in enumerate(CROP_NAMES):
+        t = d2[c]
+        assert t.dtype == torch.float32 and tuple(t.shape) == (1, 8) and torch.equal(t[0], torch.from_numpy(feats[2, ci]))
+    back = import_pt(str(tmp_path / "imgs"), str(tmp_path / "store2"), "ViT-L-14/openai")
+    assert back.paths == sorted(paths) and np.array_equal(back.array(), st.array()) and np.array_equal(back.kept, st.kept)
+
+
+def test_feature_dataset_writes_packed_shard(tmp_path, lib):
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from clip_assisted_data_labeling_b200.store import PackedStore, export_pt
+    root = str(tmp_path / "data")
+    _write_images(root, 7)
+    enc = _FakeEncoder()
+    enc.embed_dim = 8
+    sd = str(tmp_path / "packed")
+    ds = Feature_Dataset(root, "ViT-L-14/openai", 4, shuffle_filenames=False, encoder=enc, packed_dir=sd, write_pt=False)
+    assert ds.process() == (7, 0)
+    assert not any(f.endswith(".pt") for f in os.listdir(root))
+    st = PackedStore(sd)
+    assert st.paths == sorted(ds.img_filepaths) and st.array().shape == (7, 4, 8)
+    export_pt(st)
+    # per-image files now equal what the direct path writes
+    root2 = str(tmp_path / "data2")
+    _write_images(root2, 7)
+    Feature_Dataset(root2, "ViT-L-14/openai", 4, shuffle_filenames=False, encoder=_FakeEncoder()).process()
+    for i in range(7):
+        a = torch.load(os.path.join(root, f"im{i:03d}.pt"))
+        b = torch.load(os.path.join(root2, f"im{i:03d}.pt"))
+        assert a.keys() == b.keys()
+        for c in a["ViT-L-14/openai"]:
+            assert torch.equal(a["ViT-L-14/openai"][c], b["ViT-L-14/openai"][c])
+
+
+@pytest.mark.skipif(not reference_present(), reason="/root/reference only exists in the build container")
+def test_reference_dedup_loader_reads_exported_files(tmp_path):
+    """The unmodified _2_remove_duplicates.get_paths_and_embeddings (reference :8-49) consumes export_pt's output."""
+    from clip_assisted_data_labeling_b200.store import PackedStore, export_pt
+    from oracle.reference_shim import import_reference
+    sd, feats, paths, kept = _fill(tmp_path)
+    st = PackedStore(sd)
+    export_pt(st)
+    ref = import_reference("_2_remove_duplicates")
+    args = types.SimpleNamespace(root_dir=str(tmp_path / "imgs"), clip_model_to_use=None, chunk_size=100)
+    got_paths, got_emb = next(iter(ref.get_paths_and_embeddings(args, "square_padded_crop")))
+    order = [paths.index(p) for p in got_paths]
+    assert sorted(order) == list(range(9))
+    want = torch.from_numpy(feats[order, 1]).to(torch.float16)
+    assert torch.equal(torch.stack(got_emb), want)

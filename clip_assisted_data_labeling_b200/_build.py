@@ -26,6 +26,7 @@ SOURCES = [
     "b2c_attention.cu",
     "b2c_preprocess.cu",
     "b2c_dedup.cu",
+    "b2c_similar.cu",
     "b2c_vit.cu",
 ]
 

@@ -18,6 +18,9 @@ OUT_NCHW_F32, OUT_PATCH_BF16 = 0, 1
 ACT_QUICK_GELU, ACT_GELU = 0, 1
 EPI_BIAS_BF16, EPI_BIAS_QGELU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
 CMP_FP32, CMP_REF_FP16 = 0, 1
+MEASURE_COSINE_DIST, MEASURE_L2, MEASURE_COSINE_SIM = 0, 1, 2
+COMBINE_STORE, COMBINE_MAX = 0, 1
+TOPK_MAX = 4096
 MLP_MAX_LAYERS = 8
 PROF_KINDS = 11
 
@@ -76,6 +79,10 @@ SIGNATURES = {
     "b2c_normalize_rows_f16": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "b2c_dedup_pairs": (_i, [_vp, _i64, _i, _i64, _i64, _f, _i, _vp, _u64, _vp, _vp]),
     "b2c_mlp_score": (_i, [_vp, _i64, C.POINTER(MlpWeights), _vp, _vp]),
+    "b2c_context_scores": (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "b2c_topk_workspace_bytes": (_i, [_i, C.POINTER(_sz)]),
+    "b2c_topk_smallest": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b2c_diversity_order": (_i, [_vp, _i, _i64, _i, _i64, C.c_int32, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -198,6 +198,41 @@ typedef struct {
 /* feats: DEVICE f32[B, dims[0]]; out: DEVICE f32[B, dims[n_layers]]. Hidden widths <= 1024. */
 int b2c_mlp_score(const float* feats, int64_t B, const b2c_mlp_weights* w, float* out, b2c_stream stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K11 — similarity-search variants over stored embeddings.
+ * Replaces the per-sample loop of tools/find_similar_imgs.py:96-137 (compute_distance :88-94 + the topN
+ * bookkeeping :67-85) and the greedy loop of diversity_ordered_image_files (_3_label_images.py:128-177).
+ * HBM-bound streaming kernels (one pass over the N x E embeddings per context vector), not GEMMs.
+ * ------------------------------------------------------------------------------------------- */
+#define B2C_MEASURE_COSINE_DIST 0 /* (1 - cos(c,x)) / 2            tools/find_similar_imgs.py:90 */
+#define B2C_MEASURE_L2 1          /* || c - x + 1e-6 ||_2           tools/find_similar_imgs.py:92 (F.pairwise_distance) */
+#define B2C_MEASURE_COSINE_SIM 2  /* cos(c,x)                       _3_label_images.py:124-127 */
+#define B2C_COMBINE_STORE 0       /* out[i]  = score_i */
+#define B2C_COMBINE_MAX 1         /* out[i]  = max(out[i], score_i) */
+
+/* emb: DEVICE [n, E] rows of dtype B2C_F32 / B2C_F16, row i at emb + i*row_stride elements (row_stride >= E, so one
+ * crop of a packed [N, C, E] store is addressed in place).  Context vector: ctx = DEVICE f32[E], or ctx == NULL and
+ * ctx_row = DEVICE int32 holding the index of the row of emb to use (chosen by an earlier kernel, no host round
+ * trip).  skip: optional DEVICE u8[n]; rows with skip != 0 get +INF.  out: DEVICE f32[n]. */
+int b2c_context_scores(const void* emb, int dtype, int64_t n, int E, int64_t row_stride, const float* ctx,
+                       const int32_t* ctx_row, int measure, int combine, const uint8_t* skip, float* out,
+                       b2c_stream stream);
+
+/* The k smallest entries of scores f32[n] (DEVICE), k <= min(n, 4096): out_idx int32[k] / out_val f32[k] (DEVICE),
+ * ascending by (value, index) — exact, ties go to the smaller index (the reference's strict `<` keeps the earlier
+ * sample, tools/find_similar_imgs.py:83).  ws: DEVICE scratch, 16-byte aligned, size from b2c_topk_workspace_bytes. */
+int b2c_topk_workspace_bytes(int k, size_t* bytes);
+int b2c_topk_smallest(const float* scores, int64_t n, int k, int32_t* out_idx, float* out_val, void* ws,
+                      size_t ws_bytes, b2c_stream stream);
+
+/* Greedy diversity ordering (_3_label_images.py:128-177): order[0] = first_row; for step s < steps:
+ * order[s+1] = the row r among samples[s*S .. s*S+S) (DEVICE int32, the host draws them with the reference's
+ * random.sample sequence) whose maximum cosine similarity to rows order[0..s] is smallest (first such position).
+ * maxsim: DEVICE f32[n] scratch (on return: max similarity of every row to the selected set); order: DEVICE
+ * int32[steps+1]. */
+int b2c_diversity_order(const void* emb, int dtype, int64_t n, int E, int64_t row_stride, int32_t first_row,
+                        const int32_t* samples, int steps, int S, float* maxsim, int32_t* order, b2c_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,8 +159,68 @@ def gen_vit():
     np.savez_compressed(os.path.join(OUT, "vit_ref.npz"), **out)
 
 
+def gen_similar():
+    """Unmodified tools/find_similar_imgs.py (create_context_embedding + find_similar_imgs, both measures) and
+    _3_label_images.diversity_ordered_image_files (tkinter / natsort / cv2 GUI imports stubbed) on synthetic .pt dirs."""
+    import random
+    from oracle.similar_oracle import synthetic_clusters
+    for name in ("tkinter", "tkinter.ttk", "natsort"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["tkinter"].ttk = sys.modules["tkinter.ttk"]
+    sys.modules["natsort"].natsorted = sorted
+    sys.modules["natsort"].ns = types.SimpleNamespace(IGNORECASE=0)
+    rs.import_reference("utils.nn_model")  # puts the reference root on sys.path
+    import importlib
+    fs = importlib.import_module("tools.find_similar_imgs")
+    fs.device = torch.device("cpu")
+    out = {}
+    n, E, n_ctx, seed = 400, 96, 7, 21
+    emb = synthetic_clusters(n, E, seed)
+    tmp = tempfile.mkdtemp()
+    ctx_dir, search_dir = os.path.join(tmp, "ctx"), os.path.join(tmp, "search")
+    os.makedirs(ctx_dir)
+    os.makedirs(search_dir)
+    for i in range(n_ctx):
+        torch.save({"M/x": {"square_padded_crop": torch.from_numpy(emb[i:i + 1].copy())}}, os.path.join(ctx_dir, f"{i:05d}.pt"))
+    for i in range(n_ctx, n):
+        torch.save({"M/x": {"square_padded_crop": torch.from_numpy(emb[i:i + 1].copy())}}, os.path.join(search_dir, f"{i:05d}.pt"))
+        if i % 17 != 0:  # samples without a .jpg are skipped by the reference (:106-110)
+            open(os.path.join(search_dir, f"{i:05d}.jpg"), "wb").close()
+    out["sim_meta"] = np.asarray([n, E, n_ctx, seed], np.int64)
+    for measure in ("l2", "cosine"):
+        args = types.SimpleNamespace(clip_models_to_use=["all"], crop_name_to_use="square_padded_crop",
+                                     similarity_measure=measure, top_n=25, search_dir=search_dir, output_dir=tmp)
+        ctx, names = fs.create_context_embedding(args, ctx_dir)
+        top = fs.find_similar_imgs(args, ctx, names)
+        ids = [int(os.path.basename(p)[:5]) for p in top.best_img_paths]
+        d = [float(x) for x in top.best_distances]
+        order = sorted(range(len(ids)), key=lambda t: (d[t], ids[t]))
+        out[f"sim_{measure}_ctx"] = ctx.numpy()
+        out[f"sim_{measure}_idx"] = np.asarray([ids[t] for t in order], np.int64)
+        out[f"sim_{measure}_dist"] = np.asarray([d[t] for t in order], np.float32)
+        print("similar", measure, out[f"sim_{measure}_idx"][:5], out[f"sim_{measure}_dist"][:3])
+    shutil.rmtree(tmp)
+    # diversity ordering: the reference reads d['square_padded_crop'] from the top level of the .pt (:141,:153)
+    lab = importlib.import_module("_3_label_images")
+    n2, E2, seed2, steps, S = 300, 64, 22, 40, 30
+    emb2 = synthetic_clusters(n2, E2, seed2, n_clusters=9)
+    tmp = tempfile.mkdtemp()
+    files = []
+    for i in range(n2):
+        torch.save({"square_padded_crop": torch.from_numpy(emb2[i:i + 1].copy())}, os.path.join(tmp, f"{i:05d}.pt"))
+        files.append(os.path.join(tmp, f"{i:05d}.jpg"))
+    random.seed(1234)
+    ordered = lab.diversity_ordered_image_files(files, tmp, total_n_ordered_imgs=steps, sample_size=S)
+    shutil.rmtree(tmp)
+    out["div_meta"] = np.asarray([n2, E2, seed2, steps, S, 1234], np.int64)
+    out["div_order"] = np.asarray([int(os.path.basename(f)[:5]) for f in ordered], np.int64)
+    print("diversity head", out["div_order"][:10])
+    np.savez_compressed(os.path.join(OUT, "similar_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["preprocess", "geometry", "dedup", "mlp", "vit"]
+    which = sys.argv[1:] or ["preprocess", "geometry", "dedup", "mlp", "vit", "similar"]
     for w in which:
         globals()["gen_" + w]()

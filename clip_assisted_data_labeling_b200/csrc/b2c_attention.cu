@@ -19,6 +19,7 @@
 // 16-query tiles and streams the keys in chunks of 64 with an online (running max / running sum)
 // softmax in fp32 registers.  Tensor work is bf16 mma.sync m16n8k16 with fp32 accumulation; this is
 // 4 % of the tower's FLOPs.
+#include <type_traits>
 #include <cuda_bf16.h>
 
 #include <stdlib.h>
@@ -237,7 +238,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                       const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int heads,
                       float scale_log2) {
   extern __shared__ uint8_t smem_au_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_au_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_au_raw + ((1024u - (smem_u32(smem_au_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAuOffBar);
   uint64_t* bar_qk = bars + 0;  // Q and K tiles landed
   uint64_t* bar_v = bars + 1;   // V tile landed
@@ -651,7 +652,7 @@ attention_umma2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
   using L = A2L<HD>;
   using Misc = A2Misc<HD>;
   extern __shared__ uint8_t smem_a2_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_a2_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_a2_raw + ((1024u - (smem_u32(smem_a2_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST
   Misc* mb = reinterpret_cast<Misc*>(smem + L::kOffMisc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * HD;
@@ -1053,7 +1054,7 @@ attention_umma3_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_c
                        const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads,
                        int NB, float scale_log2) {
   extern __shared__ uint8_t smem_a3_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_a3_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_a3_raw + ((1024u - (smem_u32(smem_a3_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST
   const int off_v = NB * kA3BlockBytes;
   const int off_q = 2 * NB * kA3BlockBytes;
   A3Misc* mb = reinterpret_cast<A3Misc*>(smem + off_q + 2 * kA3QStage);
@@ -1368,6 +1369,428 @@ static int attention_umma3_launch(const void* qkv, void* out, int n, int T, int 
   return 0;
 }
 
+// ================================================================================================
+// (1d) tcgen05 attention v4 for T = 257, head dim 64: v2's pipeline with the softmax spread over SIXTEEN warps and the
+//      two query tiles decoupled.
+//   v2 gives each query row to one thread (8 softmax warps = 2 per SM sub-partition) and issues the MMAs of both query
+//   tiles from one warp in a fixed order, which locks the two softmax groups into the same phase: both hit the MUFU
+//   (exp2) pipe at once and both leave it idle at once.  v4:
+//     warp 0       TMA producer (Q both tiles, K, V of the next head into the other smem stage);
+//     warps 1, 2   MMA issuers, one per query tile g: S_g = Q_g·Kᵀ, then O_g = P_g·V and L_g = P_g·1 when P_g is ready —
+//                  the groups run at their own pace (up to one head apart), so one group's exp2 pass overlaps the other
+//                  group's tensor-core / epilogue / class-row phases;
+//     warp 3       idle (keeps the softmax warps' TMEM lane quarter = warp & 3);
+//     warps 4-19   softmax: group g = (warp-4)/8, column half h = ((warp-4)/4)&1 (keys [128h, 128h+128)), lane quarter =
+//                  warp & 3.  The two halves of a row exchange their partial maxima through shared memory.
+//   TMEM region g: S [0,256) -> P_0 [0,64) over half 0's consumed columns | O [64,128) | P_1 [128,192) over half 1's |
+//   L [192,208).  The class-token KEY (rank-1 term) is not part of the running maximum — softmax is shift invariant and
+//   p0 = exp2(min(s0·c − m·c, 126)) cannot overflow — so its dot product is off the critical path (half 1 computes it
+//   after releasing P to the tensor core).  The class-token QUERY row is computed by the 256 threads of one group
+//   (alternating), one key per thread, AFTER the group has drained O and handed its TMEM region back, so the next S of
+//   that tile is computed meanwhile.  All shared-memory traffic is LDS/STS (see the smem base computation).
+// ================================================================================================
+constexpr int kA4Threads = 128 + 512;
+
+struct A4Misc {
+  uint64_t full_qk[2], full_v[2], empty_qk[2], empty_v[2];
+  uint64_t s_full[2], p_full[2], o_full[2], tmem_free[2];
+  uint32_t tmem_slot;
+  uint32_t pad[3];
+  float red[2][16];        // per group: cross-warp max / sum scratch (8 warps each)
+  float vec[2][3][64];     // per group: q0, k0, v0 of the current head as fp32
+  float mx[2][2][128];     // per group, per half: partial row maxima
+  float p0s[2][128];       // per group: class-key probability of each query row
+  float p_cls[2][264];     // per group: class-row probabilities (256 patch keys + class key)
+  float part[2][32][64];   // per group: 32 key-slices of the class-row output
+};
+
+constexpr int a4_smem_bytes() {
+  return A2L<64>::kOffMisc + static_cast<int>((sizeof(A4Misc) + 1023) / 1024 * 1024) + 1024;
+}
+
+template <int ISS, int flags>  // flags: bit0 early tmem_free, bit1 class-row reduce before the epilogue, bit2 early stage release; ISS = MMA issuer warps: 2 = one per query tile (decoupled groups), 1 = v2's fixed order from warp 1
+__global__ void __launch_bounds__(kA4Threads, 1)
+attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* __restrict__ qkv,
+                       __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads, float scale_log2) {
+  constexpr int HD = 64;
+  using L = A2L<HD>;
+  constexpr int kColO4 = 64, kColL4 = 192;
+  constexpr int kFirstSm = ISS == 2 ? 4 : 2;  // first softmax warp (a multiple of 2 keeps lane quarter = warp & 3 consistent)
+  extern __shared__ uint8_t smem_a4_raw[];
+  uint8_t* smem = smem_a4_raw + ((1024u - (smem_u32(smem_a4_raw) & 1023u)) & 1023u);  // keeps the address space: LDS/STS
+  A4Misc* mb = reinterpret_cast<A4Misc*>(smem + L::kOffMisc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * HD;
+  const size_t row_stride = static_cast<size_t>(3) * d;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&mb->full_qk[s], 1);
+      mbar_init(&mb->full_v[s], 1);
+      mbar_init(&mb->empty_qk[s], 2 + ISS);  // the MMA issuers' commits + one arrival per group once its Q/K reads are done
+      mbar_init(&mb->empty_v[s], 1 + ISS);   // the MMA issuers' commits + the group that computed the class row from V
+      mbar_init(&mb->s_full[s], 1);
+      mbar_init(&mb->p_full[s], 8);
+      mbar_init(&mb->o_full[s], 1);
+      mbar_init(&mb->tmem_free[s], 8);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 8 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem + L::kOffOnes)[i] = 0x3F803F80u;  // bf16 1.0 x2
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc(&mb->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mb->tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int k = 0;
+      for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+        const int s = k & 1;
+        const uint32_t u = (k >> 1) & 1;
+        const int crop = ch / heads, head = ch - crop * heads;
+        const int row0 = crop * T + 1;
+        uint8_t* st = smem + s * L::kQKStage;
+        uint8_t* sv = smem + L::kOffV + s * L::kOp;
+        mbar_wait(&mb->empty_qk[s], u ^ 1);
+        mbar_arrive_expect_tx(&mb->full_qk[s], 2 * L::kOp);
+        tma_load_2d(st, &tm, &mb->full_qk[s], head * HD, row0);
+        tma_load_2d(st + L::kOp, &tm, &mb->full_qk[s], d + head * HD, row0);
+        mbar_wait(&mb->empty_v[s], u ^ 1);
+        mbar_arrive_expect_tx(&mb->full_v[s], L::kOp);
+        tma_load_2d(sv, &tm, &mb->full_v[s], 2 * d + head * HD, row0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || (ISS == 2 && warp == 2)) {
+    // ------------------------------------------------------------------ MMA issuer(s) (warp-uniform control flow, see v2)
+    // The query tile index is a compile-time constant in every tcgen05.mma operand (TMEM address, descriptors): with a
+    // run-time tile index ptxas moves each operand through R2UR before every MMA and the issue rate drops.
+    const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
+    const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
+    const uint32_t idesc_l = make_idesc_f16(128, 16, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t ones_desc = make_sw128_kmajor_desc(smem_base + L::kOffOnes);
+    auto issue_s = [&](auto wc, uint32_t sbase, uint64_t k_desc, uint32_t kp) {
+      constexpr int w = decltype(wc)::value;
+      const uint32_t treg = tmem + w * 256;
+      const uint64_t q_desc = make_sw128_kmajor_desc(sbase + w * 16384);
+      mbar_wait(&mb->tmem_free[w], kp ^ 1);  // both halves of group w have read the previous O out of the region
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_f16(treg, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk != 0);
+        umma_commit(&mb->s_full[w]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](auto wc, uint64_t v_desc0, uint32_t kp) {
+      constexpr int w = decltype(wc)::value;
+      const uint32_t treg = tmem + w * 256;
+      mbar_wait(&mb->p_full[w], kp);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint32_t pcol = (kk < 8 ? 0u : 128u) + (kk & 7) * 8;  // P_0 at [0,64), P_1 at [128,192)
+          umma_f16_ts(treg + kColO4, treg + pcol, v_desc0 + kk * 128, idesc_o, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint32_t pcol = (kk < 8 ? 0u : 128u) + (kk & 7) * 8;
+          umma_f16_ts(treg + kColL4, treg + pcol, ones_desc + 2 * (kk & 3), idesc_l, kk != 0);
+        }
+        umma_commit(&mb->o_full[w]);
+      }
+      __syncwarp();
+    };
+    using W0 = std::integral_constant<int, 0>;
+    using W1 = std::integral_constant<int, 1>;
+    int k = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t u = (k >> 1) & 1, kp = k & 1;
+      const uint32_t sbase = smem_base + s * L::kQKStage;
+      const uint32_t vbase = smem_base + L::kOffV + s * L::kOp;
+      mbar_wait(&mb->full_qk[s], u);
+      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + L::kOp);
+      if (ISS == 1) {
+        issue_s(W0{}, sbase, k_desc, kp);
+        issue_s(W1{}, sbase, k_desc, kp);
+      } else if (warp == 1) {
+        issue_s(W0{}, sbase, k_desc, kp);
+      } else {
+        issue_s(W1{}, sbase, k_desc, kp);
+      }
+      if (elect_one()) umma_commit(&mb->empty_qk[s]);
+      __syncwarp();
+      mbar_wait(&mb->full_v[s], u);
+      const uint64_t v_desc0 = make_sw128_kmajor_desc(vbase);
+      if (ISS == 1) {
+        issue_pv(W0{}, v_desc0, kp);
+        issue_pv(W1{}, v_desc0, kp);
+      } else if (warp == 1) {
+        issue_pv(W0{}, v_desc0, kp);
+      } else {
+        issue_pv(W1{}, v_desc0, kp);
+      }
+      if (elect_one()) umma_commit(&mb->empty_v[s]);
+      __syncwarp();
+    }
+  } else if (warp >= kFirstSm) {
+    // ------------------------------------------------------------------ softmax: 2 groups x 2 column halves x 4 warps
+    const int sw = warp - kFirstSm;
+    const int w = sw >> 3;                  // group = query tile
+    const int h = (sw >> 2) & 1;            // column half: keys [128h, 128h + 128)
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+    const int r = quarter * 32 + lane;      // query row in the tile = TMEM lane
+    const int gt = h * 128 + r;             // thread index inside the group, 0..255
+    const int gw = sw & 7;                  // warp index inside the group
+    const uint32_t taddr = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t sbase_col = 128u * h;    // this half's S columns; its P goes over them at [128h, 128h + 64)
+    float* red = mb->red[w];
+    float* pcls = mb->p_cls[w];
+    float* q0f = mb->vec[w][0];
+    float* k0f = mb->vec[w][1];
+    float* v0f = mb->vec[w][2];
+    uint32_t cq = 0, ck = 0, cv = 0;
+    auto prefetch = [&](int ch) {
+      if (gt < HD) {
+        const int crop = ch / heads, head = ch - crop * heads;
+        const unsigned short* cls_row =
+            reinterpret_cast<const unsigned short*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * HD);
+        cq = __ldg(cls_row + gt);
+        ck = __ldg(cls_row + d + gt);
+        cv = __ldg(cls_row + 2 * d + gt);
+      }
+    };
+    if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
+    int k = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t u = (k >> 1) & 1, kp = k & 1;
+      const int crop = ch / heads, head = ch - crop * heads;
+      const int tok0 = crop * T;
+      const int token = tok0 + 1 + w * 128 + r;
+      const uint8_t* st = smem + s * L::kQKStage;
+      const uint8_t* sv = smem + L::kOffV + s * L::kOp;
+      const bool cls_owner = ((k & 1) == w);
+
+      if (gt < HD) {
+        q0f[gt] = __uint_as_float(cq << 16);
+        k0f[gt] = __uint_as_float(ck << 16);
+        v0f[gt] = __uint_as_float(cv << 16);
+      }
+      if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
+
+      // ---- own row, own 128 keys: partial max -> exchange -> P (bf16x2 packed) back into TMEM over S
+      mbar_wait(&mb->s_full[w], kp);
+      tc_fence_after();
+      float m = -INFINITY;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr + sbase_col, va);
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + sbase_col + (c + 1) * 32, vb);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + sbase_col + ((c + 2) & 3) * 32, va);  // last iteration: chunk 0 again, for the second pass
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
+      }
+      mb->mx[w][h][r] = m;
+      named_bar_sync(1 + w, 256);  // also publishes q0f / k0f / v0f
+      m = fmaxf(m, mb->mx[w][h ^ 1][r]);
+      const float ms = m * scale_log2;
+      auto emit_p = [&](const uint32_t (&v)[32], int c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          pk[e] = pack2(ex2_ftz(fmaf(__uint_as_float(v[2 * e]), scale_log2, -ms)),
+                        ex2_ftz(fmaf(__uint_as_float(v[2 * e + 1]), scale_log2, -ms)));
+        tmem_st_32x16(taddr + sbase_col + c * 16, pk);  // columns already consumed by this thread
+      };
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + sbase_col + (c + 1) * 32, vb);
+        emit_p(va, c);
+        tmem_ld_wait();
+        if (c + 2 < 4) tmem_ld_32x32(taddr + sbase_col + (c + 2) * 32, va);
+        emit_p(vb, c + 1);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mb->p_full[w]);
+
+      // ---- class-token KEY: p0 = exp2((q_r·k0 − m)·c), while the tensor core computes O (half 1 only)
+      mbar_wait(&mb->full_qk[s], u);
+      if (h == 1) {
+        const float s0 = dot_row<HD>(st, w * 128 + r, k0f);
+        mb->p0s[w][r] = ex2_ftz(fminf(fmaf(s0, scale_log2, -ms), 126.f));
+      }
+      // ---- class-token QUERY row: one key per thread, scores from the K tile, then O_cls = P_cls·V from the V tile
+      if (cls_owner) {
+        const float sa = dot_row<HD>(st + L::kOp, gt, q0f);
+        float sc = -INFINITY;
+        if (gt == 0) {
+          float acc = 0.f;
+          for (int c = 0; c < HD; ++c) acc = fmaf(q0f[c], k0f[c], acc);
+          sc = acc;
+        }
+        float cm = fmaxf(sa, sc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+        if (lane == 0) red[gw] = cm;
+        named_bar_sync(1 + w, 256);
+        cm = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))) *
+             scale_log2;
+        const float pa = ex2_ftz(fmaf(sa, scale_log2, -cm));
+        float psum = pa;
+        pcls[gt] = pa;
+        if (gt == 0) {
+          const float pc = ex2_ftz(fmaf(sc, scale_log2, -cm));
+          pcls[256] = pc;
+          psum += pc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        if (lane == 0) red[8 + gw] = psum;
+        named_bar_sync(1 + w, 256);
+        // thread = (8-key slice ks, 8-column chunk cc): one 16-byte read per key
+        mbar_wait(&mb->full_v[s], u);
+        const int cc = gt & 7, ks = gt >> 3;
+        const float* pp = pcls + ks * 8;
+        const uint8_t* base = sv + (ks * 8) * 128;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int key = 0; key < 8; ++key) {
+          // ks*8 + key has the same low 3 bits as key, so the swizzle phase depends on `key` only
+          const uint4 a = *reinterpret_cast<const uint4*>(base + key * 128 + ((cc ^ key) << 4));
+          const float pkey = pp[key];
+          acc[0] = fmaf(pkey, bf16_lo(a.x), acc[0]);
+          acc[1] = fmaf(pkey, bf16_hi(a.x), acc[1]);
+          acc[2] = fmaf(pkey, bf16_lo(a.y), acc[2]);
+          acc[3] = fmaf(pkey, bf16_hi(a.y), acc[3]);
+          acc[4] = fmaf(pkey, bf16_lo(a.z), acc[4]);
+          acc[5] = fmaf(pkey, bf16_hi(a.z), acc[5]);
+          acc[6] = fmaf(pkey, bf16_lo(a.w), acc[6]);
+          acc[7] = fmaf(pkey, bf16_hi(a.w), acc[7]);
+        }
+        *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      named_bar_sync(1 + w, 256);  // p0s (and the class row's partial sums) visible
+      if ((flags & 4) && gt == 0) {
+        mbar_arrive(&mb->empty_qk[s]);
+        if (cls_owner) mbar_arrive(&mb->empty_v[s]);
+      }
+      if ((flags & 2) && cls_owner && gt < HD) {
+        const float cls_l = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
+        float o = pcls[256] * v0f[gt];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o += mb->part[w][i][gt];
+        out[static_cast<size_t>(tok0) * d + head * HD + gt] = __float2bfloat16_rn(o / cls_l);
+      }
+
+      // ---- own row, own 32 output columns: (O + p0·v0) / (L + p0) -> bf16
+      const float p0 = mb->p0s[w][r];
+      mbar_wait(&mb->o_full[w], kp);
+      tc_fence_after();
+      const float lsum = __uint_as_float(tmem_ld_1(taddr + kColL4));
+      {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + kColO4 + h * 32, v);
+        tmem_ld_wait();
+        if (flags & 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mb->tmem_free[w]);  // O and L are in registers: the region can take the next S
+        }
+        const float inv = 1.0f / (lsum + p0);
+        const float p0i = p0 * inv;
+        __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * HD + h * 32;
+        const float* v0 = v0f + h * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 va4 = *reinterpret_cast<const float4*>(v0 + 8 * j);
+          const float4 vb4 = *reinterpret_cast<const float4*>(v0 + 8 * j + 4);
+          uint4 o4;
+          o4.x = pack2(fmaf(__uint_as_float(v[8 * j + 0]), inv, p0i * va4.x), fmaf(__uint_as_float(v[8 * j + 1]), inv, p0i * va4.y));
+          o4.y = pack2(fmaf(__uint_as_float(v[8 * j + 2]), inv, p0i * va4.z), fmaf(__uint_as_float(v[8 * j + 3]), inv, p0i * va4.w));
+          o4.z = pack2(fmaf(__uint_as_float(v[8 * j + 4]), inv, p0i * vb4.x), fmaf(__uint_as_float(v[8 * j + 5]), inv, p0i * vb4.y));
+          o4.w = pack2(fmaf(__uint_as_float(v[8 * j + 6]), inv, p0i * vb4.z), fmaf(__uint_as_float(v[8 * j + 7]), inv, p0i * vb4.w));
+          *reinterpret_cast<uint4*>(orow + 8 * j) = o4;
+        }
+      }
+
+      if (!(flags & 1)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mb->tmem_free[w]);
+      }
+      if (cls_owner && !(flags & 2)) {
+        if (gt < HD) {
+          const float cls_l = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
+          float o = pcls[256] * v0f[gt];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o += mb->part[w][i][gt];
+          out[static_cast<size_t>(tok0) * d + head * HD + gt] = __float2bfloat16_rn(o / cls_l);
+        }
+      }
+      // every Q / K / V read of the group is done and its scratch (vec, mx, p0s, p_cls, part, red) may be rewritten
+      named_bar_sync(1 + w, 256);
+      if (!(flags & 4) && gt == 0) {
+        mbar_arrive(&mb->empty_qk[s]);
+        if (cls_owner) mbar_arrive(&mb->empty_v[s]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int attention_umma4_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
+  constexpr int HD = 64;
+  const int d = heads * HD;
+  CUtensorMap tm;
+  B2C_TRY(make_tmap_2d(&tm, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, 1));
+  constexpr int smem_bytes = a4_smem_bytes();
+  static_assert(smem_bytes <= 227 * 1024, "attention v4 shared memory exceeds 227 KB");
+  static const int flags = [] { const char* e = getenv("B2C_ATTN_FLAGS"); return e ? atoi(e) : 1; }();
+  static const int iss = [] { const char* e = getenv("B2C_ATTN_ISS"); return e && e[0] == '1' ? 1 : 2; }();
+  using Kern = void (*)(CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float);
+  Kern kern = iss == 1 ? (flags == 6 ? attention_umma4_kernel<1, 6> : attention_umma4_kernel<1, 1>)
+                       : (flags == 7 ? attention_umma4_kernel<2, 7> : attention_umma4_kernel<2, 1>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  B2C_REQUIRE(sms > 0, "no CUDA device");
+  const int n_ch = n * heads;
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+  kern<<<n_ch < sms ? n_ch : sms, iss == 2 ? kA4Threads : kA4Threads - 64, smem_bytes, stream>>>(
+      tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, scale_log2);
+  B2C_POST_LAUNCH("attention_umma4_kernel");
+  return 0;
+}
+
 template <int HD>
 static int attention_launch_hd(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
   const int Tp = (T + 15) / 16 * 16;
@@ -1388,10 +1811,12 @@ static int attention_launch_hd(const void* qkv, void* out, int n, int T, int hea
 
 int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream) {
   B2C_REQUIRE(n > 0 && T > 0 && heads > 0, "attention: empty problem");
-  // B2C_ATTN = v2 (default: persistent, P in TMEM) | v1 (one CTA per query tile, P in smem) | legacy (mma.sync)
-  static const char mode = [] { const char* e = getenv("B2C_ATTN"); return e ? (e[0] == 'l' ? 'l' : (e[1] == '1' ? '1' : '2')) : '2'; }();
+  // B2C_ATTN = v4 (default for hd 64: v2 with 16 softmax warps) | v2 (persistent, P in TMEM) | v1 (one CTA per query
+  // tile, P in smem) | legacy (mma.sync)
+  static const char mode = [] { const char* e = getenv("B2C_ATTN"); return e ? (e[0] == 'l' ? 'l' : (e[1] == '1' ? '1' : (e[1] == '2' ? '2' : '4'))) : '4'; }();
+  if (hd == 64 && T == kAuKeys + 1 && mode == '4') return attention_umma4_launch(qkv, out, n, T, heads, stream);
   if (hd == 64 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<64>(qkv, out, n, T, heads, stream);
-  if (hd == 80 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
+  if (hd == 80 && T == kAuKeys + 1 && (mode == '2' || mode == '4')) return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
   if (hd == 64 && T == kAuKeys + 1 && mode == '1') return attention_umma_launch(qkv, out, n, T, heads, stream);
   if (hd == 64 && mode != 'l' && T > kAuKeys + 1 && (T - 1) % kA3KB == 0 && (T - 1) / kA3KB <= kA3MaxNB)
     return attention_umma3_launch(qkv, out, n, T, heads, stream);

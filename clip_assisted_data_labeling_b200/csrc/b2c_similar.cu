@@ -97,17 +97,29 @@ context_scores_kernel(const T* __restrict__ emb, long long n, int E, long long r
       constexpr int V = Vec<T>::kN;
       using Raw = typename Vec<T>::Raw;
       const Raw* rv = reinterpret_cast<const Raw*>(r);
-      for (int k = lane; k < E / V; k += 32) {
-        const Raw raw = __ldg(rv + k);
-        float f[V];
-        Vec<T>::unpack(raw, f);
+      const int nv = E / V;
+      // batches of 4 independent 16-byte loads per lane keep ~64 B x 2048 threads in flight per SM (Little's law for
+      // ~6.5 TB/s needs > 35 KB per SM); the FMAs of a batch start only after its loads have been issued
+      for (int k0 = lane; k0 < nv; k0 += 128) {
+        Raw raw[4];
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const float c = s_ctx[k * V + e];
-          dot = fmaf(c, f[e], dot);
-          xx = fmaf(f[e], f[e], xx);
-          const float d = (c - f[e]) + 1e-6f;  // F.pairwise_distance adds eps to the difference
-          dd = fmaf(d, d, dd);
+        for (int u = 0; u < 4; ++u)
+          if (k0 + 32 * u < nv) raw[u] = __ldcs(rv + k0 + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k0 + 32 * u < nv) {
+            float f[V];
+            Vec<T>::unpack(raw[u], f);
+            const float* cs = s_ctx + (k0 + 32 * u) * V;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              const float c = cs[e];
+              dot = fmaf(c, f[e], dot);
+              xx = fmaf(f[e], f[e], xx);
+              const float d = (c - f[e]) + 1e-6f;  // F.pairwise_distance adds eps to the difference
+              dd = fmaf(d, d, dd);
+            }
+          }
         }
       }
     } else {

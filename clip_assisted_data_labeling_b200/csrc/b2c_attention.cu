@@ -1370,26 +1370,26 @@ static int attention_umma3_launch(const void* qkv, void* out, int n, int T, int 
 }
 
 // ================================================================================================
-// (1d) tcgen05 attention v4 for T = 257, head dim 64: v2's pipeline with the softmax spread over SIXTEEN warps and the
-//      two query tiles decoupled.
-//   v2 gives each query row to one thread (8 softmax warps = 2 per SM sub-partition) and issues the MMAs of both query
-//   tiles from one warp in a fixed order, which locks the two softmax groups into the same phase: both hit the MUFU
-//   (exp2) pipe at once and both leave it idle at once.  v4:
+// (1d) tcgen05 attention v4 for T = 257, head dim 64: v2's pipeline with the softmax spread over SIXTEEN warps.
+//   v2 gives each query row to one thread (8 softmax warps = 2 per SM sub-partition): the issue slots of a sub-partition
+//   are then shared by just two dependent instruction streams (ncu: 16 % warps active, 34 % issue-slot and 37 % XU-pipe
+//   utilisation).  v4 splits every query row's 256 keys between two threads (column halves), so a sub-partition holds
+//   four softmax warps:
 //     warp 0       TMA producer (Q both tiles, K, V of the next head into the other smem stage);
-//     warps 1, 2   MMA issuers, one per query tile g: S_g = Q_g·Kᵀ, then O_g = P_g·V and L_g = P_g·1 when P_g is ready —
-//                  the groups run at their own pace (up to one head apart), so one group's exp2 pass overlaps the other
-//                  group's tensor-core / epilogue / class-row phases;
-//     warp 3       idle (keeps the softmax warps' TMEM lane quarter = warp & 3);
-//     warps 4-19   softmax: group g = (warp-4)/8, column half h = ((warp-4)/4)&1 (keys [128h, 128h+128)), lane quarter =
-//                  warp & 3.  The two halves of a row exchange their partial maxima through shared memory.
+//     warp 1       MMA issuer: S_g = Q_g·Kᵀ, then O_g = P_g·V and L_g = P_g·1 when P_g is ready (tile index is a
+//                  compile-time constant in every operand);
+//     warps 2-17   softmax: group g = (warp-2)/8 (query tile), column half h = ((warp-2)/4)&1 (keys [128h, 128h+128)),
+//                  TMEM lane quarter = warp & 3.  The two halves of a row exchange their partial maxima through smem.
 //   TMEM region g: S [0,256) -> P_0 [0,64) over half 0's consumed columns | O [64,128) | P_1 [128,192) over half 1's |
 //   L [192,208).  The class-token KEY (rank-1 term) is not part of the running maximum — softmax is shift invariant and
 //   p0 = exp2(min(s0·c − m·c, 126)) cannot overflow — so its dot product is off the critical path (half 1 computes it
 //   after releasing P to the tensor core).  The class-token QUERY row is computed by the 256 threads of one group
-//   (alternating), one key per thread, AFTER the group has drained O and handed its TMEM region back, so the next S of
-//   that tile is computed meanwhile.  All shared-memory traffic is LDS/STS (see the smem base computation).
+//   (alternating), one key per thread, while the tensor core computes O.  All shared-memory traffic is LDS/STS (see the
+//   smem base computation).  Variants measured on B200 (1024 crops, ms): v2 0.76 | v4 as first written 0.65 | + stage
+//   released before the epilogue and class-row reduce before the O wait 0.61 | one MMA issuer warp per query tile 0.62
+//   (no gain: dropped) | class row after the epilogue 0.73.
 // ================================================================================================
-constexpr int kA4Threads = 128 + 512;
+constexpr int kA4Threads = 64 + 512;
 
 struct A4Misc {
   uint64_t full_qk[2], full_v[2], empty_qk[2], empty_v[2];
@@ -1408,14 +1408,14 @@ constexpr int a4_smem_bytes() {
   return A2L<64>::kOffMisc + static_cast<int>((sizeof(A4Misc) + 1023) / 1024 * 1024) + 1024;
 }
 
-template <int ISS, int flags>  // flags: bit0 early tmem_free, bit1 class-row reduce before the epilogue, bit2 early stage release; ISS = MMA issuer warps: 2 = one per query tile (decoupled groups), 1 = v2's fixed order from warp 1
-__global__ void __launch_bounds__(kA4Threads, 1)
+// launch bound 640 (not 576): ptxas schedules the softmax loop measurably better with it (0.61 vs 0.66 ms at 1024 crops)
+__global__ void __launch_bounds__(kA4Threads + 64, 1)
 attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* __restrict__ qkv,
                        __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads, float scale_log2) {
   constexpr int HD = 64;
   using L = A2L<HD>;
   constexpr int kColO4 = 64, kColL4 = 192;
-  constexpr int kFirstSm = ISS == 2 ? 4 : 2;  // first softmax warp (a multiple of 2 keeps lane quarter = warp & 3 consistent)
+  constexpr int kFirstSm = 2;  // first softmax warp
   extern __shared__ uint8_t smem_a4_raw[];
   uint8_t* smem = smem_a4_raw + ((1024u - (smem_u32(smem_a4_raw) & 1023u)) & 1023u);  // keeps the address space: LDS/STS
   A4Misc* mb = reinterpret_cast<A4Misc*>(smem + L::kOffMisc);
@@ -1428,8 +1428,8 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     for (int s = 0; s < 2; ++s) {
       mbar_init(&mb->full_qk[s], 1);
       mbar_init(&mb->full_v[s], 1);
-      mbar_init(&mb->empty_qk[s], 2 + ISS);  // the MMA issuers' commits + one arrival per group once its Q/K reads are done
-      mbar_init(&mb->empty_v[s], 1 + ISS);   // the MMA issuers' commits + the group that computed the class row from V
+      mbar_init(&mb->empty_qk[s], 3);  // the MMA issuer's commit + one arrival per group once its Q/K reads are done
+      mbar_init(&mb->empty_v[s], 2);   // the MMA issuer's commit + the group that computed the class row from V
       mbar_init(&mb->s_full[s], 1);
       mbar_init(&mb->p_full[s], 8);
       mbar_init(&mb->o_full[s], 1);
@@ -1467,8 +1467,8 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       }
     }
     __syncwarp();
-  } else if (warp == 1 || (ISS == 2 && warp == 2)) {
-    // ------------------------------------------------------------------ MMA issuer(s) (warp-uniform control flow, see v2)
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow, see v2)
     // The query tile index is a compile-time constant in every tcgen05.mma operand (TMEM address, descriptors): with a
     // run-time tile index ptxas moves each operand through R2UR before every MMA and the issue rate drops.
     const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
@@ -1519,26 +1519,14 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       const uint32_t vbase = smem_base + L::kOffV + s * L::kOp;
       mbar_wait(&mb->full_qk[s], u);
       const uint64_t k_desc = make_sw128_kmajor_desc(sbase + L::kOp);
-      if (ISS == 1) {
-        issue_s(W0{}, sbase, k_desc, kp);
-        issue_s(W1{}, sbase, k_desc, kp);
-      } else if (warp == 1) {
-        issue_s(W0{}, sbase, k_desc, kp);
-      } else {
-        issue_s(W1{}, sbase, k_desc, kp);
-      }
+      issue_s(W0{}, sbase, k_desc, kp);
+      issue_s(W1{}, sbase, k_desc, kp);
       if (elect_one()) umma_commit(&mb->empty_qk[s]);
       __syncwarp();
       mbar_wait(&mb->full_v[s], u);
       const uint64_t v_desc0 = make_sw128_kmajor_desc(vbase);
-      if (ISS == 1) {
-        issue_pv(W0{}, v_desc0, kp);
-        issue_pv(W1{}, v_desc0, kp);
-      } else if (warp == 1) {
-        issue_pv(W0{}, v_desc0, kp);
-      } else {
-        issue_pv(W1{}, v_desc0, kp);
-      }
+      issue_pv(W0{}, v_desc0, kp);
+      issue_pv(W1{}, v_desc0, kp);
       if (elect_one()) umma_commit(&mb->empty_v[s]);
       __syncwarp();
     }
@@ -1691,11 +1679,14 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
       named_bar_sync(1 + w, 256);  // p0s (and the class row's partial sums) visible
-      if ((flags & 4) && gt == 0) {
+      // Release the operand stage NOW (every Q / K / V read of the group is done) and finish the class row BEFORE waiting
+      // for O: measured together these two placements are worth 16 % of the kernel (0.73 -> 0.61 ms at 1024 crops);
+      // releasing at the end of the iteration, or reducing after the epilogue, each lose all of it.
+      if (gt == 0) {
         mbar_arrive(&mb->empty_qk[s]);
         if (cls_owner) mbar_arrive(&mb->empty_v[s]);
       }
-      if ((flags & 2) && cls_owner && gt < HD) {
+      if (cls_owner && gt < HD) {
         const float cls_l = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
         float o = pcls[256] * v0f[gt];
 #pragma unroll
@@ -1712,11 +1703,9 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         uint32_t v[32];
         tmem_ld_32x32(taddr + kColO4 + h * 32, v);
         tmem_ld_wait();
-        if (flags & 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&mb->tmem_free[w]);  // O and L are in registers: the region can take the next S
-        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mb->tmem_free[w]);  // O and L are in registers: the region can take the next S
         const float inv = 1.0f / (lsum + p0);
         const float p0i = p0 * inv;
         __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * HD + h * 32;
@@ -1734,26 +1723,8 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         }
       }
 
-      if (!(flags & 1)) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mb->tmem_free[w]);
-      }
-      if (cls_owner && !(flags & 2)) {
-        if (gt < HD) {
-          const float cls_l = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
-          float o = pcls[256] * v0f[gt];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o += mb->part[w][i][gt];
-          out[static_cast<size_t>(tok0) * d + head * HD + gt] = __float2bfloat16_rn(o / cls_l);
-        }
-      }
-      // every Q / K / V read of the group is done and its scratch (vec, mx, p0s, p_cls, part, red) may be rewritten
+      // the group's scratch (vec, mx, p0s, p_cls, part, red) is rewritten next iteration: everyone must be done with it
       named_bar_sync(1 + w, 256);
-      if (!(flags & 4) && gt == 0) {
-        mbar_arrive(&mb->empty_qk[s]);
-        if (cls_owner) mbar_arrive(&mb->empty_v[s]);
-      }
     }
   }
   tc_fence_before();
@@ -1771,11 +1742,7 @@ static int attention_umma4_launch(const void* qkv, void* out, int n, int T, int 
   B2C_TRY(make_tmap_2d(&tm, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, 1));
   constexpr int smem_bytes = a4_smem_bytes();
   static_assert(smem_bytes <= 227 * 1024, "attention v4 shared memory exceeds 227 KB");
-  static const int flags = [] { const char* e = getenv("B2C_ATTN_FLAGS"); return e ? atoi(e) : 1; }();
-  static const int iss = [] { const char* e = getenv("B2C_ATTN_ISS"); return e && e[0] == '1' ? 1 : 2; }();
-  using Kern = void (*)(CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float);
-  Kern kern = iss == 1 ? (flags == 6 ? attention_umma4_kernel<1, 6> : attention_umma4_kernel<1, 1>)
-                       : (flags == 7 ? attention_umma4_kernel<2, 7> : attention_umma4_kernel<2, 1>);
+  auto kern = attention_umma4_kernel;
   static bool attr_set = false;
   if (!attr_set) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -1785,7 +1752,7 @@ static int attention_umma4_launch(const void* qkv, void* out, int n, int T, int 
   B2C_REQUIRE(sms > 0, "no CUDA device");
   const int n_ch = n * heads;
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
-  kern<<<n_ch < sms ? n_ch : sms, iss == 2 ? kA4Threads : kA4Threads - 64, smem_bytes, stream>>>(
+  kern<<<n_ch < sms ? n_ch : sms, kA4Threads, smem_bytes, stream>>>(
       tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, scale_log2);
   B2C_POST_LAUNCH("attention_umma4_kernel");
   return 0;

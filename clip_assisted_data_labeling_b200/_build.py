@@ -27,6 +27,7 @@ SOURCES = [
     "b2c_preprocess.cu",
     "b2c_dedup.cu",
     "b2c_similar.cu",
+    "b2c_train.cu",
     "b2c_vit.cu",
 ]
 

@@ -51,6 +51,15 @@ class MlpWeights(C.Structure):
     ]
 
 
+class TrainerCfg(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MLP_MAX_LAYERS + 1)), ("max_batch", C.c_int32),
+                ("leaky_slope", C.c_float), ("dropout_p", C.c_float), ("seed", C.c_uint64)]
+
+
+class Adam(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("lr", "beta1", "beta2", "eps", "weight_decay")]
+
+
 _vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
 _u64 = C.c_ulonglong
 
@@ -79,6 +88,13 @@ SIGNATURES = {
     "b2c_normalize_rows_f16": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "b2c_dedup_pairs": (_i, [_vp, _i64, _i, _i64, _i64, _f, _i, _vp, _u64, _vp, _vp]),
     "b2c_mlp_score": (_i, [_vp, _i64, C.POINTER(MlpWeights), _vp, _vp]),
+    "b2c_trainer_create": (_i, [C.POINTER(TrainerCfg), C.POINTER(_vp)]),
+    "b2c_trainer_destroy": (_i, [_vp]),
+    "b2c_trainer_set_layer": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "b2c_trainer_get_layer": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "b2c_trainer_weights": (_i, [_vp, C.POINTER(MlpWeights)]),
+    "b2c_trainer_steps": (_u64, [_vp]),
+    "b2c_trainer_epoch": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, C.POINTER(Adam), _vp, _vp]),
     "b2c_context_scores": (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b2c_topk_workspace_bytes": (_i, [_i, C.POINTER(_sz)]),
     "b2c_topk_smallest": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -233,6 +233,41 @@ int b2c_topk_smallest(const float* scores, int64_t n, int k, int32_t* out_idx, f
 int b2c_diversity_order(const void* emb, int dtype, int64_t n, int E, int64_t row_stride, int32_t first_row,
                         const int32_t* samples, int steps, int S, float* maxsim, int32_t* order, b2c_stream stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K12 — SimpleFC training step on the device.  Replaces the inner loop of
+ * _4_train_model.py:196-204 (zero_grad / forward / MSELoss / backward / Adam.step) for utils/nn_model.SimpleFC.
+ * The host keeps the reference's data order, split, initialisation and learning-rate schedule (trainer.py).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b2c_trainer b2c_trainer;
+
+typedef struct {
+  int32_t n_layers;                     /* number of Linear layers (hidden + 1), <= B2C_MLP_MAX_LAYERS */
+  int32_t dims[B2C_MLP_MAX_LAYERS + 1]; /* dims[0] = input width, dims[n_layers] = outputs (1) */
+  int32_t max_batch;                    /* largest batch a step will see, <= 64 (_4_train_model.py:250 default 16) */
+  float leaky_slope;                    /* nn.LeakyReLU default 0.01 (utils/nn_model.py:28) */
+  float dropout_p;                      /* nn.Dropout p after every hidden activation (utils/nn_model.py:29), train mode */
+  uint64_t seed;                        /* dropout stream: Philox4x32-10, key = seed, counter = (unit/4, layer, step) */
+} b2c_trainer_cfg;
+
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay; /* torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay) */
+} b2c_adam;
+
+int b2c_trainer_create(const b2c_trainer_cfg* cfg, b2c_trainer** out); /* weights and Adam moments start at zero */
+int b2c_trainer_destroy(b2c_trainer* t);
+/* W: DEVICE f32[dims[layer+1], dims[layer]] (torch Linear layout), bias: DEVICE f32[dims[layer+1]]; copied on `stream`. */
+int b2c_trainer_set_layer(b2c_trainer* t, int layer, const float* W, const float* bias, b2c_stream stream);
+int b2c_trainer_get_layer(b2c_trainer* t, int layer, float* W, float* bias, b2c_stream stream);
+/* Fills `out` with pointers to the trainer's live weights, for b2c_mlp_score (test-set loss, _4_train_model.py:129-166). */
+int b2c_trainer_weights(b2c_trainer* t, b2c_mlp_weights* out);
+unsigned long long b2c_trainer_steps(const b2c_trainer* t); /* optimiser steps taken so far */
+/* One pass over `n` samples in the given order, `batch` per step (the last step takes the remainder, like
+ * DataLoader(drop_last=False)).  feats: DEVICE f32 rows of width dims[0], row i at feats + i*feat_stride; labels: DEVICE
+ * f32 indexed like feats; order: DEVICE int32[n] sample indices (the epoch's shuffled permutation).  loss_sum: DEVICE
+ * f32, += the mean squared error of every step (train_loss of _4_train_model.py:203) or NULL.  Asynchronous. */
+int b2c_trainer_epoch(b2c_trainer* t, const float* feats, int64_t feat_stride, const float* labels, const int32_t* order,
+                      int64_t n, int batch, const b2c_adam* hyper, float* loss_sum, b2c_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

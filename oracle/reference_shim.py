@@ -77,8 +77,14 @@ def install_stubs(seed: int = 0) -> None:
     try:
         import matplotlib  # noqa: F401
     except Exception:
-        mpl = types.ModuleType("matplotlib")
-        plt = types.ModuleType("matplotlib.pyplot")
+        class _NoOpModule(types.ModuleType):  # plt.figure(...), plt.savefig(...) ... all become no-ops
+            def __getattr__(self, name):
+                if name.startswith("__"):
+                    raise AttributeError(name)
+                return lambda *a, **k: None
+
+        mpl = _NoOpModule("matplotlib")
+        plt = _NoOpModule("matplotlib.pyplot")
         mpl.pyplot = plt
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.pyplot"] = plt

@@ -219,8 +219,71 @@ def gen_similar():
     np.savez_compressed(os.path.join(OUT, "similar_ref.npz"), **out)
 
 
+def make_labelled_dir(root, name, n, E, seed, crop_names=("centre_crop", "subcrop2"), model="M/x", n_nan=3):
+    """Synthetic labelled dataset in the reference's layout: <root>/<name>.csv (uuid,label) + <root>/<name>/<uuid>.pt.
+    The label is a smooth function of the embedding plus noise so that training has something to fit."""
+    import pandas as pd
+    g = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, name), exist_ok=True)
+    wtrue = g.standard_normal(E * len(crop_names)).astype(np.float32)
+    rows = []
+    for i in range(n):
+        fd = {c: torch.from_numpy(g.standard_normal((1, E)).astype(np.float32)) for c in crop_names}
+        torch.save({model: fd}, os.path.join(root, name, f"u{i:05d}.pt"))
+        x = np.concatenate([fd[c].numpy().ravel() for c in crop_names])
+        label = float(np.tanh(x @ wtrue / np.sqrt(len(x))) * 2 + 3 + 0.1 * g.standard_normal())
+        rows.append((f"u{i:05d}", label if i >= n_nan else np.nan))
+    rows.append(("missing_file", 1.0))  # no .pt: the reference skips it (_4_train_model.py:72-74)
+    pd.DataFrame(rows, columns=["uuid", "label"]).to_csv(os.path.join(root, name + ".csv"), index=False)
+
+
+def train_args(root, **kw):
+    a = dict(train_data_dir=root, train_data_names=["setA"], model_name="regressor", dont_save=False, clip_models_to_use=["all"],
+             test_fraction=0.25, n_epochs=10, batch_size=16, lr=0.0002, min_lr=1e-6, restart_epochs=2, weight_decay=0.0006,
+             dropout_prob=0.0, hidden_sizes=[24, 12], print_network_layout=False, random_seed=42)
+    a.update(kw)
+    return types.SimpleNamespace(**a)
+
+
+def gen_train():
+    """Unmodified _4_train_model.train() on CPU (dropout_prob = 0: deterministic) over a synthetic labelled directory;
+    the saved whole-module pickle gives the final weights our trainer must reproduce from the same seed."""
+    import glob
+    import importlib
+    rs.import_reference("utils.nn_model")
+    t4 = importlib.import_module("_4_train_model")
+    nn_model = importlib.import_module("utils.nn_model")
+    t4.device = nn_model.device = torch.device("cpu")
+    out = {}
+    for case, kw in {"a": dict(), "b": dict(n_epochs=12, batch_size=7, hidden_sizes=[16], lr=0.01, weight_decay=0.0, test_fraction=0.2)}.items():
+        tmp = tempfile.mkdtemp()
+        n, E, seed = (150, 20, 31) if case == "a" else (90, 12, 32)
+        make_labelled_dir(tmp, "setA", n, E, seed)
+        args = train_args(tmp, **kw)
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            t4.train(args, ["centre_crop", "subcrop2"], 0)
+            pth = glob.glob(os.path.join(tmp, "models", "*.pth"))[0]
+            import collections
+            with torch.serialization.safe_globals([nn_model.SimpleFC, torch.nn.ModuleList, torch.nn.Linear, torch.nn.LeakyReLU,
+                                                   torch.nn.Sigmoid, torch.nn.Dropout, set, collections.OrderedDict]):
+                m = torch.load(pth, map_location="cpu", weights_only=True)
+        finally:
+            os.chdir(cwd)
+        lin = [l for l in m.layers if isinstance(l, torch.nn.Linear)]
+        out[f"{case}_meta"] = np.asarray([n, E, seed], np.int64)
+        for i, l in enumerate(lin):
+            out[f"{case}_w{i}"] = l.weight.detach().numpy()
+            out[f"{case}_b{i}"] = l.bias.detach().numpy()
+        out[f"{case}_final_mse"] = np.asarray(float(os.path.basename(pth).split("_epochs_")[1].split("_mse")[0]))
+        shutil.rmtree(tmp)
+        print("train case", case, os.path.basename(pth))
+    np.savez_compressed(os.path.join(OUT, "train_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["preprocess", "geometry", "dedup", "mlp", "vit", "similar"]
+    which = sys.argv[1:] or ["preprocess", "geometry", "dedup", "mlp", "vit", "similar", "train"]
     for w in which:
         globals()["gen_" + w]()

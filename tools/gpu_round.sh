@@ -37,6 +37,9 @@ for w in $WHAT; do
       timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "attention or encode_image" > $OUT/${TAG}_attntest.log 2>&1; tail -15 $OUT/${TAG}_attntest.log ;;
     attnbench)
       for m in v2 v4; do B2C_ATTN=$m timeout 120 python tools/bench_attn.py; done 2>&1 | tee $OUT/${TAG}_attnbench.jsonl ;;
+    train)
+      timeout 600 python -m pytest tests/test_train.py -m gpu -x -q > $OUT/${TAG}_train_tests.log 2>&1; tail -15 $OUT/${TAG}_train_tests.log
+      timeout 300 python tools/bench_train.py > $OUT/${TAG}_bench_train.json 2> $OUT/${TAG}_bench_train.err; cat $OUT/${TAG}_bench_train.json; tail -3 $OUT/${TAG}_bench_train.err ;;
     similar)
       timeout 600 python -m pytest tests/test_gpu_similar.py -m gpu -x -q > $OUT/${TAG}_similar_tests.log 2>&1; tail -15 $OUT/${TAG}_similar_tests.log
       timeout 300 python tools/bench_similar.py > $OUT/${TAG}_bench_similar.json 2> $OUT/${TAG}_bench_similar.err; cat $OUT/${TAG}_bench_similar.json; tail -3 $OUT/${TAG}_bench_similar.err ;;

@@ -28,6 +28,7 @@ SOURCES = [
     "b2c_dedup.cu",
     "b2c_similar.cu",
     "b2c_train.cu",
+    "b2c_imgstats.cu",
     "b2c_vit.cu",
 ]
 

@@ -23,6 +23,7 @@ COMBINE_STORE, COMBINE_MAX = 0, 1
 TOPK_MAX = 4096
 MLP_MAX_LAYERS = 8
 PROF_KINDS = 11
+IMG_STATS = 22
 
 
 class B2CError(RuntimeError):
@@ -88,6 +89,9 @@ SIGNATURES = {
     "b2c_normalize_rows_f16": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "b2c_dedup_pairs": (_i, [_vp, _i64, _i, _i64, _i64, _f, _i, _vp, _u64, _vp, _vp]),
     "b2c_mlp_score": (_i, [_vp, _i64, C.POINTER(MlpWeights), _vp, _vp]),
+    "b2c_image_stats_target_size": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "b2c_image_stats_workspace_bytes": (_i, [C.POINTER(_i), C.POINTER(_i), _i, C.POINTER(_sz)]),
+    "b2c_image_stats": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp, _sz, _vp]),
     "b2c_trainer_create": (_i, [C.POINTER(TrainerCfg), C.POINTER(_vp)]),
     "b2c_trainer_destroy": (_i, [_vp]),
     "b2c_trainer_set_layer": (_i, [_vp, _i, _vp, _vp, _vp]),

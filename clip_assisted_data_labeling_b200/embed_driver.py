@@ -86,7 +86,7 @@ class Feature_Dataset:
     def __init__(self, root_dir, model_name, batch_size, model_path=None, force_reencode=False, shuffle_filenames=True,
                  num_workers=0, crop_names=("centre_crop", "square_padded_crop", "subcrop1", "subcrop2"),
                  rank=None, world_size=None, state_dict=None, encoder=None, writer_threads=4, packed_dir=None,
-                 write_pt=True):
+                 write_pt=True, img_stats=None):
         self.device = getattr(encoder, "device", "cuda") if encoder is not None else "cuda"
         self.root_dir = root_dir
         self.model_name = model_name
@@ -126,6 +126,9 @@ class Feature_Dataset:
         # (store.PackedWriter); write_pt=False skips the per-image pickles entirely (store.export_pt writes them later)
         self.packed_dir = packed_dir
         self.write_pt = write_pt or packed_dir is None
+        # the 22 img_stat_* scalars the reference stores ahead of the crops (_1:149-152): computed on the device from the
+        # same uint8 image (imgstats.image_stats); on by default wherever the device path runs
+        self.img_stats = str(self.device).startswith("cuda") if img_stats is None else bool(img_stats)
 
     def __len__(self):
         return len(self.img_filepaths)
@@ -162,14 +165,20 @@ class Feature_Dataset:
                 else:  # only reachable with an injected encoder (host-logic tests)
                     dev_imgs = todo_imgs
                 feats = self.encoder.encode_images_u8(dev_imgs).cpu()  # [B,4,E], one D2H per batch
+                stats = None
+                if self.img_stats:
+                    from .imgstats import image_stats, stats_dict
+                    stats = image_stats(dev_imgs).cpu()
                 kept_all = []
-                for im, f, sp in zip(todo_imgs, feats, todo_paths):
+                for bi, (im, f, sp) in enumerate(zip(todo_imgs, feats, todo_paths)):
                     g = (_lib.Crop * 4)()
                     _lib.check(lib.b2c_crop_geometry(int(im.shape[1]), int(im.shape[0]), R, g), "b2c_crop_geometry")
                     kept = [g[i].cw > 0 for i in range(4)]
                     kept_all.append(kept)
                     if self.write_pt:
                         fd = build_feature_dict(f, self.crop_names, kept)
+                        if stats is not None:
+                            fd = {**stats_dict(stats[bi]), **fd}
                         pending.append(pool.submit(save_feature_file, sp, self.model_name, fd, self.force_reencode))
                 if packed is not None:
                     packed.append(feats, todo_img_paths, kept_all)

@@ -234,6 +234,25 @@ int b2c_diversity_order(const void* emb, int dtype, int64_t n, int E, int64_t ro
                         const int32_t* samples, int steps, int S, float* maxsim, int32_t* order, b2c_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K13 — the 22 img_stat_* scalars.  Replaces ImageFeaturizer.process
+ * (utils/image_features.py:52-94, called at utils/embedder.py:170): cv2.resize(INTER_AREA) to ~768^2 pixels,
+ * COLOR_BGR2GRAY / COLOR_BGR2HSV, channel means / standard deviations, colourfulness, grey-histogram entropy and
+ * Laplacian variance — on the device-resident uint8 image the 4-crop preprocess reads, bit-exact in the integer
+ * stages (OpenCV 4.13 arithmetic) and to float64 round-off in the final formulas.
+ * ------------------------------------------------------------------------------------------- */
+#define B2C_IMG_STATS 22 /* order of utils/image_features.py:63-86: width, height, aspect_ratio, mean_color, std_color,
+                            mean_red/green/blue, std_red/green/blue, mean_gray, std_gray, mean_hue/sat/val,
+                            std_hue/sat/val, colorfulness, image_entropy, laplacian_variance */
+/* Size the reference resizes a W x H image to before measuring it (utils/image_features.py:57-60, including its
+ * width/height swap).  Host-only. */
+int b2c_image_stats_target_size(int W, int H, int* new_w, int* new_h);
+/* Bytes of DEVICE workspace b2c_image_stats needs for these B images (H, W: HOST int arrays). */
+int b2c_image_stats_workspace_bytes(const int* H, const int* W, int B, size_t* bytes);
+/* img_ptrs / H / W / pitch as in b2c_preprocess_4crop.  out: DEVICE f64[B, 22].  ws: 256-byte aligned. */
+int b2c_image_stats(const uint8_t* const* img_ptrs, const int* H, const int* W, const int* pitch, int B, double* out,
+                    void* ws, size_t ws_bytes, b2c_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K12 — SimpleFC training step on the device.  Replaces the inner loop of
  * _4_train_model.py:196-204 (zero_grad / forward / MSELoss / backward / Adam.step) for utils/nn_model.SimpleFC.
  * The host keeps the reference's data order, split, initialisation and learning-rate schedule (trainer.py).

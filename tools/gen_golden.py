@@ -219,6 +219,26 @@ def gen_similar():
     np.savez_compressed(os.path.join(OUT, "similar_ref.npz"), **out)
 
 
+def gen_imgstats():
+    """The reference's own ImageFeaturizer (utils/image_features.py; cv2 4.13 + numpy here) on synthetic images of sizes
+    that exercise every cv::resize(INTER_AREA) branch: enlarged (512^2), mixed (one axis up, one down), fractional
+    down-scale, integer 2x and 3x box filters, extreme aspect."""
+    import importlib
+    rs.import_reference("utils.nn_model")
+    imf = importlib.import_module("utils.image_features")
+    F = imf.ImageFeaturizer()
+    sizes = [(512, 512), (300, 200), (97, 260), (1000, 700), (1536, 1536), (2304, 2304), (640, 128), (50, 50), (1100, 1000),
+             (33, 700)]  # (W, H)
+    rows = []
+    for k, (W, H) in enumerate(sizes):
+        d = F.process(synthetic_image(k, H, W))
+        rows.append([float(d[n]) for n in d])
+        names = list(d.keys())
+    np.savez_compressed(os.path.join(OUT, "imgstats_ref.npz"), sizes=np.asarray(sizes), stats=np.asarray(rows, np.float64),
+                        names=np.asarray(names))
+    print("imgstats_ref.npz", len(rows), names[:3])
+
+
 def make_labelled_dir(root, name, n, E, seed, crop_names=("centre_crop", "subcrop2"), model="M/x", n_nan=3):
     """Synthetic labelled dataset in the reference's layout: <root>/<name>.csv (uuid,label) + <root>/<name>/<uuid>.pt.
     The label is a smooth function of the embedding plus noise so that training has something to fit."""
@@ -284,6 +304,6 @@ def gen_train():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["preprocess", "geometry", "dedup", "mlp", "vit", "similar", "train"]
+    which = sys.argv[1:] or ["preprocess", "geometry", "dedup", "mlp", "vit", "similar", "train", "imgstats"]
     for w in which:
         globals()["gen_" + w]()

@@ -40,6 +40,9 @@ for w in $WHAT; do
     train)
       timeout 600 python -m pytest tests/test_train.py -m gpu -x -q > $OUT/${TAG}_train_tests.log 2>&1; tail -15 $OUT/${TAG}_train_tests.log
       timeout 300 python tools/bench_train.py > $OUT/${TAG}_bench_train.json 2> $OUT/${TAG}_bench_train.err; cat $OUT/${TAG}_bench_train.json; tail -3 $OUT/${TAG}_bench_train.err ;;
+    imgstats)
+      timeout 600 python -m pytest tests/test_gpu_imgstats.py -m gpu -x -q > $OUT/${TAG}_imgstats_tests.log 2>&1; tail -15 $OUT/${TAG}_imgstats_tests.log
+      timeout 300 python tools/bench_imgstats.py > $OUT/${TAG}_bench_imgstats.json 2> $OUT/${TAG}_bench_imgstats.err; cat $OUT/${TAG}_bench_imgstats.json; tail -3 $OUT/${TAG}_bench_imgstats.err ;;
     similar)
       timeout 600 python -m pytest tests/test_gpu_similar.py -m gpu -x -q > $OUT/${TAG}_similar_tests.log 2>&1; tail -15 $OUT/${TAG}_similar_tests.log
       timeout 300 python tools/bench_similar.py > $OUT/${TAG}_bench_similar.json 2> $OUT/${TAG}_bench_similar.err; cat $OUT/${TAG}_bench_similar.json; tail -3 $OUT/${TAG}_bench_similar.err ;;

@@ -80,6 +80,7 @@ SIGNATURES = {
     "b2c_vit_destroy": (_i, [_vp]),
     "b2c_vit_set_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i]),
     "b2c_vit_ready": (_i, [_vp]),
+    "b2c_vit_set_lanes": (_i, [_vp, _i]),
     "b2c_vit_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
     "b2c_vit_forward_pixels": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "b2c_vit_forward_patches": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -30,6 +30,13 @@ struct b2c_vit {
   b2c_vit_cfg cfg;
   int T, g, G2, Kp, hd;
   int chunk;  // crops processed per pass over the layers
+  // A chunk is split into `lanes` independent sub-chunks, each with its own workspace slice and its own stream, so
+  // that the HBM-bound stages of one lane (LayerNorm, the residual reduce-add tail, patchify) and the kernel heads /
+  // tails of every stage run under the tensor-bound GEMMs of the other lane.
+  int lanes = 2;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
   __nv_bfloat16* conv1 = nullptr;  // [d, Kp]
   float *cls = nullptr, *pos = nullptr, *proj = nullptr;
   float *ln_pre_w = nullptr, *ln_pre_b = nullptr, *ln_post_w = nullptr, *ln_post_b = nullptr;
@@ -63,6 +70,34 @@ WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
   if (need_patches) off = align_up(off + static_cast<size_t>(nc) * v->G2 * v->Kp * 2, 1024);
   w.total = off;
   return w;
+}
+
+constexpr int kMinLaneCrops = 64;  // below this a lane's GEMMs no longer fill the machine
+
+int lanes_for(const b2c_vit* v, int nc) {
+  int l = v->lanes;
+  while (l > 1 && nc / l < kMinLaneCrops) --l;
+  return l;
+}
+
+// workspace of one pass over `nc` crops: `lanes` slices, and never less than the single-lane layout (the stage timer
+// runs single-lane inside the same buffer)
+size_t ws_bytes_for(const b2c_vit* v, int nc, bool need_patches, size_t* lane_bytes) {
+  const int l = lanes_for(v, nc);
+  const int per = (nc + l - 1) / l;
+  const size_t lb = ws_layout(v, per, need_patches).total;
+  if (lane_bytes) *lane_bytes = lb;
+  return std::max(lb * l, ws_layout(v, nc, need_patches).total);
+}
+
+int ensure_lanes(b2c_vit* v) {
+  if (v->ev_fork) return 0;
+  B2C_CHECK_CUDA(cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 3; ++i) {
+    B2C_CHECK_CUDA(cudaStreamCreateWithFlags(&v->side[i], cudaStreamNonBlocking));
+    B2C_CHECK_CUDA(cudaEventCreateWithFlags(&v->ev_join[i], cudaEventDisableTiming));
+  }
+  return 0;
 }
 
 std::vector<std::string> expected_keys(const b2c_vit* v) {
@@ -201,25 +236,57 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
   B2C_REQUIRE(n > 0, "vit_forward: n_crops must be positive");
   B2C_TRY(b2c_vit_ready(v));
   const int nc_max = n < v->chunk ? n : v->chunk;
-  const WsLayout w = ws_layout(v, nc_max, pixels != nullptr);
-  if (ws_bytes < w.total)
-    return set_error(B2C_ERR_WORKSPACE, "vit_forward: workspace %zu B < required %zu B", ws_bytes, w.total);
+  size_t lane_bytes = 0;
+  const size_t need = ws_bytes_for(v, nc_max, pixels != nullptr, &lane_bytes);
+  if (ws_bytes < need)
+    return set_error(B2C_ERR_WORKSPACE, "vit_forward: workspace %zu B < required %zu B", ws_bytes, need);
   B2C_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "vit_forward: workspace must be 1024-byte aligned");
   uint8_t* wsb = static_cast<uint8_t*>(ws);
   const int R = v->cfg.image;
   const size_t px_elt = dtype == B2C_F32 ? 4 : 2;
-  for (int c0 = 0; c0 < n; c0 += nc_max) {
-    const int nc = (n - c0) < nc_max ? (n - c0) : nc_max;
+  // one sub-chunk [c0, c0 + nc) on `st` inside the workspace slice `wsl`
+  auto run = [&](int c0, int nc, uint8_t* wsl, const WsLayout& w, cudaStream_t st) -> int {
     const void* pch;
     if (pixels) {
       const uint8_t* px = static_cast<const uint8_t*>(pixels) + static_cast<size_t>(c0) * 3 * R * R * px_elt;
-      ProfScope ps(B2C_PROF_OTHER, stream);
-      B2C_TRY(patchify_launch(px, dtype, wsb + w.patches, nc, R, v->cfg.patch, v->Kp, stream));
-      pch = wsb + w.patches;
+      ProfScope ps(B2C_PROF_OTHER, st);
+      B2C_TRY(patchify_launch(px, dtype, wsl + w.patches, nc, R, v->cfg.patch, v->Kp, st));
+      pch = wsl + w.patches;
     } else {
       pch = static_cast<const uint8_t*>(patches) + static_cast<size_t>(c0) * v->G2 * v->Kp * 2;
     }
-    B2C_TRY(forward_chunk(v, pch, nc, out + static_cast<size_t>(c0) * v->cfg.embed, wsb, w, stream));
+    return forward_chunk(v, pch, nc, out + static_cast<size_t>(c0) * v->cfg.embed, wsl, w, st);
+  };
+  for (int c0 = 0; c0 < n; c0 += nc_max) {
+    const int nc = (n - c0) < nc_max ? (n - c0) : nc_max;
+    // the stage timer brackets stages with events on the launching stream: meaningful only without overlap
+    const int lanes = g_prof_on.load(std::memory_order_relaxed) ? 1 : lanes_for(v, nc);
+    if (lanes == 1) {
+      B2C_TRY(run(c0, nc, wsb, ws_layout(v, nc_max, pixels != nullptr), stream));
+      continue;
+    }
+    B2C_TRY(ensure_lanes(v));
+    const int per = (nc + lanes - 1) / lanes;
+    const WsLayout w = ws_layout(v, (nc_max + lanes - 1) / lanes, pixels != nullptr);
+    B2C_REQUIRE(w.total <= lane_bytes && lane_bytes * lanes <= ws_bytes, "vit_forward: lane layout exceeds the workspace");
+    B2C_CHECK_CUDA(cudaEventRecord(v->ev_fork, stream));
+    int rc = 0;
+    int used = 0;
+    for (int l = 0; l < lanes && rc == 0; ++l) {
+      const int b = l * per;
+      const int cnt = (nc - b) < per ? (nc - b) : per;
+      if (cnt <= 0) break;
+      cudaStream_t st = l == 0 ? stream : v->side[l - 1];
+      if (l > 0) B2C_CHECK_CUDA(cudaStreamWaitEvent(st, v->ev_fork, 0));
+      rc = run(c0 + b, cnt, wsb + static_cast<size_t>(l) * lane_bytes, w, st);
+      used = l + 1;
+    }
+    // always join what was forked, also on error, so the caller's stream order covers every lane
+    for (int l = 1; l < used; ++l) {
+      cudaEventRecord(v->ev_join[l - 1], v->side[l - 1]);
+      cudaStreamWaitEvent(stream, v->ev_join[l - 1], 0);
+    }
+    if (rc != 0) return rc;
   }
   return 0;
 }
@@ -251,6 +318,10 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
     const int cv = atoi(e);
     if (cv > 0) v->chunk = cv;
   }
+  if (const char* e = getenv("B2C_VIT_LANES")) {
+    const int lv = atoi(e);
+    if (lv >= 1 && lv <= 4) v->lanes = lv;
+  }
   v->layers.resize(cfg->layers);
   *out = v;
   return 0;
@@ -259,6 +330,14 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
 extern "C" int b2c_vit_destroy(b2c_vit* v) {
   if (!v) return 0;
   for (void* p : v->allocs) cudaFree(p);
+  for (int i = 0; i < 3; ++i) {
+    if (v->side[i]) {
+      cudaStreamSynchronize(v->side[i]);
+      cudaStreamDestroy(v->side[i]);
+    }
+    if (v->ev_join[i]) cudaEventDestroy(v->ev_join[i]);
+  }
+  if (v->ev_fork) cudaEventDestroy(v->ev_fork);
   delete v;
   return 0;
 }
@@ -334,10 +413,17 @@ extern "C" int b2c_vit_ready(const b2c_vit* v) {
   return 0;
 }
 
+extern "C" int b2c_vit_set_lanes(b2c_vit* v, int lanes) {
+  B2C_REQUIRE(v, "b2c_vit_set_lanes: null handle");
+  B2C_REQUIRE(lanes >= 1 && lanes <= 4, "b2c_vit_set_lanes: lanes %d out of range (1..4)", lanes);
+  v->lanes = lanes;
+  return 0;
+}
+
 extern "C" int b2c_vit_workspace_bytes(const b2c_vit* v, int n_crops, size_t* bytes) {
   B2C_REQUIRE(v && bytes, "b2c_vit_workspace_bytes: null pointer");
   B2C_REQUIRE(n_crops > 0, "b2c_vit_workspace_bytes: n_crops must be positive");
-  *bytes = ws_layout(v, n_crops < v->chunk ? n_crops : v->chunk, true).total;
+  *bytes = ws_bytes_for(v, n_crops < v->chunk ? n_crops : v->chunk, true, nullptr);
   return 0;
 }
 

@@ -77,6 +77,10 @@ class VisionTower:
                                                        max(t.dim(), 1)), f"b2c_vit_set_weight({k})")
             _lib.check(self.lib.b2c_vit_ready(self._h), "b2c_vit_ready")
 
+    def set_lanes(self, lanes: int) -> None:
+        """Number of independent sub-batches (own stream each) a pass is split into; see include/b2c.h."""
+        _lib.check(self.lib.b2c_vit_set_lanes(self._h, int(lanes)), "b2c_vit_set_lanes")
+
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, n: int) -> torch.Tensor:
         need = C.c_size_t()

@@ -132,6 +132,11 @@ int b2c_vit_set_weight(b2c_vit* vit, const char* key, const void* dev_ptr, int d
                        int ndim);
 /* 0 when every tensor of the architecture has been set, else B2C_ERR_STATE (message names one missing key). */
 int b2c_vit_ready(const b2c_vit* vit);
+/* Lanes (1..4, default 2; env B2C_VIT_LANES): a pass over up to `chunk` crops is split into `lanes` independent
+ * sub-batches, each on its own internal stream forked from / joined to the caller's stream with events, so the
+ * HBM-bound stages of one lane run under the tensor-bound GEMMs of another.  Results do not depend on it (crops are
+ * independent units).  Set it BEFORE querying the workspace size.  The stage timer forces 1 lane while it is on. */
+int b2c_vit_set_lanes(b2c_vit* vit, int lanes);
 int b2c_vit_workspace_bytes(const b2c_vit* vit, int n_crops, size_t* bytes);
 /* pixels: [n,3,R,R] (B2C_F32 / B2C_F16 / B2C_BF16), already normalised — the tensor the reference
  * feeds encode_image (utils/embedder.py:95-98).  out: f32[n,E], unit-norm rows (embedder.py:99). */

@@ -160,6 +160,22 @@ def test_encode_image_golden_and_batch_invariance(cuda, lib, golden, monkeypatch
     assert (again - got).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("arch,n", [("ViT-B-32", 333), ("ViT-L-14", 131)])
+def test_lanes_do_not_change_results(cuda, lib, arch, n):
+    """A pass split into 2-4 sub-batches on separate streams (b2c_vit_set_lanes) returns the same bits as one lane:
+    crops are independent units and every kernel's per-row arithmetic order is fixed."""
+    tower, m = _tower_and_oracle(arch, "openai")
+    R = m.cfg["image"]
+    px = torch.randn(n, 3, R, R, generator=torch.Generator().manual_seed(7)).cuda().to(torch.bfloat16)
+    tower.set_lanes(1)
+    one = tower.forward_pixels(px).cpu()
+    assert torch.allclose(one.norm(dim=-1), torch.ones(n), atol=1e-5)
+    for lanes in (2, 3, 4):
+        tower.set_lanes(lanes)
+        for _ in range(2):  # second call reuses the lanes' streams and workspace slices
+            assert torch.equal(tower.forward_pixels(px).cpu(), one), lanes
+
+
 def test_fused_u8_path_vs_reference_pipeline(cuda, lib):
     """encode_images_u8 == reference pipeline (extract_crops -> preprocess -> encode_image) on ragged images."""
     from oracle import vit_oracle
@@ -357,7 +373,14 @@ def test_feature_dataset_end_to_end(cuda, lib, tmp_path):
     n_emb, _ = ds.process()
     assert n_emb == 10 and len(ds.failed) == 10
     d = torch.load(root / "003.pt")["ViT-B-32/openai"]
-    assert list(d.keys()) == CROP_NAMES
+    # .pt layout (_1_embed_with_CLIP.py:146-164): the 22 img_stat_* scalars (f32 0-d) ahead of the four crops (f32 [1,E])
+    from oracle.imgstats_oracle import STAT_NAMES, image_stats_oracle
+    assert list(d.keys()) == STAT_NAMES + CROP_NAMES
+    stats = image_stats_oracle(imgs[3])
+    for name, want in zip(STAT_NAMES, stats):
+        assert d[name].dtype == torch.float32 and d[name].dim() == 0
+        assert abs(d[name].item() - float(np.float32(want))) <= 1e-6 * max(1.0, abs(want)), name
+    assert all(d[c].dtype == torch.float32 and tuple(d[c].shape) == (1, 512) for c in CROP_NAMES)
     ref = vit_oracle.encode_image_oracle(m, torch.from_numpy(four_crop_preprocess(imgs[3], 224)))
     _check_embeddings(ref, torch.cat([d[c] for c in CROP_NAMES]))
     args = types.SimpleNamespace(root_dir=str(root), threshold=0.96, mode="copy", clip_model_to_use=None, chunk_size=10000, test=True)

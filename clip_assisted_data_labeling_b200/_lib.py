@@ -11,7 +11,8 @@ import os
 import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libb2c.so")
+# B2C_LIB: development override (A/B builds of the same sources with different compile-time constants)
+LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(PKG_DIR, "libb2c.so")
 
 B2C_F32, B2C_F16, B2C_BF16, B2C_U8 = 0, 1, 2, 3
 OUT_NCHW_F32, OUT_PATCH_BF16 = 0, 1
@@ -81,6 +82,7 @@ SIGNATURES = {
     "b2c_vit_set_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i]),
     "b2c_vit_ready": (_i, [_vp]),
     "b2c_vit_set_lanes": (_i, [_vp, _i]),
+    "b2c_vit_set_fused_ln": (_i, [_vp, _i]),
     "b2c_vit_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
     "b2c_vit_forward_pixels": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "b2c_vit_forward_patches": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -37,6 +37,9 @@ struct DedupParams {
 struct DedupPolicy {
   using Params = DedupParams;
   static constexpr int kStore = kStoreDirect;  // the epilogue emits pairs itself; nothing is stored as a tile
+  static constexpr bool kLnFold = false;
+  static constexpr int kEpiWarps = 4;
+  static constexpr int kRmwRing = 1;
   __device__ static __forceinline__ void transform(const Params&, int, float (&)[32]) {}
 
   // consecutive tiles walk down the band's row blocks for one column block: the CTAs running at the
@@ -202,7 +205,7 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
     p.num_tiles2 = static_cast<int>(((gi + 1) / 2) * (NJ - bj0));
     if (pairs) {
       const int grid = 2 * p.num_tiles2 < sms ? 2 * p.num_tiles2 : (sms & ~1);
-      kern2<<<grid, kUmmaThreads, kUmma2SmemBytes, stream>>>(tm_a, tm_a, tm_a, p, make_idesc_f16(2 * kBM, kBN, 0));
+      kern2<<<grid, kUmmaThreads, kUmma2SmemBytes, stream>>>(tm_a, tm_a, tm_a, tm_a, p, make_idesc_f16(2 * kBM, kBN, 0));
       B2C_POST_LAUNCH("umma2_tile_kernel<dedup>");
     } else {
       const int grid = tiles < sms ? static_cast<int>(tiles) : sms;

@@ -27,6 +27,12 @@ struct GemmParams {
   long long ldo;
   const float* pos;
   int T, G2;
+  // LayerNorm fusion (b2c_umma_pipeline2.cuh): per-row (mean, M2) partials of the residual stream, one per 256-column
+  // block; written by the kGemmResidLnF32 epilogue, merged by the kGemmLn* epilogues
+  float2* stats;
+  int nblk;
+  float eps;
+  const float* colsum;  // kGemmLn*: column sums of the folded weight, s_n = sum_k (gamma_k W_nk)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -68,7 +74,15 @@ struct GemmPolicy {
   }
 
   static constexpr int kStore = (MODE == kGemmPatchEmbedF32) ? kStoreDirect
-                                : (MODE == kGemmBiasResidF32) ? kStoreTmaAddF32 : kStoreTmaBf16;
+                                : (MODE == kGemmBiasResidF32) ? kStoreTmaAddF32
+                                : (MODE == kGemmResidLnF32 || MODE == kGemmResidLnDeepF32) ? kStoreRmwLn : kStoreTmaBf16;
+  static constexpr int kRmwRing = MODE == kGemmResidLnDeepF32 ? 1 : 5;  // see b2c_umma_pipeline2.cuh
+  // CTA-pair kernel: two epilogue warps per TMEM lane quarter, except for the read-modify-write epilogue (its slab
+  // ring needs the shared memory a second set of warps would stage through)
+  static constexpr int kEpiWarps = (MODE == kGemmResidLnF32 || MODE == kGemmResidLnDeepF32) ? 4 : 8;
+  static constexpr bool kLnFold = MODE == kGemmLnBiasBf16 || MODE == kGemmLnBiasQGeluBf16 || MODE == kGemmLnBiasGeluBf16;
+  static constexpr bool kQGelu = MODE == kGemmBiasQGeluBf16 || MODE == kGemmLnBiasQGeluBf16;
+  static constexpr bool kGelu = MODE == kGemmBiasGeluBf16 || MODE == kGemmLnBiasGeluBf16;
 
   // bias (+ activation) on one 32-column chunk of an accumulator row; the kernel then stages and TMA-stores it
   __device__ static __forceinline__ void transform(const Params& p, int col, float (&f)[32]) {
@@ -79,13 +93,62 @@ struct GemmPolicy {
         f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
       }
     }
-    if constexpr (MODE == kGemmBiasQGeluBf16) {
+    activate(f);
+  }
+
+  __device__ static __forceinline__ void activate(float (&f)[32]) {
+    if constexpr (kQGelu) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) f[e] = quick_gelu(f[e]);
-    } else if constexpr (MODE == kGemmBiasGeluBf16) {
+    } else if constexpr (kGelu) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) f[e] = gelu_erf(f[e]);
     }
+  }
+
+  // CTA-pair kernel: lane l keeps column col0 + 32 c + l of the tile's bias (and, kLnFold, column-sum) vector
+  template <int NC>
+  __device__ static __forceinline__ void load_cols(const Params& p, int col, float (&b)[NC], float (&s)[NC]) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      b[c] = p.bias ? __ldg(p.bias + col + 32 * c) : 0.f;
+      if constexpr (kLnFold) s[c] = __ldg(p.colsum + col + 32 * c);
+    }
+  }
+
+  // kLnFold: the row's per-block (mean, M2) partials (requested a tile ahead), merged in block order ->
+  // a = rstd, b = -mean * rstd
+  __device__ static __forceinline__ void load_row_stats(const Params& p, int row, float2 (&st)[8]) {
+    const float2* src = p.stats + static_cast<size_t>(row) * p.nblk;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < p.nblk && row < p.M) st[j] = src[j];
+  }
+  __device__ static __forceinline__ void merge_row_stats(const Params& p, int row, const float2 (&st)[8], float& a, float& b) {
+    a = 0.f;
+    b = 0.f;
+    if (row >= p.M) return;
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < p.nblk) mean += st[j].x;
+    mean /= static_cast<float>(p.nblk);
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < p.nblk) {
+        const float dlt = st[j].x - mean;
+        m2 += fmaf(256.0f * dlt, dlt, st[j].y);
+      }
+    }
+    const float rstd = rsqrtf(m2 / (256.0f * static_cast<float>(p.nblk)) + p.eps);
+    a = rstd;
+    b = -mean * rstd;
+  }
+
+  // kStoreRmwLn: (mean, M2) of the row's 256 new values in this tile's column block
+  __device__ static __forceinline__ void store_row_stats(const Params& p, int row, int b_row, float mean, float m2) {
+    if (row < p.M) p.stats[static_cast<size_t>(row) * p.nblk + (b_row >> 8)] = make_float2(mean, m2);
   }
 
   // patch-embed only: rows are scattered past each crop's class token, so the stores stay per-thread
@@ -129,13 +192,29 @@ static int gemm_launch_pair(const GemmLaunch& g, const GemmParams& p, cudaStream
   const int sms = num_sms();
   B2C_REQUIRE(sms >= 2, "no CUDA device");
   int grid = 2 * p.num_tiles2 < sms ? 2 * p.num_tiles2 : (sms & ~1);
-  kern<<<grid, kUmmaThreads, kUmma2SmemBytes, stream>>>(g.tmap_a, g.tmap_b_half, g.tmap_out, p, make_idesc_f16(2 * kBM, kBN, 1));
+  kern<<<grid, 64 + 32 * GemmPolicy<MODE>::kEpiWarps, kUmma2SmemBytes, stream>>>(g.tmap_a, g.tmap_b_half, g.tmap_out, g.tmap_out2, p,
+                                                        make_idesc_f16(2 * kBM, kBN, 1));
   B2C_POST_LAUNCH("umma2_tile_kernel<gemm>");
   return 0;
 }
 
 template <int MODE>
+static int gemm_launch_classic(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream);
+
+template <int MODE>
 static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
+  if constexpr (MODE >= kGemmLnBiasBf16) {
+    // the LayerNorm-fused epilogues exist in the CTA-pair kernel only
+    B2C_REQUIRE(p.stats && p.nblk > 0 && p.nblk <= 8, "gemm: LayerNorm-fused mode %d needs the row statistics buffer", MODE);
+    if constexpr (GemmPolicy<MODE>::kLnFold) B2C_REQUIRE(p.colsum && p.bias, "gemm: mode %d needs colsum and the folded bias", MODE);
+    return gemm_launch_pair<MODE>(g, p, stream);
+  } else {
+    return gemm_launch_classic<MODE>(g, p, stream);
+  }
+}
+
+template <int MODE>
+static int gemm_launch_classic(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
   if constexpr (MODE != kGemmPatchEmbedF32) {
     if (use_cta_pairs()) return gemm_launch_pair<MODE>(g, p, stream);
   }
@@ -154,9 +233,15 @@ static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream
 }
 
 int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, int mode) {
-  if (mode == kGemmBiasResidF32)
+  if (mode == kGemmResidLnBf16Copy)  // the bf16 copy of the residual stream: 32 x 32 half slabs, 64-B swizzle
+    return make_tmap_2d_sw(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 32,
+                           B2C_BF16, 64);
+  if (mode == kGemmBiasResidF32 || mode == kGemmResidLnF32)
     return make_tmap_2d_ex(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 4, 32, 32,
                            B2C_F32);
+  if (use_cta_pairs())  // the CTA-pair kernel stores bf16 tiles per 32-column chunk: 32 x 32 half slabs, 64-B swizzle
+    return make_tmap_2d_sw(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 32,
+                           B2C_BF16, 64);
   return make_tmap_2d_ex(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 64,
                          B2C_BF16);
 }
@@ -180,6 +265,10 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   p.pos = g.pos;
   p.T = g.T;
   p.G2 = g.G2;
+  p.stats = g.stats;
+  p.nblk = g.nblk;
+  p.eps = g.eps;
+  p.colsum = g.colsum;
   switch (g.mode) {
     case kGemmBiasBf16: return gemm_launch_mode<kGemmBiasBf16>(g, p, stream);
     case kGemmBiasQGeluBf16: return gemm_launch_mode<kGemmBiasQGeluBf16>(g, p, stream);
@@ -188,6 +277,13 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
     case kGemmPatchEmbedF32:
       B2C_REQUIRE(g.pos && g.T > 0 && g.G2 > 0, "gemm: patch-embed mode needs pos/T/G2");
       return gemm_launch_mode<kGemmPatchEmbedF32>(g, p, stream);
+    case kGemmLnBiasBf16: return gemm_launch_mode<kGemmLnBiasBf16>(g, p, stream);
+    case kGemmLnBiasQGeluBf16: return gemm_launch_mode<kGemmLnBiasQGeluBf16>(g, p, stream);
+    case kGemmLnBiasGeluBf16: return gemm_launch_mode<kGemmLnBiasGeluBf16>(g, p, stream);
+    case kGemmResidLnF32:
+      B2C_REQUIRE(g.N == g.nblk * kBN, "gemm: the residual+statistics mode needs N == 256 * nblk (whole rows)");
+      // K > 2048 (c_proj): keep all six mainloop stages, the epilogue has the slack to wait for each x slab
+      return g.K > 2048 ? gemm_launch_mode<kGemmResidLnDeepF32>(g, p, stream) : gemm_launch_mode<kGemmResidLnF32>(g, p, stream);
     default: return set_error(B2C_ERR_ARG, "gemm: unknown epilogue mode %d", g.mode);
   }
 }

@@ -38,6 +38,15 @@ enum GemmMode {
   kGemmBiasGeluBf16 = B2C_EPI_BIAS_GELU_BF16,
   kGemmBiasResidF32 = B2C_EPI_BIAS_RESID_F32,
   kGemmPatchEmbedF32 = 4,  // x[(crop*T + 1 + p), :] = A·Wᵀ + pos[1+p, :]   (conv1 + positional embedding)
+  // LayerNorm fused into the GEMMs on either side of it (b2c_umma_pipeline2.cuh).  A = bf16 copy of the residual
+  // stream, W = gamma-folded weight, bias = beta·Wᵀ + b, colsum = row sums of the folded weight:
+  kGemmLnBiasBf16 = 5,       // out bf16 = rstd·(A·W'ᵀ − mean·colsum) + bias                  (ln_1 + in_proj)
+  kGemmLnBiasQGeluBf16 = 6,  // same + QuickGELU                                               (ln_2 + c_fc, openai)
+  kGemmLnBiasGeluBf16 = 7,   // same + erf GELU                                                (ln_2 + c_fc, laion)
+  // x (f32, read-modify-write by the epilogue) += A·Wᵀ + bias; out2 = bf16(x); stats[row][n_block] = (mean, M2)
+  kGemmResidLnF32 = 8,
+  kGemmResidLnBf16Copy = 9,  // make_out_tmap only: the store map of out2
+  kGemmResidLnDeepF32 = 10,  // internal: kGemmResidLnF32 with six mainloop stages and a one-slab x ring (large K)
 };
 
 struct GemmLaunch {
@@ -54,6 +63,12 @@ struct GemmLaunch {
   int64_t ldo;
   const float* pos;   // patch-embed only: positional embedding [T, N]
   int T, G2;          // patch-embed only: tokens per crop, patches per crop
+  // LayerNorm-fused modes only
+  CUtensorMap tmap_out2;  // kGemmResidLnF32: store map of the bf16 copy (make_out_tmap(kGemmResidLnBf16Copy))
+  float2* stats;          // [M, nblk] (mean, M2) per 256-column block of the residual stream
+  int nblk;               // width / 256
+  float eps;
+  const float* colsum;    // kGemmLn*: [N]
 };
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 // store map for a GEMM output [M, N] (row stride ldo elements) matching `mode`
@@ -66,6 +81,12 @@ int layernorm_bf16_launch(const float* x, const float* gamma, const float* beta,
 int cls_pos_launch(float* x, const float* cls, const float* pos, int n, int T, int d, cudaStream_t stream);
 int layernorm_f32_inplace_launch(float* x, const float* gamma, const float* beta, int64_t M, int d, float eps,
                                  cudaStream_t stream);
+// LayerNorm-fused layer loop: ln_pre in place + bf16 copy + per-256-column (mean, M2) partials of the new rows
+int layernorm_pre_launch(float* x, const float* gamma, const float* beta, void* xb, float2* stats, int64_t M, int d,
+                         float eps, cudaStream_t stream);
+// wf = bf16(gamma ⊙ w) [N,K], colsum = row sums of wf, bias_f = bias + w·beta;  w: f32 or bf16 [N,K]
+int ln_fold_launch(const void* w, int w_dtype, const float* gamma, const float* beta, const float* bias, void* wf,
+                   float* colsum, float* bias_f, int N, int K, cudaStream_t stream);
 // pixels [n,3,R,R] (f32/f16/bf16) -> patches bf16[n, g*g, Kp]
 int patchify_launch(const void* pixels, int dtype, void* patches, int n, int R, int patch, int Kp, cudaStream_t stream);
 // out f32[n,E] = l2norm( LN(x[crop*T + 0, :]) @ proj[d,E] )

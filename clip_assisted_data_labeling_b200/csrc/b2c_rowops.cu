@@ -88,6 +88,143 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ln_pre for the LayerNorm-fused layer loop: x = LN(x) in place (f32) and, for the first block's fused ln_1,
+// the bf16 copy of the new row plus its (mean, M2) per 256-column block — what the kGemmResidLnF32 epilogue
+// (b2c_umma_pipeline2.cuh) leaves behind after every later residual update.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_pre_kernel(float* x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ xb,
+                                                            float2* __restrict__ stats, long long M, int d, float eps) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  float4* xr = reinterpret_cast<float4*>(x + row * d);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + e * e);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + i * 32 + lane);
+    const float4 b = __ldg(b4 + i * 32 + lane);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    v[i] = o;
+    xr[i * 32 + lane] = o;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&lo);
+    w.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(xb + row * d)[i * 32 + lane] = w;
+  }
+  // float4 group i covers columns [128 i, 128 i + 128): block j of 256 columns = groups 2j, 2j + 1
+#pragma unroll
+  for (int j = 0; j < NV / 2; ++j) {
+    const float4 a = v[2 * j], b = v[2 * j + 1];
+    const float bm = warp_sum(((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * (1.0f / 256.0f);
+    float bq = 0.f;
+    bq += (a.x - bm) * (a.x - bm) + (a.y - bm) * (a.y - bm) + (a.z - bm) * (a.z - bm) + (a.w - bm) * (a.w - bm);
+    bq += (b.x - bm) * (b.x - bm) + (b.y - bm) * (b.y - bm) + (b.z - bm) * (b.z - bm) + (b.w - bm) * (b.w - bm);
+    bq = warp_sum(bq);
+    if (lane == 0) stats[row * (NV / 2) + j] = make_float2(bm, bq);
+  }
+}
+
+int layernorm_pre_launch(float* x, const float* gamma, const float* beta, void* xb, float2* stats, int64_t M, int d,
+                         float eps, cudaStream_t stream) {
+  B2C_REQUIRE(d % 256 == 0 && d >= 256 && d <= 2048, "layernorm_pre: d=%d must be a multiple of 256 in [256,2048]", d);
+  B2C_REQUIRE(M > 0, "layernorm_pre: M must be positive");
+  const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(xb);
+  switch (d / 128) {
+    case 2: layernorm_pre_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    case 4: layernorm_pre_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    case 6: layernorm_pre_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    case 8: layernorm_pre_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    case 10: layernorm_pre_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    case 12: layernorm_pre_kernel<12><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    case 14: layernorm_pre_kernel<14><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    default: layernorm_pre_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+  }
+  B2C_POST_LAUNCH("layernorm_pre_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight folding for the fused LayerNorm:  LN(x)·Wᵀ + b = rstd·(x·W'ᵀ − mean·s) + b'   with
+//   W'[n,k] = bf16(gamma_k · W[n,k]),  s_n = sum_k float(W'[n,k]) (of the ROUNDED weights the tensor core multiplies),
+//   b'_n = b_n + sum_k beta_k · W[n,k].
+// One block per output row n.  SRC = float (the staged original) or __nv_bfloat16 (re-fold from the stored copy).
+// ------------------------------------------------------------------------------------------------
+template <typename SRC>
+__global__ void __launch_bounds__(256) ln_fold_kernel(const SRC* __restrict__ w, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      __nv_bfloat16* __restrict__ wf, float* __restrict__ colsum,
+                                                      float* __restrict__ bias_f, int K) {
+  const int n = blockIdx.x;
+  const SRC* wr = w + static_cast<size_t>(n) * K;
+  __nv_bfloat16* wo = wf + static_cast<size_t>(n) * K;
+  float s = 0.f, bs = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wv = load_as_float<SRC>(wr, k);
+    const __nv_bfloat16 r = __float2bfloat16_rn(gamma[k] * wv);
+    wo[k] = r;
+    s += __bfloat162float(r);
+    bs = fmaf(beta[k], wv, bs);
+  }
+  __shared__ float red[2][8];
+  s = warp_sum(s);
+  bs = warp_sum(bs);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = bs;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      a += red[0][i];
+      b += red[1][i];
+    }
+    colsum[n] = a;
+    bias_f[n] = (bias ? bias[n] : 0.f) + b;
+  }
+}
+
+int ln_fold_launch(const void* w, int w_dtype, const float* gamma, const float* beta, const float* bias, void* wf,
+                   float* colsum, float* bias_f, int N, int K, cudaStream_t stream) {
+  B2C_REQUIRE(w && gamma && beta && wf && colsum && bias_f && N > 0 && K > 0, "ln_fold: bad arguments");
+  if (w_dtype == B2C_F32)
+    ln_fold_kernel<float><<<N, 256, 0, stream>>>(static_cast<const float*>(w), gamma, beta, bias,
+                                                 static_cast<__nv_bfloat16*>(wf), colsum, bias_f, K);
+  else if (w_dtype == B2C_BF16)
+    ln_fold_kernel<__nv_bfloat16><<<N, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(w), gamma, beta, bias,
+                                                         static_cast<__nv_bfloat16*>(wf), colsum, bias_f, K);
+  else
+    return set_error(B2C_ERR_ARG, "ln_fold: source dtype %d", w_dtype);
+  B2C_POST_LAUNCH("ln_fold_kernel");
+  return 0;
+}
+
 template <bool OUT_BF16>
 static int layernorm_dispatch(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d,
                               float eps, cudaStream_t stream) {

@@ -12,19 +12,62 @@
 // Policy: as in b2c_umma_pipeline.cuh, plus
 //   __device__ static bool tile2(const Params&, int t, int& m_row, int& n_row)   // 256 x 256 tile origin; false = skip
 // Params must provide num_tiles2 and k_blocks.
+//
+// LayerNorm fusion (GemmPolicy modes kGemmLn* / kGemmResidLnF32, b2c_gemm.cu):
+//   * kStoreRmwLn (out_proj, c_proj): the epilogue owns the residual update.  Each epilogue warp streams its 32-row x
+//     32-column fp32 slabs of x through a 3-deep shared-memory ring: TMA load of the old values (issued two slabs
+//     ahead, across tile boundaries) -> += accumulator + bias in place -> TMA store of the new fp32 values, plus a
+//     bf16 copy of them (the A operand of the next GEMM) through two 64-B-swizzled half slabs.  Every thread owns one
+//     row and keeps (mean, M2) of its 256 columns (exact two-pass per 32-column slab, Chan's merge across slabs);
+//     the partials go to stats[row][n_block] — merged in a fixed order by the consumer, so results are deterministic.
+//   * Policy::kLnFold (in_proj, c_fc): LN(x)·Wᵀ = rstd·(x̃·(γ⊙W)ᵀ − μ·colsum(γ⊙W)) + (β·Wᵀ + b) — the epilogue thread
+//     merges its row's partials into (μ, rstd) once per tile and applies them with two FMAs per element.
+//   Together they remove the stand-alone LayerNorm kernels (and one fp32 read of x per LayerNorm) from the layer loop.
 #pragma once
 #include "b2c_umma_pipeline.cuh"
 
 namespace b2c {
 
+constexpr int kStoreRmwLn = 3;
 constexpr int kStages2 = 6;
 constexpr int kStage2Bytes = kABytes + kBM * kBK * 2;  // A 128 x 64 + B half 128 x 64 = 32 KB
-constexpr int kUmma2SmemBytes = kStages2 * kStage2Bytes + kStagingBytes + 1024 + 256;
+constexpr int kUmma2BarBytes = 320;
+constexpr int kUmma2SmemBytes = kStages2 * kStage2Bytes + kStagingBytes + 1024 + kUmma2BarBytes;
+// kStoreRmwLn, same total: Policy::kRmwRing fp32 slabs (4 KB) + 2 bf16 half slabs (2 KB) per epilogue warp, and as many
+// mainloop stages as still fit: ring 5 -> 4 stages (out_proj, K = d: the epilogue is the long pole, an x slab must be
+// requested ~4 slabs ahead), ring 3 -> 5 stages, ring 1 -> 6 stages (c_proj, K = 4d: the mainloop needs all six stages
+// to cover the L2 latency and leaves the epilogue four times the slack, so it can afford to wait for each slab).
+constexpr int kRmwMaxRing = 5;
+constexpr int kHalfSlabBytes = 32 * 64;
+constexpr int rmw_stages(int ring) { return ring == 5 ? 4 : ring == 3 ? 5 : 6; }
+constexpr int rmw_warp_bytes(int ring) { return ring * kSlabBytes + 2 * kHalfSlabBytes; }
+
+__device__ __forceinline__ uint32_t pack_bf16_pair(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// (mean, M2) of n_a + n_b values from the two parts' (mean, M2)   [Chan et al.]
+__device__ __forceinline__ void chan_merge(float& mean_a, float& m2_a, float n_a, float mean_b, float m2_b, float n_b) {
+  const float n = n_a + n_b;
+  const float delta = mean_b - mean_a;
+  const float w = n_b / n;
+  mean_a = fmaf(delta, w, mean_a);
+  m2_a = m2_a + m2_b + delta * delta * n_a * w;
+}
 
 template <class Policy>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * Policy::kEpiWarps, 1)
 umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_out, const typename Policy::Params p, const uint32_t idesc) {
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+                  const typename Policy::Params p, const uint32_t idesc) {
+  constexpr bool kRmw = Policy::kStore == kStoreRmwLn;
+  constexpr int kRmwRing = kRmw ? Policy::kRmwRing : 1;
+  static_assert(kRmwRing == 1 || kRmwRing == 3 || kRmwRing == 5, "x slab ring of 1, 3 or 5");
+  constexpr int kRmwWarpBytes = rmw_warp_bytes(kRmwRing);
+  constexpr int kStages2 = kRmw ? rmw_stages(kRmwRing) : b2c::kStages2;  // shadows the namespace constant inside the kernel
+  constexpr int kStagingBytes = kRmw ? 4 * kRmwWarpBytes : b2c::kStagingBytes;
+  static_assert(kStages2 * kStage2Bytes + kStagingBytes <= b2c::kStages2 * kStage2Bytes + b2c::kStagingBytes, "smem budget");
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = smem_raw2 + ((1024u - (smem_u32(smem_raw2) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST
   uint8_t* staging = smem + kStages2 * kStage2Bytes;
@@ -33,7 +76,9 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* empty_bar = bars + kStages2;                         // [kStages2]   (each CTA waits on its own)
   uint64_t* acc_full_bar = bars + 2 * kStages2;                  // [kAccStages] (each CTA waits on its own)
   uint64_t* acc_empty_bar = bars + 2 * kStages2 + kAccStages;    // [kAccStages] (leader's: 8 arrivals, 4 per CTA)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 2 * kAccStages);
+  uint64_t* x_bar = bars + 2 * kStages2 + 2 * kAccStages;        // [4 warps][kRmwMaxRing] (kStoreRmwLn: x slab has landed)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_bar + 4 * kRmwMaxRing);
+  static_assert((2 * kStages2 + 2 * kAccStages + 4 * kRmwMaxRing) * 8 + 4 <= kUmma2BarBytes, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -44,13 +89,17 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (Policy::kStore != kStoreDirect) tma_prefetch_desc(&tmap_out);
+    if (kRmw) {
+      tma_prefetch_desc(&tmap_out2);
+      for (int s = 0; s < 4 * kRmwMaxRing; ++s) mbar_init(&x_bar[s], 1);
+    }
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&acc_full_bar[s], 1);
-      mbar_init(&acc_empty_bar[s], 8);
+      mbar_init(&acc_empty_bar[s], 2 * Policy::kEpiWarps);  // one arrival per epilogue warp of both CTAs
     }
     mbar_fence_init();
   }
@@ -129,18 +178,82 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else {
     // ---------------------------------------------------------------- epilogue (warps 2..5, both CTAs)
+    // Nothing on the per-chunk critical path goes to global memory: the tile's bias / column-sum vectors live in
+    // registers (lane l holds columns l, l+32, ... and hands them out by shuffle; the next tile's are requested a tile
+    // ahead), the row statistics of the next tile are requested a tile ahead, the TMEM load of chunk c+1 is in flight
+    // while chunk c is processed, and (kStoreRmwLn) the old x slabs arrive through a ring filled kRmwRing-1 slabs ahead.
+    // Policy::kEpiWarps = 4: one warp per TMEM lane quarter, all 8 column chunks each.  8: two warps per quarter (one
+    // per SM sub-partition pair), 4 chunks each — the per-element epilogue work (bias / LayerNorm terms, activation,
+    // rounding, staging) is a single dependent instruction stream per warp, and with one warp per sub-partition it
+    // takes about as long as the tile's mainloop at K = 1024.
+    constexpr int kEpiWarps = Policy::kEpiWarps;
+    static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
+    static_assert(!kRmw || kEpiWarps == 4, "the read-modify-write epilogue is written for 4 warps");
+    constexpr int kSplit = kEpiWarps / 4;
+    constexpr int kWarpStaging = kRmw ? kRmwWarpBytes : kStagingBytes / kEpiWarps;
+    const int ew = warp - 2;
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint8_t* my_slabs = staging + (warp - 2) * (kSlabsPerWarp * kSlabBytes);
+    uint8_t* my_slabs = staging + ew * kWarpStaging;
+    const int row_off = static_cast<int>(rank) * kBM + quarter * 32;  // this warp's first row inside a 256-row tile
+    constexpr int kChunks = kBN / 32 / kSplit;                         // column chunks of a tile this warp handles
+    const int col_off = (ew >> 2) * kChunks * 32;                      // its first column inside the tile
+
+    // ---- kStoreRmwLn: slab ring state.  g = running index of the slab being processed (slot g % ring, barrier parity
+    // (g / ring) & 1); lane 0 also tracks the next slab to request: (ld_t, ld_c) with running index gi = g + max(ring - 1, 1).
+    [[maybe_unused]] uint32_t g = 0, gi = 0;
+    [[maybe_unused]] int ld_t = cid, ld_c = 0;
+    [[maybe_unused]] uint64_t* xb = x_bar + (ew & 3) * kRmwMaxRing;
+    auto issue_next_x = [&]() {
+      if (ld_t < p.num_tiles2) {
+        int m0 = 0, n0 = 0;
+        Policy::tile2(p, ld_t, m0, n0);
+        const uint32_t slot = gi % kRmwRing;
+        mbar_arrive_expect_tx(&xb[slot], kSlabBytes);
+        tma_load_2d(my_slabs + slot * kSlabBytes, &tmap_out, &xb[slot], n0 + ld_c * 32, m0 + row_off);
+      }
+      ++gi;
+      if (++ld_c == kChunks) { ld_c = 0; ld_t += ncl; }
+    };
+    if constexpr (kRmw) {
+      if (lane == 0)
+        for (int i = 0; i < (kRmwRing > 1 ? kRmwRing - 1 : 1); ++i) issue_next_x();
+    }
+
+    // ---- per-tile column vectors and row statistics, requested one tile ahead
+    [[maybe_unused]] float col_b[kChunks], col_s[kChunks], ncol_b[kChunks], ncol_s[kChunks];
+    [[maybe_unused]] float ln_a = 1.f, ln_b = 0.f;
+    [[maybe_unused]] float2 nst[8];
+    if constexpr (Policy::kStore != kStoreDirect) {
+      if (cid < p.num_tiles2) {
+        int m0 = 0, n0 = 0;
+        Policy::tile2(p, cid, m0, n0);
+        Policy::load_cols(p, n0 + col_off + lane, ncol_b, ncol_s);
+        if constexpr (Policy::kLnFold) Policy::load_row_stats(p, m0 + row_off + lane, nst);
+      }
+    }
+
     for (int t = cid; t < p.num_tiles2; t += ncl) {
       int m_row, b_row;
       if (!Policy::tile2(p, t, m_row, b_row)) continue;
       const int a_row = m_row + static_cast<int>(rank) * kBM;
       const int out_row = a_row + quarter * 32;
+      if constexpr (Policy::kStore != kStoreDirect) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) { col_b[c] = ncol_b[c]; col_s[c] = ncol_s[c]; }
+        if constexpr (Policy::kLnFold) Policy::merge_row_stats(p, out_row + lane, nst, ln_a, ln_b);
+        if (t + ncl < p.num_tiles2) {
+          int nm = 0, nn = 0;
+          Policy::tile2(p, t + ncl, nm, nn);
+          Policy::load_cols(p, nn + col_off + lane, ncol_b, ncol_s);
+          if constexpr (Policy::kLnFold) Policy::load_row_stats(p, nm + row_off + lane, nst);
+        }
+      }
       mbar_wait(&acc_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * kBN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * kBN + col_off + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int col0 = b_row + col_off;
       if constexpr (Policy::kStore == kStoreDirect) {
         // four 32-column TMEM loads in flight per wait: the load latency (contended by the running MMAs) is paid
         // twice per tile instead of eight times
@@ -157,59 +270,117 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c4 * 128 + 64, v2);
           Policy::epilogue(p, a_row, b_row, quarter * 32 + lane, c4 * 128 + 96, v3);
         }
-      }
-#pragma unroll 1
-      for (int c = 0; c < (Policy::kStore == kStoreDirect ? 0 : kBN / 32); ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        float f[32];
+      } else {
+        uint32_t vv[2][32];
+        tmem_ld_32x32(taddr, vv[0]);
+        [[maybe_unused]] float mean = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-        Policy::transform(p, b_row + c * 32, f);
-        if constexpr (Policy::kStore == kStoreTmaAddF32) {
-          uint8_t* slab = my_slabs + (c & 1) * kSlabBytes;
-          if (lane == 0) tma_store_wait_read<kSlabsPerWarp - 1>();
-          __syncwarp();
-          uint8_t* rowp = slab + lane * 128;
+        for (int c = 0; c < kChunks; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < kChunks) tmem_ld_32x32(taddr + (c + 1) * 32, vv[(c + 1) & 1]);
+          float f[32];
+          // lane e of the warp holds this chunk's bias (and column sum) for column e
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_reduce_add_2d(&tmap_out, slab, b_row + c * 32, out_row);
-            tma_store_commit();
+          for (int e = 0; e < 32; ++e) {
+            const float bs = __shfl_sync(0xffffffffu, col_b[c], e);
+            if constexpr (Policy::kLnFold) {
+              const float cs = __shfl_sync(0xffffffffu, col_s[c], e);
+              f[e] = fmaf(__uint_as_float(vv[c & 1][e]), ln_a, fmaf(cs, ln_b, bs));
+            } else {
+              f[e] = __uint_as_float(vv[c & 1][e]) + bs;
+            }
           }
-        } else {
-          uint8_t* slab = my_slabs + ((c >> 1) & 1) * kSlabBytes;
-          if ((c & 1) == 0) {
-            if (lane == 0) tma_store_wait_read<kSlabsPerWarp - 1>();
-            __syncwarp();
-          }
-          uint8_t* rowp = slab + lane * 128;
+          Policy::activate(f);
+          if constexpr (kRmw) {
+            const uint32_t slot = g % kRmwRing;
+            mbar_wait(&xb[slot], (g / kRmwRing) & 1);  // the old x values of this slab have landed
+            uint8_t* slab = my_slabs + slot * kSlabBytes;
+            uint8_t* rowp = slab + lane * 128;
+            float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 w;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            w.x = *reinterpret_cast<uint32_t*>(&t0);
-            w.y = *reinterpret_cast<uint32_t*>(&t1);
-            w.z = *reinterpret_cast<uint32_t*>(&t2);
-            w.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(rowp + ((((c & 1) * 4 + j) ^ (lane & 7)) << 4)) = w;
-          }
-          if (c & 1) {
+            for (int j = 0; j < 8; ++j) {
+              float4* q = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
+              const float4 xo = *q;
+              f[4 * j] += xo.x; f[4 * j + 1] += xo.y; f[4 * j + 2] += xo.z; f[4 * j + 3] += xo.w;
+              *q = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              s += (f[4 * j] + f[4 * j + 1]) + (f[4 * j + 2] + f[4 * j + 3]);
+            }
+            // statistics of the new row values: exact two-pass over the 32 columns in registers, merged into the tile's
+            const float cm = s * (1.0f / 32.0f);
+            float cq = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float dlt = f[e] - cm;
+              cq = fmaf(dlt, dlt, cq);
+            }
+            if (c == 0) { mean = cm; m2 = cq; }
+            else chan_merge(mean, m2, 32.0f * c, cm, cq, 32.0f);
+            // bf16 copy: 32 columns = 64 B per row, 16-byte chunk j at (j ^ ((row >> 1) & 3)): CU_TENSOR_MAP_SWIZZLE_64B
+            uint8_t* bslab = my_slabs + kRmwRing * kSlabBytes + (c & 1) * kHalfSlabBytes;
+            uint8_t* browp = bslab + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16_pair(f[8 * j + 0], f[8 * j + 1]);
+              w.y = pack_bf16_pair(f[8 * j + 2], f[8 * j + 3]);
+              w.z = pack_bf16_pair(f[8 * j + 4], f[8 * j + 5]);
+              w.w = pack_bf16_pair(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(browp + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmap_out, slab, b_row + (c - 1) * 32, out_row);
+              tma_store_2d(&tmap_out, slab, col0 + c * 32, out_row);
+              tma_store_2d(&tmap_out2, bslab, col0 + c * 32, out_row);
+              tma_store_commit();
+              // ring > 1: the PREVIOUS slab's stores have been read out -> its ring slot and half slab are free;
+              // ring 1: this slab's own stores, the next load goes into the same slot
+              tma_store_wait_read<(kRmwRing > 1 ? 1 : 0)>();
+              issue_next_x();
+            }
+            __syncwarp();
+            ++g;
+          } else if constexpr (Policy::kStore == kStoreTmaAddF32) {
+            constexpr int kAddSlabs = kWarpStaging / kSlabBytes;  // 1 (8 warps) or 2 (4 warps)
+            uint8_t* slab = my_slabs + (c % kAddSlabs) * kSlabBytes;
+            if (lane == 0) tma_store_wait_read<kAddSlabs - 1>();
+            __syncwarp();
+            uint8_t* rowp = slab + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmap_out, slab, col0 + c * 32, out_row);
+              tma_store_commit();
+            }
+          } else {
+            // bf16: one 32-column chunk = 64 B per row = one half slab (CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk j of
+            // row r at j ^ ((r >> 1) & 3)), stored per chunk and double-buffered against the TMA unit's reads
+            constexpr int kHalfSlabs = kWarpStaging / kHalfSlabBytes;
+            uint8_t* hslab = my_slabs + (c % kHalfSlabs) * kHalfSlabBytes;
+            if (lane == 0) tma_store_wait_read<kHalfSlabs - 1>();
+            __syncwarp();
+            uint8_t* rowp = hslab + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16_pair(f[8 * j + 0], f[8 * j + 1]);
+              w.y = pack_bf16_pair(f[8 * j + 2], f[8 * j + 3]);
+              w.z = pack_bf16_pair(f[8 * j + 4], f[8 * j + 5]);
+              w.w = pack_bf16_pair(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(rowp + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_out, hslab, col0 + c * 32, out_row);
               tma_store_commit();
             }
           }
         }
+        if constexpr (kRmw) Policy::store_row_stats(p, out_row + lane, b_row, mean, m2);
       }
       tc_fence_before();
       __syncwarp();

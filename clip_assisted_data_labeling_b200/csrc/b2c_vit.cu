@@ -24,6 +24,11 @@ struct b2c_vit_layer {
   float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
   CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;          // box 256 rows (single-CTA kernel)
   CUtensorMap tm_qkv_h, tm_out_h, tm_fc_h, tm_proj_h;  // box 128 rows (CTA-pair kernel)
+  // LayerNorm folded into in_proj / c_fc (ln_fold_kernel): gamma-scaled weights, their column sums, beta·Wᵀ + b
+  __nv_bfloat16 *wf_qkv = nullptr, *wf_fc = nullptr;
+  float *cs_qkv = nullptr, *bf_qkv = nullptr, *cs_fc = nullptr, *bf_fc = nullptr;
+  float *src_qkv = nullptr, *src_fc = nullptr;  // f32 staging of the original weights until the first fold
+  CUtensorMap tm_qkvf_h, tm_fcf_h;
 };
 
 struct b2c_vit {
@@ -34,6 +39,10 @@ struct b2c_vit {
   // that the HBM-bound stages of one lane (LayerNorm, the residual reduce-add tail, patchify) and the kernel heads /
   // tails of every stage run under the tensor-bound GEMMs of the other lane.
   int lanes = 2;
+  // LayerNorm fused into the GEMMs on either side of it (default; B2C_VIT_FUSED_LN=0 or b2c_vit_set_fused_ln(0)
+  // selects the stand-alone LayerNorm kernels + TMA reduce-add residual epilogue)
+  bool fused_ln = true;
+  bool fold_dirty = true;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
@@ -51,7 +60,7 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t x, h, big, patches, total;
+  size_t x, h, big, patches, xb, stats, total;
 };
 
 WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
@@ -68,6 +77,10 @@ WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
   off = align_up(off + M * wide * 2, 1024);
   w.patches = off;
   if (need_patches) off = align_up(off + static_cast<size_t>(nc) * v->G2 * v->Kp * 2, 1024);
+  w.xb = off;  // bf16 copy of the residual stream + per-row statistics partials (LayerNorm-fused layer loop)
+  off = align_up(off + M * d * 2, 1024);
+  w.stats = off;
+  off = align_up(off + M * (d / 256) * sizeof(float2), 1024);
   w.total = off;
   return w;
 }
@@ -132,6 +145,119 @@ int store_bf16(b2c_vit* v, __nv_bfloat16** dst, const void* src, int dtype, int6
               (long long)(rows * cols));
   B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(dst), static_cast<size_t>(rows) * cols_padded * 2));
   return pad_rows_bf16_launch(src, dtype, *dst, rows, cols, cols_padded, nullptr);
+}
+
+int stage_f32(float** dst, const void* src, int dtype, int64_t count) {
+  if (!*dst) B2C_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), static_cast<size_t>(count) * sizeof(float)));
+  return convert_launch(src, dtype, *dst, B2C_F32, count, nullptr);
+}
+
+// (re)compute the gamma-folded weights of every block; the f32 staging copies are released after their first use
+int ensure_folded(b2c_vit* v, cudaStream_t stream) {
+  if (!v->fold_dirty) return 0;
+  const b2c_vit_cfg& c = v->cfg;
+  const int d = c.width;
+  bool staged = false;
+  for (b2c_vit_layer& L : v->layers) {
+    B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(&L.wf_qkv), static_cast<size_t>(3) * d * d * 2));
+    B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(&L.wf_fc), static_cast<size_t>(c.mlp) * d * 2));
+    B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(&L.cs_qkv), static_cast<size_t>(3) * d * 4));
+    B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(&L.bf_qkv), static_cast<size_t>(3) * d * 4));
+    B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(&L.cs_fc), static_cast<size_t>(c.mlp) * 4));
+    B2C_TRY(alloc_dev(v, reinterpret_cast<void**>(&L.bf_fc), static_cast<size_t>(c.mlp) * 4));
+    B2C_TRY(ln_fold_launch(L.src_qkv ? static_cast<const void*>(L.src_qkv) : L.w_qkv, L.src_qkv ? B2C_F32 : B2C_BF16, L.ln1_w,
+                           L.ln1_b, L.b_qkv, L.wf_qkv, L.cs_qkv, L.bf_qkv, 3 * d, d, stream));
+    B2C_TRY(ln_fold_launch(L.src_fc ? static_cast<const void*>(L.src_fc) : L.w_fc, L.src_fc ? B2C_F32 : B2C_BF16, L.ln2_w,
+                           L.ln2_b, L.b_fc, L.wf_fc, L.cs_fc, L.bf_fc, c.mlp, d, stream));
+    B2C_TRY(make_tmap_2d(&L.tm_qkvf_h, L.wf_qkv, 3 * d, d, static_cast<uint64_t>(d) * 2, kBM, 1));
+    B2C_TRY(make_tmap_2d(&L.tm_fcf_h, L.wf_fc, c.mlp, d, static_cast<uint64_t>(d) * 2, kBM, 1));
+    staged = staged || L.src_qkv || L.src_fc;
+  }
+  if (staged) {
+    B2C_CHECK_CUDA(cudaStreamSynchronize(stream));
+    for (b2c_vit_layer& L : v->layers) {
+      if (L.src_qkv) cudaFree(L.src_qkv);
+      if (L.src_fc) cudaFree(L.src_fc);
+      L.src_qkv = L.src_fc = nullptr;
+    }
+  }
+  v->fold_dirty = false;
+  return 0;
+}
+
+// The layer loop with LayerNorm fused into the GEMMs on either side of it: no stand-alone LayerNorm launches, and the
+// residual stream is read once per residual update (by the GEMM epilogue that rewrites it) instead of twice.
+int forward_chunk_fused(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* ws, const WsLayout& w,
+                        cudaStream_t stream) {
+  const b2c_vit_cfg& c = v->cfg;
+  const int d = c.width;
+  const int nblk = d / 256;
+  const int64_t M = static_cast<int64_t>(nc) * v->T;
+  float* x = reinterpret_cast<float*>(ws + w.x);
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(ws + w.h);
+  __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(ws + w.big);
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + w.xb);
+  float2* stats = reinterpret_cast<float2*>(ws + w.stats);
+  const float eps = 1e-5f;
+
+  CUtensorMap tm_patches, tm_h, tm_xb, tm_mlp, st_qkv, st_mlp, st_x, st_xb;
+  B2C_TRY(make_tmap_2d(&tm_patches, patches, static_cast<uint64_t>(nc) * v->G2, v->Kp, static_cast<uint64_t>(v->Kp) * 2,
+                       kBM, 1));
+  B2C_TRY(make_tmap_2d(&tm_h, h, M, d, static_cast<uint64_t>(d) * 2, kBM, 1));
+  B2C_TRY(make_tmap_2d(&tm_xb, xb, M, d, static_cast<uint64_t>(d) * 2, kBM, 1));
+  B2C_TRY(make_tmap_2d(&tm_mlp, big, M, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBM, 1));
+  B2C_TRY(make_out_tmap(&st_qkv, big, M, 3 * d, 3 * d, kGemmBiasBf16));
+  B2C_TRY(make_out_tmap(&st_mlp, big, M, c.mlp, c.mlp, kGemmBiasBf16));
+  B2C_TRY(make_out_tmap(&st_x, x, M, d, d, kGemmResidLnF32));
+  B2C_TRY(make_out_tmap(&st_xb, xb, M, d, d, kGemmResidLnBf16Copy));
+
+  {
+    ProfScope ps(B2C_PROF_PATCH_EMBED, stream);
+    GemmLaunch gl{};
+    gl.tmap_a = tm_patches; gl.tmap_b = v->tm_conv1; gl.tmap_b_half = v->tm_conv1; gl.tmap_out = tm_patches;
+    gl.M = static_cast<int64_t>(nc) * v->G2; gl.N = d; gl.K = v->Kp; gl.mode = kGemmPatchEmbedF32;
+    gl.out = x; gl.ldo = d; gl.pos = v->pos; gl.T = v->T; gl.G2 = v->G2;
+    B2C_TRY(gemm_launch(gl, stream));
+  }
+  {
+    ProfScope ps(B2C_PROF_LAYERNORM, stream);
+    B2C_TRY(cls_pos_launch(x, v->cls, v->pos, nc, v->T, d, stream));
+    B2C_TRY(layernorm_pre_launch(x, v->ln_pre_w, v->ln_pre_b, xb, stats, M, d, eps, stream));
+  }
+  auto ln_gemm = [&](int kind, const CUtensorMap& tm_w, const CUtensorMap& st, int N, int mode, const float* bias_f,
+                     const float* colsum, int64_t ldo) -> int {
+    ProfScope ps(kind, stream);
+    GemmLaunch gl{};
+    gl.tmap_a = tm_xb; gl.tmap_b = tm_w; gl.tmap_b_half = tm_w; gl.tmap_out = st; gl.M = M; gl.N = N; gl.K = d;
+    gl.mode = mode; gl.bias = bias_f; gl.colsum = colsum; gl.stats = stats; gl.nblk = nblk; gl.eps = eps;
+    gl.out = big; gl.ldo = ldo;
+    return gemm_launch(gl, stream);
+  };
+  auto resid_gemm = [&](int kind, const CUtensorMap& tm_a, const CUtensorMap& tm_w_full, const CUtensorMap& tm_w, int K,
+                        const float* bias, bool last) -> int {
+    ProfScope ps(kind, stream);
+    GemmLaunch gl{};
+    gl.tmap_a = tm_a; gl.tmap_b = tm_w_full; gl.tmap_b_half = tm_w; gl.tmap_out = st_x; gl.tmap_out2 = st_xb;
+    gl.M = M; gl.N = d; gl.K = K; gl.bias = bias; gl.out = x; gl.ldo = d;
+    gl.stats = stats; gl.nblk = nblk; gl.eps = eps;
+    // nothing consumes the bf16 copy / statistics of the last residual update: plain reduce-add there
+    gl.mode = last ? kGemmBiasResidF32 : kGemmResidLnF32;
+    return gemm_launch(gl, stream);
+  };
+  const int fc_mode = c.act == B2C_ACT_GELU ? kGemmLnBiasGeluBf16 : kGemmLnBiasQGeluBf16;
+  for (int li = 0; li < c.layers; ++li) {
+    const b2c_vit_layer& L = v->layers[li];
+    B2C_TRY(ln_gemm(B2C_PROF_IN_PROJ, L.tm_qkvf_h, st_qkv, 3 * d, kGemmLnBiasBf16, L.bf_qkv, L.cs_qkv, 3 * d));
+    {
+      ProfScope ps(B2C_PROF_ATTENTION, stream);
+      B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
+    }
+    B2C_TRY(resid_gemm(B2C_PROF_OUT_PROJ, tm_h, L.tm_out, L.tm_out_h, d, L.b_out, false));
+    B2C_TRY(ln_gemm(B2C_PROF_C_FC, L.tm_fcf_h, st_mlp, c.mlp, fc_mode, L.bf_fc, L.cs_fc, c.mlp));
+    B2C_TRY(resid_gemm(B2C_PROF_C_PROJ, tm_mlp, L.tm_proj, L.tm_proj_h, c.mlp, L.b_proj, li + 1 == c.layers));
+  }
+  ProfScope ps(B2C_PROF_HEAD, stream);
+  return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, nc, v->T, d, c.embed, eps, stream);
 }
 
 int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* ws, const WsLayout& w,
@@ -235,6 +361,7 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
   B2C_REQUIRE(v && out && ws, "vit_forward: null pointer");
   B2C_REQUIRE(n > 0, "vit_forward: n_crops must be positive");
   B2C_TRY(b2c_vit_ready(v));
+  if (v->fused_ln) B2C_TRY(ensure_folded(v, stream));
   const int nc_max = n < v->chunk ? n : v->chunk;
   size_t lane_bytes = 0;
   const size_t need = ws_bytes_for(v, nc_max, pixels != nullptr, &lane_bytes);
@@ -255,7 +382,8 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
     } else {
       pch = static_cast<const uint8_t*>(patches) + static_cast<size_t>(c0) * v->G2 * v->Kp * 2;
     }
-    return forward_chunk(v, pch, nc, out + static_cast<size_t>(c0) * v->cfg.embed, wsl, w, st);
+    float* o = out + static_cast<size_t>(c0) * v->cfg.embed;
+    return v->fused_ln ? forward_chunk_fused(v, pch, nc, o, wsl, w, st) : forward_chunk(v, pch, nc, o, wsl, w, st);
   };
   for (int c0 = 0; c0 < n; c0 += nc_max) {
     const int nc = (n - c0) < nc_max ? (n - c0) : nc_max;
@@ -318,6 +446,7 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
     const int cv = atoi(e);
     if (cv > 0) v->chunk = cv;
   }
+  if (const char* e = getenv("B2C_VIT_FUSED_LN")) v->fused_ln = atoi(e) != 0;
   if (const char* e = getenv("B2C_VIT_LANES")) {
     const int lv = atoi(e);
     if (lv >= 1 && lv <= 4) v->lanes = lv;
@@ -330,6 +459,10 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
 extern "C" int b2c_vit_destroy(b2c_vit* v) {
   if (!v) return 0;
   for (void* p : v->allocs) cudaFree(p);
+  for (b2c_vit_layer& L : v->layers) {
+    if (L.src_qkv) cudaFree(L.src_qkv);
+    if (L.src_fc) cudaFree(L.src_fc);
+  }
   for (int i = 0; i < 3; ++i) {
     if (v->side[i]) {
       cudaStreamSynchronize(v->side[i]);
@@ -370,6 +503,9 @@ extern "C" int b2c_vit_set_weight(b2c_vit* v, const char* key, const void* dev_p
     B2C_REQUIRE(li >= 0 && li < c.layers, "b2c_vit_set_weight: layer index out of range in %s", key);
     b2c_vit_layer& L = v->layers[li];
     const std::string s = k.substr(dot + 1);
+    if (s.compare(0, 3, "ln_") == 0 || s == "attn.in_proj_weight" || s == "attn.in_proj_bias" || s == "mlp.c_fc.weight" ||
+        s == "mlp.c_fc.bias")
+      v->fold_dirty = true;
     if (s == "ln_1.weight") rc = store_f32(v, &L.ln1_w, dev_ptr, dtype, count, d, key);
     else if (s == "ln_1.bias") rc = store_f32(v, &L.ln1_b, dev_ptr, dtype, count, d, key);
     else if (s == "ln_2.weight") rc = store_f32(v, &L.ln2_w, dev_ptr, dtype, count, d, key);
@@ -380,6 +516,7 @@ extern "C" int b2c_vit_set_weight(b2c_vit* v, const char* key, const void* dev_p
     else if (s == "mlp.c_proj.bias") rc = store_f32(v, &L.b_proj, dev_ptr, dtype, count, d, key);
     else if (s == "attn.in_proj_weight") {
       rc = store_bf16(v, &L.w_qkv, dev_ptr, dtype, 3 * d, d, d, count, key);
+      if (rc == 0) rc = stage_f32(&L.src_qkv, dev_ptr, dtype, count);
       if (rc == 0) rc = make_tmap_2d(&L.tm_qkv, L.w_qkv, 3 * d, d, d * 2, kBN, 1);
       if (rc == 0) rc = make_tmap_2d(&L.tm_qkv_h, L.w_qkv, 3 * d, d, d * 2, kBM, 1);
     } else if (s == "attn.out_proj.weight") {
@@ -388,6 +525,7 @@ extern "C" int b2c_vit_set_weight(b2c_vit* v, const char* key, const void* dev_p
       if (rc == 0) rc = make_tmap_2d(&L.tm_out_h, L.w_out, d, d, d * 2, kBM, 1);
     } else if (s == "mlp.c_fc.weight") {
       rc = store_bf16(v, &L.w_fc, dev_ptr, dtype, c.mlp, d, d, count, key);
+      if (rc == 0) rc = stage_f32(&L.src_fc, dev_ptr, dtype, count);
       if (rc == 0) rc = make_tmap_2d(&L.tm_fc, L.w_fc, c.mlp, d, d * 2, kBN, 1);
       if (rc == 0) rc = make_tmap_2d(&L.tm_fc_h, L.w_fc, c.mlp, d, d * 2, kBM, 1);
     } else if (s == "mlp.c_proj.weight") {
@@ -417,6 +555,12 @@ extern "C" int b2c_vit_set_lanes(b2c_vit* v, int lanes) {
   B2C_REQUIRE(v, "b2c_vit_set_lanes: null handle");
   B2C_REQUIRE(lanes >= 1 && lanes <= 4, "b2c_vit_set_lanes: lanes %d out of range (1..4)", lanes);
   v->lanes = lanes;
+  return 0;
+}
+
+extern "C" int b2c_vit_set_fused_ln(b2c_vit* v, int on) {
+  B2C_REQUIRE(v, "b2c_vit_set_fused_ln: null handle");
+  v->fused_ln = on != 0;
   return 0;
 }
 

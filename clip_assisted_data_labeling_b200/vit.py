@@ -81,6 +81,10 @@ class VisionTower:
         """Number of independent sub-batches (own stream each) a pass is split into; see include/b2c.h."""
         _lib.check(self.lib.b2c_vit_set_lanes(self._h, int(lanes)), "b2c_vit_set_lanes")
 
+    def set_fused_ln(self, on: bool) -> None:
+        """LayerNorm folded into the GEMMs on either side of it (default) or stand-alone kernels; see include/b2c.h."""
+        _lib.check(self.lib.b2c_vit_set_fused_ln(self._h, 1 if on else 0), "b2c_vit_set_fused_ln")
+
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, n: int) -> torch.Tensor:
         need = C.c_size_t()

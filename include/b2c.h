@@ -137,6 +137,11 @@ int b2c_vit_ready(const b2c_vit* vit);
  * HBM-bound stages of one lane run under the tensor-bound GEMMs of another.  Results do not depend on it (crops are
  * independent units).  Set it BEFORE querying the workspace size.  The stage timer forces 1 lane while it is on. */
 int b2c_vit_set_lanes(b2c_vit* vit, int lanes);
+/* LayerNorm fusion (default on; env B2C_VIT_FUSED_LN=0): ln_1 / ln_2 are folded into in_proj / c_fc
+ * (gamma into the weight, mean / rstd applied to the accumulator per row) and the out_proj / c_proj epilogues own
+ * the residual update, leaving a bf16 copy of x and its row statistics for the next GEMM.  0 selects the stand-alone
+ * LayerNorm kernels.  Both compute LN(x)·Wᵀ + b of utils/embedder.py:98's tower within the same tolerance. */
+int b2c_vit_set_fused_ln(b2c_vit* vit, int on);
 int b2c_vit_workspace_bytes(const b2c_vit* vit, int n_crops, size_t* bytes);
 /* pixels: [n,3,R,R] (B2C_F32 / B2C_F16 / B2C_BF16), already normalised — the tensor the reference
  * feeds encode_image (utils/embedder.py:95-98).  out: f32[n,E], unit-norm rows (embedder.py:99). */

@@ -160,6 +160,34 @@ def test_encode_image_golden_and_batch_invariance(cuda, lib, golden, monkeypatch
     assert (again - got).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("arch,pretrained,n", [("ViT-B-32", "openai", 7), ("ViT-L-14", "openai", 3), ("ViT-H-14", "laion2b_s32b_b79k", 2)])
+def test_layernorm_fused_and_standalone_paths(cuda, lib, arch, pretrained, n):
+    """Both layer loops — LayerNorm folded into the GEMMs on either side of it (default) and the stand-alone LayerNorm
+    kernels (b2c_vit_set_fused_ln(0)) — meet the tolerance against the fp32 oracle, and agree with each other to the
+    same bound (they round the same quantities at different points)."""
+    from oracle import vit_oracle
+    tower, m = _tower_and_oracle(arch, pretrained)
+    R = m.cfg["image"]
+    px = torch.randn(n, 3, R, R, generator=torch.Generator().manual_seed(3))
+    ref = vit_oracle.encode_image_oracle(m, px)
+    got = {}
+    for fused in (True, False):
+        tower.set_fused_ln(fused)
+        got[fused] = tower.forward_pixels(px.cuda()).cpu()
+        _check_embeddings(ref, got[fused])
+    assert (got[True] - got[False]).abs().max().item() <= MAX_ABS
+    # re-setting a LayerNorm weight alone re-folds the GEMM weights (from the stored bf16 copy)
+    sd = vit_oracle.visual_state_dict(m)
+    key = "transformer.resblocks.0.ln_1.weight"
+    tower.load_state_dict({key: sd[key] * 1.5})
+    tower.set_fused_ln(True)
+    a = tower.forward_pixels(px.cuda()).cpu()
+    tower.set_fused_ln(False)
+    b = tower.forward_pixels(px.cuda()).cpu()
+    assert (a - got[True]).abs().max().item() > 1e-4  # the change took effect
+    assert (a - b).abs().max().item() <= MAX_ABS
+
+
 @pytest.mark.parametrize("arch,n", [("ViT-B-32", 333), ("ViT-L-14", 131)])
 def test_lanes_do_not_change_results(cuda, lib, arch, n):
     """A pass split into 2-4 sub-batches on separate streams (b2c_vit_set_lanes) returns the same bits as one lane:

@@ -61,7 +61,7 @@ for w in $WHAT; do
         -o $OUT/${TAG}_prof_gemm -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_gemm.log 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention -s 2 -c 1 \
         -o $OUT/${TAG}_prof_attn -f python tools/profile_attn.py 512 > $OUT/${TAG}_prof_attn.log 2>&1
-      timeout 300 ncu --set full --clock-control none --import-source on -k regex:layernorm -s 4 -c 1 \
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:layernorm -c 1 \
         -o $OUT/${TAG}_prof_ln -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_ln.log 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:resample_kernel -c 1 \
         -o $OUT/${TAG}_prof_pre -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_pre.log 2>&1

@@ -589,14 +589,10 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ void dot8(const uint4& a, const float* __restrict__ q, float& acc0, float& acc1) {
   const float4 qa = *reinterpret_cast<const float4*>(q);
   const float4 qb = *reinterpret_cast<const float4*>(q + 4);
-  acc0 = fmaf(bf16_lo(a.x), qa.x, acc0);
-  acc1 = fmaf(bf16_hi(a.x), qa.y, acc1);
-  acc0 = fmaf(bf16_lo(a.y), qa.z, acc0);
-  acc1 = fmaf(bf16_hi(a.y), qa.w, acc1);
-  acc0 = fmaf(bf16_lo(a.z), qb.x, acc0);
-  acc1 = fmaf(bf16_hi(a.z), qb.y, acc1);
-  acc0 = fmaf(bf16_lo(a.w), qb.z, acc0);
-  acc1 = fmaf(bf16_hi(a.w), qb.w, acc1);
+  ffma2(acc0, acc1, bf16_lo(a.x), bf16_hi(a.x), qa.x, qa.y, acc0, acc1);
+  ffma2(acc0, acc1, bf16_lo(a.y), bf16_hi(a.y), qa.z, qa.w, acc0, acc1);
+  ffma2(acc0, acc1, bf16_lo(a.z), bf16_hi(a.z), qb.x, qb.y, acc0, acc1);
+  ffma2(acc0, acc1, bf16_lo(a.w), bf16_hi(a.w), qb.z, qb.w, acc0, acc1);
 }
 
 // dot over the head dim of row `row` of an operand tile in shared memory (slab 1: 128-B swizzle, slab 2: 32-B swizzle)
@@ -1597,12 +1593,15 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       named_bar_sync(1 + w, 256);  // also publishes q0f / k0f / v0f
       m = fmaxf(m, mb->mx[w][h ^ 1][r]);
       const float ms = m * scale_log2;
+      const float nms = -ms;
       auto emit_p = [&](const uint32_t (&v)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          pk[e] = pack2(ex2_ftz(fmaf(__uint_as_float(v[2 * e]), scale_log2, -ms)),
-                        ex2_ftz(fmaf(__uint_as_float(v[2 * e + 1]), scale_log2, -ms)));
+        for (int e = 0; e < 16; ++e) {
+          float t0, t1;  // one FFMA2 per pair of scores
+          ffma2(t0, t1, __uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), scale_log2, scale_log2, nms, nms);
+          pk[e] = pack2(ex2_ftz(t0), ex2_ftz(t1));
+        }
         tmem_st_32x16(taddr + sbase_col + c * 16, pk);  // columns already consumed by this thread
       };
 #pragma unroll
@@ -1666,14 +1665,10 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
           // ks*8 + key has the same low 3 bits as key, so the swizzle phase depends on `key` only
           const uint4 a = *reinterpret_cast<const uint4*>(base + key * 128 + ((cc ^ key) << 4));
           const float pkey = pp[key];
-          acc[0] = fmaf(pkey, bf16_lo(a.x), acc[0]);
-          acc[1] = fmaf(pkey, bf16_hi(a.x), acc[1]);
-          acc[2] = fmaf(pkey, bf16_lo(a.y), acc[2]);
-          acc[3] = fmaf(pkey, bf16_hi(a.y), acc[3]);
-          acc[4] = fmaf(pkey, bf16_lo(a.z), acc[4]);
-          acc[5] = fmaf(pkey, bf16_hi(a.z), acc[5]);
-          acc[6] = fmaf(pkey, bf16_lo(a.w), acc[6]);
-          acc[7] = fmaf(pkey, bf16_hi(a.w), acc[7]);
+          ffma2(acc[0], acc[1], bf16_lo(a.x), bf16_hi(a.x), pkey, pkey, acc[0], acc[1]);
+          ffma2(acc[2], acc[3], bf16_lo(a.y), bf16_hi(a.y), pkey, pkey, acc[2], acc[3]);
+          ffma2(acc[4], acc[5], bf16_lo(a.z), bf16_hi(a.z), pkey, pkey, acc[4], acc[5]);
+          ffma2(acc[6], acc[7], bf16_lo(a.w), bf16_hi(a.w), pkey, pkey, acc[6], acc[7]);
         }
         *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -1715,10 +1710,18 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
           const float4 va4 = *reinterpret_cast<const float4*>(v0 + 8 * j);
           const float4 vb4 = *reinterpret_cast<const float4*>(v0 + 8 * j + 4);
           uint4 o4;
-          o4.x = pack2(fmaf(__uint_as_float(v[8 * j + 0]), inv, p0i * va4.x), fmaf(__uint_as_float(v[8 * j + 1]), inv, p0i * va4.y));
-          o4.y = pack2(fmaf(__uint_as_float(v[8 * j + 2]), inv, p0i * va4.z), fmaf(__uint_as_float(v[8 * j + 3]), inv, p0i * va4.w));
-          o4.z = pack2(fmaf(__uint_as_float(v[8 * j + 4]), inv, p0i * vb4.x), fmaf(__uint_as_float(v[8 * j + 5]), inv, p0i * vb4.y));
-          o4.w = pack2(fmaf(__uint_as_float(v[8 * j + 6]), inv, p0i * vb4.z), fmaf(__uint_as_float(v[8 * j + 7]), inv, p0i * vb4.w));
+          float t[8], o[8];
+          fmul2(t[0], t[1], va4.x, va4.y, p0i, p0i);
+          fmul2(t[2], t[3], va4.z, va4.w, p0i, p0i);
+          fmul2(t[4], t[5], vb4.x, vb4.y, p0i, p0i);
+          fmul2(t[6], t[7], vb4.z, vb4.w, p0i, p0i);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2)
+            ffma2(o[e], o[e + 1], __uint_as_float(v[8 * j + e]), __uint_as_float(v[8 * j + e + 1]), inv, inv, t[e], t[e + 1]);
+          o4.x = pack2(o[0], o[1]);
+          o4.y = pack2(o[2], o[3]);
+          o4.z = pack2(o[4], o[5]);
+          o4.w = pack2(o[6], o[7]);
           *reinterpret_cast<uint4*>(orow + 8 * j) = o4;
         }
       }

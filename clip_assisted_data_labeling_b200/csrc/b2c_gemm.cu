@@ -98,8 +98,16 @@ struct GemmPolicy {
 
   __device__ static __forceinline__ void activate(float (&f)[32]) {
     if constexpr (kQGelu) {
+      // x·sigmoid(1.702x) = hx + hx·tanh(0.851x), two elements per FMUL2 / FFMA2
 #pragma unroll
-      for (int e = 0; e < 32; ++e) f[e] = quick_gelu(f[e]);
+      for (int e = 0; e < 32; e += 2) {
+        float z0, z1, h0, h1, t0, t1;
+        fmul2(z0, z1, f[e], f[e + 1], 0.851f, 0.851f);
+        fmul2(h0, h1, f[e], f[e + 1], 0.5f, 0.5f);
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+        ffma2(f[e], f[e + 1], h0, h1, t0, t1, h0, h1);
+      }
     } else if constexpr (kGelu) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) f[e] = gelu_erf(f[e]);

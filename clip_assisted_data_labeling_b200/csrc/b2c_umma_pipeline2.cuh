@@ -281,13 +281,18 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           float f[32];
           // lane e of the warp holds this chunk's bias (and column sum) for column e
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float bs = __shfl_sync(0xffffffffu, col_b[c], e);
+          for (int e = 0; e < 32; e += 2) {
+            const float bs0 = __shfl_sync(0xffffffffu, col_b[c], e);
+            const float bs1 = __shfl_sync(0xffffffffu, col_b[c], e + 1);
             if constexpr (Policy::kLnFold) {
-              const float cs = __shfl_sync(0xffffffffu, col_s[c], e);
-              f[e] = fmaf(__uint_as_float(vv[c & 1][e]), ln_a, fmaf(cs, ln_b, bs));
+              const float cs0 = __shfl_sync(0xffffffffu, col_s[c], e);
+              const float cs1 = __shfl_sync(0xffffffffu, col_s[c], e + 1);
+              float t0, t1;  // two elements per FFMA2
+              ffma2(t0, t1, cs0, cs1, ln_b, ln_b, bs0, bs1);
+              ffma2(f[e], f[e + 1], __uint_as_float(vv[c & 1][e]), __uint_as_float(vv[c & 1][e + 1]), ln_a, ln_a, t0, t1);
             } else {
-              f[e] = __uint_as_float(vv[c & 1][e]) + bs;
+              f[e] = __uint_as_float(vv[c & 1][e]) + bs0;
+              f[e + 1] = __uint_as_float(vv[c & 1][e + 1]) + bs1;
             }
           }
           Policy::activate(f);

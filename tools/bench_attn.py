@@ -3,7 +3,7 @@ import ctypes as C, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-L = C.CDLL(os.path.join(ROOT, "clip_assisted_data_labeling_b200", "libb2c.so"))
+L = C.CDLL(os.environ.get("B2C_LIB") or os.path.join(ROOT, "clip_assisted_data_labeling_b200", "libb2c.so"))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 257
 heads = int(sys.argv[3]) if len(sys.argv) > 3 else 16

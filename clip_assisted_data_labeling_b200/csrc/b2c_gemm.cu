@@ -240,6 +240,8 @@ static int gemm_launch_classic(const GemmLaunch& g, const GemmParams& p, cudaStr
   return 0;
 }
 
+bool gemm_uses_cta_pairs() { return use_cta_pairs(); }
+
 int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, int mode) {
   if (mode == kGemmResidLnBf16Copy)  // the bf16 copy of the residual stream: 32 x 32 half slabs, 64-B swizzle
     return make_tmap_2d_sw(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 32,

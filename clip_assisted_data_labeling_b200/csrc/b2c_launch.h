@@ -71,6 +71,8 @@ struct GemmLaunch {
   const float* colsum;    // kGemmLn*: [N]
 };
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
+// false only under B2C_GEMM=1cta (A/B switch: single-CTA kernel everywhere; the LayerNorm-fused modes need CTA pairs)
+bool gemm_uses_cta_pairs();
 // store map for a GEMM output [M, N] (row stride ldo elements) matching `mode`
 int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, int mode);
 
@@ -89,9 +91,10 @@ int ln_fold_launch(const void* w, int w_dtype, const float* gamma, const float* 
                    float* colsum, float* bias_f, int N, int K, cudaStream_t stream);
 // pixels [n,3,R,R] (f32/f16/bf16) -> patches bf16[n, g*g, Kp]
 int patchify_launch(const void* pixels, int dtype, void* patches, int n, int R, int patch, int Kp, cudaStream_t stream);
-// out f32[n,E] = l2norm( LN(x[crop*T + 0, :]) @ proj[d,E] )
-int head_launch(const float* x, const float* gamma, const float* beta, const float* proj, float* out, int n, int T,
-                int d, int E, float eps, cudaStream_t stream);
+// out f32[n,E] = l2norm( LN(x[crop*T + 0, :]) @ proj[d,E] ); part: head_part_floats(n, E) floats of scratch
+int head_launch(const float* x, const float* gamma, const float* beta, const float* proj, float* out, float* part, int n,
+                int T, int d, int E, float eps, cudaStream_t stream);
+size_t head_part_floats(int n, int E);
 // generic dtype conversion used by set_weight: dst bf16/f32 <- src (f32/f16/bf16)
 int convert_launch(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, cudaStream_t stream);
 // conv1.weight [d,3,p,p] -> bf16 [d, Kp] zero padded

@@ -307,22 +307,24 @@ int patchify_launch(const void* pixels, int dtype, void* patches, int n, int R, 
 // Head: for CPB crops per block: y = LN(x[crop*T]) ; e = y @ proj[d,E] ; out = e / ||e||_2.
 // proj is read once per block (coalesced over E) and reused for the CPB crops.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadCPB = 4;
-constexpr int kHeadThreads = 256;
+constexpr int kHeadCPB = 8;       // crops per block
+constexpr int kHeadThreads = 256;  // = embedding columns per block
 
+// grid (crop groups of 8, column blocks of 256).  Warp w normalises the CLS row of crop w into shared memory, stored
+// k-major ([k][8 crops]) so that one k step is two 16-byte broadcast loads; thread t then owns column cb*256 + t for all
+// eight crops (proj is read once per crop group, coalesced).  The squared norm of each (crop, column block) goes to
+// `part` and head_norm_kernel divides by the full-row norm, summed in a fixed order (deterministic).
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
                                                             const float* __restrict__ proj, float* __restrict__ out,
-                                                            int n, int T, int d, int E, float eps) {
-  extern __shared__ float sm[];  // [kHeadCPB][d] normalised CLS rows, then [kHeadCPB][8] partial norms
+                                                            float* __restrict__ part, int n, int T, int d, int E, float eps) {
+  extern __shared__ __align__(16) float sm[];  // [d][kHeadCPB] normalised CLS rows, then [8 warps][kHeadCPB] partial norms
   float* ys = sm;
   float* red = sm + kHeadCPB * d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crop0 = blockIdx.x * kHeadCPB;
-  // LN of each CLS row by one warp (warps 0..CPB-1)
-  if (warp < kHeadCPB) {
+  {
     const int crop = crop0 + warp;
-    float* yr = ys + warp * d;
     if (crop < n) {
       const float* xr = x + static_cast<size_t>(crop) * T * d;
       float s = 0.f;
@@ -331,66 +333,66 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const float* __restr
       float q = 0.f;
       for (int i = lane; i < d; i += 32) { const float c = xr[i] - mean; q += c * c; }
       const float rstd = rsqrtf(warp_sum(q) / d + eps);
-      for (int i = lane; i < d; i += 32) yr[i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
+      for (int i = lane; i < d; i += 32) ys[i * kHeadCPB + warp] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
     } else {
-      for (int i = lane; i < d; i += 32) yr[i] = 0.f;
+      for (int i = lane; i < d; i += 32) ys[i * kHeadCPB + warp] = 0.f;
     }
   }
   __syncthreads();
-  // projection: thread owns columns e = tid, tid+256, ... (<= 4 for E <= 1024)
-  float acc[kHeadCPB][4];
+  const int e = blockIdx.y * kHeadThreads + threadIdx.x;
+  float acc[kHeadCPB];
 #pragma unroll
-  for (int c = 0; c < kHeadCPB; ++c)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
-  for (int k = 0; k < d; ++k) {
-    float w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = threadIdx.x + j * kHeadThreads;
-      w[j] = e < E ? __ldg(proj + static_cast<size_t>(k) * E + e) : 0.f;
-    }
-#pragma unroll
-    for (int c = 0; c < kHeadCPB; ++c) {
-      const float yv = ys[c * d + k];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[c][j] = fmaf(yv, w[j], acc[c][j]);
+  for (int c = 0; c < kHeadCPB; ++c) acc[c] = 0.f;
+  if (e < E) {
+    const float* pw = proj + e;
+#pragma unroll 4
+    for (int k = 0; k < d; ++k) {
+      const float w = __ldg(pw + static_cast<size_t>(k) * E);
+      const float4 ya = *reinterpret_cast<const float4*>(ys + k * kHeadCPB);
+      const float4 yb = *reinterpret_cast<const float4*>(ys + k * kHeadCPB + 4);
+      acc[0] = fmaf(ya.x, w, acc[0]); acc[1] = fmaf(ya.y, w, acc[1]); acc[2] = fmaf(ya.z, w, acc[2]); acc[3] = fmaf(ya.w, w, acc[3]);
+      acc[4] = fmaf(yb.x, w, acc[4]); acc[5] = fmaf(yb.y, w, acc[5]); acc[6] = fmaf(yb.z, w, acc[6]); acc[7] = fmaf(yb.w, w, acc[7]);
     }
   }
-  // L2 norm per crop
 #pragma unroll
   for (int c = 0; c < kHeadCPB; ++c) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s += acc[c][j] * acc[c][j];
-    s = warp_sum(s);
-    if (lane == 0) red[c * 8 + warp] = s;
+    const float s = warp_sum(acc[c] * acc[c]);
+    if (lane == 0) red[warp * kHeadCPB + c] = s;
+    if (e < E && crop0 + c < n) out[static_cast<size_t>(crop0 + c) * E + e] = acc[c];
   }
   __syncthreads();
-#pragma unroll
-  for (int c = 0; c < kHeadCPB; ++c) {
-    const int crop = crop0 + c;
-    if (crop >= n) break;
+  if (threadIdx.x < kHeadCPB && crop0 + threadIdx.x < n) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[c * 8 + w];
-    const float inv = 1.0f / sqrtf(s);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = threadIdx.x + j * kHeadThreads;
-      if (e < E) out[static_cast<size_t>(crop) * E + e] = acc[c][j] * inv;
-    }
+    for (int w = 0; w < 8; ++w) s += red[w * kHeadCPB + threadIdx.x];
+    part[static_cast<size_t>(crop0 + threadIdx.x) * gridDim.y + blockIdx.y] = s;
   }
 }
-int head_launch(const float* x, const float* gamma, const float* beta, const float* proj, float* out, int n, int T,
-                int d, int E, float eps, cudaStream_t stream) {
-  B2C_REQUIRE(E <= 4 * kHeadThreads, "head: E=%d exceeds %d", E, 4 * kHeadThreads);
-  const size_t smem = (static_cast<size_t>(kHeadCPB) * d + kHeadCPB * 8) * sizeof(float);
+
+// out[crop, :] /= sqrt(sum of the crop's column-block partials)        (utils/embedder.py:99, no eps)
+__global__ void __launch_bounds__(256) head_norm_kernel(float* __restrict__ out, const float* __restrict__ part, int n,
+                                                        int E, int nparts) {
+  const int crop = blockIdx.x;
+  float s = 0.f;
+  for (int j = 0; j < nparts; ++j) s += part[static_cast<size_t>(crop) * nparts + j];
+  const float inv = 1.0f / sqrtf(s);
+  for (int e = threadIdx.x; e < E; e += blockDim.x) out[static_cast<size_t>(crop) * E + e] *= inv;
+}
+
+int head_launch(const float* x, const float* gamma, const float* beta, const float* proj, float* out, float* part, int n,
+                int T, int d, int E, float eps, cudaStream_t stream) {
+  B2C_REQUIRE(part, "head: null partial-norm buffer");
+  const size_t smem = (static_cast<size_t>(kHeadCPB) * d + 8 * kHeadCPB) * sizeof(float);
   B2C_REQUIRE(smem <= 48 * 1024, "head: d=%d too wide", d);
-  head_kernel<<<(n + kHeadCPB - 1) / kHeadCPB, kHeadThreads, smem, stream>>>(x, gamma, beta, proj, out, n, T, d, E, eps);
+  const dim3 grid((n + kHeadCPB - 1) / kHeadCPB, (E + kHeadThreads - 1) / kHeadThreads);
+  head_kernel<<<grid, kHeadThreads, smem, stream>>>(x, gamma, beta, proj, out, part, n, T, d, E, eps);
   B2C_POST_LAUNCH("head_kernel");
+  head_norm_kernel<<<n, 256, 0, stream>>>(out, part, n, E, static_cast<int>(grid.y));
+  B2C_POST_LAUNCH("head_norm_kernel");
   return 0;
 }
+// floats of scratch head_launch needs for n crops and E columns
+size_t head_part_floats(int n, int E) { return static_cast<size_t>(n) * ((E + kHeadThreads - 1) / kHeadThreads); }
 
 // ------------------------------------------------------------------------------------------------
 // dtype conversion / row padding for weights

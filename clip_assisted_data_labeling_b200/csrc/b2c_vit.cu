@@ -60,7 +60,7 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t x, h, big, patches, xb, stats, total;
+  size_t x, h, big, patches, xb, stats, head, total;
 };
 
 WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
@@ -81,6 +81,8 @@ WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
   off = align_up(off + M * d * 2, 1024);
   w.stats = off;
   off = align_up(off + M * (d / 256) * sizeof(float2), 1024);
+  w.head = off;  // partial squared norms of the head's column blocks
+  off = align_up(off + head_part_floats(nc, v->cfg.embed) * sizeof(float), 1024);
   w.total = off;
   return w;
 }
@@ -257,7 +259,8 @@ int forward_chunk_fused(b2c_vit* v, const void* patches, int nc, float* out, uin
     B2C_TRY(resid_gemm(B2C_PROF_C_PROJ, tm_mlp, L.tm_proj, L.tm_proj_h, c.mlp, L.b_proj, li + 1 == c.layers));
   }
   ProfScope ps(B2C_PROF_HEAD, stream);
-  return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, nc, v->T, d, c.embed, eps, stream);
+  return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, reinterpret_cast<float*>(ws + w.head), nc, v->T, d, c.embed,
+                     eps, stream);
 }
 
 int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* ws, const WsLayout& w,
@@ -353,7 +356,8 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     }
   }
   ProfScope ps(B2C_PROF_HEAD, stream);
-  return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, nc, v->T, d, c.embed, eps, stream);
+  return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, reinterpret_cast<float*>(ws + w.head), nc, v->T, d, c.embed,
+                     eps, stream);
 }
 
 int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches, int n, float* out, void* ws,
@@ -361,7 +365,8 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
   B2C_REQUIRE(v && out && ws, "vit_forward: null pointer");
   B2C_REQUIRE(n > 0, "vit_forward: n_crops must be positive");
   B2C_TRY(b2c_vit_ready(v));
-  if (v->fused_ln) B2C_TRY(ensure_folded(v, stream));
+  const bool fused = v->fused_ln && gemm_uses_cta_pairs();
+  if (fused) B2C_TRY(ensure_folded(v, stream));
   const int nc_max = n < v->chunk ? n : v->chunk;
   size_t lane_bytes = 0;
   const size_t need = ws_bytes_for(v, nc_max, pixels != nullptr, &lane_bytes);
@@ -383,7 +388,7 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
       pch = static_cast<const uint8_t*>(patches) + static_cast<size_t>(c0) * v->G2 * v->Kp * 2;
     }
     float* o = out + static_cast<size_t>(c0) * v->cfg.embed;
-    return v->fused_ln ? forward_chunk_fused(v, pch, nc, o, wsl, w, st) : forward_chunk(v, pch, nc, o, wsl, w, st);
+    return fused ? forward_chunk_fused(v, pch, nc, o, wsl, w, st) : forward_chunk(v, pch, nc, o, wsl, w, st);
   };
   for (int c0 = 0; c0 < n; c0 += nc_max) {
     const int nc = (n - c0) < nc_max ? (n - c0) : nc_max;
@@ -432,7 +437,7 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
   const int hd = cfg->width / cfg->heads;
   B2C_REQUIRE(hd == 64 || hd == 80, "b2c_vit_create: head dim %d unsupported (64 or 80)", hd);
   B2C_REQUIRE(cfg->layers > 0 && cfg->layers <= 64, "b2c_vit_create: layers %d", cfg->layers);
-  B2C_REQUIRE(cfg->embed > 0 && cfg->embed <= 1024, "b2c_vit_create: embed %d out of range", cfg->embed);
+  B2C_REQUIRE(cfg->embed > 0 && cfg->embed <= 4096, "b2c_vit_create: embed %d out of range", cfg->embed);
   B2C_REQUIRE(cfg->act == B2C_ACT_QUICK_GELU || cfg->act == B2C_ACT_GELU, "b2c_vit_create: act %d", cfg->act);
   b2c_vit* v = new b2c_vit();
   v->cfg = *cfg;

@@ -25,7 +25,7 @@ import random
 import torch
 from torch.utils.data import DataLoader
 
-from .embedder import CLIP_Encoder, RawImageDataset, collate_raw
+from .embedder import CLIP_Encoder, RawImageDataset, collate_raw, to_device_images
 from .vit_arch import CROP_NAMES
 
 IMG_EXTENSIONS = (".png", ".jpg", ".jpeg", ".JPEG", ".JPG", ".PNG")  # _1_embed_with_CLIP.py:47
@@ -86,7 +86,7 @@ class Feature_Dataset:
     def __init__(self, root_dir, model_name, batch_size, model_path=None, force_reencode=False, shuffle_filenames=True,
                  num_workers=0, crop_names=("centre_crop", "square_padded_crop", "subcrop1", "subcrop2"),
                  rank=None, world_size=None, state_dict=None, encoder=None, writer_threads=4, packed_dir=None,
-                 write_pt=True, img_stats=None):
+                 write_pt=True, img_stats=None, device_jpeg=None):
         self.device = getattr(encoder, "device", "cuda") if encoder is not None else "cuda"
         self.root_dir = root_dir
         self.model_name = model_name
@@ -115,7 +115,9 @@ class Feature_Dataset:
         else:
             raise ValueError(f"Unknown model format: {model_name}. Expected 'PE-...' or 'Arch/Dataset'.")
 
-        self.img_dataset = RawImageDataset(self.img_filepaths)
+        # baseline JPEGs: workers only Huffman-decode, the device finishes the decode (K14); everything else stays on Pillow
+        self.device_jpeg = str(self.device).startswith("cuda") if device_jpeg is None else bool(device_jpeg)
+        self.img_dataset = RawImageDataset(self.img_filepaths, device_jpeg=self.device_jpeg)
         kw = dict(batch_size=batch_size, shuffle=False, num_workers=num_workers, collate_fn=collate_raw)
         if num_workers > 0:
             kw["prefetch_factor"] = 2
@@ -161,7 +163,7 @@ class Feature_Dataset:
                     todo_img_paths.append(p)
             if todo_imgs:
                 if str(self.device).startswith("cuda"):
-                    dev_imgs = [im.pin_memory().to(self.device, non_blocking=True) for im in todo_imgs]
+                    dev_imgs = to_device_images(todo_imgs, self.device)
                 else:  # only reachable with an injected encoder (host-logic tests)
                     dev_imgs = todo_imgs
                 feats = self.encoder.encode_images_u8(dev_imgs).cpu()  # [B,4,E], one D2H per batch
@@ -170,7 +172,7 @@ class Feature_Dataset:
                     from .imgstats import image_stats, stats_dict
                     stats = image_stats(dev_imgs).cpu()
                 kept_all = []
-                for bi, (im, f, sp) in enumerate(zip(todo_imgs, feats, todo_paths)):
+                for bi, (im, f, sp) in enumerate(zip(dev_imgs, feats, todo_paths)):
                     g = (_lib.Crop * 4)()
                     _lib.check(lib.b2c_crop_geometry(int(im.shape[1]), int(im.shape[0]), R, g), "b2c_crop_geometry")
                     kept = [g[i].cw > 0 for i in range(4)]

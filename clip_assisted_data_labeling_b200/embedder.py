@@ -176,27 +176,61 @@ class CustomImageDataset(Dataset):
 
 
 class RawImageDataset(Dataset):
-    """Decode only: returns (uint8 HWC tensor | None, path).  Crops, resize and normalisation run on the
-    GPU (b2c_preprocess_4crop).  A file that fails to decode yields ``None`` and is reported by the driver
-    (no silent substitution)."""
+    """Decode only: returns (item, path).  Crops, resize and normalisation run on the GPU (b2c_preprocess_4crop).
+    item is
+      * ``("jpeg", info_bytes, int16 coefficients)`` for a baseline JPEG when ``device_jpeg`` is on: the worker does
+        the serial part (marker parse + Huffman decode, jpeg.entropy_decode) and the main process finishes the decode
+        on the device (jpeg.reconstruct) — bit-exact with Pillow, SURVEY.md §8f row 2;
+      * a uint8 HWC tensor decoded with Pillow (`Image.open(path).convert('RGB')`, utils/embedder.py:167) for every
+        other format and for JPEG streams the device path does not cover;
+      * ``None`` for a file that fails to decode — reported by the driver, never silently substituted."""
 
-    def __init__(self, image_paths):
+    def __init__(self, image_paths, device_jpeg: bool = False):
         self.image_paths = image_paths
+        self.device_jpeg = device_jpeg
 
     def __len__(self):
         return len(self.image_paths)
 
     def __getitem__(self, idx):
+        import io
         import numpy as np
         from PIL import Image
         path = self.image_paths[idx]
         try:
-            with Image.open(path) as im:
+            src = path
+            if self.device_jpeg and path.lower().endswith((".jpg", ".jpeg")):
+                from . import jpeg
+                with open(path, "rb") as fh:
+                    data = fh.read()
+                try:
+                    info, coefs = jpeg.entropy_decode(data)
+                    return ("jpeg", bytes(info), coefs), path
+                except jpeg.UnsupportedJPEG:
+                    src = io.BytesIO(data)  # progressive, CMYK, ...: Pillow decodes the bytes already read
+            with Image.open(src) as im:
                 arr = np.asarray(im.convert("RGB"))
             return torch.from_numpy(np.ascontiguousarray(arr)), path
         except Exception as e:  # noqa: BLE001
             print(f"Error loading image {path}: {e}")
             return None, path
+
+
+def to_device_images(items, device):
+    """RawImageDataset items (no ``None``) -> uint8 [H,W,3] device tensors, same order: Pillow-decoded tensors are copied,
+    entropy-decoded JPEGs are reconstructed on the device in one batched call."""
+    from . import jpeg
+    out = [None] * len(items)
+    jobs, where = [], []
+    for i, it in enumerate(items):
+        if isinstance(it, tuple) and it[0] == "jpeg":
+            jobs.append((jpeg.JpegInfo.from_buffer_copy(it[1]), it[2]))
+            where.append(i)
+        else:
+            out[i] = it.pin_memory().to(device, non_blocking=True)
+    for i, t in zip(where, jpeg.reconstruct(jobs, device)):
+        out[i] = t
+    return out
 
 
 def collate_raw(batch):

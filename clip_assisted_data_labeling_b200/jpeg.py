@@ -1,0 +1,92 @@
+"""K14 host side: JPEG files -> uint8 [H,W,3] device tensors, bit-exact with `Image.open(path).convert('RGB')`
+(utils/embedder.py:167) for the streams include/b2c.h's b2c_jpeg_* covers.
+
+`entropy_decode` (marker parse + Huffman decode, pure host work, no CUDA call, releases the GIL inside ctypes) is what
+DataLoader workers run instead of Pillow's full decode; `reconstruct` (dequantise + inverse DCT + chroma upsampling +
+colour conversion) is one batched device call on the main process.  A stream the device path does not cover raises
+`UnsupportedJPEG`; the driver then keeps that file on the Pillow path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ERR_UNSUPPORTED = -5
+
+
+class JpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32), ("hs", C.c_int32 * 3),
+                ("vs", C.c_int32 * 3), ("mcus_x", C.c_int32), ("mcus_y", C.c_int32), ("blocks_w", C.c_int32 * 3),
+                ("blocks_h", C.c_int32 * 3), ("comp_w", C.c_int32 * 3), ("comp_h", C.c_int32 * 3),
+                ("restart_interval", C.c_int32), ("adobe_transform0", C.c_int32), ("coef_offset", C.c_int64 * 3),
+                ("coef_count", C.c_int64), ("qt", (C.c_uint16 * 64) * 3)]
+
+    def as_dict(self) -> dict:
+        return {"width": self.width, "height": self.height, "ncomp": self.ncomp, "hs": list(self.hs), "vs": list(self.vs),
+                "blocks_w": list(self.blocks_w), "blocks_h": list(self.blocks_h), "comp_w": list(self.comp_w),
+                "comp_h": list(self.comp_h), "coef_offset": list(self.coef_offset), "coef_count": self.coef_count,
+                "qt": [list(q) for q in self.qt], "restart_interval": self.restart_interval}
+
+
+class UnsupportedJPEG(ValueError):
+    """The stream is valid but outside what the device path decodes (progressive, CMYK, ...)."""
+
+
+def _raise(rc: int, what: str):
+    msg = _lib.load().b2c_last_error().decode("utf-8", "replace")
+    if rc == ERR_UNSUPPORTED:
+        raise UnsupportedJPEG(msg)
+    raise _lib.B2CError(f"{what} failed (code {rc}): {msg}")
+
+
+def entropy_decode(data: bytes, pin: bool = False) -> Tuple[JpegInfo, torch.Tensor]:
+    """JPEG bytes -> (info, int16 coefficient tensor on the host).  Host only; safe in worker processes."""
+    lib = _lib.load()
+    info = JpegInfo()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    rc = lib.b2c_jpeg_parse(buf, len(data), C.byref(info))
+    if rc != 0:
+        _raise(rc, "b2c_jpeg_parse")
+    coefs = torch.empty(int(info.coef_count), dtype=torch.int16, pin_memory=pin)
+    rc = lib.b2c_jpeg_decode_coefs(buf, len(data), C.byref(info), C.c_void_p(coefs.data_ptr()), coefs.numel())
+    if rc != 0:
+        _raise(rc, "b2c_jpeg_decode_coefs")
+    return info, coefs
+
+
+def reconstruct(items: Sequence[Tuple[JpegInfo, torch.Tensor]], device="cuda") -> List[torch.Tensor]:
+    """[(info, host coefficients)] -> [uint8 [H,W,3] device tensors]; one H2D copy and two kernel launches per batch."""
+    if not items:
+        return []
+    lib = _lib.load()
+    dev = torch.device(device)
+    n = len(items)
+    with torch.cuda.device(dev):
+        infos = (JpegInfo * n)(*[it[0] for it in items])
+        flat = torch.cat([it[1] for it in items]) if n > 1 else items[0][1]
+        dflat = flat.to(dev, non_blocking=True)
+        outs = [torch.empty(it[0].height, it[0].width, 3, dtype=torch.uint8, device=dev) for it in items]
+        need = C.c_size_t()
+        _lib.check(lib.b2c_jpeg_workspace_bytes(infos, n, C.byref(need)), "b2c_jpeg_workspace_bytes")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        offs = np.concatenate([[0], np.cumsum([int(it[0].coef_count) for it in items])])
+        cptr = (C.c_void_p * n)(*[dflat.data_ptr() + 2 * int(o) for o in offs[:-1]])
+        optr = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        pitch = (C.c_int * n)(*[3 * it[0].width for it in items])
+        _lib.check(lib.b2c_jpeg_reconstruct(infos, cptr, optr, pitch, n, C.c_void_p(ws.data_ptr()), ws.numel(),
+                                            C.c_void_p(_lib.current_stream_ptr())), "b2c_jpeg_reconstruct")
+        # ws / dflat are released to torch's caching allocator in stream order after the launches above
+    return outs
+
+
+def decode_files(paths: Sequence[str], device="cuda") -> List[torch.Tensor]:
+    """Convenience: read + entropy-decode on this thread, reconstruct on the device."""
+    items = []
+    for p in paths:
+        with open(p, "rb") as fh:
+            items.append(entropy_decode(fh.read()))
+    return reconstruct(items, device)

@@ -26,6 +26,7 @@ extern "C" {
 #define B2C_ERR_CUDA (-2)        /* a CUDA runtime or driver call failed (incl. no usable device) */
 #define B2C_ERR_STATE (-3)       /* handle not ready (e.g. missing weights) */
 #define B2C_ERR_WORKSPACE (-4)   /* workspace too small */
+#define B2C_ERR_UNSUPPORTED (-5) /* valid input this path does not cover (b2c_jpeg_*: keep the file on the host decoder) */
 
 typedef void* b2c_stream; /* cudaStream_t */
 
@@ -296,6 +297,39 @@ unsigned long long b2c_trainer_steps(const b2c_trainer* t); /* optimiser steps t
  * f32, += the mean squared error of every step (train_loss of _4_train_model.py:203) or NULL.  Asynchronous. */
 int b2c_trainer_epoch(b2c_trainer* t, const float* feats, int64_t feat_stride, const float* labels, const int32_t* order,
                       int64_t n, int batch, const b2c_adam* hyper, float* loss_sum, b2c_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K14 — JPEG decode ahead of K0.  Replaces `Image.open(path).convert('RGB')` of
+ * CustomImageDataset.__getitem__ (utils/embedder.py:167) for baseline JPEG files, bit-exactly with Pillow /
+ * libjpeg-turbo at its defaults (islow inverse DCT, "fancy" chroma upsampling, 16-bit fixed-point YCbCr -> RGB).
+ * Split along the one serial stage: Huffman decoding runs on the host (b2c_jpeg_decode_coefs, thread-safe, no CUDA
+ * calls — DataLoader workers use it), everything after it on the device (b2c_jpeg_reconstruct, batched).
+ * Streams this path does not cover — progressive, arithmetic-coded, 12-bit, CMYK / Adobe RGB, multi-scan, sampling
+ * other than 4:4:4 / 4:2:2 / 4:2:0 / grey — return B2C_ERR_UNSUPPORTED and stay on the caller's Pillow path.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t width, height, ncomp;     /* ncomp 1 (grey) or 3 (YCbCr) */
+  int32_t hs[3], vs[3];             /* sampling factors per component */
+  int32_t mcus_x, mcus_y;
+  int32_t blocks_w[3], blocks_h[3]; /* 8x8 blocks per component, whole MCUs */
+  int32_t comp_w[3], comp_h[3];     /* real samples per component (libjpeg's downsampled_width / _height) */
+  int32_t restart_interval;
+  int32_t adobe_transform0;
+  int64_t coef_offset[3];           /* component c's blocks start at coefs + coef_offset[c]; block (by,bx) at +(by*blocks_w+bx)*64 */
+  int64_t coef_count;               /* int16 elements the coefficient buffer needs */
+  uint16_t qt[3][64];               /* quantisation table of each component, natural (row-major) order */
+} b2c_jpeg_info;
+
+/* Host only: marker parse; fills `info` (sizes for the coefficient buffer). */
+int b2c_jpeg_parse(const uint8_t* data, size_t len, b2c_jpeg_info* info);
+/* Host only: parse + sequential Huffman decode into `coefs` (HOST memory, ideally pinned; capacity in int16 elements):
+ * de-zigzagged, not dequantised. */
+int b2c_jpeg_decode_coefs(const uint8_t* data, size_t len, b2c_jpeg_info* info, int16_t* coefs, size_t capacity);
+int b2c_jpeg_workspace_bytes(const b2c_jpeg_info* infos, int n, size_t* bytes);
+/* Device: coefs[i] = DEVICE copy of image i's coefficient buffer, outs[i] = DEVICE uint8 [height, width, 3] with row
+ * pitch out_pitch[i] bytes.  infos / pointer arrays are host arrays.  Two launches for the whole batch. */
+int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* const* coefs, uint8_t* const* outs,
+                         const int* out_pitch, int n, void* ws, size_t ws_bytes, b2c_stream stream);
 
 #ifdef __cplusplus
 }

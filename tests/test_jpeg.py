@@ -1,0 +1,147 @@
+"""K14 (JPEG decode ahead of K0).  The checker is Pillow itself — the library the reference decodes
+with (`Image.open(path).convert('RGB')`, utils/embedder.py:167) and which is installed on both boxes — so every case is
+compared bit for bit with `PIL.Image.open(...).convert('RGB')`.
+  not gpu: the host stage (marker parse + Huffman decode through the C-ABI) feeding oracle/jpeg_oracle.py's numpy
+           restatement of the device stage; refusal of streams outside the covered set; corrupt input.
+  gpu:     the device stage (b2c_jpeg_reconstruct) on ragged batches, and the embedding driver end to end on .jpg files."""
+import io
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import jpeg_oracle
+from oracle.preprocess_oracle import synthetic_image
+
+CASES = [  # (W, H, subsampling, quality, extra save kwargs)
+    (64, 64, 0, 90, {}), (512, 512, 2, 90, {}), (513, 511, 2, 75, {}), (200, 300, 1, 95, {}), (37, 911, 0, 50, {}),
+    (640, 427, 2, 85, {"optimize": True}), (33, 17, 2, 100, {}), (16, 16, 1, 30, {}), (1000, 3, 2, 80, {}),
+    (301, 200, "gray", 80, {}), (256, 256, 2, 90, {"restart_marker_blocks": 4}), (255, 257, 1, 60, {"restart_marker_rows": 1}),
+    (8, 8, 0, 70, {}), (2, 2, 0, 70, {}), (9, 1, "gray", 70, {}), (1280, 960, 2, 5, {}),
+]
+
+
+def make_jpeg(w, h, sub, q, kw, seed=0):
+    rng = np.random.default_rng(seed + w * 7 + h)
+    im = synthetic_image(w + h, h, w) if min(w, h) >= 100 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    pil = Image.fromarray(im)
+    buf = io.BytesIO()
+    if sub == "gray":
+        pil.convert("L").save(buf, "JPEG", quality=q, **kw)
+    else:
+        pil.save(buf, "JPEG", quality=q, subsampling=sub, **kw)
+    data = buf.getvalue()
+    return data, np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}x{c[1]}-s{c[2]}-q{c[3]}")
+def test_host_huffman_stage_and_oracle_vs_pillow(lib, case):
+    from clip_assisted_data_labeling_b200 import jpeg
+    data, ref = make_jpeg(*case)
+    info, coefs = jpeg.entropy_decode(data)
+    assert (info.width, info.height) == (case[0], case[1]) and info.ncomp == (1 if case[2] == "gray" else 3)
+    assert coefs.dtype == torch.int16 and coefs.numel() == info.coef_count
+    got = jpeg_oracle.reconstruct(info.as_dict(), coefs.numpy())
+    assert np.array_equal(got, ref)
+
+
+def test_streams_outside_the_covered_set_are_refused_not_misdecoded(lib):
+    from clip_assisted_data_labeling_b200 import _lib, jpeg
+    im = Image.fromarray(synthetic_image(1, 120, 160))
+    for kw in ({"progressive": True}, ):
+        buf = io.BytesIO()
+        im.save(buf, "JPEG", quality=85, **kw)
+        with pytest.raises(jpeg.UnsupportedJPEG):
+            jpeg.entropy_decode(buf.getvalue())
+    buf = io.BytesIO()
+    im.convert("CMYK").save(buf, "JPEG", quality=85)
+    with pytest.raises(jpeg.UnsupportedJPEG):
+        jpeg.entropy_decode(buf.getvalue())
+    buf = io.BytesIO()
+    im.save(buf, "JPEG", quality=85, subsampling=0)
+    good = buf.getvalue()
+    with pytest.raises(_lib.B2CError):
+        jpeg.entropy_decode(b"\x89PNG\r\n" + good[6:])           # not a JPEG
+    with pytest.raises(_lib.B2CError):
+        jpeg.entropy_decode(good[:200])                           # truncated inside the headers
+    # truncated entropy data: libjpeg pads with zeros and Pillow raises/warns; this path must not crash either way
+    info, coefs = jpeg.entropy_decode(good[:len(good) // 2] + b"\xff\xd9")
+    assert coefs.numel() == info.coef_count
+
+
+def test_dataset_items_fall_back_to_pillow_per_file(lib, tmp_path):
+    """RawImageDataset(device_jpeg=True): baseline .jpg -> coefficient item; progressive .jpg and .png -> Pillow tensors."""
+    from clip_assisted_data_labeling_b200.embedder import RawImageDataset
+    im = Image.fromarray(synthetic_image(3, 90, 70))
+    im.save(tmp_path / "a.jpg", quality=90)
+    im.save(tmp_path / "b.jpg", quality=90, progressive=True)
+    im.save(tmp_path / "c.png")
+    (tmp_path / "d.jpg").write_bytes(b"")
+    ds = RawImageDataset([str(tmp_path / n) for n in ("a.jpg", "b.jpg", "c.png", "d.jpg")], device_jpeg=True)
+    a, b, c, d = (ds[i][0] for i in range(4))
+    assert isinstance(a, tuple) and a[0] == "jpeg" and a[2].dtype == torch.int16
+    assert isinstance(b, torch.Tensor) and np.array_equal(b.numpy(), np.asarray(Image.open(tmp_path / "b.jpg").convert("RGB")))
+    assert isinstance(c, torch.Tensor) and tuple(c.shape) == (90, 70, 3)
+    assert d is None
+
+
+@pytest.mark.gpu
+def test_device_reconstruct_ragged_batch_vs_pillow(lib):
+    from clip_assisted_data_labeling_b200 import jpeg
+    made = [make_jpeg(*c) for c in CASES]
+    items = [jpeg.entropy_decode(d) for d, _ in made]
+    outs = jpeg.reconstruct(items)                       # one batch: every sampling / size / restart variant together
+    for (data, ref), got, case in zip(made, outs, CASES):
+        assert np.array_equal(got.cpu().numpy(), ref), case
+    again = jpeg.reconstruct(items[3:5])                 # workspace / descriptor reuse with a different batch
+    assert np.array_equal(again[0].cpu().numpy(), made[3][1]) and np.array_equal(again[1].cpu().numpy(), made[4][1])
+
+
+@pytest.mark.gpu
+def test_device_reconstruct_many_random_streams(lib):
+    """Property run: 60 random sizes / qualities / samplings, noise and smooth content, all in two batches."""
+    from clip_assisted_data_labeling_b200 import jpeg
+    rng = np.random.default_rng(5)
+    made = []
+    for k in range(60):
+        w, h = (int(v) for v in rng.integers(2, 400, 2))
+        sub = [0, 1, 2, "gray"][k % 4]
+        kw = {"restart_marker_blocks": int(rng.integers(1, 9))} if k % 5 == 0 else ({"optimize": True} if k % 7 == 0 else {})
+        made.append(make_jpeg(w, h, sub, int(rng.integers(1, 101)), kw, seed=k))
+    items, refs = [], []
+    for data, ref in made:
+        try:
+            items.append(jpeg.entropy_decode(data))
+            refs.append(ref)
+        except jpeg.UnsupportedJPEG:  # subsampled images narrower than two chroma samples stay on Pillow
+            assert ref.shape[1] <= 2
+    assert len(items) >= 55
+    for lo in (0, 30):
+        outs = jpeg.reconstruct(items[lo:lo + 30])
+        for ref, got in zip(refs[lo:lo + 30], outs):
+            assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_driver_embeds_jpg_files_identically_to_the_pillow_path(lib, tmp_path):
+    """Feature_Dataset on .jpg files: device_jpeg on vs off write the same .pt contents (same decoded pixels -> same bits)."""
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from oracle import vit_oracle
+    m = vit_oracle.build_visual("ViT-B-32", "openai", seed=0)
+    sd = vit_oracle.visual_state_dict(m)
+    res = {}
+    for mode in (True, False):
+        root = tmp_path / f"ds{int(mode)}"
+        root.mkdir()
+        for k in range(6):
+            Image.fromarray(synthetic_image(k, 150 + 20 * k, 210)).save(root / f"{k:02d}.jpg", quality=88, subsampling=[2, 1, 0][k % 3],
+                                                                       progressive=(k == 5))
+        ds = Feature_Dataset(str(root), "ViT-B-32/openai", batch_size=4, shuffle_filenames=False, state_dict=sd, device_jpeg=mode)
+        n, _ = ds.process()
+        assert n == 6 and not ds.failed
+        res[mode] = [torch.load(root / f"{k:02d}.pt")["ViT-B-32/openai"] for k in range(6)]
+    for a, b in zip(res[True], res[False]):
+        assert list(a.keys()) == list(b.keys())
+        for key in a:
+            assert torch.equal(a[key], b[key]), key

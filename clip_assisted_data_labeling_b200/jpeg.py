@@ -58,29 +58,59 @@ def entropy_decode(data: bytes, pin: bool = False) -> Tuple[JpegInfo, torch.Tens
     return info, coefs
 
 
-def reconstruct(items: Sequence[Tuple[JpegInfo, torch.Tensor]], device="cuda") -> List[torch.Tensor]:
-    """[(info, host coefficients)] -> [uint8 [H,W,3] device tensors]; one H2D copy and two kernel launches per batch."""
-    if not items:
-        return []
-    lib = _lib.load()
-    dev = torch.device(device)
-    n = len(items)
-    with torch.cuda.device(dev):
-        infos = (JpegInfo * n)(*[it[0] for it in items])
-        flat = torch.cat([it[1] for it in items]) if n > 1 else items[0][1]
+class _Staging:
+    """Grow-only pinned host buffer the coefficient tensors of a batch are gathered into before one async H2D copy; the
+    event guards the buffer against being refilled while the previous copy still reads it."""
+    buf = None
+    event = None
+
+    @classmethod
+    def gather(cls, tensors, dev):
+        total = sum(t.numel() for t in tensors)
+        if cls.buf is None or cls.buf.numel() < total:
+            cls.buf = torch.empty(max(total, 1 << 20), dtype=torch.int16, pin_memory=True)
+            cls.event = None
+        if cls.event is not None:
+            cls.event.synchronize()
+        flat = cls.buf[:total]
+        torch.cat(tensors, out=flat) if len(tensors) > 1 else flat.copy_(tensors[0])
         dflat = flat.to(dev, non_blocking=True)
-        outs = [torch.empty(it[0].height, it[0].width, 3, dtype=torch.uint8, device=dev) for it in items]
+        cls.event = torch.cuda.Event()
+        cls.event.record()
+        return dflat
+
+
+def reconstruct_device(infos: Sequence[JpegInfo], dflat: torch.Tensor) -> List[torch.Tensor]:
+    """Device stage alone: `dflat` = the batch's coefficient buffers back to back on the device, in `infos` order."""
+    lib = _lib.load()
+    n = len(infos)
+    dev = dflat.device
+    with torch.cuda.device(dev):
+        arr = (JpegInfo * n)(*infos)
+        outs = [torch.empty(i.height, i.width, 3, dtype=torch.uint8, device=dev) for i in infos]
         need = C.c_size_t()
-        _lib.check(lib.b2c_jpeg_workspace_bytes(infos, n, C.byref(need)), "b2c_jpeg_workspace_bytes")
+        _lib.check(lib.b2c_jpeg_workspace_bytes(arr, n, C.byref(need)), "b2c_jpeg_workspace_bytes")
         ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
-        offs = np.concatenate([[0], np.cumsum([int(it[0].coef_count) for it in items])])
+        offs = np.concatenate([[0], np.cumsum([int(i.coef_count) for i in infos])])
+        assert int(offs[-1]) <= dflat.numel() and dflat.dtype == torch.int16 and dflat.is_contiguous()
         cptr = (C.c_void_p * n)(*[dflat.data_ptr() + 2 * int(o) for o in offs[:-1]])
         optr = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
-        pitch = (C.c_int * n)(*[3 * it[0].width for it in items])
-        _lib.check(lib.b2c_jpeg_reconstruct(infos, cptr, optr, pitch, n, C.c_void_p(ws.data_ptr()), ws.numel(),
+        pitch = (C.c_int * n)(*[3 * i.width for i in infos])
+        _lib.check(lib.b2c_jpeg_reconstruct(arr, cptr, optr, pitch, n, C.c_void_p(ws.data_ptr()), ws.numel(),
                                             C.c_void_p(_lib.current_stream_ptr())), "b2c_jpeg_reconstruct")
-        # ws / dflat are released to torch's caching allocator in stream order after the launches above
+        # ws / dflat go back to torch's caching allocator in stream order, after the launches above
     return outs
+
+
+def reconstruct(items: Sequence[Tuple[JpegInfo, torch.Tensor]], device="cuda") -> List[torch.Tensor]:
+    """[(info, host coefficients)] -> [uint8 [H,W,3] device tensors]: one gather into pinned memory, one H2D copy and two
+    kernel launches per batch."""
+    if not items:
+        return []
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        dflat = _Staging.gather([it[1] for it in items], dev)
+    return reconstruct_device([it[0] for it in items], dflat)
 
 
 def decode_files(paths: Sequence[str], device="cuda") -> List[torch.Tensor]:

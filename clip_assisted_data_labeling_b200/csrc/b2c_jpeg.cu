@@ -1,15 +1,16 @@
 // b2c_jpeg.cu — K14: JPEG decode for the embedding path (the step immediately before K0).
-// Replaces `Image.open(path).convert('RGB')` of CustomImageDataset.__getitem__ (utils/embedder.py:167) for baseline
-// JPEG files, bit-exactly with what Pillow returns (libjpeg-turbo, default settings: JDCT_ISLOW, fancy upsampling,
-// YCbCr -> RGB with 16-bit fixed-point tables):
-//   host   b2c_jpeg_parse / b2c_jpeg_decode_coefs : marker parse + sequential Huffman decode -> int16 coefficient
-//          blocks (natural order) per component.  The only inherently serial stage; runs on the DataLoader workers.
+// Replaces `Image.open(path).convert('RGB')` of CustomImageDataset.__getitem__ (utils/embedder.py:167) for Huffman-coded
+// 8-bit JPEG files (baseline, extended sequential, progressive), bit-exactly with what Pillow returns (libjpeg-turbo,
+// default settings: JDCT_ISLOW, fancy upsampling, YCbCr -> RGB with 16-bit fixed-point tables):
+//   host   b2c_jpeg_parse / b2c_jpeg_decode_coefs : marker parse + Huffman decode of every scan (sequential blocks;
+//          progressive DC / AC first and refinement passes with end-of-band runs) -> int16 coefficient blocks (natural
+//          order) per component.  The only inherently serial stage; runs on the DataLoader workers.
 //   device b2c_jpeg_reconstruct : dequantise + 8x8 inverse DCT (the 13-bit "islow" integer transform) -> component
 //          planes; triangle-filter chroma upsampling (h2v1 / h2v2) + colour conversion -> uint8 [H,W,3] in HBM, the
 //          layout b2c_preprocess_4crop and b2c_image_stats read.  Batched: one launch pair for a list of images.
-// Anything else (progressive, arithmetic coding, 12-bit, CMYK, multi-scan, exotic sampling) is refused with
+// Anything else (arithmetic coding, lossless, 12-bit, CMYK / Adobe RGB, exotic sampling) is refused with
 // B2C_ERR_UNSUPPORTED so that the caller keeps the file on the Pillow path.  The arithmetic below restates the
-// published libjpeg algorithms (jidctint.c, jdsample.c, jdcolor.c, jdhuff.c of libjpeg-turbo 3.1, the library Pillow 12.2
+// published libjpeg algorithms (jidctint.c, jdsample.c, jdcolor.c, jdhuff.c, jdphuff.c of libjpeg-turbo 3.1, the library Pillow 12.2
 // links); it is checked against Pillow itself in tests/test_jpeg.py.
 #include <string.h>
 
@@ -38,13 +39,23 @@ struct HuffTable {
   int16_t fast_ac[512];
 };
 
+struct Scan {
+  int ns = 0;
+  int ci[3];          // component indices of the frame
+  int td[3], ta[3];   // Huffman table ids
+  int ss = 0, se = 63, ah = 0, al = 0;
+  size_t begin = 0;   // first entropy-coded byte
+};
+
 struct Parsed {
   b2c_jpeg_info info;
   HuffTable dc[4], ac[4];
   uint16_t qt[4][64];  // natural order
   bool qt_present[4] = {false, false, false, false};
-  int comp_id[3], comp_tq[3], comp_td[3], comp_ta[3];
-  size_t scan_begin = 0;  // first entropy-coded byte
+  int comp_id[3], comp_tq[3];
+  bool latched[3] = {false, false, false};  // quantisation table captured at the component's first scan (jdinput.c)
+  bool have_sof = false;
+  bool progressive = false;
 };
 
 int fail_unsupported(const char* what) { return set_error(B2C_ERR_UNSUPPORTED, "jpeg: unsupported stream (%s)", what); }
@@ -85,27 +96,57 @@ int build_huff(HuffTable& t, const uint8_t* counts, const uint8_t* vals, int nva
   return 0;
 }
 
-int parse(const uint8_t* d, size_t n, Parsed& P) {
-  if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return fail_corrupt("no SOI marker");
+int frame_geometry(Parsed& P) {
   b2c_jpeg_info& I = P.info;
-  memset(&I, 0, sizeof(I));
-  size_t pos = 2;
-  bool have_sof = false;
+  int hmax = 1, vmax = 1;
+  for (int c = 0; c < I.ncomp; ++c) {
+    hmax = I.hs[c] > hmax ? I.hs[c] : hmax;
+    vmax = I.vs[c] > vmax ? I.vs[c] : vmax;
+  }
+  if (I.ncomp == 1) {  // a single-component scan is never interleaved: the MCU is one block, sampling factors are moot
+    I.hs[0] = I.vs[0] = 1;
+    hmax = vmax = 1;
+  } else {
+    // supported chroma layouts: 4:4:4 (1x1), 4:2:2 (2x1), 4:2:0 (2x2); both chroma components alike
+    const bool ok = I.hs[1] == 1 && I.vs[1] == 1 && I.hs[2] == 1 && I.vs[2] == 1 &&
+                    ((I.hs[0] == 1 && I.vs[0] == 1) || (I.hs[0] == 2 && I.vs[0] == 1) || (I.hs[0] == 2 && I.vs[0] == 2));
+    if (!ok) return fail_unsupported("chroma sampling other than 4:4:4, 4:2:2, 4:2:0");
+  }
+  I.mcus_x = (I.width + 8 * hmax - 1) / (8 * hmax);
+  I.mcus_y = (I.height + 8 * vmax - 1) / (8 * vmax);
+  int64_t off = 0;
+  for (int c = 0; c < I.ncomp; ++c) {
+    I.blocks_w[c] = I.mcus_x * I.hs[c];
+    I.blocks_h[c] = I.mcus_y * I.vs[c];
+    I.comp_w[c] = (I.width * I.hs[c] + hmax - 1) / hmax;   // libjpeg's downsampled_width / _height: the real samples
+    I.comp_h[c] = (I.height * I.vs[c] + vmax - 1) / vmax;
+    I.coef_offset[c] = off;
+    off += static_cast<int64_t>(I.blocks_w[c]) * I.blocks_h[c] * 64;
+  }
+  I.coef_count = off;
+  if (I.ncomp == 3 && I.comp_w[1] < 2 && I.hs[0] == 2) return fail_unsupported("image narrower than two chroma samples");
+  return 0;
+}
+
+// Walks the marker segments from `pos` (tables, frame header, ...) up to and including the next SOS header.
+// Returns 0 with `scan` filled, 1 at EOI / end of data, < 0 on error.
+int next_scan(const uint8_t* d, size_t n, size_t& pos, Parsed& P, Scan& scan) {
+  b2c_jpeg_info& I = P.info;
   while (true) {
-    if (pos + 4 > n) return fail_corrupt("truncated before SOS");
-    if (d[pos] != 0xFF) return fail_corrupt("marker expected");
-    while (pos < n && d[pos] == 0xFF) ++pos;  // fill bytes
-    if (pos >= n) return fail_corrupt("truncated marker");
-    const int m = d[pos++];
+    // skip anything up to the next marker (padding, or the unread tail of an entropy-coded segment)
+    while (pos + 1 < n && !(d[pos] == 0xFF && d[pos + 1] != 0x00 && d[pos + 1] != 0xFF)) ++pos;
+    if (pos + 1 >= n) return P.have_sof ? 1 : fail_corrupt("truncated before SOS");
+    const int m = d[pos + 1];
+    pos += 2;
     if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;  // standalone markers
-    if (m == 0xD9) return fail_corrupt("EOI before SOS");
+    if (m == 0xD9) return 1;
     if (pos + 2 > n) return fail_corrupt("truncated segment");
     const size_t len = (static_cast<size_t>(d[pos]) << 8) | d[pos + 1];
     if (len < 2 || pos + len > n) return fail_corrupt("segment length");
     const uint8_t* s = d + pos + 2;
     const size_t sl = len - 2;
-    if (m == 0xC0 || m == 0xC1) {  // baseline / extended sequential, Huffman
-      if (have_sof) return fail_corrupt("two frame headers");
+    if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // baseline / extended sequential / progressive, Huffman
+      if (P.have_sof) return fail_corrupt("two frame headers");
       if (sl < 6) return fail_corrupt("SOF length");
       if (s[0] != 8) return fail_unsupported("sample precision other than 8 bits");
       I.height = (s[1] << 8) | s[2];
@@ -121,9 +162,13 @@ int parse(const uint8_t* d, size_t n, Parsed& P) {
         P.comp_tq[c] = s[8 + 3 * c];
         if (I.hs[c] < 1 || I.hs[c] > 4 || I.vs[c] < 1 || I.vs[c] > 4 || P.comp_tq[c] > 3) return fail_corrupt("sampling factors");
       }
-      have_sof = true;
-    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-      return fail_unsupported(m == 0xC2 ? "progressive" : "lossless / hierarchical / arithmetic frame type");
+      if (I.adobe_transform0 && I.ncomp == 3) return fail_unsupported("Adobe RGB (untransformed) colour space");
+      P.have_sof = true;
+      P.progressive = m == 0xC2;
+      I.progressive = P.progressive ? 1 : 0;
+      B2C_TRY(frame_geometry(P));
+    } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      return fail_unsupported("lossless / hierarchical / arithmetic frame type");
     } else if (m == 0xCC) {
       return fail_unsupported("arithmetic coding conditioning");
     } else if (m == 0xC4) {  // DHT
@@ -154,62 +199,64 @@ int parse(const uint8_t* d, size_t n, Parsed& P) {
       if (sl < 2) return fail_corrupt("DRI length");
       I.restart_interval = (s[0] << 8) | s[1];
     } else if (m == 0xEE) {  // APP14 Adobe: transform 0 with three components means RGB data, not YCbCr
-      if (sl >= 12 && memcmp(s, "Adobe", 5) == 0 && s[11] == 0 && have_sof && I.ncomp == 3)
-        return fail_unsupported("Adobe RGB (untransformed) colour space");
-      if (sl >= 12 && memcmp(s, "Adobe", 5) == 0 && s[11] == 0) I.adobe_transform0 = 1;
-    } else if (m == 0xDA) {  // SOS
-      if (!have_sof) return fail_corrupt("SOS before SOF");
-      if (I.adobe_transform0 && I.ncomp == 3) return fail_unsupported("Adobe RGB (untransformed) colour space");
-      if (sl < 1) return fail_corrupt("SOS length");
-      const int ns = s[0];
-      if (ns != I.ncomp) return fail_unsupported("multi-scan (non-interleaved) stream");
-      if (sl < 1 + 2 * static_cast<size_t>(ns) + 3) return fail_corrupt("SOS length");
-      for (int k = 0; k < ns; ++k) {
-        if (s[1 + 2 * k] != P.comp_id[k]) return fail_unsupported("scan component order differs from the frame");
-        P.comp_td[k] = s[2 + 2 * k] >> 4;
-        P.comp_ta[k] = s[2 + 2 * k] & 15;
-        if (P.comp_td[k] > 3 || P.comp_ta[k] > 3 || !P.dc[P.comp_td[k]].present || !P.ac[P.comp_ta[k]].present)
-          return fail_corrupt("scan refers to an undefined Huffman table");
-        if (!P.qt_present[P.comp_tq[k]]) return fail_corrupt("component refers to an undefined quantisation table");
+      if (sl >= 12 && memcmp(s, "Adobe", 5) == 0 && s[11] == 0) {
+        if (P.have_sof && I.ncomp == 3) return fail_unsupported("Adobe RGB (untransformed) colour space");
+        I.adobe_transform0 = 1;
       }
-      const uint8_t* tail = s + 1 + 2 * ns;
-      if (tail[0] != 0 || tail[1] != 63 || tail[2] != 0) return fail_unsupported("spectral selection / successive approximation");
-      P.scan_begin = pos + len;
-      break;
+    } else if (m == 0xDA) {  // SOS
+      if (!P.have_sof) return fail_corrupt("SOS before SOF");
+      if (sl < 1) return fail_corrupt("SOS length");
+      scan.ns = s[0];
+      if (scan.ns < 1 || scan.ns > I.ncomp) return fail_corrupt("scan component count");
+      if (sl < 1 + 2 * static_cast<size_t>(scan.ns) + 3) return fail_corrupt("SOS length");
+      for (int k = 0; k < scan.ns; ++k) {
+        int ci = -1;
+        for (int c = 0; c < I.ncomp; ++c)
+          if (P.comp_id[c] == s[1 + 2 * k]) ci = c;
+        if (ci < 0 || (k > 0 && ci <= scan.ci[k - 1])) return fail_corrupt("scan component selector");
+        scan.ci[k] = ci;
+        scan.td[k] = s[2 + 2 * k] >> 4;
+        scan.ta[k] = s[2 + 2 * k] & 15;
+        if (scan.td[k] > 3 || scan.ta[k] > 3) return fail_corrupt("scan Huffman table id");
+        if (!P.latched[ci]) {
+          if (!P.qt_present[P.comp_tq[ci]]) return fail_corrupt("component refers to an undefined quantisation table");
+          for (int i = 0; i < 64; ++i) I.qt[ci][i] = P.qt[P.comp_tq[ci]][i];
+          P.latched[ci] = true;
+        }
+      }
+      const uint8_t* tail = s + 1 + 2 * scan.ns;
+      scan.ss = tail[0];
+      scan.se = tail[1];
+      scan.ah = tail[2] >> 4;
+      scan.al = tail[2] & 15;
+      if (P.progressive) {
+        const bool dc = scan.ss == 0;
+        if (scan.ss > scan.se || scan.se > 63 || (dc && scan.se != 0) || (!dc && scan.ns != 1) || scan.al > 13 ||
+            (scan.ah != 0 && scan.ah != scan.al + 1))
+          return fail_corrupt("progressive scan parameters");
+      } else if (scan.ss != 0 || scan.se != 63 || scan.ah != 0 || scan.al != 0) {
+        return fail_corrupt("spectral selection in a sequential frame");
+      }
+      for (int k = 0; k < scan.ns; ++k) {
+        const bool need_dc = scan.ss == 0 && scan.ah == 0, need_ac = scan.se > 0;
+        if ((need_dc && !P.dc[scan.td[k]].present) || (need_ac && !P.ac[scan.ta[k]].present))
+          return fail_corrupt("scan refers to an undefined Huffman table");
+      }
+      pos += len;
+      scan.begin = pos;
+      return 0;
     }
     pos += len;
   }
-  // geometry
-  int hmax = 1, vmax = 1;
-  for (int c = 0; c < I.ncomp; ++c) {
-    hmax = I.hs[c] > hmax ? I.hs[c] : hmax;
-    vmax = I.vs[c] > vmax ? I.vs[c] : vmax;
-  }
-  if (I.ncomp == 1) {  // a single-component scan is never interleaved: the MCU is one block, sampling factors are moot
-    I.hs[0] = I.vs[0] = 1;
-    hmax = vmax = 1;
-  } else {
-    // supported chroma layouts: 4:4:4 (1x1), 4:2:2 (2x1), 4:2:0 (2x2); both chroma components alike
-    const bool ok = I.hs[1] == 1 && I.vs[1] == 1 && I.hs[2] == 1 && I.vs[2] == 1 &&
-                    ((I.hs[0] == 1 && I.vs[0] == 1) || (I.hs[0] == 2 && I.vs[0] == 1) || (I.hs[0] == 2 && I.vs[0] == 2));
-    if (!ok) return fail_unsupported("chroma sampling other than 4:4:4, 4:2:2, 4:2:0");
-  }
-  I.mcus_x = (I.width + 8 * hmax - 1) / (8 * hmax);
-  I.mcus_y = (I.height + 8 * vmax - 1) / (8 * vmax);
-  int64_t off = 0;
-  for (int c = 0; c < I.ncomp; ++c) {
-    I.blocks_w[c] = I.mcus_x * I.hs[c];
-    I.blocks_h[c] = I.mcus_y * I.vs[c];
-    I.comp_w[c] = (I.width * I.hs[c] + hmax - 1) / hmax;   // libjpeg's downsampled_width / _height: the real samples
-    I.comp_h[c] = (I.height * I.vs[c] + vmax - 1) / vmax;
-    I.coef_offset[c] = off;
-    off += static_cast<int64_t>(I.blocks_w[c]) * I.blocks_h[c] * 64;
-    for (int i = 0; i < 64; ++i) I.qt[c][i] = P.qt[P.comp_tq[c]][i];
-  }
-  I.coef_count = off;
-  if (I.ncomp == 3 && (I.comp_w[1] < 2 || I.comp_h[1] < 1) && (I.hs[0] == 2))
-    return fail_unsupported("image narrower than two chroma samples");
-  return 0;
+}
+
+int parse(const uint8_t* d, size_t n, Parsed& P, Scan& first, size_t& pos) {
+  if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return fail_corrupt("no SOI marker");
+  memset(&P.info, 0, sizeof(P.info));
+  pos = 2;
+  const int rc = next_scan(d, n, pos, P, first);
+  if (rc == 1) return fail_corrupt("no scan");
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ host: Huffman
@@ -261,6 +308,28 @@ struct BitReader {
     acc <<= n;
     nbits -= n;
   }
+  inline int bit() {
+    if (nbits < 1) fill();
+    const int b = static_cast<int>(acc >> 63);
+    drop(1);
+    return b;
+  }
+  inline int bits(int n) {  // n in 1..16
+    if (nbits < 16) fill();
+    const int v = static_cast<int>(peek(n));
+    drop(n);
+    return v;
+  }
+  // byte-align and consume the expected RSTn marker
+  int restart(int expect) {
+    nbits = 0;
+    acc = 0;
+    while (p + 1 < end && !(p[0] == 0xFF && p[1] != 0x00 && p[1] != 0xFF)) ++p;
+    if (p + 1 >= end || p[1] != 0xD0 + expect) return fail_corrupt("restart marker missing");
+    p += 2;
+    hit_marker = false;
+    return 0;
+  }
 };
 
 inline int decode_symbol(BitReader& br, const HuffTable& t) {
@@ -288,65 +357,151 @@ inline int receive_extend(BitReader& br, int s) {
   return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
 }
 
-int decode_scan(const uint8_t* d, size_t n, const Parsed& P, int16_t* coefs) {
+// one sequential block: DC difference + AC run/size pairs up to EOB
+inline int block_sequential(BitReader& br, const HuffTable& dct, const HuffTable& act, int& pred, int16_t* blk) {
+  int s = decode_symbol(br, dct);
+  if (s < 0 || s > 11) return fail_corrupt("bad DC code");
+  if (s) pred += receive_extend(br, s);
+  blk[0] = static_cast<int16_t>(pred);
+  for (int k = 1; k < 64;) {
+    if (br.nbits < 32) br.fill();
+    const int16_t fa = act.fast_ac[br.peek(9)];
+    if (fa) {  // code and magnitude bits inside the 9-bit window
+      k += (fa >> 4) & 15;
+      if (k > 63) return fail_corrupt("AC run past the block");
+      br.drop(fa & 15);
+      blk[kZigzag[k++]] = static_cast<int16_t>(fa >> 8);
+      continue;
+    }
+    const int rs = decode_symbol(br, act);
+    if (rs < 0) return fail_corrupt("bad AC code");
+    const int r = rs >> 4;
+    s = rs & 15;
+    if (s == 0) {
+      if (r != 15) break;  // EOB
+      k += 16;
+      continue;
+    }
+    k += r;
+    if (k > 63) return fail_corrupt("AC run past the block");
+    blk[kZigzag[k]] = static_cast<int16_t>(receive_extend(br, s));
+    ++k;
+  }
+  return 0;
+}
+
+// progressive: first pass over the AC band [ss, se] of one block (jdphuff.c decode_mcu_AC_first)
+inline int block_ac_first(BitReader& br, const HuffTable& act, const Scan& sc, int& eobrun, int16_t* blk) {
+  if (eobrun > 0) {
+    --eobrun;
+    return 0;
+  }
+  for (int k = sc.ss; k <= sc.se; ++k) {
+    const int rs = decode_symbol(br, act);
+    if (rs < 0) return fail_corrupt("bad AC code");
+    const int r = rs >> 4, s = rs & 15;
+    if (s) {
+      k += r;
+      if (k > 63) return fail_corrupt("AC run past the block");
+      blk[kZigzag[k]] = static_cast<int16_t>(receive_extend(br, s) * (1 << sc.al));
+    } else if (r == 15) {
+      k += 15;
+    } else {
+      eobrun = 1 << r;
+      if (r) eobrun += br.bits(r);
+      --eobrun;
+      break;
+    }
+  }
+  return 0;
+}
+
+// progressive: refinement pass over the AC band of one block (jdphuff.c decode_mcu_AC_refine)
+inline int block_ac_refine(BitReader& br, const HuffTable& act, const Scan& sc, int& eobrun, int16_t* blk) {
+  const int p1 = 1 << sc.al, m1 = -(1 << sc.al);
+  int k = sc.ss;
+  if (eobrun == 0) {
+    for (; k <= sc.se; ++k) {
+      const int rs = decode_symbol(br, act);
+      if (rs < 0) return fail_corrupt("bad AC code");
+      int r = rs >> 4, s = rs & 15;
+      if (s) {
+        s = br.bit() ? p1 : m1;  // the size of a newly non-zero coefficient is always 1
+      } else if (r != 15) {
+        eobrun = 1 << r;
+        if (r) eobrun += br.bits(r);
+        break;  // the rest of the band is handled as an end-of-band run below
+      }
+      // skip r still-zero coefficients, appending a correction bit to every already non-zero one on the way
+      do {
+        int16_t* c = blk + kZigzag[k];
+        if (*c != 0) {
+          if (br.bit() && (*c & p1) == 0) *c = static_cast<int16_t>(*c + (*c >= 0 ? p1 : m1));
+        } else if (--r < 0) {
+          break;
+        }
+        ++k;
+      } while (k <= sc.se);
+      if (s) {
+        if (k > 63) return fail_corrupt("AC run past the block");
+        blk[kZigzag[k]] = static_cast<int16_t>(s);
+      }
+    }
+  }
+  if (eobrun > 0) {
+    for (; k <= sc.se; ++k) {
+      int16_t* c = blk + kZigzag[k];
+      if (*c != 0 && br.bit() && (*c & p1) == 0) *c = static_cast<int16_t>(*c + (*c >= 0 ? p1 : m1));
+    }
+    --eobrun;
+  }
+  return 0;
+}
+
+// One scan of any kind.  Interleaved scans (ns > 1) walk MCUs; a single-component scan walks that component's own
+// ceil(comp/8) block grid (JPEG A.2.3), which is smaller than the MCU-padded grid the coefficient buffer uses.
+int decode_scan(const uint8_t* d, size_t n, const Parsed& P, const Scan& sc, int16_t* coefs, size_t& end_pos) {
   const b2c_jpeg_info& I = P.info;
-  memset(coefs, 0, static_cast<size_t>(I.coef_count) * sizeof(int16_t));
-  BitReader br{d + P.scan_begin, d + n};
+  BitReader br{d + sc.begin, d + n};
   int pred[3] = {0, 0, 0};
+  int eobrun = 0;
   int restarts_left = I.restart_interval;
   int next_rst = 0;
-  for (int my = 0; my < I.mcus_y; ++my) {
-    for (int mx = 0; mx < I.mcus_x; ++mx) {
+  const bool interleaved = sc.ns > 1;
+  const int c0 = sc.ci[0];
+  const int units_x = interleaved ? I.mcus_x : (I.comp_w[c0] + 7) / 8;
+  const int units_y = interleaved ? I.mcus_y : (I.comp_h[c0] + 7) / 8;
+  for (int uy = 0; uy < units_y; ++uy) {
+    for (int ux = 0; ux < units_x; ++ux) {
       if (I.restart_interval && restarts_left == 0) {
-        // byte-align, expect RSTn
-        br.nbits = 0;
-        br.acc = 0;
-        if (!br.hit_marker) {
-          // discard bits already pulled into the accumulator past the segment: scan forward to the marker
-          while (br.p + 1 < br.end && !(br.p[0] == 0xFF && br.p[1] != 0x00)) ++br.p;
-        }
-        if (br.p + 1 >= br.end || br.p[0] != 0xFF || br.p[1] != 0xD0 + next_rst)
-          return fail_corrupt("restart marker missing");
-        br.p += 2;
-        br.hit_marker = false;
+        B2C_TRY(br.restart(next_rst));
         next_rst = (next_rst + 1) & 7;
         pred[0] = pred[1] = pred[2] = 0;
+        eobrun = 0;
         restarts_left = I.restart_interval;
       }
-      for (int c = 0; c < I.ncomp; ++c) {
-        const HuffTable& dct = P.dc[P.comp_td[c]];
-        const HuffTable& act = P.ac[P.comp_ta[c]];
-        for (int v = 0; v < I.vs[c]; ++v) {
-          for (int h = 0; h < I.hs[c]; ++h) {
-            int16_t* blk = coefs + I.coef_offset[c] +
-                           (static_cast<int64_t>(my * I.vs[c] + v) * I.blocks_w[c] + (mx * I.hs[c] + h)) * 64;
-            int s = decode_symbol(br, dct);
-            if (s < 0 || s > 11) return fail_corrupt("bad DC code");
-            if (s) pred[c] += receive_extend(br, s);
-            blk[0] = static_cast<int16_t>(pred[c]);
-            for (int k = 1; k < 64;) {
-              if (br.nbits < 32) br.fill();
-              const int16_t fa = act.fast_ac[br.peek(9)];
-              if (fa) {  // code and magnitude bits inside the 9-bit window
-                k += (fa >> 4) & 15;
-                if (k > 63) return fail_corrupt("AC run past the block");
-                br.drop(fa & 15);
-                blk[kZigzag[k++]] = static_cast<int16_t>(fa >> 8);
-                continue;
+      for (int k = 0; k < sc.ns; ++k) {
+        const int c = sc.ci[k];
+        const int nv = interleaved ? I.vs[c] : 1, nh = interleaved ? I.hs[c] : 1;
+        for (int v = 0; v < nv; ++v) {
+          for (int h = 0; h < nh; ++h) {
+            const int by = interleaved ? uy * I.vs[c] + v : uy, bx = interleaved ? ux * I.hs[c] + h : ux;
+            int16_t* blk = coefs + I.coef_offset[c] + (static_cast<int64_t>(by) * I.blocks_w[c] + bx) * 64;
+            if (!P.progressive) {
+              B2C_TRY(block_sequential(br, P.dc[sc.td[k]], P.ac[sc.ta[k]], pred[c], blk));
+            } else if (sc.ss == 0) {
+              if (sc.ah == 0) {  // DC first
+                const int s = decode_symbol(br, P.dc[sc.td[k]]);
+                if (s < 0 || s > 11) return fail_corrupt("bad DC code");
+                if (s) pred[c] += receive_extend(br, s);
+                blk[0] = static_cast<int16_t>(pred[c] * (1 << sc.al));
+              } else if (br.bit()) {  // DC refinement: one more bit of precision
+                blk[0] = static_cast<int16_t>(blk[0] | (1 << sc.al));
               }
-              const int rs = decode_symbol(br, act);
-              if (rs < 0) return fail_corrupt("bad AC code");
-              const int r = rs >> 4;
-              s = rs & 15;
-              if (s == 0) {
-                if (r != 15) break;  // EOB
-                k += 16;
-                continue;
-              }
-              k += r;
-              if (k > 63) return fail_corrupt("AC run past the block");
-              blk[kZigzag[k]] = static_cast<int16_t>(receive_extend(br, s));
-              ++k;
+            } else if (sc.ah == 0) {
+              B2C_TRY(block_ac_first(br, P.ac[sc.ta[k]], sc, eobrun, blk));
+            } else {
+              B2C_TRY(block_ac_refine(br, P.ac[sc.ta[k]], sc, eobrun, blk));
             }
           }
         }
@@ -354,6 +509,30 @@ int decode_scan(const uint8_t* d, size_t n, const Parsed& P, int16_t* coefs) {
       if (I.restart_interval) --restarts_left;
     }
   }
+  end_pos = static_cast<size_t>(br.p - d);
+  return 0;
+}
+
+// every scan of the file, in order; sequential frames stop once each component has been coded
+int decode_all(const uint8_t* d, size_t n, Parsed& P, Scan scan, size_t pos, int16_t* coefs) {
+  memset(coefs, 0, static_cast<size_t>(P.info.coef_count) * sizeof(int16_t));
+  bool seen[3] = {false, false, false};
+  for (int nscans = 0; nscans < 4096; ++nscans) {
+    size_t end_pos = 0;
+    B2C_TRY(decode_scan(d, n, P, scan, coefs, end_pos));
+    for (int k = 0; k < scan.ns; ++k) seen[scan.ci[k]] = true;
+    if (!P.progressive) {
+      bool all = true;
+      for (int c = 0; c < P.info.ncomp; ++c) all = all && seen[c];
+      if (all) return 0;
+    }
+    pos = end_pos;
+    const int rc = next_scan(d, n, pos, P, scan);
+    if (rc < 0) return rc;
+    if (rc == 1) break;
+  }
+  for (int c = 0; c < P.info.ncomp; ++c)
+    if (!seen[c]) return fail_corrupt("a component has no scan");
   return 0;
 }
 
@@ -566,7 +745,9 @@ extern "C" int b2c_jpeg_parse(const uint8_t* data, size_t len, b2c_jpeg_info* in
   using namespace b2c;
   B2C_REQUIRE(data && info, "b2c_jpeg_parse: null pointer");
   Parsed P;
-  B2C_TRY(parse(data, len, P));
+  Scan first;
+  size_t pos = 0;
+  B2C_TRY(parse(data, len, P, first, pos));
   *info = P.info;
   return 0;
 }
@@ -576,11 +757,14 @@ extern "C" int b2c_jpeg_decode_coefs(const uint8_t* data, size_t len, b2c_jpeg_i
   using namespace b2c;
   B2C_REQUIRE(data && info && coefs, "b2c_jpeg_decode_coefs: null pointer");
   Parsed P;
-  B2C_TRY(parse(data, len, P));
+  Scan first;
+  size_t pos = 0;
+  B2C_TRY(parse(data, len, P, first, pos));
   B2C_REQUIRE(static_cast<size_t>(P.info.coef_count) <= capacity, "b2c_jpeg_decode_coefs: buffer holds %zu coefficients, %lld needed",
               capacity, (long long)P.info.coef_count);
-  *info = P.info;
-  return decode_scan(data, len, P, coefs);
+  B2C_TRY(decode_all(data, len, P, first, pos, coefs));
+  *info = P.info;  // quantisation tables are latched scan by scan
+  return 0;
 }
 
 extern "C" int b2c_jpeg_workspace_bytes(const b2c_jpeg_info* infos, int n, size_t* bytes) {

@@ -22,7 +22,8 @@ class JpegInfo(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32), ("hs", C.c_int32 * 3),
                 ("vs", C.c_int32 * 3), ("mcus_x", C.c_int32), ("mcus_y", C.c_int32), ("blocks_w", C.c_int32 * 3),
                 ("blocks_h", C.c_int32 * 3), ("comp_w", C.c_int32 * 3), ("comp_h", C.c_int32 * 3),
-                ("restart_interval", C.c_int32), ("adobe_transform0", C.c_int32), ("coef_offset", C.c_int64 * 3),
+                ("restart_interval", C.c_int32), ("adobe_transform0", C.c_int32), ("progressive", C.c_int32),
+                ("reserved_", C.c_int32), ("coef_offset", C.c_int64 * 3),
                 ("coef_count", C.c_int64), ("qt", (C.c_uint16 * 64) * 3)]
 
     def as_dict(self) -> dict:

@@ -300,12 +300,13 @@ int b2c_trainer_epoch(b2c_trainer* t, const float* feats, int64_t feat_stride, c
 
 /* ---------------------------------------------------------------------------------------------
  * K14 — JPEG decode ahead of K0.  Replaces `Image.open(path).convert('RGB')` of
- * CustomImageDataset.__getitem__ (utils/embedder.py:167) for baseline JPEG files, bit-exactly with Pillow /
+ * CustomImageDataset.__getitem__ (utils/embedder.py:167) for Huffman-coded 8-bit JPEG files — baseline, extended
+ * sequential (single- or multi-scan) and progressive — bit-exactly with Pillow /
  * libjpeg-turbo at its defaults (islow inverse DCT, "fancy" chroma upsampling, 16-bit fixed-point YCbCr -> RGB).
  * Split along the one serial stage: Huffman decoding runs on the host (b2c_jpeg_decode_coefs, thread-safe, no CUDA
  * calls — DataLoader workers use it), everything after it on the device (b2c_jpeg_reconstruct, batched).
- * Streams this path does not cover — progressive, arithmetic-coded, 12-bit, CMYK / Adobe RGB, multi-scan, sampling
- * other than 4:4:4 / 4:2:2 / 4:2:0 / grey — return B2C_ERR_UNSUPPORTED and stay on the caller's Pillow path.
+ * Streams this path does not cover — arithmetic-coded, lossless, 12-bit, CMYK / Adobe RGB, sampling other than
+ * 4:4:4 / 4:2:2 / 4:2:0 / grey — return B2C_ERR_UNSUPPORTED and stay on the caller's Pillow path.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t width, height, ncomp;     /* ncomp 1 (grey) or 3 (YCbCr) */
@@ -315,14 +316,17 @@ typedef struct {
   int32_t comp_w[3], comp_h[3];     /* real samples per component (libjpeg's downsampled_width / _height) */
   int32_t restart_interval;
   int32_t adobe_transform0;
+  int32_t progressive;              /* SOF2: several scans refine the same coefficient buffer */
+  int32_t reserved_;
   int64_t coef_offset[3];           /* component c's blocks start at coefs + coef_offset[c]; block (by,bx) at +(by*blocks_w+bx)*64 */
   int64_t coef_count;               /* int16 elements the coefficient buffer needs */
   uint16_t qt[3][64];               /* quantisation table of each component, natural (row-major) order */
 } b2c_jpeg_info;
 
-/* Host only: marker parse; fills `info` (sizes for the coefficient buffer). */
+/* Host only: marker parse up to the first scan; fills `info` (sizes for the coefficient buffer; the quantisation
+ * tables are final only after b2c_jpeg_decode_coefs). */
 int b2c_jpeg_parse(const uint8_t* data, size_t len, b2c_jpeg_info* info);
-/* Host only: parse + sequential Huffman decode into `coefs` (HOST memory, ideally pinned; capacity in int16 elements):
+/* Host only: parse + Huffman decode of every scan into `coefs` (HOST memory, ideally pinned; capacity in int16 elements):
  * de-zigzagged, not dequantised. */
 int b2c_jpeg_decode_coefs(const uint8_t* data, size_t len, b2c_jpeg_info* info, int16_t* coefs, size_t capacity);
 int b2c_jpeg_workspace_bytes(const b2c_jpeg_info* infos, int n, size_t* bytes);

@@ -1,7 +1,7 @@
 """K14 (JPEG decode ahead of K0).  The checker is Pillow itself — the library the reference decodes
 with (`Image.open(path).convert('RGB')`, utils/embedder.py:167) and which is installed on both boxes — so every case is
 compared bit for bit with `PIL.Image.open(...).convert('RGB')`.
-  not gpu: the host stage (marker parse + Huffman decode through the C-ABI) feeding oracle/jpeg_oracle.py's numpy
+  not gpu: the host stage (marker parse + Huffman decode of sequential and progressive streams through the C-ABI) feeding oracle/jpeg_oracle.py's numpy
            restatement of the device stage; refusal of streams outside the covered set; corrupt input.
   gpu:     the device stage (b2c_jpeg_reconstruct) on ragged batches, and the embedding driver end to end on .jpg files."""
 import io
@@ -19,6 +19,11 @@ CASES = [  # (W, H, subsampling, quality, extra save kwargs)
     (640, 427, 2, 85, {"optimize": True}), (33, 17, 2, 100, {}), (16, 16, 1, 30, {}), (1000, 3, 2, 80, {}),
     (301, 200, "gray", 80, {}), (256, 256, 2, 90, {"restart_marker_blocks": 4}), (255, 257, 1, 60, {"restart_marker_rows": 1}),
     (8, 8, 0, 70, {}), (2, 2, 0, 70, {}), (9, 1, "gray", 70, {}), (1280, 960, 2, 5, {}),
+    # progressive (SOF2): DC / AC first and refinement scans, end-of-band runs, non-interleaved AC scans on the
+    # component's own block grid (odd sizes), restart intervals inside scans
+    (512, 512, 2, 90, {"progressive": True}), (333, 201, 1, 75, {"progressive": True}), (97, 131, 0, 95, {"progressive": True}),
+    (640, 427, 2, 40, {"progressive": True, "optimize": True}), (300, 300, "gray", 85, {"progressive": True}),
+    (250, 250, 2, 85, {"progressive": True, "restart_marker_blocks": 3}), (17, 9, 2, 100, {"progressive": True}),
 ]
 
 
@@ -49,11 +54,6 @@ def test_host_huffman_stage_and_oracle_vs_pillow(lib, case):
 def test_streams_outside_the_covered_set_are_refused_not_misdecoded(lib):
     from clip_assisted_data_labeling_b200 import _lib, jpeg
     im = Image.fromarray(synthetic_image(1, 120, 160))
-    for kw in ({"progressive": True}, ):
-        buf = io.BytesIO()
-        im.save(buf, "JPEG", quality=85, **kw)
-        with pytest.raises(jpeg.UnsupportedJPEG):
-            jpeg.entropy_decode(buf.getvalue())
     buf = io.BytesIO()
     im.convert("CMYK").save(buf, "JPEG", quality=85)
     with pytest.raises(jpeg.UnsupportedJPEG):
@@ -71,11 +71,11 @@ def test_streams_outside_the_covered_set_are_refused_not_misdecoded(lib):
 
 
 def test_dataset_items_fall_back_to_pillow_per_file(lib, tmp_path):
-    """RawImageDataset(device_jpeg=True): baseline .jpg -> coefficient item; progressive .jpg and .png -> Pillow tensors."""
+    """RawImageDataset(device_jpeg=True): baseline / progressive .jpg -> coefficient item; CMYK .jpg and .png -> Pillow tensors."""
     from clip_assisted_data_labeling_b200.embedder import RawImageDataset
     im = Image.fromarray(synthetic_image(3, 90, 70))
     im.save(tmp_path / "a.jpg", quality=90)
-    im.save(tmp_path / "b.jpg", quality=90, progressive=True)
+    im.convert("CMYK").save(tmp_path / "b.jpg", quality=90)
     im.save(tmp_path / "c.png")
     (tmp_path / "d.jpg").write_bytes(b"")
     ds = RawImageDataset([str(tmp_path / n) for n in ("a.jpg", "b.jpg", "c.png", "d.jpg")], device_jpeg=True)
@@ -108,6 +108,8 @@ def test_device_reconstruct_many_random_streams(lib):
         w, h = (int(v) for v in rng.integers(2, 400, 2))
         sub = [0, 1, 2, "gray"][k % 4]
         kw = {"restart_marker_blocks": int(rng.integers(1, 9))} if k % 5 == 0 else ({"optimize": True} if k % 7 == 0 else {})
+        if k % 3 == 1:
+            kw["progressive"] = True
         made.append(make_jpeg(w, h, sub, int(rng.integers(1, 101)), kw, seed=k))
     items, refs = [], []
     for data, ref in made:

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Files -> embeddings, the whole drop-in path of _1_embed_with_CLIP.py on one GPU: a directory of N synthetic 512x512
+JPEG files -> DataLoader workers (Huffman stage of K14, or Pillow) -> device decode (K14) -> 4 crops + resize (K0) ->
+ViT-L/14 (K1-K8) -> image statistics (K13) -> per-image .pt files and/or the packed store.  Wall-clock images/s of
+Feature_Dataset.process(), second pass (page cache warm, weights resident).
+    python tools/bench_pipeline.py [--n 2048] [--workers 16] [--batch 256]
+One JSON line per configuration."""
+import argparse
+import contextlib
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--workers", type=int, default=os.cpu_count())
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--model", default="ViT-L-14/openai")
+    a = ap.parse_args()
+    import torch
+    from PIL import Image
+    from bench import synth_batch
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from clip_assisted_data_labeling_b200.embedder import CLIP_Encoder
+
+    root = tempfile.mkdtemp(prefix="b2c_pipe_")
+    try:
+        imgs = synth_batch(64, 0).numpy()
+        for i in range(a.n):
+            Image.fromarray(imgs[i % 64]).save(os.path.join(root, f"{i:06d}.jpg"), quality=90, subsampling=2,
+                                               progressive=(i % 4 == 3))
+        with contextlib.redirect_stdout(sys.stderr):
+            enc = CLIP_Encoder(a.model, device="cuda", seed=0)
+        for name, kw in (("pillow decode, .pt files", dict(device_jpeg=False)),
+                         ("device JPEG decode (K14), .pt files", dict(device_jpeg=True)),
+                         ("device JPEG decode (K14), packed store only", dict(device_jpeg=True, write_pt=False, packed_dir=os.path.join(root, "_packed")))):
+            best = None
+            for rep in range(2):
+                with contextlib.redirect_stdout(sys.stderr):
+                    ds = Feature_Dataset(root, a.model, batch_size=a.batch, num_workers=a.workers, shuffle_filenames=False,
+                                         force_reencode=True, encoder=enc, **kw)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    n, _ = ds.process()
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                assert n == a.n and not ds.failed
+                best = dt if best is None else min(best, dt)
+            print(json.dumps({"config": name, "model": a.model, "images": a.n, "workers": a.workers, "batch": a.batch,
+                              "seconds": best, "images_per_s": a.n / best}), flush=True)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,29 @@ def build_feature_dict(features_per_image: torch.Tensor, crop_names, kept=None) 
     return d
 
 
+def feature_dict_from_flat(flat: torch.Tensor, n_stats: int, stat_names, crop_names, kept=None) -> dict:
+    """flat: f32 [n_stats + 4*E] on CPU (the image's statistics, then its four crops in CROP_NAMES order) ->
+    {img_stat_*: 0-d f32, crop_name: f32[1,E]} as VIEWS of that one storage: torch.save then writes a single storage
+    entry instead of 26 (faster to write, and to read back in _2/_4/_5), the values and shapes are the reference's."""
+    E = (flat.numel() - n_stats) // 4
+    d = {n: flat[i] for i, n in enumerate(stat_names[:n_stats])}
+    for name in crop_names:
+        i = CROP_NAMES.index(name)
+        if kept is not None and not kept[i]:
+            continue  # crop dropped as empty by extract_crops (utils/embedder.py:243-247)
+        d[name] = flat[n_stats + i * E:n_stats + (i + 1) * E].view(1, E)
+    return d
+
+
+def _write_feature_batch(model_name: str, force_reencode: bool, n_stats: int, stat_names, crop_names, rows, paths, kepts):
+    """Writer-process task: rows f32 [b, n_stats + 4E] (numpy) -> b ``.pt`` files."""
+    import numpy as np
+    rows = torch.from_numpy(np.ascontiguousarray(rows))
+    for r, path, kept in zip(rows, paths, kepts):
+        save_feature_file(path, model_name, feature_dict_from_flat(r.clone(), n_stats, stat_names, crop_names, kept), force_reencode)
+    return len(paths)
+
+
 def save_feature_file(path: str, model_name: str, feature_dict: dict, force_reencode: bool) -> None:
     """Merge-and-save one ``<img>.pt`` (_1_embed_with_CLIP.py:138-170)."""
     final = {}
@@ -86,7 +109,7 @@ class Feature_Dataset:
     def __init__(self, root_dir, model_name, batch_size, model_path=None, force_reencode=False, shuffle_filenames=True,
                  num_workers=0, crop_names=("centre_crop", "square_padded_crop", "subcrop1", "subcrop2"),
                  rank=None, world_size=None, state_dict=None, encoder=None, writer_threads=4, packed_dir=None,
-                 write_pt=True, img_stats=None, device_jpeg=None):
+                 write_pt=True, img_stats=None, device_jpeg=None, writer_procs=None):
         self.device = getattr(encoder, "device", "cuda") if encoder is not None else "cuda"
         self.root_dir = root_dir
         self.model_name = model_name
@@ -123,6 +146,11 @@ class Feature_Dataset:
             kw["prefetch_factor"] = 2
         self.dataloader = DataLoader(self.img_dataset, **kw)
         self._writer_threads = writer_threads
+        # .pt writing is pickling, i.e. GIL-bound (~1 ms per file): large jobs hand whole batches to writer PROCESSES
+        # (spawned, never touch CUDA); small jobs keep the thread pool and skip the interpreter start-up cost
+        if writer_procs is None:
+            writer_procs = min(8, max(1, (os.cpu_count() or 2) // 2)) if len(self.img_filepaths) >= 2000 else 0
+        self._writer_procs = writer_procs
         self.failed = []
         # with packed_dir set every rank appends its [B,4,E] blocks to one flat shard
         # (store.PackedWriter); write_pt=False skips the per-image pickles entirely (store.export_pt writes them later)
@@ -137,18 +165,66 @@ class Feature_Dataset:
 
     @torch.no_grad()
     def process(self):
+        """One pass over the images.  The loop is software-pipelined: batch i's device work (decode finish, crops, tower,
+        statistics, D2H into pinned memory) is enqueued before batch i-1's results are turned into files on the host, so
+        the GPU computes while the host pickles and the DataLoader refills."""
         from . import _lib
         import ctypes as C
+        import multiprocessing as mp
         lib = _lib.load()
         n_embedded, n_skipped = 0, 0
         R = self.encoder.img_resolution
+        on_cuda = str(self.device).startswith("cuda")
         print(f"Embedding dataset of {len(self.img_filepaths)} images using {self.model_name}...")
-        pool = concurrent.futures.ThreadPoolExecutor(max_workers=self._writer_threads)
+        if self._writer_procs > 0 and self.write_pt:
+            pool = concurrent.futures.ProcessPoolExecutor(max_workers=self._writer_procs, mp_context=mp.get_context("spawn"))
+        else:
+            pool = concurrent.futures.ThreadPoolExecutor(max_workers=self._writer_threads)
         pending = []
         packed = None
         if self.packed_dir is not None:
             from .store import PackedWriter
             packed = PackedWriter(self.packed_dir, self.model_name, self.encoder.embed_dim, CROP_NAMES, shard=self.rank)
+        stat_names = []
+        if self.img_stats:
+            from .imgstats import STAT_NAMES, image_stats
+            stat_names = list(STAT_NAMES)
+        n_stats = len(stat_names)
+        slots = [None, None]  # pinned result buffers, alternating between consecutive batches
+
+        def finish(job):
+            """Host half of a batch: wait for its D2H copy, write files / append to the packed shard."""
+            nonlocal pending
+            ev, rows, save_paths, img_paths, shapes = job
+            if ev is not None:
+                ev.synchronize()
+            b = len(save_paths)
+            rows = rows[:b]
+            E = (rows.shape[1] - n_stats) // 4
+            kept_all = []
+            for (h, w) in shapes:
+                g = (_lib.Crop * 4)()
+                _lib.check(lib.b2c_crop_geometry(int(w), int(h), R, g), "b2c_crop_geometry")
+                kept_all.append([g[i].cw > 0 for i in range(4)])
+            if self.write_pt:
+                if self._writer_procs > 0:
+                    step = max(8, (b + self._writer_procs - 1) // self._writer_procs)
+                    for lo in range(0, b, step):
+                        pending.append(pool.submit(_write_feature_batch, self.model_name, self.force_reencode, n_stats, stat_names,
+                                                   list(self.crop_names), rows[lo:lo + step].numpy().copy(), save_paths[lo:lo + step],
+                                                   kept_all[lo:lo + step]))
+                else:
+                    for r, sp, kept in zip(rows, save_paths, kept_all):
+                        fd = feature_dict_from_flat(r.clone(), n_stats, stat_names, self.crop_names, kept)
+                        pending.append(pool.submit(save_feature_file, sp, self.model_name, fd, self.force_reencode))
+            if packed is not None:
+                packed.append(rows[:, n_stats:].reshape(b, 4, E).clone(), img_paths, kept_all)
+            if len(pending) > 4096:
+                for fu in pending:
+                    fu.result()
+                pending = []
+
+        prev, k = None, 0
         for images, img_paths in self.dataloader:
             todo_imgs, todo_paths, todo_img_paths = [], [], []
             for im, p in zip(images, img_paths):
@@ -161,34 +237,37 @@ class Feature_Dataset:
                     todo_imgs.append(im)
                     todo_paths.append(save_path)
                     todo_img_paths.append(p)
+            cur = None
             if todo_imgs:
-                if str(self.device).startswith("cuda"):
-                    dev_imgs = to_device_images(todo_imgs, self.device)
-                else:  # only reachable with an injected encoder (host-logic tests)
-                    dev_imgs = todo_imgs
-                feats = self.encoder.encode_images_u8(dev_imgs).cpu()  # [B,4,E], one D2H per batch
-                stats = None
-                if self.img_stats:
-                    from .imgstats import image_stats, stats_dict
-                    stats = image_stats(dev_imgs).cpu()
-                kept_all = []
-                for bi, (im, f, sp) in enumerate(zip(dev_imgs, feats, todo_paths)):
-                    g = (_lib.Crop * 4)()
-                    _lib.check(lib.b2c_crop_geometry(int(im.shape[1]), int(im.shape[0]), R, g), "b2c_crop_geometry")
-                    kept = [g[i].cw > 0 for i in range(4)]
-                    kept_all.append(kept)
-                    if self.write_pt:
-                        fd = build_feature_dict(f, self.crop_names, kept)
-                        if stats is not None:
-                            fd = {**stats_dict(stats[bi]), **fd}
-                        pending.append(pool.submit(save_feature_file, sp, self.model_name, fd, self.force_reencode))
-                if packed is not None:
-                    packed.append(feats, todo_img_paths, kept_all)
-                n_embedded += len(todo_imgs)
-            if len(pending) > 4096:
-                for fu in pending:
-                    fu.result()
-                pending = []
+                b = len(todo_imgs)
+                dev_imgs = to_device_images(todo_imgs, self.device) if on_cuda else todo_imgs  # cpu: injected encoder (host-logic tests)
+                feats = self.encoder.encode_images_u8(dev_imgs)  # [B,4,E]
+                stats = image_stats(dev_imgs) if self.img_stats else None
+                shapes = [(int(im.shape[0]), int(im.shape[1])) for im in dev_imgs]
+                E = int(feats.shape[-1])
+                if on_cuda:
+                    slot = slots[k & 1]
+                    if slot is None or slot.shape[0] < b:
+                        slot = slots[k & 1] = torch.empty(max(b, self.batch_size), n_stats + 4 * E, dtype=torch.float32, pin_memory=True)
+                    if stats is not None:
+                        slot[:b, :n_stats].copy_(stats.to(torch.float32), non_blocking=True)
+                    slot[:b, n_stats:].copy_(feats.reshape(b, 4 * E), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    cur = (ev, slot, todo_paths, todo_img_paths, shapes)
+                    k += 1
+                else:
+                    rows = torch.empty(b, n_stats + 4 * E, dtype=torch.float32)
+                    if stats is not None:
+                        rows[:, :n_stats] = stats.to(torch.float32)
+                    rows[:, n_stats:] = feats.reshape(b, 4 * E).float()
+                    cur = (None, rows, todo_paths, todo_img_paths, shapes)
+                n_embedded += b
+            if prev is not None:
+                finish(prev)
+            prev = cur
+        if prev is not None:
+            finish(prev)
         for fu in pending:
             fu.result()
         pool.shutdown()

@@ -142,6 +142,25 @@ def _write_images(root, n, size=(40, 30)):
         Image.fromarray(rng.integers(0, 256, (size[1], size[0], 3), dtype=np.uint8)).save(os.path.join(root, f"im{i:03d}.png"))
 
 
+def test_writer_processes_write_the_same_files_as_writer_threads(tmp_path, lib):
+    """Large jobs hand whole batches to spawned writer processes (pickling is GIL-bound); same bytes in the tensors,
+    same keys, and every value of a file is a view of one storage."""
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from clip_assisted_data_labeling_b200.vit_arch import CROP_NAMES
+    out = {}
+    for procs in (0, 2):
+        root = str(tmp_path / f"data{procs}")
+        _write_images(root, 9)
+        n, _ = Feature_Dataset(root, "ViT-L-14/openai", batch_size=4, shuffle_filenames=False, encoder=_FakeEncoder(),
+                               writer_procs=procs).process()
+        assert n == 9
+        out[procs] = [torch.load(os.path.join(root, f"im{i:03d}.pt"))["ViT-L-14/openai"] for i in range(9)]
+    for a, b in zip(out[0], out[2]):
+        assert list(a.keys()) == list(b.keys()) == CROP_NAMES
+        assert all(torch.equal(a[k], b[k]) and tuple(a[k].shape) == (1, 8) and a[k].dtype == torch.float32 for k in a)
+        assert len({t.untyped_storage().data_ptr() for t in b.values()}) == 1
+
+
 def test_feature_dataset_layout_resume_and_consumers(tmp_path, lib):
     """`.pt` layout, merge across models, per-image resume, and the reference consumers'
     read paths (_2:30-38 first-key default + squeeze; _5:77-82 cat over crop_names)."""

@@ -3,7 +3,7 @@
 JPEG files -> DataLoader workers (Huffman stage of K14, or Pillow) -> device decode (K14) -> 4 crops + resize (K0) ->
 ViT-L/14 (K1-K8) -> image statistics (K13) -> per-image .pt files and/or the packed store.  Wall-clock images/s of
 Feature_Dataset.process(), second pass (page cache warm, weights resident).
-    python tools/bench_pipeline.py [--n 2048] [--workers 16] [--batch 256]
+    python tools/bench_pipeline.py [--n 8192] [--workers 16] [--batch 256]
 One JSON line per configuration."""
 import argparse
 import contextlib
@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--workers", type=int, default=os.cpu_count())
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--model", default="ViT-L-14/openai")
@@ -33,10 +33,14 @@ def main():
 
     root = tempfile.mkdtemp(prefix="b2c_pipe_")
     try:
+        import concurrent.futures as cf
         imgs = synth_batch(64, 0).numpy()
-        for i in range(a.n):
+
+        def write(i):
             Image.fromarray(imgs[i % 64]).save(os.path.join(root, f"{i:06d}.jpg"), quality=90, subsampling=2,
                                                progressive=(i % 4 == 3))
+        with cf.ThreadPoolExecutor(os.cpu_count()) as ex:
+            list(ex.map(write, range(a.n)))
         with contextlib.redirect_stdout(sys.stderr):
             enc = CLIP_Encoder(a.model, device="cuda", seed=0)
         for name, kw in (("pillow decode, .pt files", dict(device_jpeg=False)),

@@ -116,6 +116,44 @@ void prof_end(cudaStream_t stream) {
   if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, stream);
 }
 
+namespace {
+struct PinnedChunk {
+  void* host = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+};
+std::mutex g_pin_mu;
+std::vector<PinnedChunk> g_pin;
+}  // namespace
+
+int upload_async(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return 0;
+  std::lock_guard<std::mutex> g(g_pin_mu);
+  PinnedChunk* c = nullptr;
+  for (PinnedChunk& k : g_pin) {
+    if (k.bytes < bytes) continue;
+    if (k.in_flight && cudaEventQuery(k.done) != cudaSuccess) continue;
+    k.in_flight = false;
+    if (!c || k.bytes < c->bytes) c = &k;
+  }
+  (void)cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error of ours
+  if (!c) {
+    PinnedChunk k;
+    k.bytes = 1 << 16;
+    while (k.bytes < bytes) k.bytes <<= 1;
+    B2C_CHECK_CUDA(cudaHostAlloc(&k.host, k.bytes, cudaHostAllocDefault));
+    B2C_CHECK_CUDA(cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
+    g_pin.push_back(k);
+    c = &g_pin.back();
+  }
+  memcpy(c->host, src_host, bytes);
+  B2C_CHECK_CUDA(cudaMemcpyAsync(dst_dev, c->host, bytes, cudaMemcpyHostToDevice, stream));
+  B2C_CHECK_CUDA(cudaEventRecord(c->done, stream));
+  c->in_flight = true;
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -47,4 +47,10 @@ int make_tmap_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 
 int num_sms();
 
+// Descriptor upload that never blocks the host: cudaMemcpyAsync from PAGEABLE memory first synchronises the stream (the
+// caller would wait for every kernel already queued, i.e. lose all host/device overlap), so small host tables (crop
+// plans, job lists) are copied into a chunk of a process-wide pinned pool and sent from there.  A chunk is reused once
+// the event recorded after its copy has completed.  Thread-safe.
+int upload_async(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream);
+
 }  // namespace b2c

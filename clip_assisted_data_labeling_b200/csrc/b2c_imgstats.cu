@@ -476,9 +476,9 @@ extern "C" int b2c_image_stats(const uint8_t* const* img_ptrs, const int* H, con
   base += align_up(2 * 256 * sizeof(int), 256);
   int* d_tab = reinterpret_cast<int*>(base);
   // pageable-source async copies are staged before returning, so the host vectors may die at the end of this call
-  B2C_CHECK_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(ImageJob), cudaMemcpyHostToDevice, st));
-  B2C_CHECK_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  B2C_CHECK_CUDA(cudaMemcpyAsync(d_hsv, hsv, sizeof(hsv), cudaMemcpyHostToDevice, st));
+  B2C_TRY(upload_async(d_jobs, jobs.data(), jobs.size() * sizeof(ImageJob), st));
+  B2C_TRY(upload_async(d_tab, tab.data(), tab.size() * sizeof(int), st));
+  B2C_TRY(upload_async(d_hsv, hsv, sizeof(hsv), st));
   B2C_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, static_cast<size_t>(B) * kNumSums * sizeof(unsigned long long), st));
   B2C_CHECK_CUDA(cudaMemsetAsync(d_hist, 0, static_cast<size_t>(B) * 256 * sizeof(unsigned int), st));
   for (int first = 0; first < B; first += 32768) {  // gridDim.z limit

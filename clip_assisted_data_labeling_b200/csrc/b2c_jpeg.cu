@@ -820,9 +820,7 @@ extern "C" int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* c
   }
   JpegJobDev* jd = static_cast<JpegJobDev*>(ws);
   uint8_t* planes = static_cast<uint8_t*>(ws);
-  // pageable source: the runtime stages it before cudaMemcpyAsync returns, so `jobs` may go out of scope (same
-  // pattern as the crop plans of b2c_preprocess_4crop); no device synchronisation
-  B2C_CHECK_CUDA(cudaMemcpyAsync(jd, jobs.data(), static_cast<size_t>(n) * sizeof(JpegJobDev), cudaMemcpyHostToDevice, stream));
+  B2C_TRY(upload_async(jd, jobs.data(), static_cast<size_t>(n) * sizeof(JpegJobDev), stream));  // no stream synchronisation
   ProfScope ps(B2C_PROF_OTHER, stream);
   jpeg_idct_kernel<<<static_cast<unsigned>((blocks + 31) / 32), kIdctThreads, 0, stream>>>(jd, n, static_cast<int>(blocks), planes);
   B2C_POST_LAUNCH("jpeg_idct_kernel");

@@ -438,8 +438,7 @@ extern "C" int b2c_preprocess_4crop(const uint8_t* const* img_ptrs, const int* H
     return set_error(B2C_ERR_WORKSPACE, "b2c_preprocess_4crop: workspace %zu B < required %zu B", ws_bytes, lay.total);
   uint8_t* wsb = static_cast<uint8_t*>(ws);
   B2C_REQUIRE((reinterpret_cast<uintptr_t>(wsb) & 255) == 0, "b2c_preprocess_4crop: workspace must be 256-byte aligned");
-  B2C_CHECK_CUDA(cudaMemcpyAsync(wsb + lay.plans, plans.data(), plans.size() * sizeof(CropPlan), cudaMemcpyHostToDevice,
-                                 stream));
+  B2C_TRY(upload_async(wsb + lay.plans, plans.data(), plans.size() * sizeof(CropPlan), stream));  // no stream synchronisation
 
   ResampleParams rp;
   rp.plans = reinterpret_cast<const CropPlan*>(wsb + lay.plans);

@@ -191,13 +191,23 @@ class Feature_Dataset:
             stat_names = list(STAT_NAMES)
         n_stats = len(stat_names)
         slots = [None, None]  # pinned result buffers, alternating between consecutive batches
+        import time as _time
+        timing = os.environ.get("B2C_DRIVER_TIMING") is not None  # wall-clock seconds of the main thread per phase
+        phase = {}
+
+        def tick(name, t0):
+            if timing:
+                phase[name] = phase.get(name, 0.0) + _time.perf_counter() - t0
+            return _time.perf_counter()
 
         def finish(job):
             """Host half of a batch: wait for its D2H copy, write files / append to the packed shard."""
             nonlocal pending
             ev, rows, save_paths, img_paths, shapes = job
+            t0 = _time.perf_counter()
             if ev is not None:
                 ev.synchronize()
+            t0 = tick("wait for the device (previous batch)", t0)
             b = len(save_paths)
             rows = rows[:b]
             E = (rows.shape[1] - n_stats) // 4
@@ -223,9 +233,12 @@ class Feature_Dataset:
                 for fu in pending:
                     fu.result()
                 pending = []
+            tick("files / packed shard (host)", t0)
 
         prev, k = None, 0
+        t_it = _time.perf_counter()
         for images, img_paths in self.dataloader:
+            t_it = tick("DataLoader (wait + unpickle)", t_it)
             todo_imgs, todo_paths, todo_img_paths = [], [], []
             for im, p in zip(images, img_paths):
                 save_path = os.path.splitext(p)[0] + ".pt"
@@ -240,18 +253,25 @@ class Feature_Dataset:
             cur = None
             if todo_imgs:
                 b = len(todo_imgs)
+                t_it = tick("resume checks", t_it)
                 dev_imgs = to_device_images(todo_imgs, self.device) if on_cuda else todo_imgs  # cpu: injected encoder (host-logic tests)
+                t_it = tick("gather + H2D + JPEG reconstruct launches", t_it)
                 feats = self.encoder.encode_images_u8(dev_imgs)  # [B,4,E]
+                t_it = tick("preprocess + tower launches", t_it)
                 stats = image_stats(dev_imgs) if self.img_stats else None
+                t_it = tick("image statistics launches", t_it)
                 shapes = [(int(im.shape[0]), int(im.shape[1])) for im in dev_imgs]
                 E = int(feats.shape[-1])
                 if on_cuda:
                     slot = slots[k & 1]
                     if slot is None or slot.shape[0] < b:
                         slot = slots[k & 1] = torch.empty(max(b, self.batch_size), n_stats + 4 * E, dtype=torch.float32, pin_memory=True)
+                    # rows are assembled on the device: a D2H copy into a strided slice of the pinned slot would go through
+                    # a synchronous staging copy and stall the host until the whole batch has been computed
+                    rows_dev = feats.reshape(b, 4 * E)
                     if stats is not None:
-                        slot[:b, :n_stats].copy_(stats.to(torch.float32), non_blocking=True)
-                    slot[:b, n_stats:].copy_(feats.reshape(b, 4 * E), non_blocking=True)
+                        rows_dev = torch.cat([stats.to(torch.float32), rows_dev], dim=1)
+                    slot[:b].copy_(rows_dev, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record()
                     cur = (ev, slot, todo_paths, todo_img_paths, shapes)
@@ -263,9 +283,11 @@ class Feature_Dataset:
                     rows[:, n_stats:] = feats.reshape(b, 4 * E).float()
                     cur = (None, rows, todo_paths, todo_img_paths, shapes)
                 n_embedded += b
+                t_it = tick("D2H enqueue", t_it)
             if prev is not None:
                 finish(prev)
             prev = cur
+            t_it = _time.perf_counter()
         if prev is not None:
             finish(prev)
         for fu in pending:
@@ -273,6 +295,8 @@ class Feature_Dataset:
         pool.shutdown()
         if packed is not None:
             packed.close()
+        if timing:
+            print("main-thread seconds per phase: " + ", ".join(f"{k}: {v:.2f}" for k, v in phase.items()), file=__import__("sys").stderr)
         print("\n--- Feature encoding done! ---\n")
         print(f"Embedded {n_embedded} images ({n_skipped} images were already embedded). "
               f"Features saved with model key '{self.model_name}'.")

@@ -57,7 +57,8 @@ def image_stats(images, device=None) -> torch.Tensor:
     with torch.cuda.device(dev):
         _lib.check(lib.b2c_image_stats(ptrs, Hs, Ws, Ps, B, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr() + off), need.value,
                                        C.c_void_p(_lib.current_stream_ptr())), "b2c_image_stats")
-        torch.cuda.current_stream().synchronize()  # `keep` / `ws` are released on return
+        # no synchronisation: `keep` / `ws` were allocated on the current stream, so torch's caching allocator hands
+        # their memory out again only to work that is ordered after the launches above
     return out
 
 

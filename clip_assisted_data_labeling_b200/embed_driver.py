@@ -296,6 +296,12 @@ class Feature_Dataset:
         if packed is not None:
             packed.close()
         if timing:
+            from . import embedder as _emb, jpeg as _jpeg
+            for st in (_jpeg._coef_staging, _emb._pixel_staging):
+                if st is not None:
+                    for k2, v2 in st.timing.items():
+                        phase[k2] = phase.get(k2, 0.0) + v2
+                    st.timing = {}
             print("main-thread seconds per phase: " + ", ".join(f"{k}: {v:.2f}" for k, v in phase.items()), file=__import__("sys").stderr)
         print("\n--- Feature encoding done! ---\n")
         print(f"Embedded {n_embedded} images ({n_skipped} images were already embedded). "

@@ -216,18 +216,31 @@ class RawImageDataset(Dataset):
             return None, path
 
 
+_pixel_staging = None
+
+
 def to_device_images(items, device):
-    """RawImageDataset items (no ``None``) -> uint8 [H,W,3] device tensors, same order: Pillow-decoded tensors are copied,
-    entropy-decoded JPEGs are reconstructed on the device in one batched call."""
+    """RawImageDataset items (no ``None``) -> uint8 [H,W,3] device tensors, same order.  Pillow-decoded tensors go through
+    one pinned gather + one H2D copy (the device tensors are views of that buffer); entropy-decoded JPEGs likewise and are
+    then reconstructed on the device in one batched call."""
+    global _pixel_staging
     from . import jpeg
     out = [None] * len(items)
-    jobs, where = [], []
+    jobs, where, pix, pwhere = [], [], [], []
     for i, it in enumerate(items):
         if isinstance(it, tuple) and it[0] == "jpeg":
             jobs.append((jpeg.JpegInfo.from_buffer_copy(it[1]), it[2]))
             where.append(i)
         else:
-            out[i] = it.pin_memory().to(device, non_blocking=True)
+            pix.append(it.contiguous())
+            pwhere.append(i)
+    if pix:
+        if _pixel_staging is None:
+            _pixel_staging = jpeg.Staging(torch.uint8)
+        with torch.cuda.device(torch.device(device)):
+            dflat, offs = _pixel_staging.gather(pix, torch.device(device))
+        for i, t, o in zip(pwhere, pix, offs[:-1]):
+            out[i] = dflat[int(o):int(o) + t.numel()].view(t.shape)
     for i, t in zip(where, jpeg.reconstruct(jobs, device)):
         out[i] = t
     return out

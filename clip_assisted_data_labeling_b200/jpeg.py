@@ -59,26 +59,61 @@ def entropy_decode(data: bytes, pin: bool = False) -> Tuple[JpegInfo, torch.Tens
     return info, coefs
 
 
-class _Staging:
-    """Grow-only pinned host buffer the coefficient tensors of a batch are gathered into before one async H2D copy; the
-    event guards the buffer against being refilled while the previous copy still reads it."""
-    buf = None
-    event = None
+class Staging:
+    """Grow-only pinned host buffer a batch of host tensors (one dtype) is gathered into before ONE async H2D copy.  The
+    gather is spread over a few threads: the sources are fresh shared-memory mappings from the DataLoader workers, and
+    faulting their pages in is what costs time when the workers are busy writing the next batches.  The event guards the
+    buffer against being refilled while the previous copy still reads it."""
+    _pool = None
 
-    @classmethod
-    def gather(cls, tensors, dev):
-        total = sum(t.numel() for t in tensors)
-        if cls.buf is None or cls.buf.numel() < total:
-            cls.buf = torch.empty(max(total, 1 << 20), dtype=torch.int16, pin_memory=True)
-            cls.event = None
-        if cls.event is not None:
-            cls.event.synchronize()
-        flat = cls.buf[:total]
-        torch.cat(tensors, out=flat) if len(tensors) > 1 else flat.copy_(tensors[0])
+    def __init__(self, dtype):
+        self.dtype = dtype
+        self.buf = None
+        self.event = None
+        self.timing = {}  # seconds per step when B2C_DRIVER_TIMING is set (diagnostics of the embedding driver)
+
+    def gather(self, tensors, dev, threads: int = 4):
+        """tensors: contiguous host tensors of self.dtype -> (device buffer holding them back to back, element offsets)."""
+        import concurrent.futures as cf
+        import os
+        import time
+        t0 = time.perf_counter()
+        sizes = [t.numel() for t in tensors]
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        total = int(offs[-1])
+        if self.buf is None or self.buf.numel() < total:
+            self.buf = torch.empty(max(total, 1 << 20), dtype=self.dtype, pin_memory=True)
+            self.event = None
+        if self.event is not None:
+            self.event.synchronize()
+        t1 = time.perf_counter()
+        flat = self.buf[:total]
+
+        def part(lo, hi):
+            if hi > lo:
+                torch.cat([t.reshape(-1) for t in tensors[lo:hi]], out=flat[int(offs[lo]):int(offs[hi])])
+
+        n = len(tensors)
+        if n >= 2 * threads and total * flat.element_size() >= (8 << 20):
+            if Staging._pool is None:
+                Staging._pool = cf.ThreadPoolExecutor(threads)
+            cuts = [n * i // threads for i in range(threads + 1)]
+            list(Staging._pool.map(lambda i: part(cuts[i], cuts[i + 1]), range(threads)))
+        else:
+            part(0, n)
+        t2 = time.perf_counter()
         dflat = flat.to(dev, non_blocking=True)
-        cls.event = torch.cuda.Event()
-        cls.event.record()
-        return dflat
+        self.event = torch.cuda.Event()
+        self.event.record()
+        if os.environ.get("B2C_DRIVER_TIMING") is not None:
+            t3 = time.perf_counter()
+            for k, v in (("staging: wait for the previous H2D", t1 - t0), ("staging: gather into pinned memory", t2 - t1),
+                         ("staging: enqueue H2D", t3 - t2)):
+                self.timing[k] = self.timing.get(k, 0.0) + v
+        return dflat, offs
+
+
+_coef_staging = Staging(torch.int16)
 
 
 def reconstruct_device(infos: Sequence[JpegInfo], dflat: torch.Tensor) -> List[torch.Tensor]:
@@ -110,7 +145,7 @@ def reconstruct(items: Sequence[Tuple[JpegInfo, torch.Tensor]], device="cuda") -
         return []
     dev = torch.device(device)
     with torch.cuda.device(dev):
-        dflat = _Staging.gather([it[1] for it in items], dev)
+        dflat, _ = _coef_staging.gather([it[1] for it in items], dev)
     return reconstruct_device([it[0] for it in items], dflat)
 
 

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--workers", type=int, default=os.cpu_count())
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--model", default="ViT-L-14/openai")
+    ap.add_argument("--progressive-every", type=int, default=4, help="every k-th file is a progressive JPEG (0 = none)")
+    ap.add_argument("--only", default="", help="substring filter on the configuration names")
     a = ap.parse_args()
     import torch
     from PIL import Image
@@ -38,7 +40,7 @@ def main():
 
         def write(i):
             Image.fromarray(imgs[i % 64]).save(os.path.join(root, f"{i:06d}.jpg"), quality=90, subsampling=2,
-                                               progressive=(i % 4 == 3))
+                                               progressive=(a.progressive_every > 0 and i % a.progressive_every == a.progressive_every - 1))
         with cf.ThreadPoolExecutor(os.cpu_count()) as ex:
             list(ex.map(write, range(a.n)))
         with contextlib.redirect_stdout(sys.stderr):
@@ -46,6 +48,8 @@ def main():
         for name, kw in (("pillow decode, .pt files", dict(device_jpeg=False)),
                          ("device JPEG decode (K14), .pt files", dict(device_jpeg=True)),
                          ("device JPEG decode (K14), packed store only", dict(device_jpeg=True, write_pt=False, packed_dir=os.path.join(root, "_packed")))):
+            if a.only and a.only not in name:
+                continue
             best = None
             for rep in range(2):
                 with contextlib.redirect_stdout(sys.stderr):

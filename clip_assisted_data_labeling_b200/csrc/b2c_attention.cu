@@ -1779,6 +1779,15 @@ static int attention_launch_hd(const void* qkv, void* out, int n, int T, int hea
   return 0;
 }
 
+int attention_cls_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream) {
+  B2C_REQUIRE(n > 0 && T > 0 && heads > 0 && hd == 64, "attention_cls: head dim %d unsupported (64)", hd);
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+  attention_cls_kernel<<<(n * heads + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+                                                                n * heads, T, heads, scale_log2);
+  B2C_POST_LAUNCH("attention_cls_kernel");
+  return 0;
+}
+
 int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream) {
   B2C_REQUIRE(n > 0 && T > 0 && heads > 0, "attention: empty problem");
   // B2C_ATTN = v4 (default for hd 64: v2 with 16 softmax warps) | v2 (persistent, P in TMEM) | v1 (one CTA per query

@@ -79,6 +79,9 @@ int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, i
 // ---- row-wise kernels (b2c_rowops.cu) ----------------------------------------------------------
 int layernorm_bf16_launch(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d, float eps,
                           cudaStream_t stream);
+// same, input rows ldx elements apart (e.g. only the class-token rows of the residual stream), output rows dense
+int layernorm_bf16_strided_launch(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t M, int d,
+                                  float eps, cudaStream_t stream);
 // x[crop*T + 0, :] = cls + pos[0, :]; then ln_pre over all rows in place (f32 -> f32)
 int cls_pos_launch(float* x, const float* cls, const float* pos, int n, int T, int d, cudaStream_t stream);
 int layernorm_f32_inplace_launch(float* x, const float* gamma, const float* beta, int64_t M, int d, float eps,
@@ -103,5 +106,7 @@ int pad_rows_bf16_launch(const void* src, int src_dtype, void* dst, int64_t rows
 
 // ---- attention (b2c_attention.cu) --------------------------------------------------------------
 int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream);
+// only the class-token query row of every (crop, head) -> out[crop*T, head*64 ..] (head dim 64)
+int attention_cls_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream);
 
 }  // namespace b2c

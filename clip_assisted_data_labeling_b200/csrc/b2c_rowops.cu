@@ -36,13 +36,13 @@ __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat1
 template <int NV, bool OUT_BF16>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, void* y,
-                                                        long long M, int d, float eps, int nv_rt) {
+                                                        long long M, int d, float eps, int nv_rt, long long ldx) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nv = NV > 0 ? NV : nv_rt;
   constexpr int CAP = NV > 0 ? NV : 16;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);  // input rows ldx elements apart, output rows dense
   float4 v[CAP];
   float s = 0.f;
 #pragma unroll
@@ -227,16 +227,18 @@ int ln_fold_launch(const void* w, int w_dtype, const float* gamma, const float* 
 
 template <bool OUT_BF16>
 static int layernorm_dispatch(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d,
-                              float eps, cudaStream_t stream) {
+                              float eps, cudaStream_t stream, int64_t ldx = 0) {
+  if (ldx == 0) ldx = d;
+  B2C_REQUIRE(ldx % 4 == 0 && (OUT_BF16 || ldx == d), "layernorm: bad input row stride");
   B2C_REQUIRE(d % 128 == 0 && d >= 128 && d <= 2048, "layernorm: d=%d must be a multiple of 128 in [128,2048]", d);
   B2C_REQUIRE(M > 0, "layernorm: M must be positive");
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
   const int nv = d / 128;
   switch (nv) {
-    case 6: layernorm_kernel<6, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
-    case 8: layernorm_kernel<8, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
-    case 10: layernorm_kernel<10, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
-    default: layernorm_kernel<0, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv); break;
+    case 6: layernorm_kernel<6, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv, ldx); break;
+    case 8: layernorm_kernel<8, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv, ldx); break;
+    case 10: layernorm_kernel<10, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv, ldx); break;
+    default: layernorm_kernel<0, OUT_BF16><<<grid, 256, 0, stream>>>(x, gamma, beta, y, M, d, eps, nv, ldx); break;
   }
   B2C_POST_LAUNCH("layernorm_kernel");
   return 0;
@@ -245,6 +247,10 @@ static int layernorm_dispatch(const float* x, const float* gamma, const float* b
 int layernorm_bf16_launch(const float* x, const float* gamma, const float* beta, void* y, int64_t M, int d, float eps,
                           cudaStream_t stream) {
   return layernorm_dispatch<true>(x, gamma, beta, y, M, d, eps, stream);
+}
+int layernorm_bf16_strided_launch(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t M, int d,
+                                  float eps, cudaStream_t stream) {
+  return layernorm_dispatch<true>(x, gamma, beta, y, M, d, eps, stream, ldx);
 }
 int layernorm_f32_inplace_launch(float* x, const float* gamma, const float* beta, int64_t M, int d, float eps,
                                  cudaStream_t stream) {

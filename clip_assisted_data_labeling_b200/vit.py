@@ -81,6 +81,10 @@ class VisionTower:
         """Number of independent sub-batches (own stream each) a pass is split into; see include/b2c.h."""
         _lib.check(self.lib.b2c_vit_set_lanes(self._h, int(lanes)), "b2c_vit_set_lanes")
 
+    def set_cls_only_last_block(self, on: bool) -> None:
+        """Opt-in: the last block evaluates only the class-token row (what ln_post / proj read); see include/b2c.h."""
+        _lib.check(self.lib.b2c_vit_set_cls_only_last_block(self._h, 1 if on else 0), "b2c_vit_set_cls_only_last_block")
+
     def set_fused_ln(self, on: bool) -> None:
         """LayerNorm folded into the GEMMs on either side of it (default) or stand-alone kernels; see include/b2c.h."""
         _lib.check(self.lib.b2c_vit_set_fused_ln(self._h, 1 if on else 0), "b2c_vit_set_fused_ln")

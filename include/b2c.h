@@ -143,6 +143,12 @@ int b2c_vit_set_lanes(b2c_vit* vit, int lanes);
  * the residual update, leaving a bf16 copy of x and its row statistics for the next GEMM.  0 selects the stand-alone
  * LayerNorm kernels.  Both compute LN(x)·Wᵀ + b of utils/embedder.py:98's tower within the same tolerance. */
 int b2c_vit_set_fused_ln(b2c_vit* vit, int on);
+/* Opt-in, off by default: in the LAST block evaluate only the class-token row — the only row ln_post / proj read
+ * (utils/embedder.py:98 returns the pooled class token).  K and V of every token are still computed; the block's
+ * attention, out_proj, ln_2, c_fc and c_proj run on one row per crop (3.3 % fewer FLOPs for ViT-L/14).  The embedding is
+ * the same quantity, rounded at slightly different points (within the tower's tolerance).  Needs head dim 64 and the
+ * fused LayerNorm path; otherwise the block runs in full.  bench.py's headline keeps this off. */
+int b2c_vit_set_cls_only_last_block(b2c_vit* vit, int on);
 int b2c_vit_workspace_bytes(const b2c_vit* vit, int n_crops, size_t* bytes);
 /* pixels: [n,3,R,R] (B2C_F32 / B2C_F16 / B2C_BF16), already normalised — the tensor the reference
  * feeds encode_image (utils/embedder.py:95-98).  out: f32[n,E], unit-norm rows (embedder.py:99). */

@@ -188,6 +188,25 @@ def test_layernorm_fused_and_standalone_paths(cuda, lib, arch, pretrained, n):
     assert (a - b).abs().max().item() <= MAX_ABS
 
 
+@pytest.mark.parametrize("arch,pretrained,n", [("ViT-B-32", "openai", 9), ("ViT-L-14", "openai", 5), ("ViT-H-14", "laion2b_s32b_b79k", 2)])
+def test_class_token_only_last_block_is_the_same_embedding(cuda, lib, arch, pretrained, n):
+    """Opt-in b2c_vit_set_cls_only_last_block: the last block evaluates only the row ln_post / proj read.  Same quantity
+    (tolerance vs the fp32 oracle holds, and it agrees with the full evaluation); head dim 80 keeps the full block."""
+    from oracle import vit_oracle
+    tower, m = _tower_and_oracle(arch, pretrained)
+    R = m.cfg["image"]
+    px = torch.randn(n, 3, R, R, generator=torch.Generator().manual_seed(5))
+    ref = vit_oracle.encode_image_oracle(m, px)
+    full = tower.forward_pixels(px.cuda()).cpu()
+    tower.set_cls_only_last_block(True)
+    pruned = tower.forward_pixels(px.cuda()).cpu()
+    _check_embeddings(ref, full)
+    _check_embeddings(ref, pruned)
+    assert (full - pruned).abs().max().item() <= (0.0 if arch == "ViT-H-14" else MAX_ABS)
+    if arch != "ViT-H-14":
+        assert not torch.equal(full, pruned)  # the pruned path really ran (different rounding points)
+
+
 @pytest.mark.parametrize("arch,n", [("ViT-B-32", 333), ("ViT-L-14", 131)])
 def test_lanes_do_not_change_results(cuda, lib, arch, n):
     """A pass split into 2-4 sub-batches on separate streams (b2c_vit_set_lanes) returns the same bits as one lane:

@@ -119,6 +119,71 @@ class CLIP_Encoder:
         return self.model.encode_u8(images)
 
 
+    @torch.no_grad()
+    def encode_host_batches(self, batches):
+        """Bulk form of ``encode_images_u8`` for data that lives on the host: ``batches`` is an iterable of uint8
+        [B,H,W,3] host tensors (pinned for full speed); yields one f32 [B,4,E] pinned host tensor per batch, in order.
+        Double-buffered: the H2D copy of batch i+1 runs on a copy stream under the compute of batch i, the D2H copy of
+        the embeddings follows the compute on its stream, and batch i is handed out once its copy has landed.  A yielded
+        tensor stays valid until two more batches have been yielded."""
+        dev = torch.device(self.device)
+        with torch.cuda.device(dev):
+            compute = torch.cuda.current_stream()
+            copy = torch.cuda.Stream()
+            bufs, freed = [None, None], [None, None]   # device input ring + "its consumer has run" events
+            outs = [None, None]                         # pinned output ring
+            pending = None  # (slot, event, rows) of the batch whose embeddings are on their way to the host
+            it = iter(batches)
+
+            def stage(host, slot):
+                """H2D of one batch into ring slot `slot` on the copy stream; waits only for that slot's last consumer."""
+                if host.dim() != 4 or host.shape[-1] != 3 or host.dtype != torch.uint8:
+                    raise ValueError(f"expected uint8 [B,H,W,3], got {host.dtype} {tuple(host.shape)}")
+                if bufs[slot] is None or bufs[slot].shape[1:] != host.shape[1:] or bufs[slot].shape[0] < host.shape[0]:
+                    if freed[slot] is not None:
+                        freed[slot].synchronize()
+                    bufs[slot] = torch.empty(tuple(host.shape), dtype=torch.uint8, device=dev)
+                    copy.wait_stream(compute)  # the fresh block may be memory that work queued on `compute` still uses
+                with torch.cuda.stream(copy):
+                    if freed[slot] is not None:
+                        copy.wait_event(freed[slot])
+                    d = bufs[slot][:host.shape[0]]
+                    d.copy_(host, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                return d, ev
+
+            k = 0
+            nxt = next(it, None)
+            staged = stage(nxt, 0) if nxt is not None else None
+            while staged is not None:
+                d, ev = staged
+                slot = k & 1
+                nxt = next(it, None)
+                compute.wait_event(ev)
+                feats = self.model.encode_u8(d)
+                freed[slot] = torch.cuda.Event()
+                freed[slot].record(compute)
+                staged = stage(nxt, slot ^ 1) if nxt is not None else None  # copies under the kernels just enqueued
+                b = feats.shape[0]
+                if outs[slot] is None or outs[slot].shape[0] < b:
+                    outs[slot] = torch.empty(b, 4, feats.shape[-1], dtype=torch.float32, pin_memory=True)
+                outs[slot][:b].copy_(feats, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(compute)
+                if pending is not None:
+                    ps, pe, pb = pending
+                    pe.synchronize()
+                    yield outs[ps][:pb]
+                pending = (slot, done, b)
+                k += 1
+            if pending is not None:
+                ps, pe, pb = pending
+                pe.synchronize()
+                yield outs[ps][:pb]
+            copy.synchronize()
+
+
 class CustomImageDataset(Dataset):
     """utils/embedder.py:153-251 — host (PIL) implementation kept for the reference-compatible
     ``encode_image`` path and as the CPU side of parity tests.  ``image_features`` are not computed

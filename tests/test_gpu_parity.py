@@ -235,6 +235,23 @@ def test_fused_u8_path_vs_reference_pipeline(cuda, lib):
     _check_embeddings(ref, got.view(12, 512))
 
 
+def test_encode_host_batches_equals_per_batch_calls(cuda, lib):
+    """The double-buffered bulk API returns, batch by batch, the bits of encode_images_u8 on the same images."""
+    from clip_assisted_data_labeling_b200.embedder import CLIP_Encoder
+    from oracle import vit_oracle
+    m = vit_oracle.build_visual("ViT-B-32", "openai", seed=0)
+    enc = CLIP_Encoder("ViT-B-32/openai", device="cuda", state_dict=vit_oracle.visual_state_dict(m))
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randint(0, 256, (b, 96, 128, 3), dtype=torch.uint8, generator=g) for b in (5, 9, 1, 9, 4)]
+    pinned = [b.pin_memory() if i % 2 == 0 else b for i, b in enumerate(batches)]  # pageable sources work too
+    got = [t.clone() for t in enc.encode_host_batches(pinned)]
+    assert len(got) == len(batches)
+    for b, o in zip(batches, got):
+        assert o.is_pinned() is False or True  # clones; shapes and bits are what matters
+        assert torch.equal(o, enc.encode_images_u8(b.cuda()).cpu())
+    assert list(enc.encode_host_batches([])) == []
+
+
 def test_clip_encoder_surface(cuda, lib):
     from clip_assisted_data_labeling_b200.embedder import CLIP_Encoder
     from oracle import vit_oracle

@@ -80,16 +80,19 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synth_batch(B, seed):
-    """Synthetic 512x512 uint8 images: low-frequency colour field + noise (cheap torch version of SURVEY §8d)."""
+def synth_batch(B, seed, device="cpu"):
+    """Synthetic 512x512 uint8 images: low-frequency colour field + noise (cheap torch version of SURVEY §8d).  The
+    B200 arm generates its pool on the device (eight ranks sharing 16 host cores would spend a minute here otherwise);
+    the CPU arms generate theirs on the host.  Same distribution either way."""
     import torch
-    g = torch.Generator().manual_seed(seed)
-    yy, xx = torch.meshgrid(torch.arange(IMG_HW, dtype=torch.float32), torch.arange(IMG_HW, dtype=torch.float32), indexing="ij")
-    f = torch.rand(B, 3, 2, generator=g) * 3.5 + 0.5
-    ph = torch.rand(B, 3, 2, generator=g) * 6.2832
+    g = torch.Generator(device=device).manual_seed(seed)
+    ar = torch.arange(IMG_HW, dtype=torch.float32, device=device)
+    yy, xx = torch.meshgrid(ar, ar, indexing="ij")
+    f = torch.rand(B, 3, 2, generator=g, device=device) * 3.5 + 0.5
+    ph = torch.rand(B, 3, 2, generator=g, device=device) * 6.2832
     img = 128 + 90 * torch.sin(6.2832 * f[..., 0, None, None] * xx / IMG_HW + ph[..., 0, None, None]) * \
         torch.cos(6.2832 * f[..., 1, None, None] * yy / IMG_HW + ph[..., 1, None, None])
-    img = img + 20 * torch.randn(B, 3, IMG_HW, IMG_HW, generator=g)
+    img = img + 20 * torch.randn(B, 3, IMG_HW, IMG_HW, generator=g, device=device)
     return img.clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()  # [B,H,W,3]
 
 
@@ -225,8 +228,8 @@ def run_b200_arm(args):
         enc = CLIP_Encoder(MODEL, device="cuda", seed=0)
     enc.model.set_lanes(args.lanes)
     enc.model.set_fused_ln(not args.standalone_layernorm)
-    pool_host = [synth_batch(B, 100 * rank + i).pin_memory() for i in range(args.pool)]
-    pool_dev = [b.cuda() for b in pool_host]
+    pool_dev = [synth_batch(B, 100 * rank + i, device="cuda") for i in range(args.pool)]
+    pool_host = [b.cpu().pin_memory() for b in pool_dev]
     torch.cuda.synchronize()
 
     def barrier():

@@ -312,5 +312,17 @@ def to_device_images(items, device):
 
 
 def collate_raw(batch):
-    """Keep ragged images as a list (default_collate would try to stack them)."""
-    return [b[0] for b in batch], [b[1] for b in batch]
+    """Keep ragged images as a list (default_collate would try to stack them).  Runs in the DataLoader worker: the
+    coefficient tensors of the batch's JPEG items are concatenated into ONE tensor there, and each item keeps a view of it —
+    the main process then receives one shared-memory segment per batch instead of one per image (unpickling 256 segments
+    costs it ~55 ms per batch), and the views gather into pinned memory as before."""
+    items = [b[0] for b in batch]
+    idx = [i for i, it in enumerate(items) if isinstance(it, tuple) and it[0] == "jpeg"]
+    if len(idx) > 1:
+        pack = torch.cat([items[i][2] for i in idx])
+        off = 0
+        for i in idx:
+            n = items[i][2].numel()
+            items[i] = ("jpeg", items[i][1], pack[off:off + n])
+            off += n
+    return items, [b[1] for b in batch]

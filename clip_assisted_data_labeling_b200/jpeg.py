@@ -16,6 +16,7 @@ import torch
 from . import _lib
 
 ERR_UNSUPPORTED = -5
+MAX_PIXELS = 89_478_485  # Pillow's Image.MAX_IMAGE_PIXELS: above it Pillow warns, above twice it refuses
 
 
 class JpegInfo(C.Structure):
@@ -52,6 +53,9 @@ def entropy_decode(data: bytes, pin: bool = False) -> Tuple[JpegInfo, torch.Tens
     rc = lib.b2c_jpeg_parse(buf, len(data), C.byref(info))
     if rc != 0:
         _raise(rc, "b2c_jpeg_parse")
+    if info.width * info.height > MAX_PIXELS:
+        # a header can claim 65535 x 65535: leave such files to Pillow, whose decompression-bomb guard decides
+        raise UnsupportedJPEG(f"{info.width}x{info.height} pixels exceeds the device path's limit of {MAX_PIXELS}")
     coefs = torch.empty(int(info.coef_count), dtype=torch.int16, pin_memory=pin)
     rc = lib.b2c_jpeg_decode_coefs(buf, len(data), C.byref(info), C.c_void_p(coefs.data_ptr()), coefs.numel())
     if rc != 0:

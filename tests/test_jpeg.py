@@ -65,6 +65,12 @@ def test_streams_outside_the_covered_set_are_refused_not_misdecoded(lib):
         jpeg.entropy_decode(b"\x89PNG\r\n" + good[6:])           # not a JPEG
     with pytest.raises(_lib.B2CError):
         jpeg.entropy_decode(good[:200])                           # truncated inside the headers
+    # a header claiming a gigantic image is left to Pillow's decompression-bomb guard (no 13 GB coefficient buffer)
+    bomb = bytearray(good)
+    sof = bomb.index(b"\xff\xc0")
+    bomb[sof + 5:sof + 9] = b"\xff\xff\xff\xff"
+    with pytest.raises(jpeg.UnsupportedJPEG):
+        jpeg.entropy_decode(bytes(bomb))
     # truncated entropy data: libjpeg pads with zeros and Pillow raises/warns; this path must not crash either way
     info, coefs = jpeg.entropy_decode(good[:len(good) // 2] + b"\xff\xd9")
     assert coefs.numel() == info.coef_count

@@ -76,6 +76,38 @@ def test_streams_outside_the_covered_set_are_refused_not_misdecoded(lib):
     assert coefs.numel() == info.coef_count
 
 
+def test_host_stage_survives_corrupted_streams(lib):
+    """600 random corruptions (byte flips, truncations, insertions, header edits) of baseline / progressive / restart
+    streams: every call returns coefficients of the announced size or raises a clean error — the stage reads untrusted files."""
+    from clip_assisted_data_labeling_b200 import _lib, jpeg
+    rng = np.random.default_rng(7)
+    seeds = [make_jpeg(*c)[0] for c in [(64, 48, 2, 80, {}), (97, 131, 0, 95, {"progressive": True}), (120, 80, 1, 60, {"restart_marker_blocks": 3}),
+                                        (33, 17, "gray", 70, {}), (250, 250, 2, 85, {"progressive": True, "restart_marker_blocks": 3})]]
+    outcomes = {"ok": 0, "refused": 0, "error": 0}
+    for it in range(600):
+        d = bytearray(seeds[it % len(seeds)])
+        mode = it % 4
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 8))):
+                d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+        elif mode == 1:
+            d = d[:int(rng.integers(2, len(d)))]
+        elif mode == 2:
+            p = int(rng.integers(0, len(d)))
+            d[p:p] = bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8))
+        else:
+            d[int(rng.integers(2, min(len(d), 700)))] = int(rng.integers(0, 256))
+        try:
+            info, c = jpeg.entropy_decode(bytes(d))
+            assert c.numel() == info.coef_count and info.width > 0 and info.height > 0
+            outcomes["ok"] += 1
+        except jpeg.UnsupportedJPEG:
+            outcomes["refused"] += 1
+        except _lib.B2CError:
+            outcomes["error"] += 1
+    assert outcomes["ok"] > 100 and outcomes["error"] > 100, outcomes
+
+
 def test_dataset_items_fall_back_to_pillow_per_file(lib, tmp_path):
     """RawImageDataset(device_jpeg=True): baseline / progressive .jpg -> coefficient item; CMYK .jpg and .png -> Pillow tensors."""
     from clip_assisted_data_labeling_b200.embedder import RawImageDataset

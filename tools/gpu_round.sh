@@ -1,6 +1,7 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, bench line, ncu launch list, ncu --set full captures.  Outputs -> gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench launches full
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag] [what...]'
+#   what: tests smoke bench refbench multi launches full gemmcmp archs attntest attnbench train imgstats similar jpeg pipeline lanes power
 set -u
 TAG=${1:-run}
 shift || true
@@ -46,6 +47,16 @@ for w in $WHAT; do
     similar)
       timeout 600 python -m pytest tests/test_gpu_similar.py -m gpu -x -q > $OUT/${TAG}_similar_tests.log 2>&1; tail -15 $OUT/${TAG}_similar_tests.log
       timeout 300 python tools/bench_similar.py > $OUT/${TAG}_bench_similar.json 2> $OUT/${TAG}_bench_similar.err; cat $OUT/${TAG}_bench_similar.json; tail -3 $OUT/${TAG}_bench_similar.err ;;
+    jpeg)
+      timeout 600 python -m pytest tests/test_jpeg.py -x -q > $OUT/${TAG}_jpeg_tests.log 2>&1; tail -3 $OUT/${TAG}_jpeg_tests.log
+      timeout 300 python tools/bench_jpeg.py 256 > $OUT/${TAG}_bench_jpeg.json 2> $OUT/${TAG}_bench_jpeg.err; cat $OUT/${TAG}_bench_jpeg.json ;;
+    pipeline)
+      B2C_DRIVER_TIMING=1 timeout 900 python tools/bench_pipeline.py --n 8192 2> $OUT/${TAG}_pipeline.err | tee $OUT/${TAG}_pipeline.jsonl
+      grep main-thread $OUT/${TAG}_pipeline.err | tail -1 ;;
+    lanes)
+      timeout 400 python tools/bench_lanes.py --batches 256 --lanes 1,2,4 --fused 0,1 2> $OUT/${TAG}_lanes.err | tee $OUT/${TAG}_lanes.jsonl ;;
+    power)
+      timeout 500 python tools/power_probe.py 512 > $OUT/${TAG}_power.json 2> $OUT/${TAG}_power.err; cat $OUT/${TAG}_power.json ;;
     refbench)
       timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_refbench.json 2> $OUT/${TAG}_refbench.err
       cat $OUT/${TAG}_refbench.json ;;

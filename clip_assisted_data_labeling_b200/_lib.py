@@ -89,6 +89,8 @@ SIGNATURES = {
     "b2c_vit_forward_patches": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "b2c_jpeg_parse": (_i, [_vp, _sz, _vp]),
     "b2c_jpeg_decode_coefs": (_i, [_vp, _sz, _vp, _vp, _sz]),
+    "b2c_jpeg_decode_packed": (_i, [_vp, _sz, _vp, _vp, _sz, _vp]),
+    "b2c_jpeg_reconstruct_packed": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "b2c_jpeg_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
     "b2c_jpeg_reconstruct": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "b2c_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),

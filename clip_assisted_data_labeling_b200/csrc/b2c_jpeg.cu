@@ -124,6 +124,14 @@ int frame_geometry(Parsed& P) {
     off += static_cast<int64_t>(I.blocks_w[c]) * I.blocks_h[c] * 64;
   }
   I.coef_count = off;
+  // packed form: [counts u8 x nblocks | pad to 16 | group offsets u32 x ngroups | pad to 16 | values i16 ...], 16-B multiples
+  I.nblocks = static_cast<int32_t>(off / 64);
+  I.ngroups = (I.nblocks + 31) / 32;
+  I.counts_off = 0;
+  I.groups_off = (static_cast<int64_t>(I.nblocks) + 15) & ~15ll;
+  I.vals_off = (I.groups_off + 4ll * I.ngroups + 15) & ~15ll;
+  I.packed_capacity = I.vals_off + 2 * off;  // worst case: every block keeps all 64 coefficients
+  I.packed_bytes = 0;
   if (I.ncomp == 3 && I.comp_w[1] < 2 && I.hs[0] == 2) return fail_unsupported("image narrower than two chroma samples");
   return 0;
 }
@@ -370,7 +378,7 @@ inline int block_sequential(BitReader& br, const HuffTable& dct, const HuffTable
       k += (fa >> 4) & 15;
       if (k > 63) return fail_corrupt("AC run past the block");
       br.drop(fa & 15);
-      blk[kZigzag[k++]] = static_cast<int16_t>(fa >> 8);
+      blk[k++] = static_cast<int16_t>(fa >> 8);
       continue;
     }
     const int rs = decode_symbol(br, act);
@@ -384,7 +392,7 @@ inline int block_sequential(BitReader& br, const HuffTable& dct, const HuffTable
     }
     k += r;
     if (k > 63) return fail_corrupt("AC run past the block");
-    blk[kZigzag[k]] = static_cast<int16_t>(receive_extend(br, s));
+    blk[k] = static_cast<int16_t>(receive_extend(br, s));
     ++k;
   }
   return 0;
@@ -403,7 +411,7 @@ inline int block_ac_first(BitReader& br, const HuffTable& act, const Scan& sc, i
     if (s) {
       k += r;
       if (k > 63) return fail_corrupt("AC run past the block");
-      blk[kZigzag[k]] = static_cast<int16_t>(receive_extend(br, s) * (1 << sc.al));
+      blk[k] = static_cast<int16_t>(receive_extend(br, s) * (1 << sc.al));
     } else if (r == 15) {
       k += 15;
     } else {
@@ -434,7 +442,7 @@ inline int block_ac_refine(BitReader& br, const HuffTable& act, const Scan& sc, 
       }
       // skip r still-zero coefficients, appending a correction bit to every already non-zero one on the way
       do {
-        int16_t* c = blk + kZigzag[k];
+        int16_t* c = blk + k;
         if (*c != 0) {
           if (br.bit() && (*c & p1) == 0) *c = static_cast<int16_t>(*c + (*c >= 0 ? p1 : m1));
         } else if (--r < 0) {
@@ -444,13 +452,13 @@ inline int block_ac_refine(BitReader& br, const HuffTable& act, const Scan& sc, 
       } while (k <= sc.se);
       if (s) {
         if (k > 63) return fail_corrupt("AC run past the block");
-        blk[kZigzag[k]] = static_cast<int16_t>(s);
+        blk[k] = static_cast<int16_t>(s);
       }
     }
   }
   if (eobrun > 0) {
     for (; k <= sc.se; ++k) {
-      int16_t* c = blk + kZigzag[k];
+      int16_t* c = blk + k;
       if (*c != 0 && br.bit() && (*c & p1) == 0) *c = static_cast<int16_t>(*c + (*c >= 0 ? p1 : m1));
     }
     --eobrun;
@@ -513,7 +521,8 @@ int decode_scan(const uint8_t* d, size_t n, const Parsed& P, const Scan& sc, int
   return 0;
 }
 
-// every scan of the file, in order; sequential frames stop once each component has been coded
+// every scan of the file, in order; sequential frames stop once each component has been coded.  Blocks come out in
+// ZIGZAG order (coefficient k of the scan order at blk[k]): the packed form keeps that order, the dense API permutes.
 int decode_all(const uint8_t* d, size_t n, Parsed& P, Scan scan, size_t pos, int16_t* coefs) {
   memset(coefs, 0, static_cast<size_t>(P.info.coef_count) * sizeof(int16_t));
   bool seen[3] = {false, false, false};
@@ -536,9 +545,50 @@ int decode_all(const uint8_t* d, size_t n, Parsed& P, Scan scan, size_t pos, int
   return 0;
 }
 
+// zigzag-ordered dense blocks -> natural (row-major) order in place: what the dense API and the oracle consume
+void dezigzag_in_place(int16_t* coefs, int64_t nblocks) {
+  int16_t tmp[64];
+  for (int64_t b = 0; b < nblocks; ++b) {
+    int16_t* blk = coefs + b * 64;
+    memcpy(tmp, blk, sizeof(tmp));
+    for (int k = 0; k < 64; ++k) blk[kZigzag[k]] = tmp[k];
+  }
+}
+
+// zigzag-ordered dense blocks -> packed form (see frame_geometry); returns the bytes used (a multiple of 16)
+int64_t pack_blocks(const b2c_jpeg_info& I, const int16_t* dense, uint8_t* out) {
+  uint8_t* counts = out + I.counts_off;
+  uint32_t* groups = reinterpret_cast<uint32_t*>(out + I.groups_off);
+  int16_t* vals = reinterpret_cast<int16_t*>(out + I.vals_off);
+  memset(out, 0, static_cast<size_t>(I.vals_off));
+  uint32_t nv = 0;
+  for (int32_t b = 0; b < I.nblocks; ++b) {
+    if ((b & 31) == 0) groups[b >> 5] = nv;
+    const int16_t* blk = dense + static_cast<int64_t>(b) * 64;
+    int n = 64;
+    while (n > 0) {  // last non-zero coefficient in scan order, four at a time
+      uint64_t w;
+      memcpy(&w, blk + n - 4, 8);
+      if (w) break;
+      n -= 4;
+    }
+    while (n > 0 && blk[n - 1] == 0) --n;
+    counts[b] = static_cast<uint8_t>(n);
+    memcpy(vals + nv, blk, static_cast<size_t>(n) * 2);
+    nv += n;
+  }
+  int64_t used = I.vals_off + 2ll * nv;
+  const int64_t padded = (used + 15) & ~15ll;
+  memset(out + used, 0, static_cast<size_t>(padded - used));
+  return padded;
+}
+
 // ------------------------------------------------------------------------------------------------ device
 struct JpegJobDev {
-  const int16_t* coefs;
+  const int16_t* coefs;        // dense form (natural order) or nullptr
+  const uint8_t* packed;       // packed form or nullptr
+  int64_t counts_off, groups_off, vals_off;
+  int32_t nblocks;
   uint8_t* out;
   int32_t out_pitch;
   int32_t width, height, ncomp;
@@ -548,7 +598,7 @@ struct JpegJobDev {
   int64_t coef_offset[3];
   int64_t plane_offset[3];     // bytes into the plane workspace; plane c is [blocks_h*8][blocks_w*8] uint8
   uint16_t qt[3][64];
-  int32_t block_begin;         // first global 8x8-block index of this image (all components, in order)
+  int32_t block_begin;         // first global 8x8-block index of this image (all components, in order; multiple of 32)
   int32_t pixel_tile_begin;    // first global 32x8-pixel tile of this image
 };
 
@@ -634,17 +684,40 @@ __device__ __forceinline__ int find_job(const JpegJobDev* jobs, int n, int idx, 
   return lo;
 }
 
+__constant__ uint8_t kZigzagInv[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                                       41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                                       46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+// One CTA = 32 consecutive blocks of ONE image (every image's block range starts at a multiple of 32).
 __global__ void __launch_bounds__(kIdctThreads) jpeg_idct_kernel(const JpegJobDev* __restrict__ jobs, int njobs,
                                                                  int total_blocks, uint8_t* __restrict__ planes) {
   __shared__ int ws[32][8][9];  // [block][row][col], padded against bank conflicts
+  __shared__ uint32_t voff[32]; // packed form: element offset of each block's values
+  __shared__ uint8_t vcnt[32];  //              and how many it keeps
   const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
   const int gb = blockIdx.x * 32 + lb;
-  const bool live = gb < total_blocks;
-  const JpegJobDev* J = nullptr;
+  const JpegJobDev* J = jobs + find_job(jobs, njobs, blockIdx.x * 32, false);
+  const int b = gb - J->block_begin;  // block index inside the image
+  const bool live = gb < total_blocks && b < J->nblocks;
+  if (J->packed != nullptr) {
+    if (threadIdx.x < 32) {
+      const int bi = blockIdx.x * 32 - J->block_begin + threadIdx.x;
+      const uint32_t c = bi < J->nblocks ? J->packed[J->counts_off + bi] : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (threadIdx.x >= o) incl += v;
+      }
+      const uint32_t base = reinterpret_cast<const uint32_t*>(J->packed + J->groups_off)[(blockIdx.x * 32 - J->block_begin) >> 5];
+      voff[threadIdx.x] = base + incl - c;
+      vcnt[threadIdx.x] = static_cast<uint8_t>(c);
+    }
+    __syncthreads();
+  }
   int c = 0, bx = 0, by = 0;
   if (live) {
-    J = jobs + find_job(jobs, njobs, gb, false);
-    int rem = gb - J->block_begin;
+    int rem = b;
     while (c + 1 < J->ncomp && rem >= J->blocks_w[c] * J->blocks_h[c]) {
       rem -= J->blocks_w[c] * J->blocks_h[c];
       ++c;
@@ -652,11 +725,21 @@ __global__ void __launch_bounds__(kIdctThreads) jpeg_idct_kernel(const JpegJobDe
     by = rem / J->blocks_w[c];
     bx = rem - by * J->blocks_w[c];
     // pass 1: column t of the block, dequantised
-    const int16_t* blk = J->coefs + J->coef_offset[c] + (static_cast<int64_t>(by) * J->blocks_w[c] + bx) * 64;
     const uint16_t* q = J->qt[c];
     int in[8], o[8];
+    if (J->packed != nullptr) {
+      const int16_t* vals = reinterpret_cast<const int16_t*>(J->packed + J->vals_off) + voff[lb];
+      const int cnt = vcnt[lb];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) in[r] = static_cast<int>(blk[r * 8 + t]) * static_cast<int>(q[r * 8 + t]);
+      for (int r = 0; r < 8; ++r) {
+        const int p = kZigzagInv[r * 8 + t];  // position of natural coefficient (r, t) in scan order
+        in[r] = p < cnt ? static_cast<int>(vals[p]) * static_cast<int>(q[r * 8 + t]) : 0;
+      }
+    } else {
+      const int16_t* blk = J->coefs + static_cast<int64_t>(b) * 64;  // blocks are stored in image block order
+#pragma unroll
+      for (int r = 0; r < 8; ++r) in[r] = static_cast<int>(blk[r * 8 + t]) * static_cast<int>(q[r * 8 + t]);
+    }
     idct_1d(in, o);  // (an all-zero AC column gives dc << 2 through the same arithmetic as libjpeg's shortcut)
 #pragma unroll
     for (int r = 0; r < 8; ++r) ws[lb][r][t] = descale(o[r], 13 - 2);
@@ -763,7 +846,30 @@ extern "C" int b2c_jpeg_decode_coefs(const uint8_t* data, size_t len, b2c_jpeg_i
   B2C_REQUIRE(static_cast<size_t>(P.info.coef_count) <= capacity, "b2c_jpeg_decode_coefs: buffer holds %zu coefficients, %lld needed",
               capacity, (long long)P.info.coef_count);
   B2C_TRY(decode_all(data, len, P, first, pos, coefs));
+  dezigzag_in_place(coefs, P.info.nblocks);
   *info = P.info;  // quantisation tables are latched scan by scan
+  return 0;
+}
+
+extern "C" int b2c_jpeg_decode_packed(const uint8_t* data, size_t len, b2c_jpeg_info* info, uint8_t* packed, size_t capacity,
+                                      int16_t* scratch) {
+  using namespace b2c;
+  B2C_REQUIRE(data && info && packed, "b2c_jpeg_decode_packed: null pointer");
+  B2C_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "b2c_jpeg_decode_packed: buffer must be 16-byte aligned");
+  Parsed P;
+  Scan first;
+  size_t pos = 0;
+  B2C_TRY(parse(data, len, P, first, pos));
+  B2C_REQUIRE(static_cast<size_t>(P.info.packed_capacity) <= capacity, "b2c_jpeg_decode_packed: buffer holds %zu bytes, %lld needed",
+              capacity, (long long)P.info.packed_capacity);
+  std::vector<int16_t> own;
+  if (!scratch) {
+    own.resize(static_cast<size_t>(P.info.coef_count));
+    scratch = own.data();
+  }
+  B2C_TRY(decode_all(data, len, P, first, pos, scratch));
+  P.info.packed_bytes = pack_blocks(P.info, scratch, packed);
+  *info = P.info;
   return 0;
 }
 
@@ -777,11 +883,11 @@ extern "C" int b2c_jpeg_workspace_bytes(const b2c_jpeg_info* infos, int n, size_
   return 0;
 }
 
-extern "C" int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* const* coefs, uint8_t* const* outs,
-                                    const int* out_pitch, int n, void* ws, size_t ws_bytes, b2c_stream stream_) {
-  using namespace b2c;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  B2C_REQUIRE(infos && coefs && outs && out_pitch && ws && n > 0, "b2c_jpeg_reconstruct: bad arguments");
+namespace b2c {
+namespace {
+int reconstruct_impl(const b2c_jpeg_info* infos, const int16_t* const* coefs, const uint8_t* const* packed, uint8_t* const* outs,
+                     const int* out_pitch, int n, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  B2C_REQUIRE(infos && (coefs || packed) && outs && out_pitch && ws && n > 0, "b2c_jpeg_reconstruct: bad arguments");
   size_t need = 0;
   B2C_TRY(b2c_jpeg_workspace_bytes(infos, n, &need));
   if (ws_bytes < need) return set_error(B2C_ERR_WORKSPACE, "b2c_jpeg_reconstruct: workspace %zu B < required %zu B", ws_bytes, need);
@@ -790,11 +896,20 @@ extern "C" int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* c
   long long blocks = 0, tiles = 0;
   for (int i = 0; i < n; ++i) {
     const b2c_jpeg_info& I = infos[i];
-    B2C_REQUIRE(coefs[i] && outs[i] && out_pitch[i] >= 3 * I.width, "b2c_jpeg_reconstruct: bad buffers for image %d", i);
-    B2C_REQUIRE((I.ncomp == 1 || I.ncomp == 3) && I.width > 0 && I.height > 0, "b2c_jpeg_reconstruct: bad info for image %d", i);
+    const void* src = packed ? static_cast<const void*>(packed[i]) : static_cast<const void*>(coefs[i]);
+    B2C_REQUIRE(src && outs[i] && out_pitch[i] >= 3 * I.width, "b2c_jpeg_reconstruct: bad buffers for image %d", i);
+    B2C_REQUIRE((I.ncomp == 1 || I.ncomp == 3) && I.width > 0 && I.height > 0 && I.nblocks > 0 &&
+                    static_cast<int64_t>(I.nblocks) * 64 == I.coef_count,
+                "b2c_jpeg_reconstruct: bad info for image %d", i);
+    if (packed) B2C_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0, "b2c_jpeg_reconstruct_packed: buffer %d is not 16-byte aligned", i);
     JpegJobDev& J = jobs[i];
     memset(&J, 0, sizeof(J));
-    J.coefs = coefs[i];
+    J.coefs = packed ? nullptr : coefs[i];
+    J.packed = packed ? packed[i] : nullptr;
+    J.counts_off = I.counts_off;
+    J.groups_off = I.groups_off;
+    J.vals_off = I.vals_off;
+    J.nblocks = I.nblocks;
     J.out = outs[i];
     J.out_pitch = out_pitch[i];
     J.width = I.width;
@@ -812,9 +927,9 @@ extern "C" int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* c
       J.coef_offset[c] = I.coef_offset[c];
       J.plane_offset[c] = static_cast<int64_t>(off);
       off += a256(static_cast<size_t>(I.blocks_w[c]) * I.blocks_h[c] * 64);
-      blocks += static_cast<long long>(I.blocks_w[c]) * I.blocks_h[c];
       memcpy(J.qt[c], I.qt[c], sizeof(J.qt[c]));
     }
+    blocks += (static_cast<long long>(I.nblocks) + 31) & ~31ll;  // every image starts a fresh group of 32 blocks
     tiles += static_cast<long long>((I.width + kPixTileW - 1) / kPixTileW) * ((I.height + kPixTileH - 1) / kPixTileH);
     B2C_REQUIRE(blocks < (1ll << 31) && tiles < (1ll << 31), "b2c_jpeg_reconstruct: batch too large");
   }
@@ -822,9 +937,21 @@ extern "C" int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* c
   uint8_t* planes = static_cast<uint8_t*>(ws);
   B2C_TRY(upload_async(jd, jobs.data(), static_cast<size_t>(n) * sizeof(JpegJobDev), stream));  // no stream synchronisation
   ProfScope ps(B2C_PROF_OTHER, stream);
-  jpeg_idct_kernel<<<static_cast<unsigned>((blocks + 31) / 32), kIdctThreads, 0, stream>>>(jd, n, static_cast<int>(blocks), planes);
+  jpeg_idct_kernel<<<static_cast<unsigned>(blocks / 32), kIdctThreads, 0, stream>>>(jd, n, static_cast<int>(blocks), planes);
   B2C_POST_LAUNCH("jpeg_idct_kernel");
   jpeg_color_kernel<<<static_cast<unsigned>(tiles), kPixTileW * kPixTileH, 0, stream>>>(jd, n, planes);
   B2C_POST_LAUNCH("jpeg_color_kernel");
   return 0;
+}
+}  // namespace
+}  // namespace b2c
+
+extern "C" int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* const* coefs, uint8_t* const* outs,
+                                    const int* out_pitch, int n, void* ws, size_t ws_bytes, b2c_stream stream) {
+  return b2c::reconstruct_impl(infos, coefs, nullptr, outs, out_pitch, n, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2c_jpeg_reconstruct_packed(const b2c_jpeg_info* infos, const uint8_t* const* packed, uint8_t* const* outs,
+                                           const int* out_pitch, int n, void* ws, size_t ws_bytes, b2c_stream stream) {
+  return b2c::reconstruct_impl(infos, nullptr, packed, outs, out_pitch, n, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }

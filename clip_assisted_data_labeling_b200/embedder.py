@@ -243,9 +243,10 @@ class CustomImageDataset(Dataset):
 class RawImageDataset(Dataset):
     """Decode only: returns (item, path).  Crops, resize and normalisation run on the GPU (b2c_preprocess_4crop).
     item is
-      * ``("jpeg", info_bytes, int16 coefficients)`` for a baseline JPEG when ``device_jpeg`` is on: the worker does
-        the serial part (marker parse + Huffman decode, jpeg.entropy_decode) and the main process finishes the decode
-        on the device (jpeg.reconstruct) — bit-exact with Pillow, SURVEY.md §8f row 2;
+      * ``("jpegp", info_bytes, uint8 packed coefficients)`` for a baseline / progressive JPEG when ``device_jpeg`` is
+        on: the worker does the serial part (marker parse + Huffman decode, jpeg.entropy_decode_packed) and the main
+        process finishes the decode on the device (jpeg.reconstruct_packed) — bit-exact with Pillow, SURVEY.md §8f row 2
+        (``("jpeg", info_bytes, int16 dense coefficients)`` items are accepted too);
       * a uint8 HWC tensor decoded with Pillow (`Image.open(path).convert('RGB')`, utils/embedder.py:167) for every
         other format and for JPEG streams the device path does not cover;
       * ``None`` for a file that fails to decode — reported by the driver, never silently substituted."""
@@ -269,8 +270,8 @@ class RawImageDataset(Dataset):
                 with open(path, "rb") as fh:
                     data = fh.read()
                 try:
-                    info, coefs = jpeg.entropy_decode(data)
-                    return ("jpeg", bytes(info), coefs), path
+                    info, packed = jpeg.entropy_decode_packed(data)
+                    return ("jpegp", bytes(info), packed), path
                 except jpeg.UnsupportedJPEG:
                     src = io.BytesIO(data)  # progressive, CMYK, ...: Pillow decodes the bytes already read
             with Image.open(src) as im:
@@ -291,9 +292,12 @@ def to_device_images(items, device):
     global _pixel_staging
     from . import jpeg
     out = [None] * len(items)
-    jobs, where, pix, pwhere = [], [], [], []
+    jobs, where, pjobs, pjwhere, pix, pwhere = [], [], [], [], [], []
     for i, it in enumerate(items):
-        if isinstance(it, tuple) and it[0] == "jpeg":
+        if isinstance(it, tuple) and it[0] == "jpegp":
+            pjobs.append((jpeg.JpegInfo.from_buffer_copy(it[1]), it[2]))
+            pjwhere.append(i)
+        elif isinstance(it, tuple) and it[0] == "jpeg":
             jobs.append((jpeg.JpegInfo.from_buffer_copy(it[1]), it[2]))
             where.append(i)
         else:
@@ -306,6 +310,8 @@ def to_device_images(items, device):
             dflat, offs = _pixel_staging.gather(pix, torch.device(device))
         for i, t, o in zip(pwhere, pix, offs[:-1]):
             out[i] = dflat[int(o):int(o) + t.numel()].view(t.shape)
+    for i, t in zip(pjwhere, jpeg.reconstruct_packed(pjobs, device)):
+        out[i] = t
     for i, t in zip(where, jpeg.reconstruct(jobs, device)):
         out[i] = t
     return out
@@ -317,12 +323,13 @@ def collate_raw(batch):
     the main process then receives one shared-memory segment per batch instead of one per image (unpickling 256 segments
     costs it ~55 ms per batch), and the views gather into pinned memory as before."""
     items = [b[0] for b in batch]
-    idx = [i for i, it in enumerate(items) if isinstance(it, tuple) and it[0] == "jpeg"]
-    if len(idx) > 1:
-        pack = torch.cat([items[i][2] for i in idx])
-        off = 0
-        for i in idx:
-            n = items[i][2].numel()
-            items[i] = ("jpeg", items[i][1], pack[off:off + n])
-            off += n
+    for kind in ("jpegp", "jpeg"):
+        idx = [i for i, it in enumerate(items) if isinstance(it, tuple) and it[0] == kind]
+        if len(idx) > 1:
+            pack = torch.cat([items[i][2] for i in idx])  # packed buffers are multiples of 16 bytes: views stay aligned
+            off = 0
+            for i in idx:
+                n = items[i][2].numel()
+                items[i] = (kind, items[i][1], pack[off:off + n])
+                off += n
     return items, [b[1] for b in batch]

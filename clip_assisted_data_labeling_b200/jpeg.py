@@ -8,6 +8,7 @@ colour conversion) is one batched device call on the main process.  A stream the
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -25,7 +26,9 @@ class JpegInfo(C.Structure):
                 ("blocks_h", C.c_int32 * 3), ("comp_w", C.c_int32 * 3), ("comp_h", C.c_int32 * 3),
                 ("restart_interval", C.c_int32), ("adobe_transform0", C.c_int32), ("progressive", C.c_int32),
                 ("reserved_", C.c_int32), ("coef_offset", C.c_int64 * 3),
-                ("coef_count", C.c_int64), ("qt", (C.c_uint16 * 64) * 3)]
+                ("coef_count", C.c_int64), ("nblocks", C.c_int32), ("ngroups", C.c_int32), ("counts_off", C.c_int64),
+                ("groups_off", C.c_int64), ("vals_off", C.c_int64), ("packed_capacity", C.c_int64), ("packed_bytes", C.c_int64),
+                ("qt", (C.c_uint16 * 64) * 3)]
 
     def as_dict(self) -> dict:
         return {"width": self.width, "height": self.height, "ncomp": self.ncomp, "hs": list(self.hs), "vs": list(self.vs),
@@ -45,8 +48,58 @@ def _raise(rc: int, what: str):
     raise _lib.B2CError(f"{what} failed (code {rc}): {msg}")
 
 
+_scratch = threading.local()
+
+
+def entropy_decode_packed(data: bytes) -> Tuple[JpegInfo, torch.Tensor]:
+    """JPEG bytes -> (info, uint8 tensor holding the PACKED coefficients: per block only the coefficients up to the last
+    non-zero one in scan order, see include/b2c.h).  This is what the DataLoader workers hand to the main process: 4-10x
+    smaller than the dense form.  Host only; safe in worker processes and threads."""
+    lib = _lib.load()
+    info = JpegInfo()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    rc = lib.b2c_jpeg_parse(buf, len(data), C.byref(info))
+    if rc != 0:
+        _raise(rc, "b2c_jpeg_parse")
+    if info.width * info.height > MAX_PIXELS:
+        raise UnsupportedJPEG(f"{info.width}x{info.height} pixels exceeds the device path's limit of {MAX_PIXELS}")
+    # per-thread scratch: the dense decode target and a worst-case packed buffer, grown on demand
+    sc = getattr(_scratch, "dense", None)
+    if sc is None or sc.numel() < info.coef_count:
+        sc = _scratch.dense = torch.empty(int(info.coef_count), dtype=torch.int16)
+    pk = getattr(_scratch, "packed", None)
+    if pk is None or pk.numel() < info.packed_capacity + 16:
+        pk = _scratch.packed = torch.empty(int(info.packed_capacity) + 16, dtype=torch.uint8)
+    base = (pk.data_ptr() + 15) & ~15
+    rc = lib.b2c_jpeg_decode_packed(buf, len(data), C.byref(info), C.c_void_p(base), int(info.packed_capacity), C.c_void_p(sc.data_ptr()))
+    if rc != 0:
+        _raise(rc, "b2c_jpeg_decode_packed")
+    out = torch.empty(int(info.packed_bytes), dtype=torch.uint8)
+    C.memmove(out.data_ptr(), base, int(info.packed_bytes))  # (Tensor.clone would wake the intra-op thread pool for 100 KB)
+    return info, out
+
+
+def expand_packed(info: JpegInfo, packed: torch.Tensor) -> torch.Tensor:
+    """Packed form -> dense int16 coefficients in natural order (what entropy_decode returns): tests / the oracle."""
+    zz = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35,
+          42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+    p = packed.numpy()
+    counts = p[info.counts_off:info.counts_off + info.nblocks].astype(np.int64)
+    groups = p[info.groups_off:info.groups_off + 4 * info.ngroups].view(np.uint32).astype(np.int64)
+    nv = int(counts.sum())
+    vals = p[info.vals_off:info.vals_off + 2 * nv].view(np.int16)
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    assert np.array_equal(starts[::32], groups)
+    dense = np.zeros((info.nblocks, 64), np.int16)
+    zz = np.asarray(zz)
+    for b in np.nonzero(counts)[0]:
+        dense[b, zz[:counts[b]]] = vals[starts[b]:starts[b] + counts[b]]
+    return torch.from_numpy(dense.reshape(-1))
+
+
 def entropy_decode(data: bytes, pin: bool = False) -> Tuple[JpegInfo, torch.Tensor]:
-    """JPEG bytes -> (info, int16 coefficient tensor on the host).  Host only; safe in worker processes."""
+    """JPEG bytes -> (info, DENSE int16 coefficient tensor on the host, natural order).  Host only; safe in worker
+    processes.  The dense form is the oracle's input and the reference point of the packed form."""
     lib = _lib.load()
     info = JpegInfo()
     buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
@@ -139,6 +192,33 @@ def reconstruct_device(infos: Sequence[JpegInfo], dflat: torch.Tensor) -> List[t
         _lib.check(lib.b2c_jpeg_reconstruct(arr, cptr, optr, pitch, n, C.c_void_p(ws.data_ptr()), ws.numel(),
                                             C.c_void_p(_lib.current_stream_ptr())), "b2c_jpeg_reconstruct")
         # ws / dflat go back to torch's caching allocator in stream order, after the launches above
+    return outs
+
+
+_packed_staging = Staging(torch.uint8)
+
+
+def reconstruct_packed(items: Sequence[Tuple[JpegInfo, torch.Tensor]], device="cuda") -> List[torch.Tensor]:
+    """[(info, host PACKED coefficients)] -> [uint8 [H,W,3] device tensors]: one gather into pinned memory, one H2D copy
+    and two kernel launches per batch."""
+    if not items:
+        return []
+    lib = _lib.load()
+    dev = torch.device(device)
+    n = len(items)
+    infos = [it[0] for it in items]
+    with torch.cuda.device(dev):
+        dflat, offs = _packed_staging.gather([it[1] for it in items], dev)  # every buffer is a multiple of 16 bytes
+        arr = (JpegInfo * n)(*infos)
+        outs = [torch.empty(i.height, i.width, 3, dtype=torch.uint8, device=dev) for i in infos]
+        need = C.c_size_t()
+        _lib.check(lib.b2c_jpeg_workspace_bytes(arr, n, C.byref(need)), "b2c_jpeg_workspace_bytes")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        pptr = (C.c_void_p * n)(*[dflat.data_ptr() + int(o) for o in offs[:-1]])
+        optr = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        pitch = (C.c_int * n)(*[3 * i.width for i in infos])
+        _lib.check(lib.b2c_jpeg_reconstruct_packed(arr, pptr, optr, pitch, n, C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                   C.c_void_p(_lib.current_stream_ptr())), "b2c_jpeg_reconstruct_packed")
     return outs
 
 

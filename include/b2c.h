@@ -325,7 +325,14 @@ typedef struct {
   int32_t progressive;              /* SOF2: several scans refine the same coefficient buffer */
   int32_t reserved_;
   int64_t coef_offset[3];           /* component c's blocks start at coefs + coef_offset[c]; block (by,bx) at +(by*blocks_w+bx)*64 */
-  int64_t coef_count;               /* int16 elements the coefficient buffer needs */
+  int64_t coef_count;               /* int16 elements the (dense) coefficient buffer needs */
+  /* packed form (b2c_jpeg_decode_packed): counts u8[nblocks] | group offsets u32[ngroups] | values i16[...] at these byte
+   * offsets of one buffer; block b keeps its first counts[b] coefficients in scan (zigzag) order, the values of block
+   * 32 g start at element group_offsets[g].  Blocks are numbered component by component, row-major. */
+  int32_t nblocks, ngroups;
+  int64_t counts_off, groups_off, vals_off;
+  int64_t packed_capacity;          /* bytes a buffer must have for b2c_jpeg_decode_packed (worst case) */
+  int64_t packed_bytes;             /* bytes actually used (multiple of 16), set by b2c_jpeg_decode_packed */
   uint16_t qt[3][64];               /* quantisation table of each component, natural (row-major) order */
 } b2c_jpeg_info;
 
@@ -335,11 +342,19 @@ int b2c_jpeg_parse(const uint8_t* data, size_t len, b2c_jpeg_info* info);
 /* Host only: parse + Huffman decode of every scan into `coefs` (HOST memory, ideally pinned; capacity in int16 elements):
  * de-zigzagged, not dequantised. */
 int b2c_jpeg_decode_coefs(const uint8_t* data, size_t len, b2c_jpeg_info* info, int16_t* coefs, size_t capacity);
+/* Host only: like b2c_jpeg_decode_coefs, but the result is the packed form — typically 4-10x smaller than the dense
+ * buffer, which is what travels from the worker to the main process and over PCIe.  `scratch`: coef_count int16 of host
+ * scratch (the dense decode target; NULL = allocate internally per call). */
+int b2c_jpeg_decode_packed(const uint8_t* data, size_t len, b2c_jpeg_info* info, uint8_t* packed, size_t capacity,
+                           int16_t* scratch);
 int b2c_jpeg_workspace_bytes(const b2c_jpeg_info* infos, int n, size_t* bytes);
 /* Device: coefs[i] = DEVICE copy of image i's coefficient buffer, outs[i] = DEVICE uint8 [height, width, 3] with row
  * pitch out_pitch[i] bytes.  infos / pointer arrays are host arrays.  Two launches for the whole batch. */
 int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* const* coefs, uint8_t* const* outs,
                          const int* out_pitch, int n, void* ws, size_t ws_bytes, b2c_stream stream);
+/* Same from the packed form: packed[i] = DEVICE copy (16-byte aligned) of image i's packed buffer. */
+int b2c_jpeg_reconstruct_packed(const b2c_jpeg_info* infos, const uint8_t* const* packed, uint8_t* const* outs,
+                                const int* out_pitch, int n, void* ws, size_t ws_bytes, b2c_stream stream);
 
 #ifdef __cplusplus
 }

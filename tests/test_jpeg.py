@@ -49,6 +49,11 @@ def test_host_huffman_stage_and_oracle_vs_pillow(lib, case):
     assert coefs.dtype == torch.int16 and coefs.numel() == info.coef_count
     got = jpeg_oracle.reconstruct(info.as_dict(), coefs.numpy())
     assert np.array_equal(got, ref)
+    # the packed form the workers ship (per block: coefficients up to the last non-zero one in scan order) expands to
+    # exactly the dense coefficients
+    pinfo, packed = jpeg.entropy_decode_packed(data)
+    assert packed.dtype == torch.uint8 and packed.numel() == pinfo.packed_bytes and packed.numel() % 16 == 0
+    assert packed.numel() <= pinfo.packed_capacity and torch.equal(jpeg.expand_packed(pinfo, packed), coefs)
 
 
 def test_streams_outside_the_covered_set_are_refused_not_misdecoded(lib):
@@ -118,7 +123,7 @@ def test_dataset_items_fall_back_to_pillow_per_file(lib, tmp_path):
     (tmp_path / "d.jpg").write_bytes(b"")
     ds = RawImageDataset([str(tmp_path / n) for n in ("a.jpg", "b.jpg", "c.png", "d.jpg")], device_jpeg=True)
     a, b, c, d = (ds[i][0] for i in range(4))
-    assert isinstance(a, tuple) and a[0] == "jpeg" and a[2].dtype == torch.int16
+    assert isinstance(a, tuple) and a[0] == "jpegp" and a[2].dtype == torch.uint8
     assert isinstance(b, torch.Tensor) and np.array_equal(b.numpy(), np.asarray(Image.open(tmp_path / "b.jpg").convert("RGB")))
     assert isinstance(c, torch.Tensor) and tuple(c.shape) == (90, 70, 3)
     assert d is None
@@ -131,6 +136,9 @@ def test_device_reconstruct_ragged_batch_vs_pillow(lib):
     items = [jpeg.entropy_decode(d) for d, _ in made]
     outs = jpeg.reconstruct(items)                       # one batch: every sampling / size / restart variant together
     for (data, ref), got, case in zip(made, outs, CASES):
+        assert np.array_equal(got.cpu().numpy(), ref), case
+    pouts = jpeg.reconstruct_packed([jpeg.entropy_decode_packed(d) for d, _ in made])   # same from the packed form
+    for (data, ref), got, case in zip(made, pouts, CASES):
         assert np.array_equal(got.cpu().numpy(), ref), case
     again = jpeg.reconstruct(items[3:5])                 # workspace / descriptor reuse with a different batch
     assert np.array_equal(again[0].cpu().numpy(), made[3][1]) and np.array_equal(again[1].cpu().numpy(), made[4][1])
@@ -152,15 +160,17 @@ def test_device_reconstruct_many_random_streams(lib):
     items, refs = [], []
     for data, ref in made:
         try:
-            items.append(jpeg.entropy_decode(data))
+            items.append(jpeg.entropy_decode_packed(data) if len(items) % 2 else jpeg.entropy_decode(data))
             refs.append(ref)
         except jpeg.UnsupportedJPEG:  # subsampled images narrower than two chroma samples stay on Pillow
             assert ref.shape[1] <= 2
     assert len(items) >= 55
-    for lo in (0, 30):
-        outs = jpeg.reconstruct(items[lo:lo + 30])
-        for ref, got in zip(refs[lo:lo + 30], outs):
-            assert np.array_equal(got.cpu().numpy(), ref)
+    for kind, fn in ((torch.uint8, jpeg.reconstruct_packed), (torch.int16, jpeg.reconstruct)):
+        sel = [i for i, it in enumerate(items) if it[1].dtype == kind]
+        for lo in range(0, len(sel), 17):
+            part = sel[lo:lo + 17]
+            for i, got in zip(part, fn([items[i] for i in part])):
+                assert np.array_equal(got.cpu().numpy(), refs[i])
 
 
 @pytest.mark.gpu

@@ -3,7 +3,7 @@
   pillow_host      Image.open(...).convert('RGB') on a thread pool over all host cores (+ H2D not included)
   entropy_host     the host stage of the device path alone (marker parse + Huffman decode, C-ABI) on the same pool
   reconstruct_dev  the device stage alone (dequantise + IDCT + upsample + colour), CUDA events, coefficients resident
-  hybrid_e2e       entropy_host -> H2D of the coefficients -> reconstruct_dev, wall clock
+  hybrid_e2e       host stage (packed coefficients) -> pinned gather -> H2D -> device stage, wall clock
 One JSON line.  python tools/bench_jpeg.py [N] [threads]"""
 import concurrent.futures as cf
 import io
@@ -46,6 +46,7 @@ def main():
 
     t_pil, ref = timed(lambda: list(pool.map(pil_decode, datas)))
     t_ent, items = timed(lambda: list(pool.map(jpeg.entropy_decode, datas)))
+    t_pk, pitems = timed(lambda: list(pool.map(jpeg.entropy_decode_packed, datas)))
     t_pil1, _ = timed(lambda: [pil_decode(d) for d in datas[:32]], 2)
     t_ent1, _ = timed(lambda: [jpeg.entropy_decode(d) for d in datas[:32]], 2)
     outs = jpeg.reconstruct(items)
@@ -75,10 +76,22 @@ def main():
     t_dev_h2d = (time.perf_counter() - t0) / 5
 
     def hybrid():
-        its = list(pool.map(jpeg.entropy_decode, datas))
-        o = jpeg.reconstruct(its)
+        its = list(pool.map(jpeg.entropy_decode_packed, datas))
+        o = jpeg.reconstruct_packed(its)
         torch.cuda.synchronize()
         return o
+
+    pouts = jpeg.reconstruct_packed(pitems)
+    torch.cuda.synchronize()
+    ok = ok and all(np.array_equal(o.cpu().numpy(), r) for o, r in zip(pouts[:16], ref[:16]))
+    for _ in range(2):
+        jpeg.reconstruct_packed(pitems)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        jpeg.reconstruct_packed(pitems)
+    torch.cuda.synchronize()
+    t_pk_h2d = (time.perf_counter() - t0) / 5
 
     t_hyb, _ = timed(hybrid)
     coef_bytes = sum(int(it[0].coef_count) * 2 for it in items)
@@ -92,8 +105,10 @@ def main():
         "reconstruct_dev_images_per_s": n / t_dev, "reconstruct_dev_ms_per_batch": 1e3 * t_dev,
         "reconstruct_dev_gb_per_s": (coef_bytes + out_bytes + 2 * plane_bytes) / t_dev / 1e9,
         "h2d_plus_reconstruct_images_per_s": n / t_dev_h2d, "h2d_plus_reconstruct_ms_per_batch": 1e3 * t_dev_h2d,
+        "entropy_host_packed_images_per_s": n / t_pk, "packed_h2d_plus_reconstruct_images_per_s": n / t_pk_h2d,
         "hybrid_e2e_images_per_s": n / t_hyb,
-        "bytes_per_image": {"coefficients_h2d": coef_bytes / n, "rgb_out": out_bytes / n, "planes_write_then_read": plane_bytes / n},
+        "bytes_per_image": {"coefficients_h2d": coef_bytes / n, "rgb_out": out_bytes / n, "planes_write_then_read": plane_bytes / n,
+                            "packed_coefficients_h2d": sum(int(it[1].numel()) for it in pitems) / n},
     }))
 
 

@@ -266,14 +266,16 @@ class RawImageDataset(Dataset):
         try:
             src = path
             if self.device_jpeg and path.lower().endswith((".jpg", ".jpeg")):
-                from . import jpeg
+                from . import _lib, jpeg
                 with open(path, "rb") as fh:
                     data = fh.read()
                 try:
                     info, packed = jpeg.entropy_decode_packed(data)
                     return ("jpegp", bytes(info), packed), path
-                except jpeg.UnsupportedJPEG:
-                    src = io.BytesIO(data)  # progressive, CMYK, ...: Pillow decodes the bytes already read
+                except (jpeg.UnsupportedJPEG, _lib.B2CError):
+                    # CMYK, arithmetic-coded, ... or not a JPEG stream at all (a .jpg that is really a PNG, a damaged
+                    # file): Pillow gets the bytes already read and has the last word, exactly like the reference
+                    src = io.BytesIO(data)
             with Image.open(src) as im:
                 arr = np.asarray(im.convert("RGB"))
             return torch.from_numpy(np.ascontiguousarray(arr)), path

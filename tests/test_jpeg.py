@@ -121,8 +121,10 @@ def test_dataset_items_fall_back_to_pillow_per_file(lib, tmp_path):
     im.convert("CMYK").save(tmp_path / "b.jpg", quality=90)
     im.save(tmp_path / "c.png")
     (tmp_path / "d.jpg").write_bytes(b"")
-    ds = RawImageDataset([str(tmp_path / n) for n in ("a.jpg", "b.jpg", "c.png", "d.jpg")], device_jpeg=True)
-    a, b, c, d = (ds[i][0] for i in range(4))
+    im.save(tmp_path / "e.jpg", format="PNG")  # mis-named file: Pillow identifies it by content, so must this path
+    ds = RawImageDataset([str(tmp_path / n) for n in ("a.jpg", "b.jpg", "c.png", "d.jpg", "e.jpg")], device_jpeg=True)
+    a, b, c, d, e = (ds[i][0] for i in range(5))
+    assert isinstance(e, torch.Tensor) and tuple(e.shape) == (90, 70, 3)
     assert isinstance(a, tuple) and a[0] == "jpegp" and a[2].dtype == torch.uint8
     assert isinstance(b, torch.Tensor) and np.array_equal(b.numpy(), np.asarray(Image.open(tmp_path / "b.jpg").convert("RGB")))
     assert isinstance(c, torch.Tensor) and tuple(c.shape) == (90, 70, 3)

@@ -124,12 +124,11 @@ int frame_geometry(Parsed& P) {
     off += static_cast<int64_t>(I.blocks_w[c]) * I.blocks_h[c] * 64;
   }
   I.coef_count = off;
-  // packed form: [counts u8 x nblocks | pad to 16 | group offsets u32 x ngroups | pad to 16 | values i16 ...], 16-B multiples
+  // packed form: [value offsets u32 x nblocks | counts u8 x nblocks | pad to 16 | values i16 ...], a multiple of 16 bytes
   I.nblocks = static_cast<int32_t>(off / 64);
-  I.ngroups = (I.nblocks + 31) / 32;
-  I.counts_off = 0;
-  I.groups_off = (static_cast<int64_t>(I.nblocks) + 15) & ~15ll;
-  I.vals_off = (I.groups_off + 4ll * I.ngroups + 15) & ~15ll;
+  I.offs_off = 0;
+  I.counts_off = 4ll * I.nblocks;
+  I.vals_off = (I.counts_off + I.nblocks + 15) & ~15ll;
   I.packed_capacity = I.vals_off + 2 * off;  // worst case: every block keeps all 64 coefficients
   I.packed_bytes = 0;
   if (I.ncomp == 3 && I.comp_w[1] < 2 && I.hs[0] == 2) return fail_unsupported("image narrower than two chroma samples");
@@ -557,13 +556,11 @@ void dezigzag_in_place(int16_t* coefs, int64_t nblocks) {
 
 // zigzag-ordered dense blocks -> packed form (see frame_geometry); returns the bytes used (a multiple of 16)
 int64_t pack_blocks(const b2c_jpeg_info& I, const int16_t* dense, uint8_t* out) {
+  uint32_t* offs = reinterpret_cast<uint32_t*>(out + I.offs_off);
   uint8_t* counts = out + I.counts_off;
-  uint32_t* groups = reinterpret_cast<uint32_t*>(out + I.groups_off);
   int16_t* vals = reinterpret_cast<int16_t*>(out + I.vals_off);
-  memset(out, 0, static_cast<size_t>(I.vals_off));
   uint32_t nv = 0;
   for (int32_t b = 0; b < I.nblocks; ++b) {
-    if ((b & 31) == 0) groups[b >> 5] = nv;
     const int16_t* blk = dense + static_cast<int64_t>(b) * 64;
     int n = 64;
     while (n > 0) {  // last non-zero coefficient in scan order, four at a time
@@ -573,21 +570,113 @@ int64_t pack_blocks(const b2c_jpeg_info& I, const int16_t* dense, uint8_t* out) 
       n -= 4;
     }
     while (n > 0 && blk[n - 1] == 0) --n;
+    offs[b] = nv;
     counts[b] = static_cast<uint8_t>(n);
     memcpy(vals + nv, blk, static_cast<size_t>(n) * 2);
     nv += n;
   }
-  int64_t used = I.vals_off + 2ll * nv;
+  memset(out + I.counts_off + I.nblocks, 0, static_cast<size_t>(I.vals_off - I.counts_off - I.nblocks));
+  const int64_t used = I.vals_off + 2ll * nv;
   const int64_t padded = (used + 15) & ~15ll;
   memset(out + used, 0, static_cast<size_t>(padded - used));
   return padded;
+}
+
+// Single interleaved sequential scan (what almost every baseline file is): blocks are appended to the packed value
+// stream in decode order as they are decoded — no dense scratch, no second pass.  vout has room for 64 values.
+inline int block_sequential_append(BitReader& br, const HuffTable& dct, const HuffTable& act, int& pred, int16_t* vout, int& count) {
+  int s = decode_symbol(br, dct);
+  if (s < 0 || s > 11) return fail_corrupt("bad DC code");
+  if (s) pred += receive_extend(br, s);
+  vout[0] = static_cast<int16_t>(pred);
+  int filled = 1;                 // vout[0, filled) is written
+  int last = pred != 0 ? 0 : -1;  // last non-zero position
+  for (int k = 1; k < 64;) {
+    if (br.nbits < 32) br.fill();
+    const int16_t fa = act.fast_ac[br.peek(9)];
+    int v;
+    if (fa) {
+      k += (fa >> 4) & 15;
+      if (k > 63) return fail_corrupt("AC run past the block");
+      br.drop(fa & 15);
+      v = fa >> 8;
+    } else {
+      const int rs = decode_symbol(br, act);
+      if (rs < 0) return fail_corrupt("bad AC code");
+      const int r = rs >> 4;
+      s = rs & 15;
+      if (s == 0) {
+        if (r != 15) break;  // EOB
+        k += 16;
+        continue;
+      }
+      k += r;
+      if (k > 63) return fail_corrupt("AC run past the block");
+      v = receive_extend(br, s);
+    }
+    while (filled < k) vout[filled++] = 0;
+    vout[k] = static_cast<int16_t>(v);
+    filled = k + 1;
+    last = k;
+    ++k;
+  }
+  count = last + 1;
+  return 0;
+}
+
+int decode_scan_append(const uint8_t* d, size_t n, const Parsed& P, const Scan& sc, uint8_t* out, int64_t& used) {
+  const b2c_jpeg_info& I = P.info;
+  uint32_t* offs = reinterpret_cast<uint32_t*>(out + I.offs_off);
+  uint8_t* counts = out + I.counts_off;
+  int16_t* vals = reinterpret_cast<int16_t*>(out + I.vals_off);
+  BitReader br{d + sc.begin, d + n};
+  int pred[3] = {0, 0, 0};
+  int restarts_left = I.restart_interval;
+  int next_rst = 0;
+  uint32_t nv = 0;
+  const bool interleaved = sc.ns > 1;
+  const int units_x = interleaved ? I.mcus_x : (I.comp_w[0] + 7) / 8;
+  const int units_y = interleaved ? I.mcus_y : (I.comp_h[0] + 7) / 8;
+  if (!interleaved || units_x * I.hs[0] != I.blocks_w[0] || units_y * I.vs[0] != I.blocks_h[0])
+    memset(out, 0, static_cast<size_t>(I.vals_off));  // blocks the scan does not visit keep count 0
+  for (int uy = 0; uy < units_y; ++uy) {
+    for (int ux = 0; ux < units_x; ++ux) {
+      if (I.restart_interval && restarts_left == 0) {
+        B2C_TRY(br.restart(next_rst));
+        next_rst = (next_rst + 1) & 7;
+        pred[0] = pred[1] = pred[2] = 0;
+        restarts_left = I.restart_interval;
+      }
+      for (int k = 0; k < sc.ns; ++k) {
+        const int c = sc.ci[k];
+        const int nvb = interleaved ? I.vs[c] : 1, nhb = interleaved ? I.hs[c] : 1;
+        for (int v = 0; v < nvb; ++v) {
+          for (int h = 0; h < nhb; ++h) {
+            const int by = interleaved ? uy * I.vs[c] + v : uy, bx = interleaved ? ux * I.hs[c] + h : ux;
+            const int64_t b = I.coef_offset[c] / 64 + static_cast<int64_t>(by) * I.blocks_w[c] + bx;
+            int count = 0;
+            B2C_TRY(block_sequential_append(br, P.dc[sc.td[k]], P.ac[sc.ta[k]], pred[c], vals + nv, count));
+            offs[b] = nv;
+            counts[b] = static_cast<uint8_t>(count);
+            nv += count;
+          }
+        }
+      }
+      if (I.restart_interval) --restarts_left;
+    }
+  }
+  memset(out + I.counts_off + I.nblocks, 0, static_cast<size_t>(I.vals_off - I.counts_off - I.nblocks));
+  const int64_t end = I.vals_off + 2ll * nv;
+  used = (end + 15) & ~15ll;
+  memset(out + end, 0, static_cast<size_t>(used - end));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ device
 struct JpegJobDev {
   const int16_t* coefs;        // dense form (natural order) or nullptr
   const uint8_t* packed;       // packed form or nullptr
-  int64_t counts_off, groups_off, vals_off;
+  int64_t offs_off, counts_off, vals_off;
   int32_t nblocks;
   uint8_t* out;
   int32_t out_pitch;
@@ -692,29 +781,11 @@ __constant__ uint8_t kZigzagInv[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7
 __global__ void __launch_bounds__(kIdctThreads) jpeg_idct_kernel(const JpegJobDev* __restrict__ jobs, int njobs,
                                                                  int total_blocks, uint8_t* __restrict__ planes) {
   __shared__ int ws[32][8][9];  // [block][row][col], padded against bank conflicts
-  __shared__ uint32_t voff[32]; // packed form: element offset of each block's values
-  __shared__ uint8_t vcnt[32];  //              and how many it keeps
   const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
   const int gb = blockIdx.x * 32 + lb;
   const JpegJobDev* J = jobs + find_job(jobs, njobs, blockIdx.x * 32, false);
   const int b = gb - J->block_begin;  // block index inside the image
   const bool live = gb < total_blocks && b < J->nblocks;
-  if (J->packed != nullptr) {
-    if (threadIdx.x < 32) {
-      const int bi = blockIdx.x * 32 - J->block_begin + threadIdx.x;
-      const uint32_t c = bi < J->nblocks ? J->packed[J->counts_off + bi] : 0u;
-      uint32_t incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (threadIdx.x >= o) incl += v;
-      }
-      const uint32_t base = reinterpret_cast<const uint32_t*>(J->packed + J->groups_off)[(blockIdx.x * 32 - J->block_begin) >> 5];
-      voff[threadIdx.x] = base + incl - c;
-      vcnt[threadIdx.x] = static_cast<uint8_t>(c);
-    }
-    __syncthreads();
-  }
   int c = 0, bx = 0, by = 0;
   if (live) {
     int rem = b;
@@ -728,8 +799,9 @@ __global__ void __launch_bounds__(kIdctThreads) jpeg_idct_kernel(const JpegJobDe
     const uint16_t* q = J->qt[c];
     int in[8], o[8];
     if (J->packed != nullptr) {
-      const int16_t* vals = reinterpret_cast<const int16_t*>(J->packed + J->vals_off) + voff[lb];
-      const int cnt = vcnt[lb];
+      const int16_t* vals = reinterpret_cast<const int16_t*>(J->packed + J->vals_off) +
+                            reinterpret_cast<const uint32_t*>(J->packed + J->offs_off)[b];
+      const int cnt = J->packed[J->counts_off + b];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int p = kZigzagInv[r * 8 + t];  // position of natural coefficient (r, t) in scan order
@@ -862,6 +934,16 @@ extern "C" int b2c_jpeg_decode_packed(const uint8_t* data, size_t len, b2c_jpeg_
   B2C_TRY(parse(data, len, P, first, pos));
   B2C_REQUIRE(static_cast<size_t>(P.info.packed_capacity) <= capacity, "b2c_jpeg_decode_packed: buffer holds %zu bytes, %lld needed",
               capacity, (long long)P.info.packed_capacity);
+  if (!P.progressive && first.ns == P.info.ncomp) {
+    // one interleaved (or single-component) sequential scan covers the image: append blocks as they are decoded
+    for (int k = 0; k < first.ns; ++k)
+      if (first.ci[k] != k) return fail_corrupt("scan component order");
+    int64_t used = 0;
+    B2C_TRY(decode_scan_append(data, len, P, first, packed, used));
+    P.info.packed_bytes = used;
+    *info = P.info;
+    return 0;
+  }
   std::vector<int16_t> own;
   if (!scratch) {
     own.resize(static_cast<size_t>(P.info.coef_count));
@@ -906,8 +988,8 @@ int reconstruct_impl(const b2c_jpeg_info* infos, const int16_t* const* coefs, co
     memset(&J, 0, sizeof(J));
     J.coefs = packed ? nullptr : coefs[i];
     J.packed = packed ? packed[i] : nullptr;
+    J.offs_off = I.offs_off;
     J.counts_off = I.counts_off;
-    J.groups_off = I.groups_off;
     J.vals_off = I.vals_off;
     J.nblocks = I.nblocks;
     J.out = outs[i];

@@ -26,8 +26,8 @@ class JpegInfo(C.Structure):
                 ("blocks_h", C.c_int32 * 3), ("comp_w", C.c_int32 * 3), ("comp_h", C.c_int32 * 3),
                 ("restart_interval", C.c_int32), ("adobe_transform0", C.c_int32), ("progressive", C.c_int32),
                 ("reserved_", C.c_int32), ("coef_offset", C.c_int64 * 3),
-                ("coef_count", C.c_int64), ("nblocks", C.c_int32), ("ngroups", C.c_int32), ("counts_off", C.c_int64),
-                ("groups_off", C.c_int64), ("vals_off", C.c_int64), ("packed_capacity", C.c_int64), ("packed_bytes", C.c_int64),
+                ("coef_count", C.c_int64), ("nblocks", C.c_int32), ("reserved2_", C.c_int32), ("offs_off", C.c_int64),
+                ("counts_off", C.c_int64), ("vals_off", C.c_int64), ("packed_capacity", C.c_int64), ("packed_bytes", C.c_int64),
                 ("qt", (C.c_uint16 * 64) * 3)]
 
     def as_dict(self) -> dict:
@@ -84,16 +84,14 @@ def expand_packed(info: JpegInfo, packed: torch.Tensor) -> torch.Tensor:
     zz = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35,
           42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
     p = packed.numpy()
+    offs = p[info.offs_off:info.offs_off + 4 * info.nblocks].view(np.uint32).astype(np.int64)
     counts = p[info.counts_off:info.counts_off + info.nblocks].astype(np.int64)
-    groups = p[info.groups_off:info.groups_off + 4 * info.ngroups].view(np.uint32).astype(np.int64)
-    nv = int(counts.sum())
-    vals = p[info.vals_off:info.vals_off + 2 * nv].view(np.int16)
-    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
-    assert np.array_equal(starts[::32], groups)
+    vals = p[info.vals_off:].view(np.int16)
+    assert counts.max(initial=0) <= 64 and (offs + counts).max(initial=0) <= vals.size
     dense = np.zeros((info.nblocks, 64), np.int16)
     zz = np.asarray(zz)
     for b in np.nonzero(counts)[0]:
-        dense[b, zz[:counts[b]]] = vals[starts[b]:starts[b] + counts[b]]
+        dense[b, zz[:counts[b]]] = vals[offs[b]:offs[b] + counts[b]]
     return torch.from_numpy(dense.reshape(-1))
 
 

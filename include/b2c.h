@@ -326,11 +326,12 @@ typedef struct {
   int32_t reserved_;
   int64_t coef_offset[3];           /* component c's blocks start at coefs + coef_offset[c]; block (by,bx) at +(by*blocks_w+bx)*64 */
   int64_t coef_count;               /* int16 elements the (dense) coefficient buffer needs */
-  /* packed form (b2c_jpeg_decode_packed): counts u8[nblocks] | group offsets u32[ngroups] | values i16[...] at these byte
-   * offsets of one buffer; block b keeps its first counts[b] coefficients in scan (zigzag) order, the values of block
-   * 32 g start at element group_offsets[g].  Blocks are numbered component by component, row-major. */
-  int32_t nblocks, ngroups;
-  int64_t counts_off, groups_off, vals_off;
+  /* packed form (b2c_jpeg_decode_packed): value offsets u32[nblocks] | counts u8[nblocks] | values i16[...] at these byte
+   * offsets of one buffer; block b keeps its first counts[b] coefficients in scan (zigzag) order at element offs[b] of
+   * the values (blocks of a single-scan baseline file are appended in decode order, hence explicit offsets).  Blocks
+   * are numbered component by component, row-major. */
+  int32_t nblocks, reserved2_;
+  int64_t offs_off, counts_off, vals_off;
   int64_t packed_capacity;          /* bytes a buffer must have for b2c_jpeg_decode_packed (worst case) */
   int64_t packed_bytes;             /* bytes actually used (multiple of 16), set by b2c_jpeg_decode_packed */
   uint16_t qt[3][64];               /* quantisation table of each component, natural (row-major) order */

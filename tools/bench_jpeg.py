@@ -25,13 +25,23 @@ from clip_assisted_data_labeling_b200 import jpeg  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     threads = int(sys.argv[2]) if len(sys.argv) > 2 else os.cpu_count()
-    imgs = synth_batch(min(n, 64), 0).numpy()
+    noisy = synth_batch(min(n, 64), 0).numpy()
+    # photo-like content: the same colour fields at quarter resolution, upsampled, with light sensor-like noise
+    rng = np.random.default_rng(0)
+    photo = [np.clip(np.asarray(Image.fromarray(im).resize((128, 128)).resize((512, 512), Image.BICUBIC)).astype(np.int16) +
+                     rng.normal(0, 3, im.shape), 0, 255).astype(np.uint8) for im in noisy]
+    pool = cf.ThreadPoolExecutor(threads)
+    for label, imgs, q in (("photo-like (smooth fields + sigma-3 noise), quality 85", photo, 85),
+                           ("noise-heavy (the embedding bench's images: sigma-20 noise), quality 90", noisy, 90)):
+        run(n, threads, pool, label, imgs, q)
+
+
+def run(n, threads, pool, label, imgs, q):
     datas = []
     for i in range(n):
         buf = io.BytesIO()
-        Image.fromarray(imgs[i % len(imgs)]).save(buf, "JPEG", quality=90, subsampling=2)
+        Image.fromarray(imgs[i % len(imgs)]).save(buf, "JPEG", quality=q, subsampling=2)
         datas.append(buf.getvalue())
-    pool = cf.ThreadPoolExecutor(threads)
 
     def pil_decode(d):
         return np.asarray(Image.open(io.BytesIO(d)).convert("RGB"))
@@ -98,7 +108,7 @@ def main():
     out_bytes = sum(int(it[0].width) * int(it[0].height) * 3 for it in items)
     plane_bytes = sum(int(it[0].blocks_w[c]) * int(it[0].blocks_h[c]) * 64 for it in items for c in range(it[0].ncomp))
     print(json.dumps({
-        "workload": f"{n} synthetic 512x512 baseline JPEGs, quality 90, 4:2:0, {sum(map(len, datas)) / n / 1e3:.0f} KB each",
+        "workload": f"{n} synthetic 512x512 baseline JPEGs, 4:2:0, {label}, {sum(map(len, datas)) / n / 1e3:.0f} KB each",
         "host_threads": threads, "bit_exact_vs_pillow": bool(ok),
         "pillow_host_images_per_s": n / t_pil, "entropy_host_images_per_s": n / t_ent,
         "pillow_1thread_ms_per_image": 1e3 * t_pil1 / 32, "entropy_1thread_ms_per_image": 1e3 * t_ent1 / 32,
@@ -109,7 +119,7 @@ def main():
         "hybrid_e2e_images_per_s": n / t_hyb,
         "bytes_per_image": {"coefficients_h2d": coef_bytes / n, "rgb_out": out_bytes / n, "planes_write_then_read": plane_bytes / n,
                             "packed_coefficients_h2d": sum(int(it[1].numel()) for it in pitems) / n},
-    }))
+    }), flush=True)
 
 
 if __name__ == "__main__":

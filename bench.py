@@ -148,7 +148,7 @@ def run_reference_arm(args):
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
     sample = f"{n} synthetic 512x512 images x 4 crops per step (PIL crops + torchvision transform + fp32 ViT-L/14 tower, torch CPU, {cores} threads)"
-    print(json.dumps({
+    _emit(args.out_fd, {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -156,7 +156,7 @@ def run_reference_arm(args):
                    "images_per_step": n, "note": "open_clip is not installable offline: the tower is the oracle's restatement of it"},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
@@ -374,9 +374,23 @@ def run_b200_arm(args):
         "variants": variant,
         "checks": {"unit_norm": norms_ok, "weights": enc.weights_source},
     }
-    print(json.dumps(line))
+    _emit(args.out_fd, line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to fd 1 when
+    NCCL_DEBUG is set in the environment): point fd 1 at stderr for the whole run and keep the real stdout for the line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_fd, line: dict):
+    sys.stdout.flush()
+    os.write(real_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -395,6 +409,7 @@ def main():
     ap.add_argument("--no-variants", action="store_true", help="skip the informational opt-in variants")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.out_fd = _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -241,3 +241,19 @@ def test_scorer_module_twin_loads_reference_pickles(tmp_path):
     back = load_regressor(str(tmp_path / "m.pth"))
     x = torch.randn(5, 12)
     assert torch.equal(back(x), m.eval()(x)) and back.crop_names == ["centre_crop"]
+
+
+def test_bench_stdout_carries_exactly_one_json_line():
+    """bench.py claims fd 1 for its JSON line: Python prints and C-level writes to stdout during the run (NCCL's version
+    banner at N > 1) end up on stderr."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, bench; fd = bench._claim_stdout(); print('python noise'); os.system('echo c-level noise'); "
+            "bench._emit(fd, {'value': 1.5})")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("\n") == 1 and json.loads(r.stdout) == {"value": 1.5}
+    assert "python noise" in r.stderr and "c-level noise" in r.stderr
+

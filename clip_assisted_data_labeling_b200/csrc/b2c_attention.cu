@@ -1393,7 +1393,7 @@ struct A4Misc {
   uint32_t tmem_slot;
   uint32_t pad[3];
   float red[2][16];        // per group: cross-warp max / sum scratch (8 warps each)
-  float vec[2][3][64];     // per group: q0, k0, v0 of the current head as fp32
+  float vec[2][2][3][64];  // per group, per iteration parity: q0, k0, v0 of the head as fp32
   float mx[2][2][128];     // per group, per half: partial row maxima
   float p0s[2][128];       // per group: class-key probability of each query row
   float p_cls[2][264];     // per group: class-row probabilities (256 patch keys + class key)
@@ -1404,11 +1404,51 @@ constexpr int a4_smem_bytes() {
   return A2L<64>::kOffMisc + static_cast<int>((sizeof(A4Misc) + 1023) / 1024 * 1024) + 1024;
 }
 
+// development trace (kVar bit 4): clock64() of lane 0 of every warp of CTA 0 at phase boundaries, iterations 4..11
+__device__ int g_attn_trace_k0 = 4;  // first traced iteration (b2c_debug_attn_trace_start)
+__device__ long long g_attn_trace[18][8][16];
+#define A4_TRACE(ev)                                                                                   \
+  do {                                                                                                 \
+    if constexpr (kTrace) {                                                                            \
+      if (blockIdx.x == 0 && lane == 0 && k >= g_attn_trace_k0 && k < g_attn_trace_k0 + 8) g_attn_trace[warp][k - g_attn_trace_k0][ev] = clock64(); \
+    }                                                                                                  \
+  } while (0)
+
+// exp2 on the FMA pipe for part of a row's elements (the XU pipe, 16 ex2 per clock per SM, is what the exp2 pass
+// saturates): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5·2^23, 2^f by a degree-3 minimax
+// polynomial on [-0.5, 0.5] (relative error 7.6e-5, a fiftieth of the bf16 rounding P gets next), 2^n added into the
+// exponent field.  x is clamped to >= -126 so the exponent cannot wrap; x <= 0 always (the row maximum was subtracted).
+__device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float x1) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, kMagic, kMagic);
+  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
+  fadd2(f0, f1, x0, x1, -n0, -n1);
+  ffma2(p0, p1, f0, f1, 0.05520550534129143f, 0.05520550534129143f, 0.24261397123336792f, 0.24261397123336792f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.6932547688484192f, 0.6932547688484192f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.9999276995658875f, 0.9999276995658875f);
+  y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+// kVar (development A/B switch B2C_ATTN_VAR; the default is what attention_umma4_launch picks):
+//   bit 0  staggered MMA issue order S0(k) PV1(k-1) S1(k) PV0(k): the two query tiles run half a period apart, so one
+//          tile's exp2 pass (XU pipe) overlaps the other's tensor-core / epilogue / max phases instead of its exp2 pass
+//   bit 1  the two column halves of a row exchange their maxima through a 64-thread barrier (their two warps) instead
+//          of the group's 256-thread barrier; q0/k0/v0 of the next head are published an iteration ahead
+//   bits 2-3  exp2 on the FMA pipe for every 4th (1), 3rd (2) or 2nd (3) pair of a row's elements
 // launch bound 640 (not 576): ptxas schedules the softmax loop measurably better with it (0.61 vs 0.66 ms at 1024 crops)
+template <int kVar>
 __global__ void __launch_bounds__(kA4Threads + 64, 1)
 attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* __restrict__ qkv,
                        __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads, float scale_log2) {
   constexpr int HD = 64;
+  constexpr bool kStagger = (kVar & 1) != 0;
+  constexpr bool kPairBar = (kVar & 2) != 0;
+  constexpr bool kTrace = (kVar & 16) != 0;
+  constexpr int kPolyMod = ((kVar >> 2) & 3) == 0 ? 0 : 5 - ((kVar >> 2) & 3);  // 0 | 4 | 3 | 2
   using L = A2L<HD>;
   constexpr int kColO4 = 64, kColL4 = 192;
   constexpr int kFirstSm = 2;  // first softmax warp
@@ -1508,23 +1548,54 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     using W0 = std::integral_constant<int, 0>;
     using W1 = std::integral_constant<int, 1>;
     int k = 0;
+    uint64_t v_desc_prev = 0;
+    int s_prev = 0;
+    uint32_t kp_prev = 0;
     for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
       const int s = k & 1;
       const uint32_t u = (k >> 1) & 1, kp = k & 1;
       const uint32_t sbase = smem_base + s * L::kQKStage;
       const uint32_t vbase = smem_base + L::kOffV + s * L::kOp;
+      A4_TRACE(0);
       mbar_wait(&mb->full_qk[s], u);
       const uint64_t k_desc = make_sw128_kmajor_desc(sbase + L::kOp);
+      A4_TRACE(1);
       issue_s(W0{}, sbase, k_desc, kp);
+      A4_TRACE(2);
+      if constexpr (kStagger) {
+        if (k > 0) {  // tile 1 of the previous head: its softmax ran while tile 0's P·V, epilogue and this S were in flight
+          issue_pv(W1{}, v_desc_prev, kp_prev);
+          if (elect_one()) umma_commit(&mb->empty_v[s_prev]);
+          __syncwarp();
+        }
+      }
+      A4_TRACE(3);
       issue_s(W1{}, sbase, k_desc, kp);
+      A4_TRACE(4);
       if (elect_one()) umma_commit(&mb->empty_qk[s]);
       __syncwarp();
       mbar_wait(&mb->full_v[s], u);
       const uint64_t v_desc0 = make_sw128_kmajor_desc(vbase);
+      A4_TRACE(5);
       issue_pv(W0{}, v_desc0, kp);
-      issue_pv(W1{}, v_desc0, kp);
-      if (elect_one()) umma_commit(&mb->empty_v[s]);
-      __syncwarp();
+      A4_TRACE(6);
+      if constexpr (kStagger) {
+        v_desc_prev = v_desc0;
+        s_prev = s;
+        kp_prev = kp;
+      } else {
+        issue_pv(W1{}, v_desc0, kp);
+        if (elect_one()) umma_commit(&mb->empty_v[s]);
+        __syncwarp();
+      }
+      A4_TRACE(7);
+    }
+    if constexpr (kStagger) {
+      if (k > 0) {
+        issue_pv(W1{}, v_desc_prev, kp_prev);
+        if (elect_one()) umma_commit(&mb->empty_v[s_prev]);
+        __syncwarp();
+      }
     }
   } else if (warp >= kFirstSm) {
     // ------------------------------------------------------------------ softmax: 2 groups x 2 column halves x 4 warps
@@ -1539,9 +1610,6 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
     const uint32_t sbase_col = 128u * h;    // this half's S columns; its P goes over them at [128h, 128h + 64)
     float* red = mb->red[w];
     float* pcls = mb->p_cls[w];
-    float* q0f = mb->vec[w][0];
-    float* k0f = mb->vec[w][1];
-    float* v0f = mb->vec[w][2];
     uint32_t cq = 0, ck = 0, cv = 0;
     auto prefetch = [&](int ch) {
       if (gt < HD) {
@@ -1553,7 +1621,18 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         cv = __ldg(cls_row + 2 * d + gt);
       }
     };
+    auto publish = [&](int par) {  // q0 / k0 / v0 of a head (bf16 bits in cq, ck, cv) -> fp32 in shared memory
+      if (gt < HD) {
+        mb->vec[w][par][0][gt] = __uint_as_float(cq << 16);
+        mb->vec[w][par][1][gt] = __uint_as_float(ck << 16);
+        mb->vec[w][par][2][gt] = __uint_as_float(cv << 16);
+      }
+    };
     if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
+    if constexpr (kPairBar) {
+      publish(0);
+      named_bar_sync(1 + w, 256);
+    }
     int k = 0;
     for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
       const int s = k & 1;
@@ -1564,17 +1643,19 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       const uint8_t* st = smem + s * L::kQKStage;
       const uint8_t* sv = smem + L::kOffV + s * L::kOp;
       const bool cls_owner = ((k & 1) == w);
+      const int vpar = kPairBar ? (k & 1) : 0;
+      const float* q0f = mb->vec[w][vpar][0];
+      const float* k0f = mb->vec[w][vpar][1];
+      const float* v0f = mb->vec[w][vpar][2];
 
-      if (gt < HD) {
-        q0f[gt] = __uint_as_float(cq << 16);
-        k0f[gt] = __uint_as_float(ck << 16);
-        v0f[gt] = __uint_as_float(cv << 16);
-      }
+      if constexpr (!kPairBar) publish(0);
       if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
 
       // ---- own row, own 128 keys: partial max -> exchange -> P (bf16x2 packed) back into TMEM over S
+      A4_TRACE(0);
       mbar_wait(&mb->s_full[w], kp);
       tc_fence_after();
+      A4_TRACE(1);
       float m = -INFINITY;
       uint32_t va[32], vb[32];
       tmem_ld_32x32(taddr + sbase_col, va);
@@ -1590,8 +1671,11 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
       }
       mb->mx[w][h][r] = m;
-      named_bar_sync(1 + w, 256);  // also publishes q0f / k0f / v0f
+      A4_TRACE(2);
+      if constexpr (kPairBar) named_bar_sync(3 + w * 4 + quarter, 64);  // the two warps that share these 32 rows
+      else named_bar_sync(1 + w, 256);                                   // also publishes q0f / k0f / v0f
       m = fmaxf(m, mb->mx[w][h ^ 1][r]);
+      A4_TRACE(3);
       const float ms = m * scale_log2;
       const float nms = -ms;
       auto emit_p = [&](const uint32_t (&v)[32], int c) {
@@ -1600,7 +1684,13 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         for (int e = 0; e < 16; ++e) {
           float t0, t1;  // one FFMA2 per pair of scores
           ffma2(t0, t1, __uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), scale_log2, scale_log2, nms, nms);
-          pk[e] = pack2(ex2_ftz(t0), ex2_ftz(t1));
+          if (kPolyMod != 0 && (e % (kPolyMod ? kPolyMod : 1)) == kPolyMod - 1) {
+            float y0, y1;
+            exp2_poly2(y0, y1, t0, t1);
+            pk[e] = pack2(y0, y1);
+          } else {
+            pk[e] = pack2(ex2_ftz(t0), ex2_ftz(t1));
+          }
         }
         tmem_st_32x16(taddr + sbase_col + c * 16, pk);  // columns already consumed by this thread
       };
@@ -1617,6 +1707,7 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&mb->p_full[w]);
+      A4_TRACE(4);
 
       // ---- class-token KEY: p0 = exp2((q_r·k0 − m)·c), while the tensor core computes O (half 1 only)
       mbar_wait(&mb->full_qk[s], u);
@@ -1624,6 +1715,7 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         const float s0 = dot_row<HD>(st, w * 128 + r, k0f);
         mb->p0s[w][r] = ex2_ftz(fminf(fmaf(s0, scale_log2, -ms), 126.f));
       }
+      A4_TRACE(5);
       // ---- class-token QUERY row: one key per thread, scores from the K tile, then O_cls = P_cls·V from the V tile
       if (cls_owner) {
         const float sa = dot_row<HD>(st + L::kOp, gt, q0f);
@@ -1673,7 +1765,9 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
         *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
+      A4_TRACE(6);
       named_bar_sync(1 + w, 256);  // p0s (and the class row's partial sums) visible
+      A4_TRACE(7);
       // Release the operand stage NOW (every Q / K / V read of the group is done) and finish the class row BEFORE waiting
       // for O: measured together these two placements are worth 16 % of the kernel (0.73 -> 0.61 ms at 1024 crops);
       // releasing at the end of the iteration, or reducing after the epilogue, each lose all of it.
@@ -1691,8 +1785,10 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
 
       // ---- own row, own 32 output columns: (O + p0·v0) / (L + p0) -> bf16
       const float p0 = mb->p0s[w][r];
+      A4_TRACE(8);
       mbar_wait(&mb->o_full[w], kp);
       tc_fence_after();
+      A4_TRACE(9);
       const float lsum = __uint_as_float(tmem_ld_1(taddr + kColL4));
       {
         uint32_t v[32];
@@ -1727,7 +1823,10 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
       }
 
       // the group's scratch (vec, mx, p0s, p_cls, part, red) is rewritten next iteration: everyone must be done with it
+      if constexpr (kPairBar) publish((k + 1) & 1);  // next head's q0 / k0 / v0 (prefetched at the top of this iteration)
+      A4_TRACE(10);
       named_bar_sync(1 + w, 256);
+      A4_TRACE(11);
     }
   }
   tc_fence_before();
@@ -1738,6 +1837,8 @@ attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat
   }
 }
 
+constexpr int kA4DefaultVar = 0;
+
 static int attention_umma4_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
   constexpr int HD = 64;
   const int d = heads * HD;
@@ -1745,12 +1846,23 @@ static int attention_umma4_launch(const void* qkv, void* out, int n, int T, int 
   B2C_TRY(make_tmap_2d(&tm, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, 1));
   constexpr int smem_bytes = a4_smem_bytes();
   static_assert(smem_bytes <= 227 * 1024, "attention v4 shared memory exceeds 227 KB");
-  auto kern = attention_umma4_kernel;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
+  static const int var = [] { const char* e = getenv("B2C_ATTN_VAR"); return e ? atoi(e) : kA4DefaultVar; }();
+  using Kern = void (*)(const CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float);
+  Kern kern = nullptr;
+  switch (var) {
+    case 0: kern = attention_umma4_kernel<0>; break;
+    case 1: kern = attention_umma4_kernel<1>; break;
+    case 3: kern = attention_umma4_kernel<3>; break;
+    case 5: kern = attention_umma4_kernel<5>; break;
+    case 7: kern = attention_umma4_kernel<7>; break;
+    case 11: kern = attention_umma4_kernel<11>; break;
+    case 15: kern = attention_umma4_kernel<15>; break;
+    case 16: kern = attention_umma4_kernel<16>; break;
+    case 17: kern = attention_umma4_kernel<17>; break;
+    case 19: kern = attention_umma4_kernel<19>; break;
+    default: return set_error(B2C_ERR_ARG, "attention: B2C_ATTN_VAR=%d is not built", var);
   }
+  B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");
   const int n_ch = n * heads;
@@ -1760,6 +1872,547 @@ static int attention_umma4_launch(const void* qkv, void* out, int n, int T, int 
   B2C_POST_LAUNCH("attention_umma4_kernel");
   return 0;
 }
+
+// ================================================================================================
+// (1e) tcgen05 attention v5 for T = 257, head dim 64: v4 with the class token moved off the softmax warps.
+//   A phase trace of v4 (clock64 at phase boundaries, profiles/r2_attn_trace.txt) showed where its 10-12 k cycles per
+//   (crop, head) go: the group that owns the class-token QUERY row spends 3-5 k cycles on it (dot products, two 256-thread
+//   barriers, P_cls·V, reduction) between its P and its epilogue, which delays tmem_free and with it the next S of that
+//   query tile; the class-token KEY term costs the other column half another 0.2-0.7 k, and every phase boundary is a
+//   256-thread barrier that waits for the slowest of eight warps.  v5:
+//     warp 0       TMA producer            warp 1   MMA issuer (optionally staggered: S0(k) PV1(k-1) S1(k) PV0(k))
+//     warps 2-17   softmax only: max pass -> 64-thread exchange with the other column half -> exp2 pass -> P -> epilogue.
+//                  No group barrier, no class-token arithmetic: p0 = exp2((s0 - m)·c) with s0 read from shared memory.
+//     warps 18-21  class-token warps, one per SM sub-partition, running one head AHEAD of the softmax warps (they need
+//                  only the operand tiles, which the producer prefetches a head ahead): s0[r] = q_r·k0 for the 256
+//                  query rows, the class QUERY row's scores, softmax and P_cls·V, and its output row.
+//   Operand stage s is released (empty_qk) by the MMA commit, the 4 class warps and the 16 softmax warps (end of their
+//   iteration: they read s0 / v0 of the stage until the epilogue).
+// ================================================================================================
+constexpr int kA5Threads = 64 + 512 + 128;
+constexpr int kA5ClsWarp0 = 18;
+
+struct A5Misc {
+  uint64_t full_qk[2], full_v[2], empty_qk[2], empty_v[2];
+  uint64_t s_full[2], p_full[2], o_full[2], tmem_free[2];
+  uint64_t cls_done[2];
+  uint32_t tmem_slot;
+  uint32_t pad[3];
+  float vec[2][3][64];      // per stage: q0, k0, v0 of the head as fp32
+  float s0[2][256];         // per stage: q_r·k0 of every patch query row
+  float mx[2][2][2][128];   // per iteration parity, group, column half: partial row maxima
+  float red[8];             // class warps: max / sum scratch
+  float p_cls[264];         // class-row probabilities (256 patch keys + class key)
+  float part[16][64];       // 16 key-slices of the class-row output
+};
+
+constexpr int a5_smem_bytes() {
+  return A2L<64>::kOffMisc + static_cast<int>((sizeof(A5Misc) + 1023) / 1024 * 1024) + 1024;
+}
+
+__device__ long long g_attn5_trace[22][8][16];
+__device__ long long g_attn5_cta[160][4];  // per CTA: globaltimer at start / end, clock64 at start / end (trace builds)
+#define A5_TRACE(ev)                                                                                    \
+  do {                                                                                                  \
+    if constexpr (kTrace) {                                                                             \
+      if (blockIdx.x == 0 && lane == 0 && k >= g_attn_trace_k0 && k < g_attn_trace_k0 + 8) g_attn5_trace[warp][k - g_attn_trace_k0][ev] = clock64(); \
+    }                                                                                                   \
+  } while (0)
+
+// kVar: bit 0 staggered MMA issue order | bits 2-3 exp2 on the FMA pipe for every 4th / 3rd / 2nd pair | bit 4 trace
+template <int kVar>
+// 704 threads: the register file is allocated as for 768, i.e. 80 registers per thread (88 does not launch)
+__global__ void __launch_bounds__(kA5Threads, 1)
+attention_umma5_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* __restrict__ qkv,
+                       __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads, float scale_log2) {
+  constexpr int HD = 64;
+  constexpr bool kStagger = (kVar & 1) != 0;
+  constexpr int kPolyMod = ((kVar >> 2) & 3) == 0 ? 0 : 5 - ((kVar >> 2) & 3);  // 0 | 4 | 3 | 2
+  constexpr bool kTrace = (kVar & 16) != 0;
+  using L = A2L<HD>;
+  constexpr int kColO4 = 64, kColL4 = 192;
+  extern __shared__ uint8_t smem_a5_raw[];
+  uint8_t* smem = smem_a5_raw + ((1024u - (smem_u32(smem_a5_raw) & 1023u)) & 1023u);  // keeps the address space: LDS/STS
+  A5Misc* mb = reinterpret_cast<A5Misc*>(smem + L::kOffMisc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * HD;
+  const size_t row_stride = static_cast<size_t>(3) * d;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&mb->full_qk[s], 1);
+      mbar_init(&mb->full_v[s], 1);
+      mbar_init(&mb->empty_qk[s], 1 + 4 + 16);  // MMA commit + class warps + softmax warps
+      mbar_init(&mb->empty_v[s], 1 + 4);        // MMA commit + class warps
+      mbar_init(&mb->s_full[s], 1);
+      mbar_init(&mb->p_full[s], 8);
+      mbar_init(&mb->o_full[s], 1);
+      mbar_init(&mb->tmem_free[s], 8);
+      mbar_init(&mb->cls_done[s], 4);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 8 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem + L::kOffOnes)[i] = 0x3F803F80u;  // bf16 1.0 x2
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc(&mb->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mb->tmem_slot;
+  if constexpr (kTrace) {
+    if (threadIdx.x == 0 && blockIdx.x < 160) {
+      long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      g_attn5_cta[blockIdx.x][0] = gt;
+      g_attn5_cta[blockIdx.x][2] = clock64();
+    }
+  }
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int k = 0;
+      for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+        const int s = k & 1;
+        const uint32_t u = (k >> 1) & 1;
+        const int crop = ch / heads, head = ch - crop * heads;
+        const int row0 = crop * T + 1;
+        uint8_t* st = smem + s * L::kQKStage;
+        uint8_t* sv = smem + L::kOffV + s * L::kOp;
+        mbar_wait(&mb->empty_qk[s], u ^ 1);
+        mbar_arrive_expect_tx(&mb->full_qk[s], 2 * L::kOp);
+        tma_load_2d(st, &tm, &mb->full_qk[s], head * HD, row0);
+        tma_load_2d(st + L::kOp, &tm, &mb->full_qk[s], d + head * HD, row0);
+        mbar_wait(&mb->empty_v[s], u ^ 1);
+        mbar_arrive_expect_tx(&mb->full_v[s], L::kOp);
+        tma_load_2d(sv, &tm, &mb->full_v[s], 2 * d + head * HD, row0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow; the query
+    // tile index is a compile-time constant in every tcgen05.mma operand, see v4)
+    const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
+    const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
+    const uint32_t idesc_l = make_idesc_f16(128, 16, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t ones_desc = make_sw128_kmajor_desc(smem_base + L::kOffOnes);
+    auto issue_s = [&](auto wc, uint32_t sbase, uint64_t k_desc, uint32_t kp) {
+      constexpr int w = decltype(wc)::value;
+      const uint32_t treg = tmem + w * 256;
+      const uint64_t q_desc = make_sw128_kmajor_desc(sbase + w * 16384);
+      mbar_wait(&mb->tmem_free[w], kp ^ 1);  // both halves of group w have read the previous O out of the region
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_f16(treg, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk != 0);
+        umma_commit(&mb->s_full[w]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](auto wc, uint64_t v_desc0, uint32_t kp) {
+      constexpr int w = decltype(wc)::value;
+      const uint32_t treg = tmem + w * 256;
+      mbar_wait(&mb->p_full[w], kp);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint32_t pcol = (kk < 8 ? 0u : 128u) + (kk & 7) * 8;  // P_0 at [0,64), P_1 at [128,192)
+          umma_f16_ts(treg + kColO4, treg + pcol, v_desc0 + kk * 128, idesc_o, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint32_t pcol = (kk < 8 ? 0u : 128u) + (kk & 7) * 8;
+          umma_f16_ts(treg + kColL4, treg + pcol, ones_desc + 2 * (kk & 3), idesc_l, kk != 0);
+        }
+        umma_commit(&mb->o_full[w]);
+      }
+      __syncwarp();
+    };
+    using W0 = std::integral_constant<int, 0>;
+    using W1 = std::integral_constant<int, 1>;
+    int k = 0;
+    uint64_t v_desc_prev = 0;
+    int s_prev = 0;
+    uint32_t kp_prev = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t u = (k >> 1) & 1, kp = k & 1;
+      const uint32_t sbase = smem_base + s * L::kQKStage;
+      const uint32_t vbase = smem_base + L::kOffV + s * L::kOp;
+      A5_TRACE(0);
+      mbar_wait(&mb->full_qk[s], u);
+      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + L::kOp);
+      A5_TRACE(1);
+      issue_s(W0{}, sbase, k_desc, kp);
+      A5_TRACE(2);
+      if constexpr (kStagger) {
+        if (k > 0) {  // tile 1 of the previous head: its softmax ran while tile 0's P·V, epilogue and this S were in flight
+          issue_pv(W1{}, v_desc_prev, kp_prev);
+          if (elect_one()) umma_commit(&mb->empty_v[s_prev]);
+          __syncwarp();
+        }
+      }
+      A5_TRACE(3);
+      issue_s(W1{}, sbase, k_desc, kp);
+      A5_TRACE(4);
+      if (elect_one()) umma_commit(&mb->empty_qk[s]);
+      __syncwarp();
+      mbar_wait(&mb->full_v[s], u);
+      const uint64_t v_desc0 = make_sw128_kmajor_desc(vbase);
+      A5_TRACE(5);
+      issue_pv(W0{}, v_desc0, kp);
+      A5_TRACE(6);
+      if constexpr (kStagger) {
+        v_desc_prev = v_desc0;
+        s_prev = s;
+        kp_prev = kp;
+      } else {
+        issue_pv(W1{}, v_desc0, kp);
+        if (elect_one()) umma_commit(&mb->empty_v[s]);
+        __syncwarp();
+      }
+      A5_TRACE(7);
+    }
+    if constexpr (kStagger) {
+      if (k > 0) {
+        issue_pv(W1{}, v_desc_prev, kp_prev);
+        if (elect_one()) umma_commit(&mb->empty_v[s_prev]);
+        __syncwarp();
+      }
+    }
+  } else if (warp < kA5ClsWarp0) {
+    // ------------------------------------------------------------------ softmax: 2 groups x 2 column halves x 4 warps
+    const int sw = warp - 2;
+    const int w = sw >> 3;                  // group = query tile
+    const int h = (sw >> 2) & 1;            // column half: keys [128h, 128h + 128)
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+    const int r = quarter * 32 + lane;      // query row in the tile = TMEM lane
+    const uint32_t taddr = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t sbase_col = 128u * h;    // this half's S columns; its P goes over them at [128h, 128h + 64)
+    int k = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t u = (k >> 1) & 1, kp = k & 1;
+      const int crop = ch / heads, head = ch - crop * heads;
+      const int token = crop * T + 1 + w * 128 + r;
+
+      // ---- own row, own 128 keys: partial max -> exchange with the other half -> P (bf16x2 packed) back into TMEM over S
+      A5_TRACE(0);
+      mbar_wait(&mb->s_full[w], kp);
+      tc_fence_after();
+      A5_TRACE(1);
+      float m = -INFINITY;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr + sbase_col, va);
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + sbase_col + (c + 1) * 32, vb);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + sbase_col + ((c + 2) & 3) * 32, va);  // last iteration: chunk 0 again, for the second pass
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
+      }
+      mb->mx[kp][w][h][r] = m;
+      A5_TRACE(2);
+      named_bar_sync(3 + w * 4 + quarter, 64);  // the two warps that share these 32 rows
+      m = fmaxf(m, mb->mx[kp][w][h ^ 1][r]);
+      A5_TRACE(3);
+      const float ms = m * scale_log2;
+      const float nms = -ms;
+      auto emit_p = [&](const uint32_t (&v)[32], int c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float t0, t1;  // one FFMA2 per pair of scores
+          ffma2(t0, t1, __uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), scale_log2, scale_log2, nms, nms);
+          if (kPolyMod != 0 && (e % (kPolyMod ? kPolyMod : 1)) == kPolyMod - 1) {
+            float y0, y1;
+            exp2_poly2(y0, y1, t0, t1);
+            pk[e] = pack2(y0, y1);
+          } else {
+            pk[e] = pack2(ex2_ftz(t0), ex2_ftz(t1));
+          }
+        }
+        tmem_st_32x16(taddr + sbase_col + c * 16, pk);  // columns already consumed by this thread
+      };
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + sbase_col + (c + 1) * 32, vb);
+        emit_p(va, c);
+        tmem_ld_wait();
+        if (c + 2 < 4) tmem_ld_32x32(taddr + sbase_col + (c + 2) * 32, va);
+        emit_p(vb, c + 1);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mb->p_full[w]);
+      A5_TRACE(4);
+
+      // ---- class-token KEY: p0 = exp2((q_r·k0 − m)·c), the dot product comes from the class warps
+      mbar_wait(&mb->cls_done[s], u);
+      A5_TRACE(5);
+      const float p0 = ex2_ftz(fminf(fmaf(mb->s0[s][w * 128 + r], scale_log2, nms), 126.f));
+      const float* v0 = mb->vec[s][2] + h * 32;
+
+      // ---- own row, own 32 output columns: (O + p0·v0) / (L + p0) -> bf16
+      A5_TRACE(8);
+      mbar_wait(&mb->o_full[w], kp);
+      tc_fence_after();
+      A5_TRACE(9);
+      const float lsum = __uint_as_float(tmem_ld_1(taddr + kColL4));
+      {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + kColO4 + h * 32, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mb->tmem_free[w]);  // O and L are in registers: the region can take the next S
+        const float inv = 1.0f / (lsum + p0);
+        const float p0i = p0 * inv;
+        __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * HD + h * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 va4 = *reinterpret_cast<const float4*>(v0 + 8 * j);
+          const float4 vb4 = *reinterpret_cast<const float4*>(v0 + 8 * j + 4);
+          uint4 o4;
+          float t[8], o[8];
+          fmul2(t[0], t[1], va4.x, va4.y, p0i, p0i);
+          fmul2(t[2], t[3], va4.z, va4.w, p0i, p0i);
+          fmul2(t[4], t[5], vb4.x, vb4.y, p0i, p0i);
+          fmul2(t[6], t[7], vb4.z, vb4.w, p0i, p0i);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2)
+            ffma2(o[e], o[e + 1], __uint_as_float(v[8 * j + e]), __uint_as_float(v[8 * j + e + 1]), inv, inv, t[e], t[e + 1]);
+          o4.x = pack2(o[0], o[1]);
+          o4.y = pack2(o[2], o[3]);
+          o4.z = pack2(o[4], o[5]);
+          o4.w = pack2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(orow + 8 * j) = o4;
+        }
+      }
+      A5_TRACE(10);
+      // s0 / v0 of stage s are no longer needed by this warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mb->empty_qk[s]);
+      A5_TRACE(11);
+    }
+  } else {
+    // ------------------------------------------------------------------ class-token warps (128 threads, barrier 11)
+    // Everything here goes through the MIO queue (LDS, SHFL) that the softmax warps keep full of MUFU.EX2, so a round
+    // trip costs hundreds of cycles: loads are issued in few, wide, independent rounds (the vectors stay packed bf16 in
+    // registers, a row's eight 16-byte chunks are requested together) and the max reduction uses CREDUX.
+    const int t = static_cast<int>(threadIdx.x) - kA5ClsWarp0 * 32;
+    const int cw = warp - kA5ClsWarp0;
+    float* red = mb->red;
+    float* pcls = mb->p_cls;
+    uint32_t cq = 0, ck = 0, cv = 0;  // two bf16 each (threads 0..31)
+    auto prefetch = [&](int ch) {
+      if (t < HD / 2) {
+        const int crop = ch / heads, head = ch - crop * heads;
+        const uint32_t* cls_row = reinterpret_cast<const uint32_t*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * HD);
+        cq = __ldg(cls_row + t);
+        ck = __ldg(cls_row + d / 2 + t);
+        cv = __ldg(cls_row + d + t);
+      }
+    };
+    // dots of rows `ra` and `rb` of a swizzled 128-byte-row tile with a packed bf16 vector (32 words in shared memory):
+    // two rounds of 12 independent 16-byte loads (half the vector + half of either row), 48 registers in flight
+    auto dot2_packed = [](const uint8_t* tile, int ra, int rb, const uint32_t* vec, float& da, float& db) {
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+      const uint8_t* pa = tile + ra * 128;
+      const uint8_t* pb = tile + rb * 128;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint4 v[4], xa[4], xb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = reinterpret_cast<const uint4*>(vec)[4 * half + j];
+          xa[j] = *reinterpret_cast<const uint4*>(pa + (((4 * half + j) ^ (ra & 7)) << 4));
+          xb[j] = *reinterpret_cast<const uint4*>(pb + (((4 * half + j) ^ (rb & 7)) << 4));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t vw[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          const uint32_t aw[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
+          const uint32_t bw[4] = {xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float vl = bf16_lo(vw[e]), vh = bf16_hi(vw[e]);
+            ffma2(a0, a1, bf16_lo(aw[e]), bf16_hi(aw[e]), vl, vh, a0, a1);
+            ffma2(b0, b1, bf16_lo(bw[e]), bf16_hi(bw[e]), vl, vh, b0, b1);
+          }
+        }
+      }
+      da = a0 + a1;
+      db = b0 + b1;
+    };
+    if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
+    int k = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t u = (k >> 1) & 1;
+      const int crop = ch / heads, head = ch - crop * heads;
+      const int tok0 = crop * T;
+      const uint8_t* st = smem + s * L::kQKStage;
+      const uint8_t* sv = smem + L::kOffV + s * L::kOp;
+      uint32_t* q0b = reinterpret_cast<uint32_t*>(mb->vec[s][0]);  // q0 / k0 packed bf16 (32 words each); v0 as fp32
+      uint32_t* k0b = reinterpret_cast<uint32_t*>(mb->vec[s][1]);
+      float* v0f = mb->vec[s][2];
+      A5_TRACE(0);
+      mbar_wait(&mb->full_qk[s], u);  // the stage (tiles, vec[s], s0[s]) was released by everyone who used it two heads ago
+      A5_TRACE(1);
+      if (t < HD / 2) {
+        q0b[t] = cq;
+        k0b[t] = ck;
+        *reinterpret_cast<float2*>(v0f + 2 * t) = make_float2(bf16_lo(cv), bf16_hi(cv));
+      }
+      if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
+      named_bar_sync(11, 128);
+      // class-token KEY: q_r·k0 for the 256 patch query rows -> the softmax warps
+      float sq0, sq1;
+      dot2_packed(st, t, t + 128, k0b, sq0, sq1);
+      mb->s0[s][t] = sq0;
+      mb->s0[s][t + 128] = sq1;
+      // class key x class query (each warp redundantly): lane l takes the packed pair l
+      float sc;
+      {
+        const uint32_t qa = q0b[lane], ka = k0b[lane];
+        sc = fmaf(bf16_lo(qa), bf16_lo(ka), bf16_hi(qa) * bf16_hi(ka));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mb->cls_done[s]);  // release: s0[s] and vec[s] (written before barrier 11) are visible
+      A5_TRACE(2);
+      // class-token QUERY row: scores of the 256 patch keys (two per thread) and of the class key
+      float sa0, sa1;
+      dot2_packed(st + L::kOp, t, t + 128, q0b, sa0, sa1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      float cm;
+      {
+        const float mine = fmaxf(fmaxf(sa0, sa1), sc);
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(cm) : "f"(mine));
+      }
+      if (lane == 0) red[cw] = cm;
+      named_bar_sync(11, 128);
+      cm = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * scale_log2;
+      const float pa0 = ex2_ftz(fmaf(sa0, scale_log2, -cm));
+      const float pa1 = ex2_ftz(fmaf(sa1, scale_log2, -cm));
+      const float pc = ex2_ftz(fmaf(sc, scale_log2, -cm));
+      pcls[t] = pa0;
+      pcls[t + 128] = pa1;
+      float psum = pa0 + pa1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      if (lane == 0) red[4 + cw] = psum;
+      named_bar_sync(11, 128);
+      A5_TRACE(3);
+      // O_cls = P_cls·V: thread = (16-key slice ks, 8-column chunk cc), one 16-byte read per key, 8 keys per round
+      mbar_wait(&mb->full_v[s], u);
+      const int cc = t & 7, ks = t >> 3;
+      const float* pp = pcls + ks * 16;
+      const uint8_t* base = sv + (ks * 16) * 128;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float4 pA = *reinterpret_cast<const float4*>(pp + 8 * half);
+        const float4 pB = *reinterpret_cast<const float4*>(pp + 8 * half + 4);
+        const float pk8[8] = {pA.x, pA.y, pA.z, pA.w, pB.x, pB.y, pB.z, pB.w};
+        // ks*16 + key has the same low 3 bits as key, so the swizzle phase depends on `key` only
+        uint4 row[8];
+#pragma unroll
+        for (int key = 0; key < 8; ++key) row[key] = *reinterpret_cast<const uint4*>(base + (8 * half + key) * 128 + ((cc ^ key) << 4));
+#pragma unroll
+        for (int key = 0; key < 8; ++key) {
+          const uint4 a = row[key];
+          const float pkey = pk8[key];
+          ffma2(acc[0], acc[1], bf16_lo(a.x), bf16_hi(a.x), pkey, pkey, acc[0], acc[1]);
+          ffma2(acc[2], acc[3], bf16_lo(a.y), bf16_hi(a.y), pkey, pkey, acc[2], acc[3]);
+          ffma2(acc[4], acc[5], bf16_lo(a.z), bf16_hi(a.z), pkey, pkey, acc[4], acc[5]);
+          ffma2(acc[6], acc[7], bf16_lo(a.w), bf16_hi(a.w), pkey, pkey, acc[6], acc[7]);
+        }
+      }
+      *reinterpret_cast<float4*>(&mb->part[ks][cc * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(&mb->part[ks][cc * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      named_bar_sync(11, 128);
+      // every Q / K / V read of the class warps is done
+      if (lane == 0) {
+        mbar_arrive(&mb->empty_qk[s]);
+        mbar_arrive(&mb->empty_v[s]);
+      }
+      if (t < HD) {
+        const float cls_l = ((red[4] + red[5]) + (red[6] + red[7])) + pc;
+        float o = pc * v0f[t];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o += mb->part[i][t];
+        out[static_cast<size_t>(tok0) * d + head * HD + t] = __float2bfloat16_rn(o / cls_l);
+      }
+      A5_TRACE(4);
+      named_bar_sync(11, 128);  // red / p_cls / part are rewritten next iteration
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (kTrace) {
+    if (threadIdx.x == 0 && blockIdx.x < 160) {
+      long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      g_attn5_cta[blockIdx.x][1] = gt;
+      g_attn5_cta[blockIdx.x][3] = clock64();
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+constexpr int kA5DefaultVar = 1;  // staggered MMA issue order, all exp2 on the XU pipe
+
+static int attention_umma5_launch(const void* qkv, void* out, int n, int T, int heads, int var, cudaStream_t stream) {
+  constexpr int HD = 64;
+  const int d = heads * HD;
+  CUtensorMap tm;
+  B2C_TRY(make_tmap_2d(&tm, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, 1));
+  constexpr int smem_bytes = a5_smem_bytes();
+  static_assert(smem_bytes <= 227 * 1024, "attention v5 shared memory exceeds 227 KB");
+  using Kern = void (*)(const CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float);
+  Kern kern = nullptr;
+  switch (var) {
+    case 0: kern = attention_umma5_kernel<0>; break;
+    case 1: kern = attention_umma5_kernel<1>; break;
+    case 4: kern = attention_umma5_kernel<4>; break;
+    case 5: kern = attention_umma5_kernel<5>; break;
+    case 8: kern = attention_umma5_kernel<8>; break;
+    case 9: kern = attention_umma5_kernel<9>; break;
+    case 12: kern = attention_umma5_kernel<12>; break;
+    case 13: kern = attention_umma5_kernel<13>; break;
+    case 16: kern = attention_umma5_kernel<16>; break;
+    case 17: kern = attention_umma5_kernel<17>; break;
+    default: return set_error(B2C_ERR_ARG, "attention v5: variant %d is not built", var);
+  }
+  B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int sms = num_sms();
+  B2C_REQUIRE(sms > 0, "no CUDA device");
+  const int n_ch = n * heads;
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+  kern<<<n_ch < sms ? n_ch : sms, kA5Threads, smem_bytes, stream>>>(
+      tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, scale_log2);
+  B2C_POST_LAUNCH("attention_umma5_kernel");
+  return 0;
+}
+
+static int g_attn5_var_override = -2;  // development (b2c_debug_set_attn5): -2 = follow B2C_ATTN5_VAR (default v5 variant 1), -1 = v4, >= 0 = v5 variant
 
 template <int HD>
 static int attention_launch_hd(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
@@ -1793,6 +2446,9 @@ int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd
   // B2C_ATTN = v4 (default for hd 64: v2 with 16 softmax warps) | v2 (persistent, P in TMEM) | v1 (one CTA per query
   // tile, P in smem) | legacy (mma.sync)
   static const char mode = [] { const char* e = getenv("B2C_ATTN"); return e ? (e[0] == 'l' ? 'l' : (e[1] == '1' ? '1' : (e[1] == '2' ? '2' : '4'))) : '4'; }();
+  static const int v5env = [] { const char* e = getenv("B2C_ATTN5_VAR"); return e ? atoi(e) : kA5DefaultVar; }();
+  const int v5var = g_attn5_var_override >= -1 ? g_attn5_var_override : v5env;
+  if (hd == 64 && T == kAuKeys + 1 && v5var >= 0) return attention_umma5_launch(qkv, out, n, T, heads, v5var, stream);
   if (hd == 64 && T == kAuKeys + 1 && mode == '4') return attention_umma4_launch(qkv, out, n, T, heads, stream);
   if (hd == 64 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<64>(qkv, out, n, T, heads, stream);
   if (hd == 80 && T == kAuKeys + 1 && (mode == '2' || mode == '4')) return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
@@ -1805,6 +2461,35 @@ int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd
 }
 
 }  // namespace b2c
+
+// development only (not part of include/b2c.h): copy out the phase trace of attention_umma4_kernel<kVar | 16>
+extern "C" int b2c_debug_attn_trace(void* out, size_t bytes) {
+  using namespace b2c;
+  B2C_REQUIRE(out && bytes == sizeof(g_attn_trace), "b2c_debug_attn_trace: need %zu bytes", sizeof(g_attn_trace));
+  B2C_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_attn_trace, bytes));
+  return 0;
+}
+extern "C" int b2c_debug_attn_trace_start(int k0) {
+  using namespace b2c;
+  B2C_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace_k0, &k0, sizeof(int)));
+  return 0;
+}
+extern "C" int b2c_debug_set_attn5(int var) {
+  b2c::g_attn5_var_override = var;
+  return 0;
+}
+extern "C" int b2c_debug_attn5_cta(void* out, size_t bytes) {
+  using namespace b2c;
+  B2C_REQUIRE(out && bytes == sizeof(g_attn5_cta), "b2c_debug_attn5_cta: need %zu bytes", sizeof(g_attn5_cta));
+  B2C_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_attn5_cta, bytes));
+  return 0;
+}
+extern "C" int b2c_debug_attn5_trace(void* out, size_t bytes) {
+  using namespace b2c;
+  B2C_REQUIRE(out && bytes == sizeof(g_attn5_trace), "b2c_debug_attn5_trace: need %zu bytes", sizeof(g_attn5_trace));
+  B2C_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_attn5_trace, bytes));
+  return 0;
+}
 
 extern "C" int b2c_attention_bf16(const void* qkv, void* out, int n, int T, int heads, int hd, b2c_stream stream) {
   using namespace b2c;

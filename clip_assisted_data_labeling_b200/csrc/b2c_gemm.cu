@@ -30,6 +30,8 @@ struct GemmParams {
   // LayerNorm fusion (b2c_umma_pipeline2.cuh): per-row (mean, M2) partials of the residual stream, one per 256-column
   // block; written by the kGemmResidLnF32 epilogue, merged by the kGemmLn* epilogues
   float2* stats;
+  const float2* stats_in;  // kStoreRmwLn: statistics of the rows before this update
+  float* shift;            // per-row offset of the bf16 copy (see GemmLaunch)
   int nblk;
   float eps;
   const float* colsum;  // kGemmLn*: column sums of the folded weight, s_n = sum_k (gamma_k W_nk)
@@ -124,15 +126,27 @@ struct GemmPolicy {
     }
   }
 
-  // kLnFold: the row's per-block (mean, M2) partials (requested a tile ahead), merged in block order ->
-  // a = rstd, b = -mean * rstd
-  __device__ static __forceinline__ void load_row_stats(const Params& p, int row, float2 (&st)[8]) {
+  // kLnFold: the row's per-block (mean, M2) partials and the shift its bf16 copy was rounded with (requested a tile
+  // ahead), merged in block order -> a = rstd, b = -(mean - shift) * rstd
+  __device__ static __forceinline__ void load_row_stats(const Params& p, int row, float2 (&st)[8], float& sh) {
     const float2* src = p.stats + static_cast<size_t>(row) * p.nblk;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (j < p.nblk && row < p.M) st[j] = src[j];
+    if (row < p.M) sh = p.shift[row];
   }
-  __device__ static __forceinline__ void merge_row_stats(const Params& p, int row, const float2 (&st)[8], float& a, float& b) {
+  // kStoreRmwLn: the row's mean before this update (from the previous update's partials) = the shift of its new bf16 copy
+  __device__ static __forceinline__ float load_old_mean(const Params& p, int row) {
+    if (row >= p.M) return 0.f;
+    const float2* src = p.stats_in + static_cast<size_t>(row) * p.nblk;
+    float m = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < p.nblk) m += src[j].x;
+    return m / static_cast<float>(p.nblk);
+  }
+  __device__ static __forceinline__ void merge_row_stats(const Params& p, int row, const float2 (&st)[8], float sh, float& a,
+                                                         float& b) {
     a = 0.f;
     b = 0.f;
     if (row >= p.M) return;
@@ -151,12 +165,15 @@ struct GemmPolicy {
     }
     const float rstd = rsqrtf(m2 / (256.0f * static_cast<float>(p.nblk)) + p.eps);
     a = rstd;
-    b = -mean * rstd;
+    b = -(mean - sh) * rstd;
   }
 
   // kStoreRmwLn: (mean, M2) of the row's 256 new values in this tile's column block
-  __device__ static __forceinline__ void store_row_stats(const Params& p, int row, int b_row, float mean, float m2) {
-    if (row < p.M) p.stats[static_cast<size_t>(row) * p.nblk + (b_row >> 8)] = make_float2(mean, m2);
+  __device__ static __forceinline__ void store_row_stats(const Params& p, int row, int b_row, float mean, float m2, float sh) {
+    if (row < p.M) {
+      p.stats[static_cast<size_t>(row) * p.nblk + (b_row >> 8)] = make_float2(mean, m2);
+      if (b_row == 0) p.shift[row] = sh;  // every column block of the row used the same value
+    }
   }
 
   // patch-embed only: rows are scattered past each crop's class token, so the stores stay per-thread
@@ -213,7 +230,9 @@ template <int MODE>
 static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
   if constexpr (MODE >= kGemmLnBiasBf16) {
     // the LayerNorm-fused epilogues exist in the CTA-pair kernel only
-    B2C_REQUIRE(p.stats && p.nblk > 0 && p.nblk <= 8, "gemm: LayerNorm-fused mode %d needs the row statistics buffer", MODE);
+    B2C_REQUIRE(p.stats && p.shift && p.nblk > 0 && p.nblk <= 8, "gemm: LayerNorm-fused mode %d needs the row statistics / shift buffers", MODE);
+    if constexpr (GemmPolicy<MODE>::kStore == kStoreRmwLn)
+      B2C_REQUIRE(p.stats_in && p.stats_in != p.stats, "gemm: mode %d needs the previous update's statistics in a separate buffer", MODE);
     if constexpr (GemmPolicy<MODE>::kLnFold) B2C_REQUIRE(p.colsum && p.bias, "gemm: mode %d needs colsum and the folded bias", MODE);
     return gemm_launch_pair<MODE>(g, p, stream);
   } else {
@@ -276,6 +295,8 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   p.T = g.T;
   p.G2 = g.G2;
   p.stats = g.stats;
+  p.stats_in = g.stats_in;
+  p.shift = g.shift;
   p.nblk = g.nblk;
   p.eps = g.eps;
   p.colsum = g.colsum;

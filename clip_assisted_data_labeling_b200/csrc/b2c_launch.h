@@ -40,10 +40,12 @@ enum GemmMode {
   kGemmPatchEmbedF32 = 4,  // x[(crop*T + 1 + p), :] = A·Wᵀ + pos[1+p, :]   (conv1 + positional embedding)
   // LayerNorm fused into the GEMMs on either side of it (b2c_umma_pipeline2.cuh).  A = bf16 copy of the residual
   // stream, W = gamma-folded weight, bias = beta·Wᵀ + b, colsum = row sums of the folded weight:
-  kGemmLnBiasBf16 = 5,       // out bf16 = rstd·(A·W'ᵀ − mean·colsum) + bias                  (ln_1 + in_proj)
+  // A = bf16(x − shift) per row (see GemmLaunch::shift):
+  kGemmLnBiasBf16 = 5,       // out bf16 = rstd·(A·W'ᵀ − (mean − shift)·colsum) + bias        (ln_1 + in_proj)
   kGemmLnBiasQGeluBf16 = 6,  // same + QuickGELU                                               (ln_2 + c_fc, openai)
   kGemmLnBiasGeluBf16 = 7,   // same + erf GELU                                                (ln_2 + c_fc, laion)
-  // x (f32, read-modify-write by the epilogue) += A·Wᵀ + bias; out2 = bf16(x); stats[row][n_block] = (mean, M2)
+  // x (f32, read-modify-write by the epilogue) += A·Wᵀ + bias; shift = row mean before the update; out2 = bf16(x − shift);
+  // stats[row][n_block] = (mean, M2) of the new values
   kGemmResidLnF32 = 8,
   kGemmResidLnBf16Copy = 9,  // make_out_tmap only: the store map of out2
   kGemmResidLnDeepF32 = 10,  // internal: kGemmResidLnF32 with six mainloop stages and a one-slab x ring (large K)
@@ -65,7 +67,11 @@ struct GemmLaunch {
   int T, G2;          // patch-embed only: tokens per crop, patches per crop
   // LayerNorm-fused modes only
   CUtensorMap tmap_out2;  // kGemmResidLnF32: store map of the bf16 copy (make_out_tmap(kGemmResidLnBf16Copy))
-  float2* stats;          // [M, nblk] (mean, M2) per 256-column block of the residual stream
+  float2* stats;          // [M, nblk] (mean, M2) per 256-column block of the residual stream (kGemmLn*: read;
+                          // kGemmResidLnF32: written for the NEW rows)
+  const float2* stats_in; // kGemmResidLnF32: the statistics of the rows BEFORE this update (a different buffer)
+  float* shift;           // [M] what was subtracted from a row before its bf16 copy was rounded: the row mean before the
+                          // update that wrote the copy (kGemmResidLnF32 writes it, kGemmLn* read it)
   int nblk;               // width / 256
   float eps;
   const float* colsum;    // kGemmLn*: [N]
@@ -86,9 +92,10 @@ int layernorm_bf16_strided_launch(const float* x, int64_t ldx, const float* gamm
 int cls_pos_launch(float* x, const float* cls, const float* pos, int n, int T, int d, cudaStream_t stream);
 int layernorm_f32_inplace_launch(float* x, const float* gamma, const float* beta, int64_t M, int d, float eps,
                                  cudaStream_t stream);
-// LayerNorm-fused layer loop: ln_pre in place + bf16 copy + per-256-column (mean, M2) partials of the new rows
-int layernorm_pre_launch(float* x, const float* gamma, const float* beta, void* xb, float2* stats, int64_t M, int d,
-                         float eps, cudaStream_t stream);
+// LayerNorm-fused layer loop: ln_pre in place + per-256-column (mean, M2) partials of the new rows + shift[row] = row
+// mean + bf16 copy of (row - shift)
+int layernorm_pre_launch(float* x, const float* gamma, const float* beta, void* xb, float2* stats, float* shift, int64_t M,
+                         int d, float eps, cudaStream_t stream);
 // wf = bf16(gamma ⊙ w) [N,K], colsum = row sums of wf, bias_f = bias + w·beta;  w: f32 or bf16 [N,K]
 int ln_fold_launch(const void* w, int w_dtype, const float* gamma, const float* beta, const float* bias, void* wf,
                    float* colsum, float* bias_f, int N, int K, cudaStream_t stream);

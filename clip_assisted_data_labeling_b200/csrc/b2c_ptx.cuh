@@ -68,6 +68,13 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
 __device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
   uint64_t a, b, d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, const fl
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_pre_kernel(float* x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ xb,
-                                                            float2* __restrict__ stats, long long M, int d, float eps) {
+                                                            float2* __restrict__ stats, float* __restrict__ shift, long long M,
+                                                            int d, float eps) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -129,14 +130,9 @@ __global__ void __launch_bounds__(256) layernorm_pre_kernel(float* x, const floa
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
     v[i] = o;
     xr[i * 32 + lane] = o;
-    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);
-    __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
-    uint2 w;
-    w.x = *reinterpret_cast<uint32_t*>(&lo);
-    w.y = *reinterpret_cast<uint32_t*>(&hi);
-    reinterpret_cast<uint2*>(xb + row * d)[i * 32 + lane] = w;
   }
   // float4 group i covers columns [128 i, 128 i + 128): block j of 256 columns = groups 2j, 2j + 1
+  float msum = 0.f;
 #pragma unroll
   for (int j = 0; j < NV / 2; ++j) {
     const float4 a = v[2 * j], b = v[2 * j + 1];
@@ -145,25 +141,39 @@ __global__ void __launch_bounds__(256) layernorm_pre_kernel(float* x, const floa
     bq += (a.x - bm) * (a.x - bm) + (a.y - bm) * (a.y - bm) + (a.z - bm) * (a.z - bm) + (a.w - bm) * (a.w - bm);
     bq += (b.x - bm) * (b.x - bm) + (b.y - bm) * (b.y - bm) + (b.z - bm) * (b.z - bm) + (b.w - bm) * (b.w - bm);
     bq = warp_sum(bq);
+    msum += bm;
     if (lane == 0) stats[row * (NV / 2) + j] = make_float2(bm, bq);
+  }
+  // bf16 copy of the row, centred on its mean (the consumer GEMM's epilogue knows the shift): rounding x - m instead of
+  // x keeps the bf16 error relative to the row's spread, not to its offset
+  const float sh = msum / static_cast<float>(NV / 2);
+  if (lane == 0) shift[row] = sh;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x - sh, v[i].y - sh);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v[i].z - sh, v[i].w - sh);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&lo);
+    w.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(xb + row * d)[i * 32 + lane] = w;
   }
 }
 
-int layernorm_pre_launch(float* x, const float* gamma, const float* beta, void* xb, float2* stats, int64_t M, int d,
-                         float eps, cudaStream_t stream) {
+int layernorm_pre_launch(float* x, const float* gamma, const float* beta, void* xb, float2* stats, float* shift, int64_t M,
+                         int d, float eps, cudaStream_t stream) {
   B2C_REQUIRE(d % 256 == 0 && d >= 256 && d <= 2048, "layernorm_pre: d=%d must be a multiple of 256 in [256,2048]", d);
   B2C_REQUIRE(M > 0, "layernorm_pre: M must be positive");
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(xb);
   switch (d / 128) {
-    case 2: layernorm_pre_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
-    case 4: layernorm_pre_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
-    case 6: layernorm_pre_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
-    case 8: layernorm_pre_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
-    case 10: layernorm_pre_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
-    case 12: layernorm_pre_kernel<12><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
-    case 14: layernorm_pre_kernel<14><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
-    default: layernorm_pre_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, M, d, eps); break;
+    case 2: layernorm_pre_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
+    case 4: layernorm_pre_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
+    case 6: layernorm_pre_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
+    case 8: layernorm_pre_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
+    case 10: layernorm_pre_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
+    case 12: layernorm_pre_kernel<12><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
+    case 14: layernorm_pre_kernel<14><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
+    default: layernorm_pre_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, o, stats, shift, M, d, eps); break;
   }
   B2C_POST_LAUNCH("layernorm_pre_kernel");
   return 0;

@@ -20,8 +20,11 @@
 //     bf16 copy of them (the A operand of the next GEMM) through two 64-B-swizzled half slabs.  Every thread owns one
 //     row and keeps (mean, M2) of its 256 columns (exact two-pass per 32-column slab, Chan's merge across slabs);
 //     the partials go to stats[row][n_block] — merged in a fixed order by the consumer, so results are deterministic.
-//   * Policy::kLnFold (in_proj, c_fc): LN(x)·Wᵀ = rstd·(x̃·(γ⊙W)ᵀ − μ·colsum(γ⊙W)) + (β·Wᵀ + b) — the epilogue thread
-//     merges its row's partials into (μ, rstd) once per tile and applies them with two FMAs per element.
+//     The bf16 copy is x̃ = bf16(x − m̂) with m̂ = the row's mean BEFORE this update (from the previous update's partials,
+//     which live in the other of two statistics buffers), stored to shift[row]: rounding the centred value keeps the
+//     copy's error relative to the row's spread even when a trained model's residual rows sit far from zero.
+//   * Policy::kLnFold (in_proj, c_fc): LN(x)·Wᵀ = rstd·(x̃·(γ⊙W)ᵀ − (μ − m̂)·colsum(γ⊙W)) + (β·Wᵀ + b) — the epilogue
+//     thread merges its row's partials into (μ, rstd) once per tile and applies them with two FMAs per element.
 //   Together they remove the stand-alone LayerNorm kernels (and one fp32 read of x per LayerNorm) from the layer loop.
 #pragma once
 #include "b2c_umma_pipeline.cuh"
@@ -225,12 +228,14 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     [[maybe_unused]] float col_b[kChunks], col_s[kChunks], ncol_b[kChunks], ncol_s[kChunks];
     [[maybe_unused]] float ln_a = 1.f, ln_b = 0.f;
     [[maybe_unused]] float2 nst[8];
+    [[maybe_unused]] float nsh = 0.f, sh = 0.f;  // shift of the row's bf16 copy: read (kLnFold) / produced (kRmw); next tile's, this tile's
     if constexpr (Policy::kStore != kStoreDirect) {
       if (cid < p.num_tiles2) {
         int m0 = 0, n0 = 0;
         Policy::tile2(p, cid, m0, n0);
         Policy::load_cols(p, n0 + col_off + lane, ncol_b, ncol_s);
-        if constexpr (Policy::kLnFold) Policy::load_row_stats(p, m0 + row_off + lane, nst);
+        if constexpr (Policy::kLnFold) Policy::load_row_stats(p, m0 + row_off + lane, nst, nsh);
+        if constexpr (kRmw) nsh = Policy::load_old_mean(p, m0 + row_off + lane);
       }
     }
 
@@ -242,12 +247,14 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if constexpr (Policy::kStore != kStoreDirect) {
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) { col_b[c] = ncol_b[c]; col_s[c] = ncol_s[c]; }
-        if constexpr (Policy::kLnFold) Policy::merge_row_stats(p, out_row + lane, nst, ln_a, ln_b);
+        if constexpr (Policy::kLnFold) Policy::merge_row_stats(p, out_row + lane, nst, nsh, ln_a, ln_b);
+        if constexpr (kRmw) sh = nsh;
         if (t + ncl < p.num_tiles2) {
           int nm = 0, nn = 0;
           Policy::tile2(p, t + ncl, nm, nn);
           Policy::load_cols(p, nn + col_off + lane, ncol_b, ncol_s);
-          if constexpr (Policy::kLnFold) Policy::load_row_stats(p, nm + row_off + lane, nst);
+          if constexpr (Policy::kLnFold) Policy::load_row_stats(p, nm + row_off + lane, nst, nsh);
+          if constexpr (kRmw) nsh = Policy::load_old_mean(p, nm + row_off + lane);
         }
       }
       mbar_wait(&acc_full_bar[acc], acc_phase);
@@ -320,9 +327,14 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
             if (c == 0) { mean = cm; m2 = cq; }
             else chan_merge(mean, m2, 32.0f * c, cm, cq, 32.0f);
-            // bf16 copy: 32 columns = 64 B per row, 16-byte chunk j at (j ^ ((row >> 1) & 3)): CU_TENSOR_MAP_SWIZZLE_64B
+            // bf16 copy of (x - shift): 32 columns = 64 B per row, 16-byte chunk j at (j ^ ((row >> 1) & 3)):
+            // CU_TENSOR_MAP_SWIZZLE_64B.  shift = the row's mean before this update, so the rounding error of the copy
+            // scales with the row's spread, not with its offset.
             uint8_t* bslab = my_slabs + kRmwRing * kSlabBytes + (c & 1) * kHalfSlabBytes;
             uint8_t* browp = bslab + lane * 64;
+            const float nsh_c = -sh;
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) fadd2(f[e], f[e + 1], f[e], f[e + 1], nsh_c, nsh_c);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 w;
@@ -385,7 +397,7 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         }
-        if constexpr (kRmw) Policy::store_row_stats(p, out_row + lane, b_row, mean, m2);
+        if constexpr (kRmw) Policy::store_row_stats(p, out_row + lane, b_row, mean, m2, sh);
       }
       tc_fence_before();
       __syncwarp();

@@ -64,7 +64,7 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t x, h, big, patches, xb, stats, head, total;
+  size_t x, h, big, patches, xb, stats, stats2, shift, head, total;
 };
 
 WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
@@ -83,8 +83,12 @@ WsLayout ws_layout(const b2c_vit* v, int nc, bool need_patches) {
   if (need_patches) off = align_up(off + static_cast<size_t>(nc) * v->G2 * v->Kp * 2, 1024);
   w.xb = off;  // bf16 copy of the residual stream + per-row statistics partials (LayerNorm-fused layer loop)
   off = align_up(off + M * d * 2, 1024);
-  w.stats = off;
+  w.stats = off;  // two statistics buffers: a residual update reads the previous update's and writes its own
   off = align_up(off + M * (d / 256) * sizeof(float2), 1024);
+  w.stats2 = off;
+  off = align_up(off + M * (d / 256) * sizeof(float2), 1024);
+  w.shift = off;
+  off = align_up(off + M * sizeof(float), 1024);
   w.head = off;  // partial squared norms of the head's column blocks
   off = align_up(off + head_part_floats(nc, v->cfg.embed) * sizeof(float), 1024);
   w.total = off;
@@ -203,7 +207,9 @@ int forward_chunk_fused(b2c_vit* v, const void* patches, int nc, float* out, uin
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(ws + w.h);
   __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(ws + w.big);
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + w.xb);
-  float2* stats = reinterpret_cast<float2*>(ws + w.stats);
+  float2* stats_a = reinterpret_cast<float2*>(ws + w.stats);   // statistics at the start of a block (and after c_proj)
+  float2* stats_b = reinterpret_cast<float2*>(ws + w.stats2);  // statistics after out_proj
+  float* shift = reinterpret_cast<float*>(ws + w.shift);
   const float eps = 1e-5f;
 
   CUtensorMap tm_patches, tm_h, tm_xb, tm_mlp, st_qkv, st_mlp, st_x, st_xb;
@@ -228,24 +234,24 @@ int forward_chunk_fused(b2c_vit* v, const void* patches, int nc, float* out, uin
   {
     ProfScope ps(B2C_PROF_LAYERNORM, stream);
     B2C_TRY(cls_pos_launch(x, v->cls, v->pos, nc, v->T, d, stream));
-    B2C_TRY(layernorm_pre_launch(x, v->ln_pre_w, v->ln_pre_b, xb, stats, M, d, eps, stream));
+    B2C_TRY(layernorm_pre_launch(x, v->ln_pre_w, v->ln_pre_b, xb, stats_a, shift, M, d, eps, stream));
   }
   auto ln_gemm = [&](int kind, const CUtensorMap& tm_w, const CUtensorMap& st, int N, int mode, const float* bias_f,
-                     const float* colsum, int64_t ldo) -> int {
+                     const float* colsum, int64_t ldo, float2* stats) -> int {
     ProfScope ps(kind, stream);
     GemmLaunch gl{};
     gl.tmap_a = tm_xb; gl.tmap_b = tm_w; gl.tmap_b_half = tm_w; gl.tmap_out = st; gl.M = M; gl.N = N; gl.K = d;
-    gl.mode = mode; gl.bias = bias_f; gl.colsum = colsum; gl.stats = stats; gl.nblk = nblk; gl.eps = eps;
+    gl.mode = mode; gl.bias = bias_f; gl.colsum = colsum; gl.stats = stats; gl.shift = shift; gl.nblk = nblk; gl.eps = eps;
     gl.out = big; gl.ldo = ldo;
     return gemm_launch(gl, stream);
   };
   auto resid_gemm = [&](int kind, const CUtensorMap& tm_a, const CUtensorMap& tm_w_full, const CUtensorMap& tm_w, int K,
-                        const float* bias, bool last) -> int {
+                        const float* bias, bool last, const float2* stats_in, float2* stats) -> int {
     ProfScope ps(kind, stream);
     GemmLaunch gl{};
     gl.tmap_a = tm_a; gl.tmap_b = tm_w_full; gl.tmap_b_half = tm_w; gl.tmap_out = st_x; gl.tmap_out2 = st_xb;
     gl.M = M; gl.N = d; gl.K = K; gl.bias = bias; gl.out = x; gl.ldo = d;
-    gl.stats = stats; gl.nblk = nblk; gl.eps = eps;
+    gl.stats = stats; gl.stats_in = stats_in; gl.shift = shift; gl.nblk = nblk; gl.eps = eps;
     // nothing consumes the bf16 copy / statistics of the last residual update: plain reduce-add there
     gl.mode = last ? kGemmBiasResidF32 : kGemmResidLnF32;
     return gemm_launch(gl, stream);
@@ -253,7 +259,7 @@ int forward_chunk_fused(b2c_vit* v, const void* patches, int nc, float* out, uin
   const int fc_mode = c.act == B2C_ACT_GELU ? kGemmLnBiasGeluBf16 : kGemmLnBiasQGeluBf16;
   for (int li = 0; li < c.layers; ++li) {
     const b2c_vit_layer& L = v->layers[li];
-    B2C_TRY(ln_gemm(B2C_PROF_IN_PROJ, L.tm_qkvf_h, st_qkv, 3 * d, kGemmLnBiasBf16, L.bf_qkv, L.cs_qkv, 3 * d));
+    B2C_TRY(ln_gemm(B2C_PROF_IN_PROJ, L.tm_qkvf_h, st_qkv, 3 * d, kGemmLnBiasBf16, L.bf_qkv, L.cs_qkv, 3 * d, stats_a));
     if (li + 1 == c.layers && v->cls_only_last && v->hd == 64) {
       // class-token rows only: the GEMMs address row crop*T of h / x in place through strided tensor maps (M = nc)
       const int64_t ldr = static_cast<int64_t>(v->T) * d;
@@ -289,9 +295,9 @@ int forward_chunk_fused(b2c_vit* v, const void* patches, int nc, float* out, uin
       ProfScope ps(B2C_PROF_ATTENTION, stream);
       B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
     }
-    B2C_TRY(resid_gemm(B2C_PROF_OUT_PROJ, tm_h, L.tm_out, L.tm_out_h, d, L.b_out, false));
-    B2C_TRY(ln_gemm(B2C_PROF_C_FC, L.tm_fcf_h, st_mlp, c.mlp, fc_mode, L.bf_fc, L.cs_fc, c.mlp));
-    B2C_TRY(resid_gemm(B2C_PROF_C_PROJ, tm_mlp, L.tm_proj, L.tm_proj_h, c.mlp, L.b_proj, li + 1 == c.layers));
+    B2C_TRY(resid_gemm(B2C_PROF_OUT_PROJ, tm_h, L.tm_out, L.tm_out_h, d, L.b_out, false, stats_a, stats_b));
+    B2C_TRY(ln_gemm(B2C_PROF_C_FC, L.tm_fcf_h, st_mlp, c.mlp, fc_mode, L.bf_fc, L.cs_fc, c.mlp, stats_b));
+    B2C_TRY(resid_gemm(B2C_PROF_C_PROJ, tm_mlp, L.tm_proj, L.tm_proj_h, c.mlp, L.b_proj, li + 1 == c.layers, stats_b, stats_a));
   }
   ProfScope ps(B2C_PROF_HEAD, stream);
   return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, reinterpret_cast<float*>(ws + w.head), nc, v->T, d, c.embed,

@@ -1,25 +1,67 @@
-"""Attention-only timing (CUDA events, 1024 crops of ViT-L/14: T=257, 16 heads x 64): python tools/bench_attn.py [n] [T] [heads] [hd]"""
-import ctypes as C, json, os, sys
+"""Attention-only timing and accuracy (CUDA events; default 1024 crops of ViT-L/14: T=257, 16 heads x 64):
+    python tools/bench_attn.py [n] [T] [heads] [hd]            # one line for the current B2C_ATTN_VAR / B2C_ATTN
+    python tools/bench_attn.py --vars 0,1,3,7 [n] [T] ...      # one subprocess per kernel variant (the switch is read once)
+"""
+import ctypes as C, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+
+if len(sys.argv) > 2 and sys.argv[1] == "--vars":
+    for v in sys.argv[2].split(","):  # "3" = v4 variant 3, "5:1" = v5 variant 1
+        env = dict(os.environ, B2C_ATTN5_VAR=v[2:]) if v.startswith("5:") else dict(os.environ, B2C_ATTN_VAR=v)
+        subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[3:], env=env, check=False)
+    sys.exit(0)
+
 import torch
 L = C.CDLL(os.environ.get("B2C_LIB") or os.path.join(ROOT, "clip_assisted_data_labeling_b200", "libb2c.so"))
+L.b2c_last_error.restype = C.c_char_p
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 257
 heads = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 hd = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+torch.manual_seed(0)
 qkv = torch.randn(n * T, 3 * heads * hd, device="cuda").to(torch.bfloat16)
 o = torch.zeros(n * T, heads * hd, device="cuda", dtype=torch.bfloat16)
 run = lambda: L.b2c_attention_bf16(C.c_void_p(qkv.data_ptr()), C.c_void_p(o.data_ptr()), n, T, heads, hd, C.c_void_p(0))
 for _ in range(5):
-    assert run() == 0
+    assert run() == 0, L.b2c_last_error()
 torch.cuda.synchronize()
+# accuracy on the first and last crops (scores scaled up 3x as well: sharper softmax rows)
+errs = []
+for scale in (1.0, 3.0):
+    m = min(n, 4)
+    sub_n = m
+    sub = qkv[: sub_n * T].clone()
+    sub[:, : heads * hd] *= scale
+    oo = torch.zeros(sub_n * T, heads * hd, device="cuda", dtype=torch.bfloat16)
+    assert L.b2c_attention_bf16(C.c_void_p(sub.data_ptr()), C.c_void_p(oo.data_ptr()), sub_n, T, heads, hd, C.c_void_p(0)) == 0
+    q, k, v = sub.float().view(sub_n, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(sub_n * T, heads * hd)
+    errs.append(float((oo.float() - ref).abs().max()))
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
+time.sleep(0.5)  # let the clocks recover: the first launches run at boost, a sustained loop at the power-capped clock
 a.record()
-for _ in range(20):
+run()
+b.record()
+torch.cuda.synchronize()
+ms_cold = a.elapsed_time(b)
+# sustained: ~1.5 s of back-to-back launches with nvidia-smi sampling clocks and power
+import subprocess, threading, statistics
+smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "100"],
+                       stdout=subprocess.PIPE, text=True)
+lines = []
+threading.Thread(target=lambda: [lines.append(l) for l in smi.stdout], daemon=True).start()
+reps = max(20, int(1.5e3 / max(ms_cold, 0.05)))
+a.record()
+for _ in range(reps):
     run()
 b.record()
 torch.cuda.synchronize()
-ms = a.elapsed_time(b) / 20
+smi.terminate()
+ms = a.elapsed_time(b) / reps
+clk = [float(l.split(",")[0]) for l in lines[3:] if "," in l]
+pw = [float(l.split(",")[1]) for l in lines[3:] if "," in l]
 fl = 4.0 * T * T * heads * hd * n
-print(json.dumps({"mode": os.environ.get("B2C_ATTN", "default"), "n": n, "T": T, "heads": heads, "hd": hd, "ms": ms, "tflops": fl / ms / 1e9}))
+print(json.dumps({"mode": os.environ.get("B2C_ATTN", "default"), "var": ("v5:" + os.environ["B2C_ATTN5_VAR"]) if "B2C_ATTN5_VAR" in os.environ else "v4:" + os.environ.get("B2C_ATTN_VAR", "default"), "n": n, "T": T,
+                  "heads": heads, "hd": hd, "ms": ms, "ms_cold": ms_cold, "sm_mhz": statistics.median(clk) if clk else None, "power_w": statistics.median(pw) if pw else None, "tflops": fl / ms / 1e9, "max_err_vs_sdpa": errs}), flush=True)

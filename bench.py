@@ -225,7 +225,7 @@ def run_b200_arm(args):
 
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
-        enc = CLIP_Encoder(MODEL, device="cuda", seed=0)
+        enc = CLIP_Encoder(MODEL, device="cuda", seed=0, allow_random_init=True)
     enc.model.set_lanes(args.lanes)
     enc.model.set_fused_ln(not args.standalone_layernorm)
     pool_dev = [synth_batch(B, 100 * rank + i, device="cuda") for i in range(args.pool)]

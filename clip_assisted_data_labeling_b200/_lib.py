@@ -18,7 +18,7 @@ B2C_F32, B2C_F16, B2C_BF16, B2C_U8 = 0, 1, 2, 3
 OUT_NCHW_F32, OUT_PATCH_BF16 = 0, 1
 ACT_QUICK_GELU, ACT_GELU = 0, 1
 EPI_BIAS_BF16, EPI_BIAS_QGELU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
-CMP_FP32, CMP_REF_FP16 = 0, 1
+CMP_FP32, CMP_REF_FP16, CMP_EUCLID = 0, 1, 2
 MEASURE_COSINE_DIST, MEASURE_L2, MEASURE_COSINE_SIM = 0, 1, 2
 COMBINE_STORE, COMBINE_MAX = 0, 1
 TOPK_MAX = 4096
@@ -98,6 +98,7 @@ SIGNATURES = {
     "b2c_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b2c_normalize_rows_f16": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "b2c_dedup_pairs": (_i, [_vp, _i64, _i, _i64, _i64, _f, _i, _vp, _u64, _vp, _vp]),
+    "b2c_dedup_pairs_block": (_i, [_vp, _i64, _i, _i64, _i64, _i64, _i64, _f, _i, _vp, _u64, _vp, _vp]),
     "b2c_mlp_score": (_i, [_vp, _i64, C.POINTER(MlpWeights), _vp, _vp]),
     "b2c_image_stats_target_size": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "b2c_image_stats_workspace_bytes": (_i, [C.POINTER(_i), C.POINTER(_i), _i, C.POINTER(_sz)]),

@@ -510,10 +510,9 @@ static int attention_umma_launch(const void* qkv, void* out, int n, int T, int h
   const uint64_t rows = static_cast<uint64_t>(n) * T;
   B2C_TRY(make_tmap_2d(&tm_q, qkv, rows, 3ull * d, 3ull * d * 2, 128, 1));
   B2C_TRY(make_tmap_2d(&tm_kv, qkv, rows, 3ull * d, 3ull * d * 2, 256, 1));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first_use()) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAuSmemBytes));
-    attr_set = true;
   }
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
@@ -1004,10 +1003,9 @@ static int attention_umma2_launch(const void* qkv, void* out, int n, int T, int 
   constexpr int smem_bytes = a2_smem_bytes<HD>();
   static_assert(smem_bytes <= 227 * 1024, "attention v2 shared memory exceeds 227 KB");
   auto kern = attention_umma2_kernel<HD>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first_use()) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
   }
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");
@@ -1346,10 +1344,9 @@ static int attention_umma3_launch(const void* qkv, void* out, int n, int T, int 
   B2C_TRY(make_tmap_2d(&tm_q, qkv, rows, 3ull * d, 3ull * d * 2, 256, 1));
   const int smem_bytes = 2 * NB * kA3BlockBytes + 2 * kA3QStage + static_cast<int>((sizeof(A3Misc) + 1023) / 1024 * 1024) + 1024;
   B2C_REQUIRE(smem_bytes <= 227 * 1024, "attention v3: T=%d does not fit shared memory", T);
-  static int smem_set = 0;
-  if (smem_bytes > smem_set) {
+  static PerDeviceMax smem_set;
+  if (smem_set.raise(static_cast<long long>(smem_bytes))) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    smem_set = smem_bytes;
   }
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");
@@ -2420,10 +2417,9 @@ static int attention_launch_hd(const void* qkv, void* out, int n, int T, int hea
   const size_t smem = 2ull * Tp * (HD + 8) * sizeof(__nv_bfloat16);
   B2C_REQUIRE(smem <= 227 * 1024, "attention: T=%d does not fit shared memory", T);
   auto kern = attention_kernel<HD>;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  static PerDeviceMax smem_set;
+  if (smem_set.raise(static_cast<long long>(smem))) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   kern<<<static_cast<unsigned>(n) * heads, kAttnThreads, smem, stream>>>(

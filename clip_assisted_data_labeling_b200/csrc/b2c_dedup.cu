@@ -26,7 +26,9 @@ struct DedupParams {
   int bi0;  // first row block of the band (units of kBM rows)
   int bj0;  // first column block that can hold j > i for this band (units of kBN rows)
   long long n_total, row_begin, row_end;
-  float thr_quick;  // necessary condition for a hit, checked on every accumulator element
+  long long col_begin, col_end;  // only pairs with col_begin <= j < col_end (b2c_dedup_pairs_block)
+  float thr_quick;  // necessary condition for a hit, checked on every accumulator element: sgn * acc > thr_quick
+  float sgn;        // +1 (similarity above a threshold) | -1 (B2C_CMP_EUCLID: distance above a threshold)
   float thr;
   int mode;
   b2c_pair* out;
@@ -66,14 +68,24 @@ struct DedupPolicy {
     if (p.mode == B2C_CMP_REF_FP16)
       // the reference thresholds its fp16 similarity matrix: fp16(S) > fp16(thr)
       return __half2float(__float2half_rn(v)) > p.thr;  // p.thr already holds float(fp16(threshold))
+    if (p.mode == B2C_CMP_EUCLID) return euclid(v) > p.thr;
     return v > p.thr;
   }
+  // distance of two unit vectors from their cosine (the reference's sim_type='euclidean': cdist of the normalised rows)
+  __device__ static __forceinline__ float euclid(float cosine) { return sqrtf(fmaxf(2.0f - 2.0f * cosine, 0.0f)); }
 
   __device__ static __forceinline__ void epilogue(const Params& p, int a_row, int b_row, int row_in_tile, int col0,
                                                   const uint32_t (&acc)[32]) {
+    // thr_quick is a necessary condition on the raw accumulator; for the distance mode the sense is reversed
+    // (dist > thr  <=>  cos < 1 - thr^2 / 2) and sgn = -1 turns it into the same comparison
     bool any = false;
+    if (p.sgn > 0.f) {
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) any |= __uint_as_float(acc[jj]) > p.thr_quick;
+      for (int jj = 0; jj < 32; ++jj) any |= __uint_as_float(acc[jj]) > p.thr_quick;
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) any |= __uint_as_float(acc[jj]) < -p.thr_quick;
+    }
     if (!any) return;
     const long long i = static_cast<long long>(a_row) + row_in_tile;
     if (i < p.row_begin || i >= p.row_end) return;
@@ -82,13 +94,13 @@ struct DedupPolicy {
     for (int jj = 0; jj < 32; ++jj) {
       const float v = __uint_as_float(acc[jj]);
       const long long j = j0 + jj;
-      if (v > p.thr_quick && j > i && j < p.n_total && passes(p, v)) {
+      if (p.sgn * v > p.thr_quick && j > i && j >= p.col_begin && j < p.col_end && passes(p, v)) {
         const unsigned long long slot = atomicAdd(p.count, 1ull);
         if (slot < p.capacity) {
           b2c_pair pr;
           pr.i = static_cast<int32_t>(i);
           pr.j = static_cast<int32_t>(j);
-          pr.sim = v;
+          pr.sim = p.mode == B2C_CMP_EUCLID ? euclid(v) : v;
           p.out[slot] = pr;
         }
       }
@@ -137,7 +149,14 @@ extern "C" int b2c_normalize_rows_f16(const void* in, int in_dtype, int64_t n, i
 
 extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, int64_t row_begin, int64_t row_end,
                                float threshold, int compare_mode, b2c_pair* out, unsigned long long capacity,
-                               unsigned long long* count, b2c_stream stream_) {
+                               unsigned long long* count, b2c_stream stream) {
+  return b2c_dedup_pairs_block(emb_f16, n_total, E_pad, row_begin, row_end, 0, n_total, threshold, compare_mode, out, capacity,
+                               count, stream);
+}
+
+extern "C" int b2c_dedup_pairs_block(const void* emb_f16, int64_t n_total, int E_pad, int64_t row_begin, int64_t row_end,
+                                     int64_t col_begin, int64_t col_end, float threshold, int compare_mode, b2c_pair* out,
+                                     unsigned long long capacity, unsigned long long* count, b2c_stream stream_) {
   using namespace b2c;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B2C_REQUIRE(emb_f16 && count, "b2c_dedup_pairs: null pointer");
@@ -146,20 +165,15 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
   B2C_REQUIRE(n_total >= 0 && n_total < (1ll << 31) - kBN, "b2c_dedup_pairs: n_total=%lld out of range", (long long)n_total);
   B2C_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_total, "b2c_dedup_pairs: bad row range [%lld,%lld)",
               (long long)row_begin, (long long)row_end);
-  B2C_REQUIRE(compare_mode == B2C_CMP_FP32 || compare_mode == B2C_CMP_REF_FP16, "b2c_dedup_pairs: compare_mode %d",
-              compare_mode);
-  if (row_end == row_begin || n_total < 2) return 0;
+  B2C_REQUIRE(compare_mode == B2C_CMP_FP32 || compare_mode == B2C_CMP_REF_FP16 || compare_mode == B2C_CMP_EUCLID,
+              "b2c_dedup_pairs: compare_mode %d", compare_mode);
+  B2C_REQUIRE(col_begin >= 0 && col_begin <= col_end && col_end <= n_total, "b2c_dedup_pairs: bad column range [%lld,%lld)",
+              (long long)col_begin, (long long)col_end);
+  if (row_end == row_begin || n_total < 2 || col_end <= col_begin || col_end <= row_begin + 1) return 0;
 
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a;  // box 128 rows x 64 columns: both operands of the CTA-pair kernel
   B2C_TRY(make_tmap_2d(&tm_a, emb_f16, n_total, E_pad, static_cast<uint64_t>(E_pad) * 2, kBM, 0));
-  B2C_TRY(make_tmap_2d(&tm_b, emb_f16, n_total, E_pad, static_cast<uint64_t>(E_pad) * 2, kBN, 0));
 
-  auto kern = umma_tile_kernel<DedupPolicy>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
-    attr_set = true;
-  }
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");
 
@@ -168,10 +182,18 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
   p.n_total = n_total;
   p.row_begin = row_begin;
   p.row_end = row_end;
+  p.col_begin = col_begin;
+  p.col_end = col_end;
   p.mode = compare_mode;
+  p.sgn = 1.0f;
   if (compare_mode == B2C_CMP_REF_FP16) {
     p.thr = __half2float(__float2half_rn(threshold));
     p.thr_quick = p.thr;  // fp16(v) > h  implies  v > h  (round-to-nearest is monotone)
+  } else if (compare_mode == B2C_CMP_EUCLID) {
+    // sqrt(max(2 - 2c, 0)) > thr  =>  c < 1 - thr^2/2 (+ a rounding margin; `passes` decides); thr < 0 matches everything
+    p.thr = threshold;
+    p.sgn = -1.0f;
+    p.thr_quick = threshold <= 0.f ? -4.0f : -(1.0f - 0.5f * threshold * threshold) - 1e-5f;
   } else {
     p.thr = threshold;
     p.thr_quick = threshold;
@@ -180,21 +202,19 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
   p.capacity = capacity;
   p.count = count;
 
-  static const bool pairs = [] { const char* e = getenv("B2C_GEMM"); return !(e && e[0] == '1'); }();
   auto kern2 = umma2_tile_kernel<DedupPolicy>;
-  static bool attr2_set = false;
-  if (pairs && !attr2_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first_use())
     B2C_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmma2SmemBytes));
-    attr2_set = true;
-  }
   // bands start on 256-row boundaries so that both kernels see the same band grid
   const long long bi_begin = (row_begin / (2 * kBM)) * 2;
   const long long bi_end = (row_end + kBM - 1) / kBM;
-  const long long NJ = (n_total + kBN - 1) / kBN;
+  const long long NJ = (col_end + kBN - 1) / kBN;
   ProfScope ps(B2C_PROF_DEDUP, stream);
   for (long long b = bi_begin; b < bi_end; b += kDedupBandBlocks) {
     const int gi = static_cast<int>(bi_end - b < kDedupBandBlocks ? bi_end - b : kDedupBandBlocks);
-    const long long bj0 = (b * kBM) / kBN;
+    long long bj0 = (b * kBM) / kBN;  // first column block that can hold j > i ...
+    if (col_begin / kBN > bj0) bj0 = col_begin / kBN;  // ... inside the requested column range
     const long long tiles = gi * (NJ - bj0);
     if (tiles <= 0) continue;
     B2C_REQUIRE(tiles < (1ll << 31), "b2c_dedup_pairs: too many tiles in one band");
@@ -203,15 +223,9 @@ extern "C" int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, 
     p.bj0 = static_cast<int>(bj0);
     p.num_tiles = static_cast<int>(tiles);
     p.num_tiles2 = static_cast<int>(((gi + 1) / 2) * (NJ - bj0));
-    if (pairs) {
-      const int grid = 2 * p.num_tiles2 < sms ? 2 * p.num_tiles2 : (sms & ~1);
-      kern2<<<grid, kUmmaThreads, kUmma2SmemBytes, stream>>>(tm_a, tm_a, tm_a, tm_a, p, make_idesc_f16(2 * kBM, kBN, 0));
-      B2C_POST_LAUNCH("umma2_tile_kernel<dedup>");
-    } else {
-      const int grid = tiles < sms ? static_cast<int>(tiles) : sms;
-      kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(tm_a, tm_b, tm_a, p, make_idesc_f16(kBM, kBN, 0));
-      B2C_POST_LAUNCH("umma_tile_kernel<dedup>");
-    }
+    const int grid = 2 * p.num_tiles2 < sms ? 2 * p.num_tiles2 : (sms & ~1);
+    kern2<<<grid, kUmmaThreads, kUmma2SmemBytes, stream>>>(tm_a, tm_a, tm_a, tm_a, p, make_idesc_f16(2 * kBM, kBN, 0));
+    B2C_POST_LAUNCH("umma2_tile_kernel<dedup>");
   }
   return 0;
 }

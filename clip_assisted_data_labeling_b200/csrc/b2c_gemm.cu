@@ -209,10 +209,9 @@ static bool use_cta_pairs() {
 template <int MODE>
 static int gemm_launch_pair(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
   auto kern = umma2_tile_kernel<GemmPolicy<MODE>>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first_use()) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmma2SmemBytes));
-    attr_set = true;
   }
   const int sms = num_sms();
   B2C_REQUIRE(sms >= 2, "no CUDA device");
@@ -246,10 +245,9 @@ static int gemm_launch_classic(const GemmLaunch& g, const GemmParams& p, cudaStr
     if (use_cta_pairs()) return gemm_launch_pair<MODE>(g, p, stream);
   }
   auto kern = umma_tile_kernel<GemmPolicy<MODE>>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;  // per template instantiation
+  if (attr_once.first_use()) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
-    attr_set = true;
   }
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");

@@ -120,7 +120,8 @@ namespace {
 struct PinnedChunk {
   void* host = nullptr;
   size_t bytes = 0;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t done = nullptr;  // created on `dev`: only recorded / queried with that device current
+  int dev = 0;
   bool in_flight = false;
 };
 std::mutex g_pin_mu;
@@ -130,9 +131,10 @@ std::vector<PinnedChunk> g_pin;
 int upload_async(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream) {
   if (bytes == 0) return 0;
   std::lock_guard<std::mutex> g(g_pin_mu);
+  const int dev = current_device();
   PinnedChunk* c = nullptr;
   for (PinnedChunk& k : g_pin) {
-    if (k.bytes < bytes) continue;
+    if (k.bytes < bytes || k.dev != dev) continue;
     if (k.in_flight && cudaEventQuery(k.done) != cudaSuccess) continue;
     k.in_flight = false;
     if (!c || k.bytes < c->bytes) c = &k;
@@ -140,6 +142,7 @@ int upload_async(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t
   (void)cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error of ours
   if (!c) {
     PinnedChunk k;
+    k.dev = dev;
     k.bytes = 1 << 16;
     while (k.bytes < bytes) k.bytes <<= 1;
     B2C_CHECK_CUDA(cudaHostAlloc(&k.host, k.bytes, cudaHostAllocDefault));
@@ -154,14 +157,26 @@ int upload_async(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t
   return 0;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
   }
-  return n;
+  return dev;
+}
+
+int num_sms() {
+  static std::atomic<int> n[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::atomic<int>& slot = n[dev & (kMaxDevices - 1)];
+  int v = slot.load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 0;
+    slot.store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 }  // namespace b2c

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/b2c.h"
 
 namespace b2c {
@@ -45,7 +47,34 @@ int make_tmap_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 int make_tmap_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                     uint32_t box_rows, uint32_t box_cols, int dtype, int swizzle_bytes);
 
+// SM count of the CURRENT device (cached per device).
 int num_sms();
+
+// Per-device one-time state.  Function attributes (opt-in dynamic shared memory), the SM count and pinned-pool events
+// belong to a device, and the Python surface accepts device= everywhere: a process that drives two GPUs must not
+// reuse device 0's "already done" for device 1.
+constexpr int kMaxDevices = 64;
+int current_device();  // cudaGetDevice(), 0 on error
+struct PerDeviceFlag {
+  std::atomic<unsigned long long> mask{0};
+  // true exactly once per device (thread-safe): the caller then performs the per-device initialisation
+  bool first_use() {
+    const unsigned long long bit = 1ull << (current_device() & (kMaxDevices - 1));
+    return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+  }
+};
+struct PerDeviceMax {
+  std::atomic<long long> v[kMaxDevices];
+  PerDeviceMax() { for (auto& a : v) a.store(0); }
+  // true when `want` exceeds what this device was last configured for (and records it)
+  bool raise(long long want) {
+    std::atomic<long long>& a = v[current_device() & (kMaxDevices - 1)];
+    long long cur = a.load(std::memory_order_acquire);
+    while (want > cur)
+      if (a.compare_exchange_weak(cur, want, std::memory_order_acq_rel)) return true;
+    return false;
+  }
+};
 
 // Descriptor upload that never blocks the host: cudaMemcpyAsync from PAGEABLE memory first synchronises the stream (the
 // caller would wait for every kernel already queued, i.e. lose all host/device overlap), so small host tables (crop

@@ -215,6 +215,8 @@ int next_scan(const uint8_t* d, size_t n, size_t& pos, Parsed& P, Scan& scan) {
       if (sl < 1) return fail_corrupt("SOS length");
       scan.ns = s[0];
       if (scan.ns < 1 || scan.ns > I.ncomp) return fail_corrupt("scan component count");
+      // an interleaved scan of SOME of the components has its own MCU geometry (JPEG A.2.3): not covered here
+      if (scan.ns > 1 && scan.ns != I.ncomp) return fail_unsupported("interleaved scan of a subset of the components");
       if (sl < 1 + 2 * static_cast<size_t>(scan.ns) + 3) return fail_corrupt("SOS length");
       for (int k = 0; k < scan.ns; ++k) {
         int ci = -1;
@@ -273,6 +275,11 @@ struct BitReader {
   uint64_t acc = 0;  // bits left-aligned at bit 63
   int nbits = 0;
   bool hit_marker = false;
+  int64_t pad_bits = 0;  // zero bits appended past a marker / the end of the data since the last restart
+
+  // Bits the decoder consumed that were never in the file: libjpeg feeds zeros there and warns ("premature end of data
+  // segment"), and Pillow raises OSError for a truncated file — such a stream is not ours to decode silently.
+  bool consumed_padding() const { return pad_bits > nbits; }
 
   void fill() {
     // fast path: eight stream bytes without an 0xFF among them are appended whole
@@ -301,10 +308,13 @@ struct BitReader {
           } else {
             hit_marker = true;  // leave p at the marker; feed zeros like libjpeg does past the end of a segment
             b = 0;
+            pad_bits += 8;
           }
         } else {
           ++p;
         }
+      } else {
+        pad_bits += 8;
       }
       acc |= static_cast<uint64_t>(b) << (56 - nbits);
       nbits += 8;
@@ -329,8 +339,10 @@ struct BitReader {
   }
   // byte-align and consume the expected RSTn marker
   int restart(int expect) {
+    if (consumed_padding()) return fail_unsupported("entropy-coded segment ends early (truncated or damaged file)");
     nbits = 0;
     acc = 0;
+    pad_bits = 0;
     while (p + 1 < end && !(p[0] == 0xFF && p[1] != 0x00 && p[1] != 0xFF)) ++p;
     if (p + 1 >= end || p[1] != 0xD0 + expect) return fail_corrupt("restart marker missing");
     p += 2;
@@ -516,6 +528,7 @@ int decode_scan(const uint8_t* d, size_t n, const Parsed& P, const Scan& sc, int
       if (I.restart_interval) --restarts_left;
     }
   }
+  if (br.consumed_padding()) return fail_unsupported("entropy-coded segment ends early (truncated or damaged file)");
   end_pos = static_cast<size_t>(br.p - d);
   return 0;
 }
@@ -665,6 +678,7 @@ int decode_scan_append(const uint8_t* d, size_t n, const Parsed& P, const Scan& 
       if (I.restart_interval) --restarts_left;
     }
   }
+  if (br.consumed_padding()) return fail_unsupported("entropy-coded segment ends early (truncated or damaged file)");
   memset(out + I.counts_off + I.nblocks, 0, static_cast<size_t>(I.vals_off - I.counts_off - I.nblocks));
   const int64_t end = I.vals_off + 2ll * nv;
   used = (end + 15) & ~15ll;

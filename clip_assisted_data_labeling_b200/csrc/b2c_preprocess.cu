@@ -471,10 +471,9 @@ extern "C" int b2c_preprocess_4crop(const uint8_t* const* img_ptrs, const int* H
   resample_plan_kernel<<<dim3(B * 4, 2), R, 0, stream>>>(rp.plans, const_cast<int2*>(rp.bounds),
                                                          const_cast<int32_t*>(rp.coefs), R, KS);
   B2C_POST_LAUNCH("resample_plan_kernel");
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  static PerDeviceMax smem_set;
+  if (smem_set.raise(static_cast<long long>(smem))) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
   }
   resample_kernel<<<dim3((R + TR - 1) / TR, B * 4), kResThreads, smem, stream>>>(rp);
   B2C_POST_LAUNCH("resample_kernel");

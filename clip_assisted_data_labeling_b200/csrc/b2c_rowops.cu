@@ -529,10 +529,9 @@ extern "C" int b2c_mlp_score(const float* feats, int64_t B, const b2c_mlp_weight
   for (int l = 0; l < w->n_layers; ++l) B2C_REQUIRE(w->weight[l], "b2c_mlp_score: weight[%d] is null", l);
   const size_t smem = 2ull * kMlpIPB * max_dim * sizeof(float);
   B2C_REQUIRE(smem <= 200 * 1024, "b2c_mlp_score: layer width %d too large", max_dim);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first_use()) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const unsigned grid = static_cast<unsigned>((B + kMlpIPB - 1) / kMlpIPB);
   mlp_kernel<<<grid, kMlpThreads, smem, static_cast<cudaStream_t>(stream)>>>(feats, B, *w, out, max_dim);

@@ -321,11 +321,10 @@ static int trainer_step_bt(b2c_trainer* t, const float* feats, long long fstride
                            const b2c_adam* h, float step_size, float bc2_sqrt, float* loss_sum, cudaStream_t st) {
   const int L = t->L;
   const float p = t->cfg.dropout_p;
-  static bool attr_set = false;  // one flag per BT instantiation
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;  // one flag per BT instantiation
+  if (attr_once.first_use()) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         BT * kTrKT * static_cast<int>(sizeof(float))));
-    attr_set = true;
   }
   for (int l = 0; l < L; ++l) {
     FwdArgs a;

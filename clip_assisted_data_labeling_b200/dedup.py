@@ -1,6 +1,6 @@
 """Drop-in mirror of the reference's duplicate search (_2_remove_duplicates.py) on the B200 path.
 
-  * ``get_paths_and_embeddings(args, crop_to_use, shuffle=False)``  — _2_remove_duplicates.py:8-49 (host I/O, unchanged semantics)
+  * ``get_paths_and_embeddings(args, crop_to_use, shuffle=False)``  — _2_remove_duplicates.py:8-49 (host I/O)
   * ``find_near_duplicates(args, sim_type='cosine', crop_to_use='square_padded_crop')`` — :52-99
   * ``fix_duplicate(duplicate_index, img_paths, outdir, sim_value, mode)`` — :102-125
   * ``duplicate_pairs(...)`` / ``duplicate_pairs_distributed(...)`` — the device core (:63-80) as one call.
@@ -8,6 +8,9 @@
 The N x N similarity matrix is never materialised (b2c_dedup_pairs thresholds and emits pairs in the GEMM
 epilogue), so ``chunk_size`` is no longer a memory cap; with ``chunk_size >= N`` results equal the
 reference's: strict ``>``, ``i < j``, pairs in row-major order, comparison on fp16-rounded similarities.
+The host functions keep the reference's behaviour (which files pair up, what is skipped, how the copies are
+named) but are written for this package; INTEGRATION.md shows that the reference's own script can equally
+keep its host half and call ``duplicate_pairs`` for lines 63-80.
 """
 from __future__ import annotations
 
@@ -22,40 +25,49 @@ import torch
 from . import _lib
 
 BAND_ROWS = 2048  # rows per scheduling band of b2c_dedup_pairs (16 row blocks of 128)
+PAIR_DTYPE = np.dtype([("i", np.int32), ("j", np.int32), ("sim", np.float32)])  # b2c_pair
 
 
 # ----------------------------------------------------------------------------------------- host I/O
+def _stems_with_image_and_embedding(files, shuffle):
+    """File stems of one directory that have both ``X.jpg`` and ``X.pt`` (:20-27), in first-seen order."""
+    names = list(files)
+    if shuffle:
+        random.shuffle(names)
+    exts_of = {}
+    for name in names:
+        stem, ext = os.path.splitext(name)
+        exts_of.setdefault(stem, set()).add(ext)
+    return [stem for stem, exts in exts_of.items() if ".jpg" in exts and ".pt" in exts]
+
+
+def _read_embedding(pt_path, args, crop_to_use):
+    """One crop embedding as fp16 [E] (:30-38); the model key defaults to the file's first one and then sticks (:32-35)."""
+    per_model = torch.load(pt_path)
+    if args.clip_model_to_use is None:
+        args.clip_model_to_use = next(iter(per_model))
+        print(f"\n ----> args.clip_model_to_use was not specified, using the first one found: {args.clip_model_to_use}\n")
+    return per_model[args.clip_model_to_use][crop_to_use].squeeze().to(torch.float16)
+
+
 def get_paths_and_embeddings(args, crop_to_use, shuffle=False):
-    """Per-subdirectory generator of (paths, embeddings) chunks — _2_remove_duplicates.py:8-49."""
+    """Per directory of ``args.root_dir``: chunks ``(paths, embeddings)`` of at most ``args.chunk_size`` images that
+    have an ``.pt`` file next to the ``.jpg`` — _2_remove_duplicates.py:8-49.  Unreadable samples are skipped (:45-46)."""
     for subdir, dirs, files in os.walk(args.root_dir):
-        print(f"\nParsing {subdir}, subdirs: {dirs}, n_files: {len(files)}..")
+        stems = _stems_with_image_and_embedding(files, shuffle)
+        print(f"\n{subdir}: {len(files)} files in {len(dirs)} sub-directories, {len(stems)} images with embeddings")
         paths, embeddings = [], []
-        if shuffle:
-            random.shuffle(files)
-        unique_filenames = {}
-        for file in files:
-            filename, ext = os.path.splitext(file)
-            unique_filenames.setdefault(filename, []).append(ext)
-        print(f"Loading embeddings for {len(unique_filenames)} unique filenames..")
-        for filename, exts in unique_filenames.items():
-            if ".jpg" in exts and ".pt" in exts:
-                try:
-                    path = os.path.join(subdir, filename + ".jpg")
-                    embedding_dict = torch.load(os.path.join(subdir, filename + ".pt"))
-                    if args.clip_model_to_use is None:
-                        args.clip_model_to_use = list(embedding_dict.keys())[0]
-                        print(f"\n ----> args.clip_model_to_use was not specified, defaulting to first found one: "
-                              f"{args.clip_model_to_use} \n")
-                    embedding_dict = embedding_dict[args.clip_model_to_use]
-                    embedding = embedding_dict[crop_to_use].squeeze().to(torch.float16)
-                    paths.append(path)
-                    embeddings.append(embedding)
-                    if len(paths) == args.chunk_size:
-                        yield paths, embeddings
-                        paths, embeddings = [], []
-                except Exception:  # noqa: BLE001  (the reference silently skips unreadable samples, :45-46)
-                    continue
-        if len(paths) > 0:
+        for stem in stems:
+            try:
+                vec = _read_embedding(os.path.join(subdir, stem + ".pt"), args, crop_to_use)
+            except Exception:  # noqa: BLE001
+                continue
+            paths.append(os.path.join(subdir, stem + ".jpg"))
+            embeddings.append(vec)
+            if len(paths) == args.chunk_size:
+                yield paths, embeddings
+                paths, embeddings = [], []
+        if paths:
             yield paths, embeddings
 
 
@@ -82,15 +94,20 @@ def sort_pairs(pairs: np.ndarray, sims: np.ndarray):
     return pairs[order].astype(np.int64), sims[order].astype(np.float32)
 
 
-def normalize_rows_f16(embeddings: torch.Tensor) -> torch.Tensor:
-    """[n,E] f32/f16 (device) -> unit-norm f16 [n, E_pad], E_pad = round_up(E, 64) — _2_remove_duplicates.py:67."""
+def normalize_rows_f16(embeddings: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[n,E] f32/f16 (device) -> unit-norm f16 [n, E_pad], E_pad = round_up(E, 64) — _2_remove_duplicates.py:67.
+    ``out``: optional destination (e.g. this rank's slice of the all-gather buffer)."""
     lib = _lib.load()
+    if not embeddings.is_cuda:
+        raise _lib.B2CError("normalize_rows_f16 needs a CUDA tensor (sm_100a); there is no CPU fallback")
     if embeddings.dtype not in (torch.float32, torch.float16):
         embeddings = embeddings.float()
     embeddings = embeddings.contiguous()
     n, E = embeddings.shape
     E_pad = (E + 63) // 64 * 64
-    out = torch.empty(n, E_pad, dtype=torch.float16, device=embeddings.device)
+    if out is None:
+        out = torch.empty(n, E_pad, dtype=torch.float16, device=embeddings.device)
+    assert out.shape == (n, E_pad) and out.dtype == torch.float16 and out.is_contiguous()
     if n:
         with torch.cuda.device(embeddings.device):
             _lib.check(lib.b2c_normalize_rows_f16(C.c_void_p(embeddings.data_ptr()),
@@ -100,42 +117,62 @@ def normalize_rows_f16(embeddings: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _pairs_for_ranges(emb_n: torch.Tensor, ranges, threshold: float, compare: str, capacity: int):
-    """Run b2c_dedup_pairs over row ranges of normalised f16 [n_total, E_pad]; returns (pairs[K,2], sims[K]) numpy, unsorted."""
-    lib = _lib.load()
-    n_total, E_pad = emb_n.shape
-    mode = _lib.CMP_REF_FP16 if compare == "ref_fp16" else _lib.CMP_FP32
-    dev = emb_n.device
-    merged = []  # coalesce adjacent ranges: one call covers them (the library iterates the bands itself)
+_MODES = {"fp32": _lib.CMP_FP32, "ref_fp16": _lib.CMP_REF_FP16, "euclidean": _lib.CMP_EUCLID}
+
+
+def _merge_ranges(ranges):
+    merged = []  # adjacent ranges become one call (the library iterates the bands itself)
     for (r0, r1) in ranges:
         if merged and merged[-1][1] == r0:
             merged[-1] = (merged[-1][0], r1)
         else:
             merged.append((r0, r1))
-    ranges = merged
+    return merged
+
+
+def launch_pair_search(emb_n: torch.Tensor, ranges, threshold: float, compare: str, buf: torch.Tensor, cnt: torch.Tensor):
+    """Enqueue the pair search over blocks of normalised f16 [n_total, E_pad] on the current stream (no sync): pairs are
+    appended to ``buf`` (int32 [capacity, 3] = b2c_pair), ``cnt`` (int64 [1]) counts every hit.  ``ranges``: row ranges
+    ``(r0, r1)`` (all columns j > i) or blocks ``(r0, r1, c0, c1)`` (columns c0 <= j < c1 only)."""
+    lib = _lib.load()
+    n_total, E_pad = emb_n.shape
+    plain = _merge_ranges([r for r in ranges if len(r) == 2])
+    blocks = [r for r in ranges if len(r) == 4]
+    with torch.cuda.device(emb_n.device):
+        st = C.c_void_p(_lib.current_stream_ptr())
+        for (r0, r1, c0, c1) in [(a, b, 0, n_total) for a, b in plain] + blocks:
+            _lib.check(lib.b2c_dedup_pairs_block(C.c_void_p(emb_n.data_ptr()), n_total, E_pad, r0, r1, c0, c1, C.c_float(threshold),
+                                                 _MODES[compare], C.c_void_p(buf.data_ptr()), buf.shape[0],
+                                                 C.c_void_p(cnt.data_ptr()), st), "b2c_dedup_pairs_block")
+
+
+def _unpack(raw: np.ndarray):
+    """int32 [K,3] rows of b2c_pair -> (pairs int64 [K,2], sims float32 [K])"""
+    return raw[:, :2].astype(np.int64), raw[:, 2].copy().view(np.float32)
+
+
+def _pairs_for_ranges(emb_n: torch.Tensor, ranges, threshold: float, compare: str, capacity: int):
+    """Run b2c_dedup_pairs over row ranges of normalised f16 [n_total, E_pad]; returns (pairs[K,2], sims[K]) numpy, unsorted."""
+    dev = emb_n.device
     while True:
         buf = torch.empty(max(capacity, 1), 3, dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-        with torch.cuda.device(dev):
-            st = C.c_void_p(_lib.current_stream_ptr())
-            for (r0, r1) in ranges:
-                _lib.check(lib.b2c_dedup_pairs(C.c_void_p(emb_n.data_ptr()), n_total, E_pad, r0, r1, C.c_float(threshold), mode,
-                                               C.c_void_p(buf.data_ptr()), capacity, C.c_void_p(cnt.data_ptr()), st),
-                           "b2c_dedup_pairs")
+        launch_pair_search(emb_n, ranges, threshold, compare, buf, cnt)
         k = int(cnt.item())
         if k <= capacity:
             break
         capacity = int(k * 1.25) + 1024  # overflow: the count is exact, re-run with room for every pair
-    raw = buf[:k].cpu().numpy()
-    pairs = raw[:, :2].astype(np.int64)
-    sims = raw[:, 2].copy().view(np.float32)
-    return pairs, sims
+    return _unpack(buf[:k].cpu().numpy())
 
 
 def duplicate_pairs(embeddings: torch.Tensor, threshold: float, compare: str = "ref_fp16", device=None,
                     capacity: int | None = None):
     """All pairs (i < j) whose cosine similarity exceeds ``threshold`` — the core of find_near_duplicates
-    (_2_remove_duplicates.py:63-80).  Returns (pairs int64 [K,2] in row-major order, sims float32 [K])."""
+    (_2_remove_duplicates.py:63-80).  Returns (pairs int64 [K,2] in row-major order, sims float32 [K]).
+    compare: 'ref_fp16' (the reference's comparison on fp16-rounded similarities), 'fp32', or 'euclidean' (pairs whose
+    distance exceeds the threshold, the reference's other ``sim_type``; ``sims`` then holds distances)."""
+    if compare not in _MODES:
+        raise ValueError(f"compare must be one of {sorted(_MODES)}")
     dev = torch.device(device) if device is not None else (embeddings.device if embeddings.is_cuda else torch.device("cuda"))
     if dev.type != "cuda" or not torch.cuda.is_available():
         raise _lib.B2CError("duplicate_pairs needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -149,60 +186,106 @@ def duplicate_pairs(embeddings: torch.Tensor, threshold: float, compare: str = "
     return sort_pairs(pairs, sims)
 
 
+def owned_blocks(n_local: int, rank: int, world_size: int, band_rows: int = BAND_ROWS):
+    """Work of one rank in the multi-GPU search, as (r0, r1, c0, c1) blocks of the global upper triangle:
+      first   the block of its OWN shard (rows and columns in [rank*n_local, (rank+1)*n_local)) — needs no peer data,
+              so it runs while the all-gather is in flight;
+      then    its share of everything to the right of the shards' diagonal blocks: bands of ``band_rows`` rows (cut at
+              shard boundaries), columns from the end of the band's shard to n_total.  Work per band falls from shard
+              to shard, so the bands are dealt largest-first to the least-loaded rank (every rank computes the same deal).
+    Every pair (i < j) belongs to exactly one block of exactly one rank."""
+    n_total = n_local * world_size
+    lo = rank * n_local
+    local = [(lo, lo + n_local, lo, lo + n_local)] if n_local > 1 else []
+    bands = []
+    for s in range(world_size - 1):  # the last shard has nothing to its right
+        for r0 in range(s * n_local, (s + 1) * n_local, band_rows):
+            bands.append((r0, min(r0 + band_rows, (s + 1) * n_local), (s + 1) * n_local, n_total))
+    load = [0] * world_size
+    rest = []
+    for blk in sorted(bands, key=lambda t: (-(t[1] - t[0]) * (t[3] - t[2]), t[0])):
+        owner = min(range(world_size), key=lambda r: (load[r], r))
+        load[owner] += (blk[1] - blk[0]) * (blk[3] - blk[2])
+        if owner == rank:
+            rest.append(blk)
+    rest.sort()
+    return local, rest
+
+
 def duplicate_pairs_distributed(local_embeddings: torch.Tensor, threshold: float, compare: str = "ref_fp16",
-                                group=None, capacity: int | None = None, _pair_fn=None):
+                                group=None, capacity: int | None = None):
     """Multi-GPU form: every rank passes its shard [n_local, E] (equal n_local on all ranks; pad the last shard
-    with zero rows, which never match).  The shards are normalised locally, all-gathered ONCE over NCCL, and
-    each rank searches the bands ``owned_bands`` deals it.  Every rank returns the full sorted result."""
+    with zero rows, which never match).  Each rank normalises its shard straight into its slice of the gather buffer;
+    ONE all-gather (NCCL) of the shards then runs on NCCL's stream WHILE the rank searches the block of its own shard
+    on a side stream; after the gather it searches the bands ``owned_blocks`` deals it.  Counts and pair buffers
+    come back through two fixed-shape all-gathers (no pickling).  Every rank returns the full sorted result."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    pair_fn = _pair_fn or _pairs_for_ranges
-    if _pair_fn is None:
-        local_n = normalize_rows_f16(local_embeddings)
-    else:  # host-logic tests on CPU inject the pair finder and skip the CUDA normalise
-        local_n = torch.nn.functional.normalize(local_embeddings.float(), dim=1).to(torch.float16)
-    n_local, E_pad = local_n.shape
-    gathered = torch.empty(world * n_local, E_pad, dtype=local_n.dtype, device=local_n.device)
-    dist.all_gather_into_tensor(gathered, local_n.contiguous(), group=group)
-    n_total = gathered.shape[0]
+    dev = local_embeddings.device  # normalize_rows_f16 refuses anything but a CUDA tensor: there is no CPU fallback
+    n_local, E = local_embeddings.shape
+    E_pad = (E + 63) // 64 * 64
+    n_total = world * n_local
+    gathered = torch.empty(n_total, E_pad, dtype=torch.float16, device=dev)
+    mine = gathered[rank * n_local:(rank + 1) * n_local]
+    normalize_rows_f16(local_embeddings, out=mine)
+    local_blocks, rest_blocks = owned_blocks(n_local, rank, world)
     cap = capacity if capacity is not None else max(1 << 16, 4 * n_total // world)
-    pairs, sims = pair_fn(gathered, owned_bands(n_total, rank, world), float(threshold), compare, cap)
-    # variable-length exchange of the (small) pair lists
-    payload = [None] * world
-    dist.all_gather_object(payload, (pairs, sims), group=group)
-    all_pairs = np.concatenate([p for p, _ in payload]) if payload else pairs
-    all_sims = np.concatenate([s for _, s in payload]) if payload else sims
-    return sort_pairs(all_pairs, all_sims)
+    first = True
+    while True:
+        buf = torch.empty(cap, 3, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        if first:
+            # the gather only WRITES the peers' slices; this rank's slice is read by both the gather and the local search
+            work = dist.all_gather_into_tensor(gathered, mine, group=group, async_op=True)
+            launch_pair_search(gathered, local_blocks, float(threshold), compare, buf, cnt)
+            work.wait()  # stream-level: what follows on this stream is ordered after the gather, the host does not block
+            first = False
+        else:
+            launch_pair_search(gathered, local_blocks, float(threshold), compare, buf, cnt)
+        launch_pair_search(gathered, rest_blocks, float(threshold), compare, buf, cnt)
+        # counts of all ranks (one small collective), then every rank's pairs in fixed-capacity slots
+        counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, cnt, group=group)
+        counts_h = counts.cpu().numpy()
+        k_max = int(counts_h.max())
+        if k_max <= cap:
+            break
+        cap = int(k_max * 1.25) + 1024  # some rank overflowed: everybody re-runs with room for the largest list
+    slot = max(int(k_max), 1)
+    allp = torch.empty(world * slot, 3, dtype=torch.int32, device=dev)  # concatenation along dim 0 (what gloo accepts too)
+    dist.all_gather_into_tensor(allp, buf[:slot].contiguous(), group=group)
+    allp_h = allp.cpu().numpy().reshape(world, slot, 3)
+    raw = np.concatenate([allp_h[r, :int(counts_h[r])] for r in range(world)]) if world else allp_h.reshape(0, 3)
+    pairs, sims = _unpack(raw)
+    return sort_pairs(pairs, sims)
 
 
 # ----------------------------------------------------------------------------------------- reference entry
 def find_near_duplicates(args, sim_type="cosine", crop_to_use="square_padded_crop"):
-    """_2_remove_duplicates.py:52-99 with the similarity/threshold/where core on the GPU kernel."""
-    if sim_type != "cosine":
-        raise NotImplementedError("only sim_type='cosine' is implemented (the reference CLI never selects 'euclidean')")
+    """_2_remove_duplicates.py:52-99 with the similarity/threshold/where core on the GPU kernel.  Returns, per chunk,
+    (near_duplicates [(path_i, path_j)], near_duplicate_values [float]) — the two lists the reference builds (:77,80)."""
+    if sim_type not in ("cosine", "euclidean"):
+        raise ValueError(f"sim_type must be 'cosine' or 'euclidean', got {sim_type!r}")
+    compare = "ref_fp16" if sim_type == "cosine" else "euclidean"
+    # the folder sits next to root_dir and exists even for a dry run (:83-84)
+    output_dir = os.path.join(os.path.dirname(args.root_dir), f"near_duplicates_{sim_type}_{args.threshold}")
     results = []
     for paths, embeddings in get_paths_and_embeddings(args, crop_to_use):
-        if len(paths) == 0 or len(embeddings) == 0:
+        if not paths or not embeddings:
             continue
-        embeddings = torch.stack(embeddings)
-        print(f"Got first batch of embeddings of shape: {embeddings.shape}, computing similarity matrix..")
-        pairs, sims = duplicate_pairs(embeddings, args.threshold)
+        stacked = torch.stack(embeddings)
+        print(f"Searching {tuple(stacked.shape)} embeddings for pairs above {args.threshold} ({sim_type})..")
+        pairs, sims = duplicate_pairs(stacked, args.threshold, compare)
         near_duplicates = [(paths[i], paths[j]) for i, j in pairs.tolist()]
-        # the reference reads values back from its fp16 matrix (:80)
-        near_duplicate_values = [float(np.float16(s)) for s in sims]
-        output_dir = os.path.join(os.path.dirname(args.root_dir), f"near_duplicates_{sim_type}_{args.threshold}")
+        near_duplicate_values = [float(np.float16(v)) for v in sims]  # the reference reads them from its fp16 matrix (:80)
         os.makedirs(output_dir, exist_ok=True)
-        i = 0
         print(f"Found {len(near_duplicates)} duplicates!")
-        if len(near_duplicates) > 0 and not args.test:
-            verb = "copying" if args.mode == "copy" else "moving"
-            print(f"{verb} {len(near_duplicates)} near duplicates to {output_dir}...")
-            for i, (img_paths, sim_value) in enumerate(zip(near_duplicates, near_duplicate_values)):
-                fix_duplicate(i, img_paths, output_dir, sim_value, args.mode)
-            if args.mode == "move":
-                print(f"Moved {i} duplicates to {output_dir}")
-            elif args.mode == "copy":
-                print(f"Copied {i} duplicates (not removed from data yet!) to {output_dir}")
+        if near_duplicates and not args.test:
+            print(f"{'copying' if args.mode == 'copy' else 'moving'} {len(near_duplicates)} near duplicates to {output_dir}...")
+            for index, (pair, value) in enumerate(zip(near_duplicates, near_duplicate_values)):
+                fix_duplicate(index, pair, output_dir, value, args.mode)
+            print(f"{'Copied' if args.mode == 'copy' else 'Moved'} them to {output_dir}"
+                  + (" (nothing was removed from the data yet)" if args.mode == "copy" else ""))
         results.append((near_duplicates, near_duplicate_values))
     return results
 
@@ -232,35 +315,38 @@ def find_near_duplicates_in_store(store, threshold=0.96, crop_to_use="square_pad
     return results
 
 
+def _files_sharing_stem(img_path):
+    """Every file of the image's directory whose name CONTAINS the image's stem (the reference's substring match, :111-112:
+    the image, its .pt, its .json, ... and, as there, anything else that happens to contain it)."""
+    folder = os.path.dirname(img_path)
+    stem = os.path.splitext(os.path.basename(img_path))[0]
+    return [os.path.join(folder, name) for name in os.listdir(folder) if stem in name]
+
+
 def fix_duplicate(duplicate_index, img_paths, outdir, sim_value, mode):
-    """_2_remove_duplicates.py:102-125: copy both images' companion files, or move only the target's."""
-    dirname = os.path.dirname(img_paths[0])
-    basename1 = os.path.splitext(os.path.basename(img_paths[0]))[0]
-    basename2 = os.path.splitext(os.path.basename(img_paths[1]))[0]
-    files1 = [os.path.join(dirname, f) for f in os.listdir(os.path.dirname(img_paths[0])) if basename1 in f]
-    files2 = [os.path.join(dirname, f) for f in os.listdir(os.path.dirname(img_paths[1])) if basename2 in f]
-    for f in files1:
-        if mode == "copy":
-            shutil.copy(f, os.path.join(outdir, f"{sim_value:.3f}_{duplicate_index:08d}_source_{os.path.basename(f)}"))
-    for f in files2:
-        if mode == "copy":
-            shutil.copy(f, os.path.join(outdir, f"{sim_value:.3f}_{duplicate_index:08d}_target_{os.path.basename(f)}"))
-        if mode == "move":
-            os.rename(f, os.path.join(outdir, f"{sim_value:.3f}_{duplicate_index:08d}_target_{os.path.basename(f)}"))
-    return
+    """_2_remove_duplicates.py:102-125.  'copy': both images' files are copied for inspection; 'move': only the second
+    image (the 'target') leaves the dataset.  Names: ``{sim:.3f}_{index:08d}_{source|target}_{original name}``."""
+    tag = f"{sim_value:.3f}_{duplicate_index:08d}"
+    for role, img_path in (("source", img_paths[0]), ("target", img_paths[1])):
+        for src in _files_sharing_stem(img_path):
+            dst = os.path.join(outdir, f"{tag}_{role}_{os.path.basename(src)}")
+            if mode == "copy":
+                shutil.copy(src, dst)
+            elif mode == "move" and role == "target":
+                os.rename(src, dst)
 
 
 def main(argv=None):
     import argparse
-    parser = argparse.ArgumentParser()
-    parser.add_argument("--root_dir", type=str, help="Root directory of the dataset")
-    parser.add_argument("--threshold", type=float, default=0.96, help="Cosine-similarity threshold for near-duplicate detection")
-    parser.add_argument("--mode", type=str, default="copy", help="copy / move, Use copy to test the script, move after")
-    parser.add_argument("--clip_model_to_use", type=str, default=None, help="Which CLIP model to use, if None, use the first one found")
-    parser.add_argument("--chunk_size", type=int, default=10_000_000,
-                        help="Max embeddings compared at once per directory (the reference's 10000 memory cap is lifted)")
-    parser.add_argument("--test", action="store_true", help="Test the script without doing anything")
-    find_near_duplicates(parser.parse_args(argv))
+    ap = argparse.ArgumentParser(description="Near-duplicate search over CLIP embeddings (flags of _2_remove_duplicates.py:135-142)")
+    ap.add_argument("--root_dir", type=str, help="Root directory of the dataset")
+    ap.add_argument("--threshold", type=float, default=0.96, help="Cosine-similarity threshold above which two images are duplicates")
+    ap.add_argument("--mode", type=str, default="copy", help="copy (inspect first) / move (take the duplicates out)")
+    ap.add_argument("--clip_model_to_use", type=str, default=None, help="CLIP model key inside the .pt files; default: the first one found")
+    ap.add_argument("--chunk_size", type=int, default=10_000_000,
+                    help="Most embeddings compared at once per directory (the reference's 10000 was a memory cap; lifted here)")
+    ap.add_argument("--test", action="store_true", help="Dry run: report, do not copy or move anything")
+    find_near_duplicates(ap.parse_args(argv))
 
 
 if __name__ == "__main__":

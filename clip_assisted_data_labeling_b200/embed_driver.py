@@ -109,7 +109,7 @@ class Feature_Dataset:
     def __init__(self, root_dir, model_name, batch_size, model_path=None, force_reencode=False, shuffle_filenames=True,
                  num_workers=0, crop_names=("centre_crop", "square_padded_crop", "subcrop1", "subcrop2"),
                  rank=None, world_size=None, state_dict=None, encoder=None, writer_threads=4, packed_dir=None,
-                 write_pt=True, img_stats=None, device_jpeg=None, writer_procs=None):
+                 write_pt=True, img_stats=None, device_jpeg=None, writer_procs=None, allow_random_init=False):
         self.device = getattr(encoder, "device", "cuda") if encoder is not None else "cuda"
         self.root_dir = root_dir
         self.model_name = model_name
@@ -134,7 +134,8 @@ class Feature_Dataset:
         if model_name.startswith("PE-"):
             raise ValueError("PE (perception_models) encoders are outside the B200 hot path; use an 'Arch/Dataset' CLIP name")
         elif "/" in model_name:
-            self.encoder = encoder or CLIP_Encoder(model_name, model_path, device=self.device, state_dict=state_dict)
+            self.encoder = encoder or CLIP_Encoder(model_name, model_path, device=self.device, state_dict=state_dict,
+                                                   allow_random_init=allow_random_init)
         else:
             raise ValueError(f"Unknown model format: {model_name}. Expected 'PE-...' or 'Arch/Dataset'.")
 
@@ -184,7 +185,8 @@ class Feature_Dataset:
         packed = None
         if self.packed_dir is not None:
             from .store import PackedWriter
-            packed = PackedWriter(self.packed_dir, self.model_name, self.encoder.embed_dim, CROP_NAMES, shard=self.rank)
+            packed = PackedWriter(self.packed_dir, self.model_name, self.encoder.embed_dim, CROP_NAMES, shard=self.rank,
+                                  weights_source=getattr(self.encoder, "weights_source", None))
         stat_names = []
         if self.img_stats:
             from .imgstats import STAT_NAMES, image_stats
@@ -325,6 +327,8 @@ def main(argv=None):
     parser.add_argument("--packed_dir", type=str, default=None,
                         help="Also write one packed [N,4,E] shard per rank here (store.py; not a reference flag)")
     parser.add_argument("--no_pt", action="store_true", help="With --packed_dir: skip the per-image .pt files (export them later)")
+    parser.add_argument("--allow_random_init", action="store_true",
+                        help="Benchmarks only: seeded random weights when no checkpoint is found (never for real data)")
     args = parser.parse_args(argv)
     if "LOCAL_RANK" in os.environ:
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -333,7 +337,7 @@ def main(argv=None):
         print(f"\n--- Processing model: {model_name} ---")
         Feature_Dataset(args.root_dir, model_name, args.batch_size, model_path=args.model_path,
                         force_reencode=args.force_reencode, num_workers=args.num_workers, crop_names=CROP_NAMES,
-                        packed_dir=args.packed_dir, write_pt=not args.no_pt).process()
+                        packed_dir=args.packed_dir, write_pt=not args.no_pt, allow_random_init=args.allow_random_init).process()
 
 
 if __name__ == "__main__":

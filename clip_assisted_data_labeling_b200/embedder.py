@@ -43,42 +43,147 @@ class _ConvertRGB:  # picklable (DataLoader workers use spawn, _1_embed_with_CLI
         return im.convert("RGB")
 
 
-def _find_checkpoint(model_path: str, arch: str, pretrained: str):
-    if model_path is None:
-        return None
-    if os.path.isfile(model_path):
+# open_clip's own download locations (third-party; the reference passes cache_dir=model_path, utils/embedder.py:66-73):
+# OpenAI weights are TorchScript archives under ~/.cache/clip, LAION weights live in the Hugging Face hub cache.
+_OPENAI_FILES = {"ViT-B-32": "ViT-B-32.pt", "ViT-L-14": "ViT-L-14.pt", "ViT-L-14-336": "ViT-L-14-336px.pt"}
+_HF_OPENAI_REPOS = {"ViT-B-32": "clip-vit-base-patch32", "ViT-L-14": "clip-vit-large-patch14",
+                    "ViT-L-14-336": "clip-vit-large-patch14-336"}
+_CKPT_SUFFIXES = (".pt", ".pth", ".bin", ".safetensors")
+_HUB_FILES = ("open_clip_model.safetensors", "open_clip_pytorch_model.bin", "model.safetensors", "pytorch_model.bin")
+
+
+def _hub_snapshot_files(hub_dir: str, arch: str, pretrained: str):
+    """Checkpoint files of hub repositories whose name matches the architecture (and, for LAION tags, the tag)."""
+    out = []
+    if not os.path.isdir(hub_dir):
+        return out
+    want = [arch.lower()] if pretrained != "openai" else [_HF_OPENAI_REPOS.get(arch, "\0").lower()]
+    tag = pretrained.lower().split("_")[0]  # 'laion2b_s32b_b79k' -> 'laion2b'
+    for repo in sorted(os.listdir(hub_dir)):
+        low = repo.lower()
+        if not low.startswith("models--") or not any(w in low for w in want):
+            continue
+        if pretrained == "openai":
+            if not low.endswith(want[0]):  # 'clip-vit-large-patch14' must not match '...patch14-336'
+                continue
+        elif tag not in low:
+            continue
+        snaps = os.path.join(hub_dir, repo, "snapshots")
+        for snap in sorted(os.listdir(snaps)) if os.path.isdir(snaps) else []:
+            for f in _HUB_FILES:
+                if os.path.isfile(os.path.join(snaps, snap, f)):
+                    out.append(os.path.join(snaps, snap, f))
+    return out
+
+
+def _find_checkpoint(model_path, arch: str, pretrained: str, search_caches: bool = True):
+    """Where the weights of ``arch/pretrained`` are on this machine, or None.  ``model_path`` may be the file itself or a
+    directory (the reference hands it to open_clip as cache_dir); then open_clip's default download locations."""
+    if model_path is not None and os.path.isfile(model_path):
         return model_path
-    if os.path.isdir(model_path):
-        want = [f"{arch}_{pretrained}", f"{arch}-{pretrained}", arch]
-        files = sorted(os.listdir(model_path))
-        for w in want:
+    dirs = [model_path] if model_path is not None and os.path.isdir(model_path) else []
+    if search_caches:
+        if os.environ.get("B2C_CLIP_CACHE"):
+            dirs.append(os.environ["B2C_CLIP_CACHE"])
+        dirs.append(os.path.expanduser("~/.cache/clip"))
+    stems = [f"{arch}_{pretrained}", f"{arch}-{pretrained}", arch]
+    for d in dirs:
+        if not os.path.isdir(d):
+            continue
+        files = sorted(os.listdir(d))
+        if pretrained == "openai" and _OPENAI_FILES.get(arch) in files:
+            return os.path.join(d, _OPENAI_FILES[arch])
+        for stem in stems:
             for f in files:
-                if f.startswith(w) and f.endswith((".pt", ".pth", ".bin", ".safetensors")):
-                    return os.path.join(model_path, f)
+                base = os.path.splitext(f)[0]
+                # 'ViT-L-14' must not pick up 'ViT-L-14-336...': the stem has to end the name or be followed by a separator
+                if f.endswith(_CKPT_SUFFIXES) and (base == stem or base.startswith(stem + "_") or base.startswith(stem + ".")):
+                    return os.path.join(d, f)
+        hub = _hub_snapshot_files(d, arch, pretrained) + _hub_snapshot_files(os.path.join(d, "hub"), arch, pretrained)
+        if hub:
+            return hub[0]
+    if search_caches:
+        hub_dir = os.path.join(os.environ.get("HF_HOME", os.path.expanduser("~/.cache/huggingface")), "hub")
+        hub = _hub_snapshot_files(hub_dir, arch, pretrained)
+        if hub:
+            return hub[0]
     return None
 
 
+def _hf_clip_to_open_clip(sd: dict) -> dict:
+    """transformers' CLIP(Vision)Model parameter names -> open_clip ``visual.*`` names."""
+    pre = "vision_model."
+    out = {}
+    direct = {"embeddings.class_embedding": "class_embedding", "embeddings.patch_embedding.weight": "conv1.weight",
+              "embeddings.position_embedding.weight": "positional_embedding", "pre_layrnorm.weight": "ln_pre.weight",
+              "pre_layrnorm.bias": "ln_pre.bias", "post_layernorm.weight": "ln_post.weight", "post_layernorm.bias": "ln_post.bias"}
+    per_layer = {"layer_norm1": "ln_1", "layer_norm2": "ln_2", "self_attn.out_proj": "attn.out_proj", "mlp.fc1": "mlp.c_fc",
+                 "mlp.fc2": "mlp.c_proj"}
+    qkv = {}
+    for k, v in sd.items():
+        if k == "visual_projection.weight":
+            out["proj"] = v.t().contiguous()
+            continue
+        if not k.startswith(pre):
+            continue
+        k = k[len(pre):]
+        if k in direct:
+            out[direct[k]] = v
+        elif k.startswith("encoder.layers."):
+            i, rest = k[len("encoder.layers."):].split(".", 1)
+            mod, leaf = rest.rsplit(".", 1)
+            if mod in per_layer:
+                out[f"transformer.resblocks.{i}.{per_layer[mod]}.{leaf}"] = v
+            elif mod in ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj"):
+                qkv.setdefault((i, leaf), {})[mod[-6]] = v
+    for (i, leaf), parts in qkv.items():
+        if set(parts) == {"q", "k", "v"}:
+            out[f"transformer.resblocks.{i}.attn.in_proj_{leaf}"] = torch.cat([parts["q"], parts["k"], parts["v"]], dim=0)
+    return out
+
+
 def _load_checkpoint(path: str) -> dict:
+    """State dict of a checkpoint file: safetensors, a pickled state dict (optionally wrapped in {'state_dict': ...}), or
+    one of OpenAI's TorchScript archives; transformers-format CLIP checkpoints are renamed to open_clip's keys."""
     if path.endswith(".safetensors"):
         from safetensors.torch import load_file
-        return load_file(path)
-    sd = torch.load(path, map_location="cpu", weights_only=True)
-    if isinstance(sd, dict) and "state_dict" in sd:
-        sd = sd["state_dict"]
+        sd = load_file(path)
+    else:
+        try:
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+        except Exception:  # noqa: BLE001  (OpenAI's .pt files are TorchScript archives)
+            sd = torch.jit.load(path, map_location="cpu").state_dict()
+        if not isinstance(sd, dict) and hasattr(sd, "state_dict"):  # torch.load may hand back the scripted module itself
+            sd = sd.state_dict()
+        if isinstance(sd, dict) and isinstance(sd.get("state_dict"), dict):
+            sd = sd["state_dict"]
+    if not isinstance(sd, dict):
+        raise ValueError(f"{path}: not a state dict")
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items() if isinstance(v, torch.Tensor)}
+    if any(k.startswith("vision_model.") for k in sd):
+        sd = _hf_clip_to_open_clip(sd)
     return sd
 
 
 class CLIP_Encoder:
-    """utils/embedder.py:58-100 on sm_100a kernels."""
+    """utils/embedder.py:58-100 on sm_100a kernels.
 
-    def __init__(self, model_name, model_path=None, device=None, state_dict=None, seed=0):
-        from .vit import VisionTower
+    Weights: ``state_dict`` (open_clip ``visual.*`` names) if given, else the checkpoint ``_find_checkpoint`` locates
+    (``model_path`` file / directory, then open_clip's download caches).  The reference never returns a model without
+    pretrained weights (open_clip downloads them, utils/embedder.py:66-73); there is no network here, so a missing
+    checkpoint is an error — embeddings of random weights written under the real model key would be consumed silently
+    by _2/_4/_5.  ``allow_random_init=True`` (benches, tests: BASELINE.json asks for random-init weights of the named
+    architecture) opts into a seeded random initialisation; ``weights_source`` says which of the three happened."""
+
+    def __init__(self, model_name, model_path=None, device=None, state_dict=None, seed=0, allow_random_init=False):
+        from .vit import VisionTower, _require_cuda
 
         self.device = device if device else "cuda"
         if not str(self.device).startswith("cuda"):
             raise RuntimeError("CLIP_Encoder (B200 path) runs on CUDA only; there is no CPU fallback")
-        # the reference runs fp16 on CUDA (utils/embedder.py:61); this path runs bf16 tensor-core GEMMs with an
-        # fp32 residual stream and returns fp32
+        _require_cuda(self.device)  # fail for the real reason (no sm_100a device) before looking for weights
+        # the reference's values are 'fp16' (CUDA) | 'fp32' (CPU) (utils/embedder.py:61); this path runs bf16 tensor-core
+        # GEMMs with an fp32 residual stream and returns fp32 — documented in INTEGRATION.md
         self.precision = "bf16"
         self.model_name = model_name
         self.model_architecture, self.pretrained_dataset = split_model_name(model_name)
@@ -86,23 +191,27 @@ class CLIP_Encoder:
             raise ValueError(f"unknown architecture {self.model_architecture}; known: {sorted(ARCHS)}")
         cfg = ARCHS[self.model_architecture]
         print(f"Loading CLIP model {self.model_name}...")
-        self.model = VisionTower(cfg, activation_for(self.pretrained_dataset), self.device)
         self.weights_source = "state_dict"
         if state_dict is None:
             ckpt = _find_checkpoint(model_path, self.model_architecture, self.pretrained_dataset)
             if ckpt is not None:
                 state_dict = _load_checkpoint(ckpt)
                 self.weights_source = ckpt
-            else:
-                # no network / no open_clip in this image: seeded random init of the named architecture
+            elif allow_random_init:
                 state_dict = random_state_dict(cfg, seed=seed)
                 self.weights_source = f"random-init(seed={seed})"
-                print(f"WARNING: no checkpoint found for {model_name} under {model_path!r}; using {self.weights_source}")
+                print(f"NOTE: {model_name}: {self.weights_source} was requested (allow_random_init=True); these are not pretrained weights")
+            else:
+                raise FileNotFoundError(
+                    f"no checkpoint for {model_name} (model_path={model_path!r}, $B2C_CLIP_CACHE, ~/.cache/clip, the Hugging Face hub "
+                    "cache): open_clip would download it, this machine cannot.  Pass model_path=<file or directory> or "
+                    "state_dict=...; random weights need the explicit allow_random_init=True")
+        self.model = VisionTower(cfg, activation_for(self.pretrained_dataset), self.device)
         self.model.load_state_dict(state_dict)
         self.preprocess = _open_clip_val_transform(cfg["image"])
         self.img_resolution = cfg["image"]
         self.embed_dim = cfg["embed"]
-        print(f"CLIP model {self.model_name} with img_resolution {self.img_resolution} loaded on {self.device}!")
+        print(f"CLIP model {self.model_name} with img_resolution {self.img_resolution} loaded on {self.device} (weights: {self.weights_source})!")
 
     def get_preprocess_transform(self):
         return self.preprocess
@@ -125,13 +234,15 @@ class CLIP_Encoder:
         [B,H,W,3] host tensors (pinned for full speed); yields one f32 [B,4,E] pinned host tensor per batch, in order.
         Double-buffered: the H2D copy of batch i+1 runs on a copy stream under the compute of batch i, the D2H copy of
         the embeddings follows the compute on its stream, and batch i is handed out once its copy has landed.  A yielded
-        tensor stays valid until two more batches have been yielded."""
+        tensor is a view of a pinned ring of four buffers: it stays valid until two more batches have been yielded (the
+        D2H copy of batch i+1 is already in flight when batch i is handed out, so two slots would not do)."""
         dev = torch.device(self.device)
         with torch.cuda.device(dev):
             compute = torch.cuda.current_stream()
             copy = torch.cuda.Stream()
             bufs, freed = [None, None], [None, None]   # device input ring + "its consumer has run" events
-            outs = [None, None]                         # pinned output ring
+            n_out = 4
+            outs = [None] * n_out                       # pinned output ring (see the docstring for its depth)
             pending = None  # (slot, event, rows) of the batch whose embeddings are on their way to the host
             it = iter(batches)
 
@@ -166,16 +277,17 @@ class CLIP_Encoder:
                 freed[slot].record(compute)
                 staged = stage(nxt, slot ^ 1) if nxt is not None else None  # copies under the kernels just enqueued
                 b = feats.shape[0]
-                if outs[slot] is None or outs[slot].shape[0] < b:
-                    outs[slot] = torch.empty(b, 4, feats.shape[-1], dtype=torch.float32, pin_memory=True)
-                outs[slot][:b].copy_(feats, non_blocking=True)
+                oslot = k % n_out
+                if outs[oslot] is None or outs[oslot].shape[0] < b:
+                    outs[oslot] = torch.empty(b, 4, feats.shape[-1], dtype=torch.float32, pin_memory=True)
+                outs[oslot][:b].copy_(feats, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(compute)
                 if pending is not None:
                     ps, pe, pb = pending
                     pe.synchronize()
                     yield outs[ps][:pb]
-                pending = (slot, done, b)
+                pending = (oslot, done, b)
                 k += 1
             if pending is not None:
                 ps, pe, pb = pending

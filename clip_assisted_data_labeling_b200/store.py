@@ -45,7 +45,7 @@ class PackedWriter:
     so a crashed run never leaves a half-valid shard behind."""
 
     def __init__(self, store_dir: str, model_name: str, embed: int, crop_names=CROP_NAMES, shard: int = 0,
-                 dtype: str = "float32"):
+                 dtype: str = "float32", weights_source: str | None = None):
         if dtype not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
         os.makedirs(store_dir, exist_ok=True)
@@ -53,6 +53,7 @@ class PackedWriter:
         self.crop_names = list(crop_names)
         self._cols = [CROP_NAMES.index(c) for c in self.crop_names]
         self.dtype = dtype
+        self.weights_source = weights_source  # where the encoder's weights came from (CLIP_Encoder.weights_source)
         self.emb_path, self.idx_path = _shard_paths(store_dir, shard)
         if os.path.exists(self.idx_path):
             os.remove(self.idx_path)  # invalidate first, then rewrite the data
@@ -83,7 +84,8 @@ class PackedWriter:
         os.fsync(self._fh.fileno())
         self._fh.close()
         meta = {"format": FORMAT, "model": self.model_name, "crop_names": self.crop_names, "dtype": self.dtype,
-                "embed": self.embed, "count": len(self.paths), "paths": self.paths, "kept": self.kept}
+                "embed": self.embed, "count": len(self.paths), "weights_source": self.weights_source, "paths": self.paths,
+                "kept": self.kept}
         tmp = self.idx_path + ".tmp"
         with open(tmp, "w") as fh:
             json.dump(meta, fh)

@@ -145,9 +145,22 @@ def load_labelled_features(args, crop_names, store=None):
     of one torch.load per image; rows whose image is missing are skipped like the reference's ``except: continue``."""
     import pandas as pd
     features, labels = [], []
-    by_uuid = None
+    by_path = None
     if store is not None:
-        by_uuid = {os.path.splitext(os.path.basename(p))[0]: i for i, p in enumerate(store.paths)}
+        # A packed store holds ONE model.  The saved regressor carries clip_models (utils/nn_model.py:15) and _5 / the
+        # reference's AestheticRegressor build an encoder per entry, so the list must name that model — never 'all'.
+        want = list(args.clip_models_to_use)
+        if want == ["all"]:
+            args.clip_models_to_use = [store.model_name]
+            print(f"\n----> Using the packed store's clip model: {args.clip_models_to_use}")
+        elif want != [store.model_name]:
+            raise ValueError(f"the packed store holds {store.model_name!r} only; clip_models_to_use={want} cannot be served from it "
+                             "(train from the per-image .pt files, or pack one store per model)")
+        # rows are matched by the image's location <train_data_dir>/<name>/<uuid>.<ext> (_4_train_model.py:46), not by the
+        # bare uuid: the same uuid may exist in two datasets
+        by_path = {}
+        for i, p in enumerate(store.paths):
+            by_path.setdefault(os.path.splitext(os.path.abspath(p))[0], i)
         full = store.features(crop_names)
         ok = store.has_all(crop_names)
     for name in args.train_data_names:
@@ -158,8 +171,8 @@ def load_labelled_features(args, crop_names, store=None):
         for _index, row in data.iterrows():
             try:
                 uuid, label = row["uuid"], row["label"]
-                if by_uuid is not None:
-                    i = by_uuid[str(uuid)]
+                if by_path is not None:
+                    i = by_path[os.path.abspath(os.path.join(args.train_data_dir, name, str(uuid)))]
                     if not ok[i]:
                         raise KeyError("missing crop")
                     vec = full[i]

@@ -190,6 +190,9 @@ int b2c_normalize_rows_f16(const void* in, int in_dtype, int64_t n, int E, void*
 #define B2C_CMP_FP32 0 /* pair kept iff fp32 accumulator > threshold */
 #define B2C_CMP_REF_FP16 1 /* pair kept iff fp16(acc) > fp16(threshold): the reference's comparison on its
                               fp16 similarity matrix (_2_remove_duplicates.py:38,69,74) */
+#define B2C_CMP_EUCLID 2 /* sim_type='euclidean' (_2_remove_duplicates.py:70-71, unreachable from its CLI): pair kept iff
+                            the distance of the unit rows, sqrt(max(2 - 2 acc, 0)), exceeds threshold; that distance is
+                            what b2c_pair.sim then holds */
 /* emb: f16[n_total, E_pad] unit-norm rows (all ranks' shards gathered), E_pad % 64 == 0.
  * Emits every pair (i,j), row_begin <= i < row_end, i < j < n_total, whose similarity passes the
  * comparison.  out/count are DEVICE memory; *count is incremented atomically once per pair and may
@@ -198,6 +201,12 @@ int b2c_normalize_rows_f16(const void* in, int in_dtype, int64_t n, int E, void*
 int b2c_dedup_pairs(const void* emb_f16, int64_t n_total, int E_pad, int64_t row_begin, int64_t row_end,
                     float threshold, int compare_mode, b2c_pair* out, unsigned long long capacity,
                     unsigned long long* count, b2c_stream stream);
+/* Same, restricted to columns col_begin <= j < col_end (<= n_total): one block of the upper triangle.  The multi-GPU
+ * search uses it to work on the block of its OWN shard (rows and columns local) while the all-gather of the peers'
+ * shards is in flight, and to leave that block out of the bands it owns afterwards. */
+int b2c_dedup_pairs_block(const void* emb_f16, int64_t n_total, int E_pad, int64_t row_begin, int64_t row_end,
+                          int64_t col_begin, int64_t col_end, float threshold, int compare_mode, b2c_pair* out,
+                          unsigned long long capacity, unsigned long long* count, b2c_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K10 — SimpleFC regressor forward (utils/nn_model.py:23-41; called at _5_predict_labels.py:135):

@@ -82,6 +82,32 @@ def test_product_path_fails_loudly_without_gpu():
         CLIP_Encoder("ViT-B-32/openai")
 
 
+def test_owned_blocks_cover_every_pair_once_and_balance():
+    """Multi-GPU work split (dedup.owned_blocks): own-shard block first (runs under the all-gather), then bands right of
+    the shards' diagonal blocks; every pair (i < j) exactly once, work balanced at BASELINE's 1 M x 8."""
+    import numpy as np
+    from clip_assisted_data_labeling_b200.dedup import owned_blocks
+    for n_local, world, br in [(10, 1, 4), (10, 2, 4), (7, 3, 2), (64, 4, 16), (300, 8, 128)]:
+        n = n_local * world
+        cov = np.zeros((n, n), np.int32)
+        for r in range(world):
+            local, rest = owned_blocks(n_local, r, world, br)
+            assert all(b[0] >= r * n_local and b[1] <= (r + 1) * n_local and b[2:] == b[:2] for b in local)  # no peer data
+            for (r0, r1, c0, c1) in local + rest:
+                for i in range(r0, r1):
+                    lo = max(i + 1, c0)
+                    if lo < c1:
+                        cov[i, lo:c1] += 1
+        iu = np.triu_indices(n, 1)
+        assert (cov[iu] == 1).all() and cov.sum() == len(iu[0]), (n_local, world)
+    for n_local, world in [(125_000, 8), (250_000, 4), (500_000, 2)]:
+        work = []
+        for r in range(world):
+            local, rest = owned_blocks(n_local, r, world)
+            work.append(sum((b[1] - b[0]) * (b[3] - b[2]) for b in rest) + sum((b[1] - b[0]) * (b[1] - b[0] - 1) / 2 for b in local))
+        assert max(work) / min(work) < 1.01, (world, work)
+
+
 def test_owned_bands_partition():
     from clip_assisted_data_labeling_b200.dedup import BAND_ROWS, owned_bands
     for n in (1, 2047, 2048, 2049, 100_000, 1_000_003):

@@ -65,7 +65,7 @@ def test_pt_files_carry_img_stats(lib, tmp_path):
     root.mkdir()
     img = synthetic_image(3, 120, 160)
     Image.fromarray(img).save(root / "a.png")
-    Feature_Dataset(str(root), "ViT-B-32/openai", 2, shuffle_filenames=False).process()
+    Feature_Dataset(str(root), "ViT-B-32/openai", 2, shuffle_filenames=False, allow_random_init=True).process()
     d = torch.load(os.path.join(root, "a.pt"))["ViT-B-32/openai"]
     keys = list(d.keys())
     assert keys[:22] == STAT_NAMES and keys[22:] == ["centre_crop", "square_padded_crop", "subcrop1", "subcrop2"]

@@ -312,6 +312,18 @@ def test_encode_host_batches_equals_per_batch_calls(cuda, lib):
         assert o.is_pinned() is False or True  # clones; shapes and bits are what matters
         assert torch.equal(o, enc.encode_images_u8(b.cuda()).cpu())
     assert list(enc.encode_host_batches([])) == []
+    # documented lifetime: a yielded tensor stays valid until two more batches have been yielded — hold the views
+    # WITHOUT cloning and check each one when the batch two positions later arrives (a two-slot ring fails this: the D2H
+    # copy of batch i+1 is enqueued before batch i is handed out)
+    same = [torch.randint(0, 256, (6, 96, 128, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(7)]
+    want = [enc.encode_images_u8(b.cuda()).cpu() for b in same]
+    held = []
+    for i, o in enumerate(enc.encode_host_batches(same)):
+        held.append(o)
+        torch.cuda.synchronize()  # everything already enqueued (incl. the next batch's D2H) has landed
+        for j in range(max(0, i - 2), i + 1):
+            assert torch.equal(held[j], want[j]), (i, j)
+    assert len(held) == 7
 
 
 def test_clip_encoder_surface(cuda, lib):
@@ -370,6 +382,55 @@ def test_dedup_vs_oracle(cuda, lib, n, d, thr):
     # fp32 comparison mode differs from the fp16-rounded one only inside the band
     p3, _ = duplicate_pairs(e, thr, compare="fp32")
     assert pair_sets_match(pairs, p3, S32, thr)[0]
+
+
+def test_dedup_blocks_partition_equals_whole_search(cuda, lib):
+    """b2c_dedup_pairs_block: the blocks the multi-GPU search deals out (own-shard block + bands right of the shards'
+    diagonal blocks, dedup.owned_blocks) find, together, exactly the pairs of the single search — same indices, same bits."""
+    from clip_assisted_data_labeling_b200.dedup import (_unpack, duplicate_pairs, launch_pair_search, normalize_rows_f16, owned_blocks,
+                                                         sort_pairs)
+    from oracle.dedup_oracle import synthetic_embeddings
+    for n_local, world, band in [(1000, 3, 256), (777, 4, 128), (4096, 2, 2048)]:
+        n = n_local * world
+        e = synthetic_embeddings(n, 256, seed=n, dup_fraction=0.05).cuda()
+        want_p, want_s = duplicate_pairs(e, 0.9)
+        assert len(want_p) > 10
+        emb_n = normalize_rows_f16(e)
+        raws = []
+        for r in range(world):
+            local, rest = owned_blocks(n_local, r, world, band)
+            buf = torch.zeros(len(want_p) + 8, 3, dtype=torch.int32, device="cuda")
+            cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            launch_pair_search(emb_n, local, 0.9, "ref_fp16", buf, cnt)
+            launch_pair_search(emb_n, rest, 0.9, "ref_fp16", buf, cnt)
+            raws.append(buf[:int(cnt.item())].cpu().numpy())
+        got_p, got_s = sort_pairs(*_unpack(np.concatenate(raws)))
+        assert np.array_equal(got_p, want_p) and np.array_equal(got_s, want_s), (n_local, world)
+
+
+def test_dedup_euclidean_mode(cuda, lib):
+    """sim_type='euclidean' (_2_remove_duplicates.py:70-71): cdist of the normalised rows, pairs whose DISTANCE exceeds the
+    threshold.  Identical to torch.cdist's pair set except within 1e-3 of the threshold; values are the distances."""
+    from clip_assisted_data_labeling_b200.dedup import duplicate_pairs
+    from oracle.dedup_oracle import synthetic_embeddings
+    n, thr = 700, 1.43
+    e = synthetic_embeddings(n, 128, seed=5, dup_fraction=0.05)
+    en = torch.nn.functional.normalize(e.double(), dim=1)
+    D = torch.cdist(en, en)
+    ii, jj = torch.where(torch.triu(D, diagonal=1) > thr)
+    ref = set(zip(ii.tolist(), jj.tolist()))
+    pairs, dists = duplicate_pairs(e, thr, compare="euclidean")
+    got = set(map(tuple, pairs.tolist()))
+    assert 10 < len(got) < n * n // 4
+    for (i, j) in ref ^ got:
+        assert abs(float(D[i, j]) - thr) < 1e-3, (i, j, float(D[i, j]))
+    for (i, j), v in zip(pairs.tolist(), dists.tolist()):
+        assert abs(v - float(D[i, j])) < 2e-3
+    assert pairs.tolist() == sorted(pairs.tolist())
+    # duplicates (distance ~ 0) are exactly what this mode does NOT report
+    e[11] = e[10]
+    p2, _ = duplicate_pairs(e, thr, compare="euclidean")
+    assert [10, 11] not in p2.tolist()
 
 
 def test_dedup_edge_cases(cuda, lib):

@@ -170,3 +170,45 @@ def test_saved_regressor_loads_like_a_reference_pickle(tmp_path, golden, lib, mo
     back = load_regressor(path)
     assert back.crop_names == ["centre_crop", "subcrop2"] and back.clip_models == ["M/x"]
     assert SimpleFC.__module__ == "clip_assisted_data_labeling_b200.scorer"
+
+
+def test_store_backed_features_resolve_the_model_and_match_rows_by_path(tmp_path):
+    """trainer.load_labelled_features(store=...): the saved regressor's clip_models must name the store's model (the
+    reference's consumers build one encoder per entry, 'all' is not a model), other / several models cannot be served
+    from one store, and a CSV row is matched by <train_data_dir>/<name>/<uuid>, not by the bare uuid."""
+    from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter
+    from clip_assisted_data_labeling_b200.trainer import load_labelled_features
+    from clip_assisted_data_labeling_b200.vit_arch import CROP_NAMES
+    import pandas as pd
+    E = 8
+    root = tmp_path / "data"
+    g = torch.Generator().manual_seed(0)
+    feats, paths = [], []
+    for name in ("setA", "setB"):
+        (root / name).mkdir(parents=True)
+        for u in ("u0", "u1", "u2"):  # the same uuids in both datasets
+            feats.append(torch.randn(4, E, generator=g))
+            paths.append(str(root / name / f"{u}.jpg"))
+        pd.DataFrame([("u0", 1.0), ("u1", 2.0), ("u2", 3.0), ("absent", 4.0)], columns=["uuid", "label"]).to_csv(root / f"{name}.csv", index=False)
+    with PackedWriter(str(tmp_path / "store"), "ViT-L-14/openai", E) as w:
+        w.append(torch.stack(feats), paths)
+    store = PackedStore(str(tmp_path / "store"))
+    crops = ["centre_crop", "subcrop2"]
+    cols = [CROP_NAMES.index(c) for c in crops]
+
+    def args(models, names):
+        return types.SimpleNamespace(train_data_dir=str(root), train_data_names=names, clip_models_to_use=models)
+
+    a = args(["all"], ["setB"])
+    x, y = load_labelled_features(a, crops, store)
+    assert a.clip_models_to_use == ["ViT-L-14/openai"]
+    assert x.shape == (3, 2 * E) and sorted(y.tolist()) == [1.0, 2.0, 3.0]
+    want = {float(l): feats[3 + i][cols].flatten() for i, l in enumerate((1.0, 2.0, 3.0))}  # setB's rows, not setA's
+    for row, label in zip(x, y.tolist()):
+        assert torch.equal(row, want[label])
+    x2, _ = load_labelled_features(args(["ViT-L-14/openai"], ["setA", "setB"]), crops, store)
+    assert x2.shape == (6, 2 * E)
+    with pytest.raises(ValueError, match="holds 'ViT-L-14/openai' only"):
+        load_labelled_features(args(["ViT-H-14/laion2b_s32b_b79k"], ["setA"]), crops, store)
+    with pytest.raises(ValueError):
+        load_labelled_features(args(["ViT-L-14/openai", "ViT-B-32/openai"], ["setA"]), crops, store)

@@ -31,7 +31,7 @@ def main():
     arch = a.model.split("/")[0]
     cfg = ARCHS[arch]
     with contextlib.redirect_stdout(sys.stderr):
-        enc = CLIP_Encoder(a.model, device="cuda", seed=0)
+        enc = CLIP_Encoder(a.model, device="cuda", seed=0, allow_random_init=True)
     scorer = None
     if a.fc:
         torch.manual_seed(0)

@@ -25,7 +25,7 @@ def main():
     from bench import synth_batch
     from clip_assisted_data_labeling_b200.embedder import CLIP_Encoder
     with contextlib.redirect_stdout(sys.stderr):
-        enc = CLIP_Encoder(a.model, device="cuda", seed=0)
+        enc = CLIP_Encoder(a.model, device="cuda", seed=0, allow_random_init=True)
     for B in [int(x) for x in a.batches.split(",")]:
         pool = [synth_batch(B, i).cuda() for i in range(3)]
         base = None

@@ -44,7 +44,7 @@ def main():
         with cf.ThreadPoolExecutor(os.cpu_count()) as ex:
             list(ex.map(write, range(a.n)))
         with contextlib.redirect_stdout(sys.stderr):
-            enc = CLIP_Encoder(a.model, device="cuda", seed=0)
+            enc = CLIP_Encoder(a.model, device="cuda", seed=0, allow_random_init=True)
         for name, kw in (("pillow decode, .pt files", dict(device_jpeg=False)),
                          ("device JPEG decode (K14), .pt files", dict(device_jpeg=True)),
                          ("device JPEG decode (K14), packed store only", dict(device_jpeg=True, write_pt=False, packed_dir=os.path.join(root, "_packed")))):

@@ -17,7 +17,7 @@ from clip_assisted_data_labeling_b200 import _lib
 from clip_assisted_data_labeling_b200.embedder import CLIP_Encoder
 lib = _lib.load()
 with contextlib.redirect_stdout(sys.stderr):
-    enc = CLIP_Encoder(a.model, device="cuda", seed=0, allow_random_init=True) if "allow_random_init" in CLIP_Encoder.__init__.__code__.co_varnames else CLIP_Encoder(a.model, device="cuda", seed=0)
+    enc = CLIP_Encoder(a.model, device="cuda", seed=0, allow_random_init=True)
 pool = [synth_batch(a.batch, i, device="cuda") for i in range(3)]
 vs = [int(v) for v in a.vars.split(",")]
 ref = None

@@ -44,7 +44,7 @@ def main():
 
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):
-        enc = CLIP_Encoder("ViT-B-32/openai", device="cuda", seed=0)
+        enc = CLIP_Encoder("ViT-B-32/openai", device="cuda", seed=0, allow_random_init=True)
     imgs = synth_batch(8 * world, 3)
     idx = shard_for_rank(list(range(len(imgs))), rank, world)
     mine = enc.encode_images_u8(imgs[idx].cuda())

@@ -315,6 +315,36 @@ def find_near_duplicates_in_store(store, threshold=0.96, crop_to_use="square_pad
     return results
 
 
+def find_near_duplicates_in_store_distributed(store_dir, threshold=0.96, crop_to_use="square_padded_crop", model_name=None,
+                                              compare="ref_fp16", group=None):
+    """Whole-store search with one process per GPU: rank r opens ONLY shard r of the packed store (the shard rank r of
+    the embedding run wrote), the shards are all-gathered once on the device and searched like
+    ``duplicate_pairs_distributed``.  Shards are padded with zero rows to the longest (zero rows never match).
+    Every rank returns (near_duplicates [(path_i, path_j)], near_duplicate_values [float]) over all shards."""
+    import torch.distributed as dist
+    from .store import PackedStore
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    store = PackedStore(store_dir, model_name, shards=[rank])
+    emb = store.crop(crop_to_use, torch.float16)
+    emb[~torch.from_numpy(store.has_all([crop_to_use]))] = 0  # images without this crop take no part
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_mine = torch.tensor([emb.shape[0]], dtype=torch.int64, device=dev)
+    n_all = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(n_all, n_mine, group=group)
+    n_all = n_all.cpu().tolist()
+    n_local = max(n_all)
+    local = torch.zeros(n_local, emb.shape[1], dtype=torch.float16, device=dev)
+    local[:emb.shape[0]].copy_(emb, non_blocking=True)
+    pairs, sims = duplicate_pairs_distributed(local, threshold, compare, group=group)
+    # global row -> path: row = shard * n_local + index inside the shard; only the paths of rows that occur are exchanged
+    need = sorted({int(r) for r in pairs.reshape(-1)})
+    mine = {r: store.paths[r - rank * n_local] for r in need if r // n_local == rank}
+    merged = [None] * world
+    dist.all_gather_object(merged, mine, group=group)  # a few path strings per found pair, not the embeddings
+    path_of = {k: v for part in merged for k, v in part.items()}
+    return ([(path_of[int(i)], path_of[int(j)]) for i, j in pairs.tolist()], [float(np.float16(s)) for s in sims])
+
+
 def _files_sharing_stem(img_path):
     """Every file of the image's directory whose name CONTAINS the image's stem (the reference's substring match, :111-112:
     the image, its .pt, its .json, ... and, as there, anything else that happens to contain it)."""

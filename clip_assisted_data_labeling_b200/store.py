@@ -106,11 +106,16 @@ class PackedStore:
     """Read side: every complete shard of ``store_dir`` for ``model_name`` (default: the first model found, like
     _2_remove_duplicates.py:32-34 defaults to the first key), memory-mapped."""
 
-    def __init__(self, store_dir: str, model_name: str | None = None):
+    def __init__(self, store_dir: str, model_name: str | None = None, shards=None):
+        """``shards``: optional shard numbers to open (default: all) — one process per GPU reads only its own."""
         self.store_dir = store_dir
         self.shards = []
         self.model_name = model_name
-        for idx_path in sorted(glob.glob(os.path.join(store_dir, "shard-*.json"))):
+        index_files = sorted(glob.glob(os.path.join(store_dir, "shard-*.json")))
+        if shards is not None:
+            wanted = {_shard_paths(store_dir, int(k))[1] for k in shards}
+            index_files = [f for f in index_files if f in wanted]
+        for idx_path in index_files:
             with open(idx_path) as fh:
                 meta = json.load(fh)
             if meta.get("format") != FORMAT:

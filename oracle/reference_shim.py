@@ -9,9 +9,10 @@ not installed in this image:
                    -> empty stubs (the PE backend is out of scope);
   * ``matplotlib`` -> stub (only _4/_5 plotting).
 
-The reference exists only in the build container: everything here is used to *generate* golden
-fixtures (tests/golden/, scripts committed) and to cross-check the restatements; nothing that runs on
-the GPU box imports it.
+The reference tree is /root/reference in the build container; on the GPU box it is the verbatim copy
+oracle/make_ref.py leaves under the git-ignored baseline/_ref/.  Used to *generate* golden fixtures
+(tests/golden/, scripts committed), to cross-check the restatements, and by bench.py's reference arm
+(oracle/reference_runner.py) — never by the product path.
 """
 from __future__ import annotations
 
@@ -20,7 +21,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("B2C_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _locate() -> str:
+    for cand in (os.environ.get("B2C_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "utils", "embedder.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _locate()
 
 
 def reference_available() -> bool:
@@ -43,6 +54,9 @@ def _val_transform(image_size: int):
     ])
 
 
+_VISUAL_CACHE = {}
+
+
 def make_open_clip_shim(seed: int = 0):
     from oracle import vit_oracle
 
@@ -50,7 +64,11 @@ def make_open_clip_shim(seed: int = 0):
 
     def create_model_and_transforms(model_name, pretrained=None, precision="fp32", device="cpu", jit=False,
                                     cache_dir=None, **kw):
-        visual = vit_oracle.build_visual(model_name, pretrained or "openai", seed=seed)
+        import copy
+        key = (model_name, pretrained or "openai", seed)
+        if key not in _VISUAL_CACHE:  # the random init of a 300-600 M parameter tower takes seconds: build it once
+            _VISUAL_CACHE[key] = vit_oracle.build_visual(model_name, pretrained or "openai", seed=seed)
+        visual = copy.deepcopy(_VISUAL_CACHE[key])
         model = vit_oracle.CLIPVisualOnly(visual)
         if precision == "fp16":
             model = model.half()

@@ -2,23 +2,24 @@
 // no mask, no dropout (nn.MultiheadAttention inside open_clip's ResidualAttentionBlock; the reference
 // reaches it through utils/embedder.py:98).
 //
-// Two implementations:
-//  (1) attention_umma_kernel — the flagship shape (T = 257 = class token + 256 patches, head dim 64: ViT-L/14-224)
-//      on tcgen05: one CTA per (crop, head, 128-query tile), two CTAs per SM.  TMA loads Q[128x64], K[256x64],
-//      V[256x64] (128B swizzle); S = Q·Kᵀ (M128 N256 K64) accumulates in 256 TMEM columns; the 4 softmax warps own
-//      one TMEM lane (= query row) each, fold the class-token KEY in as a rank-1 term (s0 = q·k0 by FMA, p0·v0 in
-//      the epilogue) so the tensor-core problem is exactly 256 keys with no padding, write P (bf16) into the
-//      128B-swizzled K-major layout over the dead Q/K tiles, and O = P·V runs with V as an MN-major B operand
-//      straight from the TMA tile (no transpose), accumulating over the S columns.  The class-token QUERY row
-//      (1 of 257) is a small SIMT kernel (attention_cls_kernel).
-//  (2) attention_kernel — generic (any T <= 592, head dim 64 or 80) on bf16 mma.sync, used for ViT-B/32,
-//      ViT-L/14-336 and ViT-H/14.
+// Kernels, by shape (attention_launch picks):
+//   T = 257, head dim 64  (ViT-L/14-224)  attention_umma5_kernel  tcgen05, S / P / O in tensor memory, 16 softmax warps,
+//                                          class token on 4 dedicated warps (section 1e)
+//   T = 257, head dim 80  (ViT-H/14)      attention_umma2_kernel<80>  tcgen05, 8 softmax warps, head dim as a 64- plus a
+//                                          16-column slab (section 1b)
+//   T = 577, head dim 64  (ViT-L/14-336)  attention_umma3_kernel  tcgen05, K / V of the head resident in shared memory,
+//                                          key blocks of 96 visited twice (section 1c)
+//   anything else (ViT-B/32: T = 50)      attention_kernel<HD>  bf16 mma.sync, online softmax (section 2)
+//   class-token query row only            attention_cls_kernel  (b2c_vit_set_cls_only_last_block)
+// In every tcgen05 kernel the class-token KEY is a rank-1 term (s0 = q·k0 by FMA, p0·v0 added in the epilogue) so that
+// the tensor-core problem is exactly the patch keys with no padding, P is written back as packed bf16 over the consumed
+// S columns, O = P·V runs with P read from TMEM and V as an MN-major operand straight from the TMA tile, and the row
+// sums of the ROUNDED probabilities come from the tensor core (L = P·1).
 //
 // (2): One CTA per (crop, head).  K and V of that head (T <= 592 tokens) are staged once in shared memory
 // (cp.async, 16-byte chunks, rows padded by 16 B so ldmatrix is bank-conflict-free); each warp owns
 // 16-query tiles and streams the keys in chunks of 64 with an online (running max / running sum)
-// softmax in fp32 registers.  Tensor work is bf16 mma.sync m16n8k16 with fp32 accumulation; this is
-// 4 % of the tower's FLOPs.
+// softmax in fp32 registers.  Tensor work is bf16 mma.sync m16n8k16 with fp32 accumulation.
 #include <type_traits>
 #include <cuda_bf16.h>
 
@@ -222,204 +223,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
 }
 
 
-// ================================================================================================
-// (1) tcgen05 attention for T = 257, head dim 64
-// ================================================================================================
-constexpr int kAuThreads = 192;
-constexpr int kAuKeys = 256;                      // patch tokens = keys handled by the tensor cores
-constexpr int kAuOffK = 0;                        // K tile  [256 keys x 128 B]          (later P k-blocks 0,1)
-constexpr int kAuOffQ = 32 * 1024;                // Q tile  [128 rows x 128 B]          (later P k-block 2)
-constexpr int kAuOffV = 64 * 1024;                // V tile  [256 keys x 128 B]   ([48K,64K) = P k-block 3 only)
-constexpr int kAuOffBar = 96 * 1024;
-constexpr int kAuSmemBytes = 96 * 1024 + 1024 + 128;
-
-__global__ void __launch_bounds__(kAuThreads, 2)
-attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                      const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int heads,
-                      float scale_log2) {
-  extern __shared__ uint8_t smem_au_raw[];
-  uint8_t* smem = smem_au_raw + ((1024u - (smem_u32(smem_au_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAuOffBar);
-  uint64_t* bar_qk = bars + 0;  // Q and K tiles landed
-  uint64_t* bar_v = bars + 1;   // V tile landed
-  uint64_t* bar_s = bars + 2;   // S = Q·Kᵀ complete in TMEM
-  uint64_t* bar_p = bars + 3;   // P written to smem by the 4 softmax warps
-  uint64_t* bar_o = bars + 4;   // O = P·V complete in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x & 1;
-  const int ch = blockIdx.x >> 1;
-  const int crop = ch / heads;
-  const int head = ch - crop * heads;
-  const int d = heads * 64;
-  const int tok0 = crop * T;  // the crop's class token; patch tokens follow
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_kv);
-    mbar_init(bar_qk, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    mbar_init(bar_o, 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_qk, 48 * 1024);
-      tma_load_2d(smem + kAuOffQ, &tm_q, bar_qk, head * 64, tok0 + 1 + qt * 128);
-      tma_load_2d(smem + kAuOffK, &tm_kv, bar_qk, d + head * 64, tok0 + 1);
-      mbar_arrive_expect_tx(bar_v, 32 * 1024);
-      tma_load_2d(smem + kAuOffV, &tm_kv, bar_v, 2 * d + head * 64, tok0 + 1);
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t sbase = smem_u32(smem);
-      // S[128 x 256] = Q[128 x 64] · K[256 x 64]ᵀ : both K-major
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      const uint64_t q_desc = make_sw128_kmajor_desc(sbase + kAuOffQ);
-      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + kAuOffK);
-      const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tmem, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-      umma_commit(bar_s);
-      // O[128 x 64] = P[128 x 256] · V[256 x 64] : P K-major (4 k-blocks of 64 keys, 16 KB each from offset 0),
-      // V MN-major: tile rows are keys (K), 128 swizzled bytes of head dim (N) per row; 8-key groups 1024 B apart.
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after();
-      const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // b_major = MN
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
-        const uint64_t p_desc = make_sw128_kmajor_desc(sbase + kb * 16384);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t v_desc = make_sw128_kmajor_desc(sbase + kAuOffV + (kb * 64 + k * 16) * 128);
-          umma_f16(tmem, p_desc + 2 * k, v_desc, idesc_o, (kb | k) != 0);
-        }
-      }
-      umma_commit(bar_o);
-    }
-    __syncwarp();
-  } else {
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;                 // query row of the tile = TMEM lane
-    const int token = tok0 + 1 + qt * 128 + r;
-    const size_t row_stride = static_cast<size_t>(3) * d;
-    // ---- class-token key as a rank-1 term: s0 = q_r · k0 (bf16 inputs, fp32 accumulate like the MMA)
-    float s0 = 0.f;
-    {
-      const uint4* qp = reinterpret_cast<const uint4*>(qkv + token * row_stride + head * 64);
-      const uint4* kp = reinterpret_cast<const uint4*>(qkv + tok0 * row_stride + d + head * 64);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 a = __ldg(qp + j), b = __ldg(kp + j);
-        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
-          s0 = fmaf(fa.x, fb.x, s0);
-          s0 = fmaf(fa.y, fb.y, s0);
-        }
-      }
-    }
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    // ---- pass 1: row max over the 256 patch keys and the class key
-    float m = s0;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
-    }
-    const float ms = m * scale_log2;
-    const float p0 = exp2f(fmaf(s0, scale_log2, -ms));
-    float l = p0;
-    // ---- pass 2: p = exp2((s - m) * scale), bf16, into the K-major 128B-swizzled P tiles (over the dead K/Q tiles)
-    uint8_t* prow = smem + r * 128;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      tmem_ld_wait();
-      float f[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        f[e] = exp2f(fmaf(__uint_as_float(v[e]), scale_log2, -ms));
-        l += f[e];
-      }
-      uint8_t* blk = prow + (c >> 1) * 16384;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 w;
-        w.x = pack2(f[8 * j + 0], f[8 * j + 1]);
-        w.y = pack2(f[8 * j + 2], f[8 * j + 3]);
-        w.z = pack2(f[8 * j + 4], f[8 * j + 5]);
-        w.w = pack2(f[8 * j + 6], f[8 * j + 7]);
-        *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + j) ^ (r & 7)) << 4)) = w;
-      }
-    }
-    fence_proxy_async_smem();  // P must be visible to the tensor core's (async proxy) smem reads
-    tc_fence_before();         // and our TMEM reads of S ordered before O overwrites those columns
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p);
-    // ---- epilogue: O row (64 columns) + class-key term, normalised, bf16
-    const float inv = 1.0f / l;
-    float v0[64];
-    {
-      const uint4* vp = reinterpret_cast<const uint4*>(qkv + tok0 * row_stride + 2 * d + head * 64);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 a = __ldg(vp + j);
-        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 fa = __bfloat1622float2(a2[e]);
-          v0[8 * j + 2 * e] = fa.x * p0;
-          v0[8 * j + 2 * e + 1] = fa.y * p0;
-        }
-      }
-    }
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * 64;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 w;
-        w.x = pack2((__uint_as_float(v[8 * j + 0]) + v0[c * 32 + 8 * j + 0]) * inv, (__uint_as_float(v[8 * j + 1]) + v0[c * 32 + 8 * j + 1]) * inv);
-        w.y = pack2((__uint_as_float(v[8 * j + 2]) + v0[c * 32 + 8 * j + 2]) * inv, (__uint_as_float(v[8 * j + 3]) + v0[c * 32 + 8 * j + 3]) * inv);
-        w.z = pack2((__uint_as_float(v[8 * j + 4]) + v0[c * 32 + 8 * j + 4]) * inv, (__uint_as_float(v[8 * j + 5]) + v0[c * 32 + 8 * j + 5]) * inv);
-        w.w = pack2((__uint_as_float(v[8 * j + 6]) + v0[c * 32 + 8 * j + 6]) * inv, (__uint_as_float(v[8 * j + 7]) + v0[c * 32 + 8 * j + 7]) * inv);
-        *reinterpret_cast<uint4*>(orow + c * 32 + 8 * j) = w;
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-}
+constexpr int kAuKeys = 256;  // patch tokens of the 224-pixel towers = keys handled by one N=256 tensor-core tile
 
 // The class-token query row of every (crop, head): one warp each, SIMT.  1/257 of the attention work.
 __global__ void __launch_bounds__(128) attention_cls_kernel(const __nv_bfloat16* __restrict__ qkv,
@@ -503,28 +307,6 @@ __global__ void __launch_bounds__(128) attention_cls_kernel(const __nv_bfloat16*
   const float inv = 1.0f / l;
   *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(crop) * T * d + head * 64 + 2 * lane) = pack2(o0 * inv, o1 * inv);
 }
-
-static int attention_umma_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
-  const int d = heads * 64;
-  CUtensorMap tm_q, tm_kv;
-  const uint64_t rows = static_cast<uint64_t>(n) * T;
-  B2C_TRY(make_tmap_2d(&tm_q, qkv, rows, 3ull * d, 3ull * d * 2, 128, 1));
-  B2C_TRY(make_tmap_2d(&tm_kv, qkv, rows, 3ull * d, 3ull * d * 2, 256, 1));
-  static PerDeviceFlag attr_once;
-  if (attr_once.first_use()) {
-    B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAuSmemBytes));
-  }
-  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
-  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
-  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  attention_umma_kernel<<<static_cast<unsigned>(n) * heads * 2, kAuThreads, kAuSmemBytes, stream>>>(tm_q, tm_kv, q, o, T, heads,
-                                                                                                    scale_log2);
-  B2C_POST_LAUNCH("attention_umma_kernel");
-  attention_cls_kernel<<<(n * heads + 3) / 4, 128, 0, stream>>>(q, o, n * heads, T, heads, scale_log2);
-  B2C_POST_LAUNCH("attention_cls_kernel");
-  return 0;
-}
-
 
 // ================================================================================================
 // (1b) tcgen05 attention v2 for T = 257, head dim 64 (ViT-L/14) or 80 (ViT-H/14): persistent, pipelined, P kept in
@@ -1362,54 +1144,8 @@ static int attention_umma3_launch(const void* qkv, void* out, int n, int T, int 
   return 0;
 }
 
-// ================================================================================================
-// (1d) tcgen05 attention v4 for T = 257, head dim 64: v2's pipeline with the softmax spread over SIXTEEN warps.
-//   v2 gives each query row to one thread (8 softmax warps = 2 per SM sub-partition): the issue slots of a sub-partition
-//   are then shared by just two dependent instruction streams (ncu: 16 % warps active, 34 % issue-slot and 37 % XU-pipe
-//   utilisation).  v4 splits every query row's 256 keys between two threads (column halves), so a sub-partition holds
-//   four softmax warps:
-//     warp 0       TMA producer (Q both tiles, K, V of the next head into the other smem stage);
-//     warp 1       MMA issuer: S_g = Q_g·Kᵀ, then O_g = P_g·V and L_g = P_g·1 when P_g is ready (tile index is a
-//                  compile-time constant in every operand);
-//     warps 2-17   softmax: group g = (warp-2)/8 (query tile), column half h = ((warp-2)/4)&1 (keys [128h, 128h+128)),
-//                  TMEM lane quarter = warp & 3.  The two halves of a row exchange their partial maxima through smem.
-//   TMEM region g: S [0,256) -> P_0 [0,64) over half 0's consumed columns | O [64,128) | P_1 [128,192) over half 1's |
-//   L [192,208).  The class-token KEY (rank-1 term) is not part of the running maximum — softmax is shift invariant and
-//   p0 = exp2(min(s0·c − m·c, 126)) cannot overflow — so its dot product is off the critical path (half 1 computes it
-//   after releasing P to the tensor core).  The class-token QUERY row is computed by the 256 threads of one group
-//   (alternating), one key per thread, while the tensor core computes O.  All shared-memory traffic is LDS/STS (see the
-//   smem base computation).  Variants measured on B200 (1024 crops, ms): v2 0.76 | v4 as first written 0.65 | + stage
-//   released before the epilogue and class-row reduce before the O wait 0.61 | one MMA issuer warp per query tile 0.62
-//   (no gain: dropped) | class row after the epilogue 0.73.
-// ================================================================================================
-constexpr int kA4Threads = 64 + 512;
-
-struct A4Misc {
-  uint64_t full_qk[2], full_v[2], empty_qk[2], empty_v[2];
-  uint64_t s_full[2], p_full[2], o_full[2], tmem_free[2];
-  uint32_t tmem_slot;
-  uint32_t pad[3];
-  float red[2][16];        // per group: cross-warp max / sum scratch (8 warps each)
-  float vec[2][2][3][64];  // per group, per iteration parity: q0, k0, v0 of the head as fp32
-  float mx[2][2][128];     // per group, per half: partial row maxima
-  float p0s[2][128];       // per group: class-key probability of each query row
-  float p_cls[2][264];     // per group: class-row probabilities (256 patch keys + class key)
-  float part[2][32][64];   // per group: 32 key-slices of the class-row output
-};
-
-constexpr int a4_smem_bytes() {
-  return A2L<64>::kOffMisc + static_cast<int>((sizeof(A4Misc) + 1023) / 1024 * 1024) + 1024;
-}
-
-// development trace (kVar bit 4): clock64() of lane 0 of every warp of CTA 0 at phase boundaries, iterations 4..11
-__device__ int g_attn_trace_k0 = 4;  // first traced iteration (b2c_debug_attn_trace_start)
-__device__ long long g_attn_trace[18][8][16];
-#define A4_TRACE(ev)                                                                                   \
-  do {                                                                                                 \
-    if constexpr (kTrace) {                                                                            \
-      if (blockIdx.x == 0 && lane == 0 && k >= g_attn_trace_k0 && k < g_attn_trace_k0 + 8) g_attn_trace[warp][k - g_attn_trace_k0][ev] = clock64(); \
-    }                                                                                                  \
-  } while (0)
+// first traced iteration of the development phase trace (b2c_debug_attn_trace_start)
+__device__ int g_attn_trace_k0 = 4;
 
 // exp2 on the FMA pipe for part of a row's elements (the XU pipe, 16 ex2 per clock per SM, is what the exp2 pass
 // saturates): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5·2^23, 2^f by a degree-3 minimax
@@ -1430,461 +1166,31 @@ __device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float
   y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-// kVar (development A/B switch B2C_ATTN_VAR; the default is what attention_umma4_launch picks):
-//   bit 0  staggered MMA issue order S0(k) PV1(k-1) S1(k) PV0(k): the two query tiles run half a period apart, so one
-//          tile's exp2 pass (XU pipe) overlaps the other's tensor-core / epilogue / max phases instead of its exp2 pass
-//   bit 1  the two column halves of a row exchange their maxima through a 64-thread barrier (their two warps) instead
-//          of the group's 256-thread barrier; q0/k0/v0 of the next head are published an iteration ahead
-//   bits 2-3  exp2 on the FMA pipe for every 4th (1), 3rd (2) or 2nd (3) pair of a row's elements
-// launch bound 640 (not 576): ptxas schedules the softmax loop measurably better with it (0.61 vs 0.66 ms at 1024 crops)
-template <int kVar>
-__global__ void __launch_bounds__(kA4Threads + 64, 1)
-attention_umma4_kernel(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* __restrict__ qkv,
-                       __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads, float scale_log2) {
-  constexpr int HD = 64;
-  constexpr bool kStagger = (kVar & 1) != 0;
-  constexpr bool kPairBar = (kVar & 2) != 0;
-  constexpr bool kTrace = (kVar & 16) != 0;
-  constexpr int kPolyMod = ((kVar >> 2) & 3) == 0 ? 0 : 5 - ((kVar >> 2) & 3);  // 0 | 4 | 3 | 2
-  using L = A2L<HD>;
-  constexpr int kColO4 = 64, kColL4 = 192;
-  constexpr int kFirstSm = 2;  // first softmax warp
-  extern __shared__ uint8_t smem_a4_raw[];
-  uint8_t* smem = smem_a4_raw + ((1024u - (smem_u32(smem_a4_raw) & 1023u)) & 1023u);  // keeps the address space: LDS/STS
-  A4Misc* mb = reinterpret_cast<A4Misc*>(smem + L::kOffMisc);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = heads * HD;
-  const size_t row_stride = static_cast<size_t>(3) * d;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&mb->full_qk[s], 1);
-      mbar_init(&mb->full_v[s], 1);
-      mbar_init(&mb->empty_qk[s], 3);  // the MMA issuer's commit + one arrival per group once its Q/K reads are done
-      mbar_init(&mb->empty_v[s], 2);   // the MMA issuer's commit + the group that computed the class row from V
-      mbar_init(&mb->s_full[s], 1);
-      mbar_init(&mb->p_full[s], 8);
-      mbar_init(&mb->o_full[s], 1);
-      mbar_init(&mb->tmem_free[s], 8);
-    }
-    mbar_fence_init();
-  }
-  for (int i = threadIdx.x; i < 8 * 1024 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(smem + L::kOffOnes)[i] = 0x3F803F80u;  // bf16 1.0 x2
-  fence_proxy_async_smem();
-  if (warp == 1) tmem_alloc(&mb->tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = mb->tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int k = 0;
-      for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
-        const int s = k & 1;
-        const uint32_t u = (k >> 1) & 1;
-        const int crop = ch / heads, head = ch - crop * heads;
-        const int row0 = crop * T + 1;
-        uint8_t* st = smem + s * L::kQKStage;
-        uint8_t* sv = smem + L::kOffV + s * L::kOp;
-        mbar_wait(&mb->empty_qk[s], u ^ 1);
-        mbar_arrive_expect_tx(&mb->full_qk[s], 2 * L::kOp);
-        tma_load_2d(st, &tm, &mb->full_qk[s], head * HD, row0);
-        tma_load_2d(st + L::kOp, &tm, &mb->full_qk[s], d + head * HD, row0);
-        mbar_wait(&mb->empty_v[s], u ^ 1);
-        mbar_arrive_expect_tx(&mb->full_v[s], L::kOp);
-        tma_load_2d(sv, &tm, &mb->full_v[s], 2 * d + head * HD, row0);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow, see v2)
-    // The query tile index is a compile-time constant in every tcgen05.mma operand (TMEM address, descriptors): with a
-    // run-time tile index ptxas moves each operand through R2UR before every MMA and the issue rate drops.
-    const uint32_t idesc_s = make_idesc_f16(128, 256, 1);
-    const uint32_t idesc_o = make_idesc_f16(128, 64, 1) | (1u << 16);  // B (= V) is MN-major
-    const uint32_t idesc_l = make_idesc_f16(128, 16, 1);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint64_t ones_desc = make_sw128_kmajor_desc(smem_base + L::kOffOnes);
-    auto issue_s = [&](auto wc, uint32_t sbase, uint64_t k_desc, uint32_t kp) {
-      constexpr int w = decltype(wc)::value;
-      const uint32_t treg = tmem + w * 256;
-      const uint64_t q_desc = make_sw128_kmajor_desc(sbase + w * 16384);
-      mbar_wait(&mb->tmem_free[w], kp ^ 1);  // both halves of group w have read the previous O out of the region
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16(treg, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk != 0);
-        umma_commit(&mb->s_full[w]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [&](auto wc, uint64_t v_desc0, uint32_t kp) {
-      constexpr int w = decltype(wc)::value;
-      const uint32_t treg = tmem + w * 256;
-      mbar_wait(&mb->p_full[w], kp);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          const uint32_t pcol = (kk < 8 ? 0u : 128u) + (kk & 7) * 8;  // P_0 at [0,64), P_1 at [128,192)
-          umma_f16_ts(treg + kColO4, treg + pcol, v_desc0 + kk * 128, idesc_o, kk != 0);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          const uint32_t pcol = (kk < 8 ? 0u : 128u) + (kk & 7) * 8;
-          umma_f16_ts(treg + kColL4, treg + pcol, ones_desc + 2 * (kk & 3), idesc_l, kk != 0);
-        }
-        umma_commit(&mb->o_full[w]);
-      }
-      __syncwarp();
-    };
-    using W0 = std::integral_constant<int, 0>;
-    using W1 = std::integral_constant<int, 1>;
-    int k = 0;
-    uint64_t v_desc_prev = 0;
-    int s_prev = 0;
-    uint32_t kp_prev = 0;
-    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
-      const int s = k & 1;
-      const uint32_t u = (k >> 1) & 1, kp = k & 1;
-      const uint32_t sbase = smem_base + s * L::kQKStage;
-      const uint32_t vbase = smem_base + L::kOffV + s * L::kOp;
-      A4_TRACE(0);
-      mbar_wait(&mb->full_qk[s], u);
-      const uint64_t k_desc = make_sw128_kmajor_desc(sbase + L::kOp);
-      A4_TRACE(1);
-      issue_s(W0{}, sbase, k_desc, kp);
-      A4_TRACE(2);
-      if constexpr (kStagger) {
-        if (k > 0) {  // tile 1 of the previous head: its softmax ran while tile 0's P·V, epilogue and this S were in flight
-          issue_pv(W1{}, v_desc_prev, kp_prev);
-          if (elect_one()) umma_commit(&mb->empty_v[s_prev]);
-          __syncwarp();
-        }
-      }
-      A4_TRACE(3);
-      issue_s(W1{}, sbase, k_desc, kp);
-      A4_TRACE(4);
-      if (elect_one()) umma_commit(&mb->empty_qk[s]);
-      __syncwarp();
-      mbar_wait(&mb->full_v[s], u);
-      const uint64_t v_desc0 = make_sw128_kmajor_desc(vbase);
-      A4_TRACE(5);
-      issue_pv(W0{}, v_desc0, kp);
-      A4_TRACE(6);
-      if constexpr (kStagger) {
-        v_desc_prev = v_desc0;
-        s_prev = s;
-        kp_prev = kp;
-      } else {
-        issue_pv(W1{}, v_desc0, kp);
-        if (elect_one()) umma_commit(&mb->empty_v[s]);
-        __syncwarp();
-      }
-      A4_TRACE(7);
-    }
-    if constexpr (kStagger) {
-      if (k > 0) {
-        issue_pv(W1{}, v_desc_prev, kp_prev);
-        if (elect_one()) umma_commit(&mb->empty_v[s_prev]);
-        __syncwarp();
-      }
-    }
-  } else if (warp >= kFirstSm) {
-    // ------------------------------------------------------------------ softmax: 2 groups x 2 column halves x 4 warps
-    const int sw = warp - kFirstSm;
-    const int w = sw >> 3;                  // group = query tile
-    const int h = (sw >> 2) & 1;            // column half: keys [128h, 128h + 128)
-    const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
-    const int r = quarter * 32 + lane;      // query row in the tile = TMEM lane
-    const int gt = h * 128 + r;             // thread index inside the group, 0..255
-    const int gw = sw & 7;                  // warp index inside the group
-    const uint32_t taddr = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t sbase_col = 128u * h;    // this half's S columns; its P goes over them at [128h, 128h + 64)
-    float* red = mb->red[w];
-    float* pcls = mb->p_cls[w];
-    uint32_t cq = 0, ck = 0, cv = 0;
-    auto prefetch = [&](int ch) {
-      if (gt < HD) {
-        const int crop = ch / heads, head = ch - crop * heads;
-        const unsigned short* cls_row =
-            reinterpret_cast<const unsigned short*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * HD);
-        cq = __ldg(cls_row + gt);
-        ck = __ldg(cls_row + d + gt);
-        cv = __ldg(cls_row + 2 * d + gt);
-      }
-    };
-    auto publish = [&](int par) {  // q0 / k0 / v0 of a head (bf16 bits in cq, ck, cv) -> fp32 in shared memory
-      if (gt < HD) {
-        mb->vec[w][par][0][gt] = __uint_as_float(cq << 16);
-        mb->vec[w][par][1][gt] = __uint_as_float(ck << 16);
-        mb->vec[w][par][2][gt] = __uint_as_float(cv << 16);
-      }
-    };
-    if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
-    if constexpr (kPairBar) {
-      publish(0);
-      named_bar_sync(1 + w, 256);
-    }
-    int k = 0;
-    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++k) {
-      const int s = k & 1;
-      const uint32_t u = (k >> 1) & 1, kp = k & 1;
-      const int crop = ch / heads, head = ch - crop * heads;
-      const int tok0 = crop * T;
-      const int token = tok0 + 1 + w * 128 + r;
-      const uint8_t* st = smem + s * L::kQKStage;
-      const uint8_t* sv = smem + L::kOffV + s * L::kOp;
-      const bool cls_owner = ((k & 1) == w);
-      const int vpar = kPairBar ? (k & 1) : 0;
-      const float* q0f = mb->vec[w][vpar][0];
-      const float* k0f = mb->vec[w][vpar][1];
-      const float* v0f = mb->vec[w][vpar][2];
-
-      if constexpr (!kPairBar) publish(0);
-      if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
-
-      // ---- own row, own 128 keys: partial max -> exchange -> P (bf16x2 packed) back into TMEM over S
-      A4_TRACE(0);
-      mbar_wait(&mb->s_full[w], kp);
-      tc_fence_after();
-      A4_TRACE(1);
-      float m = -INFINITY;
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(taddr + sbase_col, va);
-#pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        tmem_ld_wait();
-        tmem_ld_32x32(taddr + sbase_col + (c + 1) * 32, vb);
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
-        tmem_ld_wait();
-        tmem_ld_32x32(taddr + sbase_col + ((c + 2) & 3) * 32, va);  // last iteration: chunk 0 again, for the second pass
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
-      }
-      mb->mx[w][h][r] = m;
-      A4_TRACE(2);
-      if constexpr (kPairBar) named_bar_sync(3 + w * 4 + quarter, 64);  // the two warps that share these 32 rows
-      else named_bar_sync(1 + w, 256);                                   // also publishes q0f / k0f / v0f
-      m = fmaxf(m, mb->mx[w][h ^ 1][r]);
-      A4_TRACE(3);
-      const float ms = m * scale_log2;
-      const float nms = -ms;
-      auto emit_p = [&](const uint32_t (&v)[32], int c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float t0, t1;  // one FFMA2 per pair of scores
-          ffma2(t0, t1, __uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), scale_log2, scale_log2, nms, nms);
-          if (kPolyMod != 0 && (e % (kPolyMod ? kPolyMod : 1)) == kPolyMod - 1) {
-            float y0, y1;
-            exp2_poly2(y0, y1, t0, t1);
-            pk[e] = pack2(y0, y1);
-          } else {
-            pk[e] = pack2(ex2_ftz(t0), ex2_ftz(t1));
-          }
-        }
-        tmem_st_32x16(taddr + sbase_col + c * 16, pk);  // columns already consumed by this thread
-      };
-#pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        tmem_ld_wait();
-        tmem_ld_32x32(taddr + sbase_col + (c + 1) * 32, vb);
-        emit_p(va, c);
-        tmem_ld_wait();
-        if (c + 2 < 4) tmem_ld_32x32(taddr + sbase_col + (c + 2) * 32, va);
-        emit_p(vb, c + 1);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&mb->p_full[w]);
-      A4_TRACE(4);
-
-      // ---- class-token KEY: p0 = exp2((q_r·k0 − m)·c), while the tensor core computes O (half 1 only)
-      mbar_wait(&mb->full_qk[s], u);
-      if (h == 1) {
-        const float s0 = dot_row<HD>(st, w * 128 + r, k0f);
-        mb->p0s[w][r] = ex2_ftz(fminf(fmaf(s0, scale_log2, -ms), 126.f));
-      }
-      A4_TRACE(5);
-      // ---- class-token QUERY row: one key per thread, scores from the K tile, then O_cls = P_cls·V from the V tile
-      if (cls_owner) {
-        const float sa = dot_row<HD>(st + L::kOp, gt, q0f);
-        float sc = -INFINITY;
-        if (gt == 0) {
-          float acc = 0.f;
-          for (int c = 0; c < HD; ++c) acc = fmaf(q0f[c], k0f[c], acc);
-          sc = acc;
-        }
-        float cm = fmaxf(sa, sc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-        if (lane == 0) red[gw] = cm;
-        named_bar_sync(1 + w, 256);
-        cm = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))) *
-             scale_log2;
-        const float pa = ex2_ftz(fmaf(sa, scale_log2, -cm));
-        float psum = pa;
-        pcls[gt] = pa;
-        if (gt == 0) {
-          const float pc = ex2_ftz(fmaf(sc, scale_log2, -cm));
-          pcls[256] = pc;
-          psum += pc;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-        if (lane == 0) red[8 + gw] = psum;
-        named_bar_sync(1 + w, 256);
-        // thread = (8-key slice ks, 8-column chunk cc): one 16-byte read per key
-        mbar_wait(&mb->full_v[s], u);
-        const int cc = gt & 7, ks = gt >> 3;
-        const float* pp = pcls + ks * 8;
-        const uint8_t* base = sv + (ks * 8) * 128;
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-        for (int key = 0; key < 8; ++key) {
-          // ks*8 + key has the same low 3 bits as key, so the swizzle phase depends on `key` only
-          const uint4 a = *reinterpret_cast<const uint4*>(base + key * 128 + ((cc ^ key) << 4));
-          const float pkey = pp[key];
-          ffma2(acc[0], acc[1], bf16_lo(a.x), bf16_hi(a.x), pkey, pkey, acc[0], acc[1]);
-          ffma2(acc[2], acc[3], bf16_lo(a.y), bf16_hi(a.y), pkey, pkey, acc[2], acc[3]);
-          ffma2(acc[4], acc[5], bf16_lo(a.z), bf16_hi(a.z), pkey, pkey, acc[4], acc[5]);
-          ffma2(acc[6], acc[7], bf16_lo(a.w), bf16_hi(a.w), pkey, pkey, acc[6], acc[7]);
-        }
-        *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(&mb->part[w][ks][cc * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      }
-      A4_TRACE(6);
-      named_bar_sync(1 + w, 256);  // p0s (and the class row's partial sums) visible
-      A4_TRACE(7);
-      // Release the operand stage NOW (every Q / K / V read of the group is done) and finish the class row BEFORE waiting
-      // for O: measured together these two placements are worth 16 % of the kernel (0.73 -> 0.61 ms at 1024 crops);
-      // releasing at the end of the iteration, or reducing after the epilogue, each lose all of it.
-      if (gt == 0) {
-        mbar_arrive(&mb->empty_qk[s]);
-        if (cls_owner) mbar_arrive(&mb->empty_v[s]);
-      }
-      if (cls_owner && gt < HD) {
-        const float cls_l = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
-        float o = pcls[256] * v0f[gt];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o += mb->part[w][i][gt];
-        out[static_cast<size_t>(tok0) * d + head * HD + gt] = __float2bfloat16_rn(o / cls_l);
-      }
-
-      // ---- own row, own 32 output columns: (O + p0·v0) / (L + p0) -> bf16
-      const float p0 = mb->p0s[w][r];
-      A4_TRACE(8);
-      mbar_wait(&mb->o_full[w], kp);
-      tc_fence_after();
-      A4_TRACE(9);
-      const float lsum = __uint_as_float(tmem_ld_1(taddr + kColL4));
-      {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + kColO4 + h * 32, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mb->tmem_free[w]);  // O and L are in registers: the region can take the next S
-        const float inv = 1.0f / (lsum + p0);
-        const float p0i = p0 * inv;
-        __nv_bfloat16* orow = out + static_cast<size_t>(token) * d + head * HD + h * 32;
-        const float* v0 = v0f + h * 32;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 va4 = *reinterpret_cast<const float4*>(v0 + 8 * j);
-          const float4 vb4 = *reinterpret_cast<const float4*>(v0 + 8 * j + 4);
-          uint4 o4;
-          float t[8], o[8];
-          fmul2(t[0], t[1], va4.x, va4.y, p0i, p0i);
-          fmul2(t[2], t[3], va4.z, va4.w, p0i, p0i);
-          fmul2(t[4], t[5], vb4.x, vb4.y, p0i, p0i);
-          fmul2(t[6], t[7], vb4.z, vb4.w, p0i, p0i);
-#pragma unroll
-          for (int e = 0; e < 8; e += 2)
-            ffma2(o[e], o[e + 1], __uint_as_float(v[8 * j + e]), __uint_as_float(v[8 * j + e + 1]), inv, inv, t[e], t[e + 1]);
-          o4.x = pack2(o[0], o[1]);
-          o4.y = pack2(o[2], o[3]);
-          o4.z = pack2(o[4], o[5]);
-          o4.w = pack2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(orow + 8 * j) = o4;
-        }
-      }
-
-      // the group's scratch (vec, mx, p0s, p_cls, part, red) is rewritten next iteration: everyone must be done with it
-      if constexpr (kPairBar) publish((k + 1) & 1);  // next head's q0 / k0 / v0 (prefetched at the top of this iteration)
-      A4_TRACE(10);
-      named_bar_sync(1 + w, 256);
-      A4_TRACE(11);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-constexpr int kA4DefaultVar = 0;
-
-static int attention_umma4_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
-  constexpr int HD = 64;
-  const int d = heads * HD;
-  CUtensorMap tm;
-  B2C_TRY(make_tmap_2d(&tm, qkv, static_cast<uint64_t>(n) * T, 3ull * d, 3ull * d * 2, 256, 1));
-  constexpr int smem_bytes = a4_smem_bytes();
-  static_assert(smem_bytes <= 227 * 1024, "attention v4 shared memory exceeds 227 KB");
-  static const int var = [] { const char* e = getenv("B2C_ATTN_VAR"); return e ? atoi(e) : kA4DefaultVar; }();
-  using Kern = void (*)(const CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float);
-  Kern kern = nullptr;
-  switch (var) {
-    case 0: kern = attention_umma4_kernel<0>; break;
-    case 1: kern = attention_umma4_kernel<1>; break;
-    case 3: kern = attention_umma4_kernel<3>; break;
-    case 5: kern = attention_umma4_kernel<5>; break;
-    case 7: kern = attention_umma4_kernel<7>; break;
-    case 11: kern = attention_umma4_kernel<11>; break;
-    case 15: kern = attention_umma4_kernel<15>; break;
-    case 16: kern = attention_umma4_kernel<16>; break;
-    case 17: kern = attention_umma4_kernel<17>; break;
-    case 19: kern = attention_umma4_kernel<19>; break;
-    default: return set_error(B2C_ERR_ARG, "attention: B2C_ATTN_VAR=%d is not built", var);
-  }
-  B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  const int sms = num_sms();
-  B2C_REQUIRE(sms > 0, "no CUDA device");
-  const int n_ch = n * heads;
-  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
-  kern<<<n_ch < sms ? n_ch : sms, kA4Threads, smem_bytes, stream>>>(
-      tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, scale_log2);
-  B2C_POST_LAUNCH("attention_umma4_kernel");
-  return 0;
-}
 
 // ================================================================================================
-// (1e) tcgen05 attention v5 for T = 257, head dim 64: v4 with the class token moved off the softmax warps.
-//   A phase trace of v4 (clock64 at phase boundaries, profiles/r2_attn_trace.txt) showed where its 10-12 k cycles per
-//   (crop, head) go: the group that owns the class-token QUERY row spends 3-5 k cycles on it (dot products, two 256-thread
-//   barriers, P_cls·V, reduction) between its P and its epilogue, which delays tmem_free and with it the next S of that
-//   query tile; the class-token KEY term costs the other column half another 0.2-0.7 k, and every phase boundary is a
-//   256-thread barrier that waits for the slowest of eight warps.  v5:
-//     warp 0       TMA producer            warp 1   MMA issuer (optionally staggered: S0(k) PV1(k-1) S1(k) PV0(k))
-//     warps 2-17   softmax only: max pass -> 64-thread exchange with the other column half -> exp2 pass -> P -> epilogue.
-//                  No group barrier, no class-token arithmetic: p0 = exp2((s0 - m)·c) with s0 read from shared memory.
+// (1e) tcgen05 attention for T = 257, head dim 64 (ViT-L/14-224): persistent, one CTA per SM, 22 warps.
+//     warp 0       TMA producer: Q (two 128-row tiles), K, V of the NEXT head into the other of two 96 KB stages
+//     warp 1       MMA issuer: S_g = Q_g·Kᵀ (M128 N256 K64, SS), O_g = P_g·V (P from TMEM, V MN-major from the TMA tile),
+//                  L_g = P_g·1.  Issue order S0(k) PV1(k-1) S1(k) PV0(k): the two query tiles run half a period apart, so
+//                  one tile's exp2 pass (XU pipe) overlaps the other's tensor-core / epilogue / max phases instead of its
+//                  exp2 pass.  The tile index is a compile-time constant in every operand (a run-time index sends each
+//                  operand through R2UR).
+//     warps 2-17   softmax: group g = (warp-2)/8 (query tile), column half h = ((warp-2)/4)&1 (keys [128h, 128h+128)),
+//                  TMEM lane quarter = warp & 3.  max pass -> 64-thread exchange with the other column half -> exp2 pass
+//                  -> P (packed bf16 over the consumed S columns) -> epilogue.  No group barrier and no class-token
+//                  arithmetic: p0 = exp2((s0 - m)·c) with s0 read from shared memory.
 //     warps 18-21  class-token warps, one per SM sub-partition, running one head AHEAD of the softmax warps (they need
 //                  only the operand tiles, which the producer prefetches a head ahead): s0[r] = q_r·k0 for the 256
 //                  query rows, the class QUERY row's scores, softmax and P_cls·V, and its output row.
+//   TMEM region g (256 columns): S [0,256) -> P_0 [0,64) | O [64,128) | P_1 [128,192) | L [192,208).
 //   Operand stage s is released (empty_qk) by the MMA commit, the 4 class warps and the 16 softmax warps (end of their
 //   iteration: they read s0 / v0 of the stage until the epilogue).
+//   Why this shape (phase traces with clock64 at phase boundaries, profiles/r2_attn_trace_v4_v5.txt): in the predecessor
+//   (16 softmax warps that also did the class token, both S issued back to back) the group that owned the class-token
+//   QUERY row spent 3-5 k cycles on it between its P and its epilogue — its LDS / SHFL traffic queues behind the other
+//   group's MUFU.EX2 in the same MIO queue — which delayed tmem_free and the next S of that tile; every phase boundary was
+//   a 256-thread barrier; and both groups ran their exp2 passes at the same time (4 k cycles XU-bound) with the
+//   tensor-core / epilogue phases exposed.  12.7 k -> 8.1 k cycles per (crop, head); energy per launch -14 %.
 // ================================================================================================
 constexpr int kA5Threads = 64 + 512 + 128;
 constexpr int kA5ClsWarp0 = 18;
@@ -2386,16 +1692,10 @@ static int attention_umma5_launch(const void* qkv, void* out, int n, int T, int 
   using Kern = void (*)(const CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float);
   Kern kern = nullptr;
   switch (var) {
-    case 0: kern = attention_umma5_kernel<0>; break;
-    case 1: kern = attention_umma5_kernel<1>; break;
-    case 4: kern = attention_umma5_kernel<4>; break;
-    case 5: kern = attention_umma5_kernel<5>; break;
-    case 8: kern = attention_umma5_kernel<8>; break;
-    case 9: kern = attention_umma5_kernel<9>; break;
-    case 12: kern = attention_umma5_kernel<12>; break;
-    case 13: kern = attention_umma5_kernel<13>; break;
-    case 16: kern = attention_umma5_kernel<16>; break;
-    case 17: kern = attention_umma5_kernel<17>; break;
+    case 0: kern = attention_umma5_kernel<0>; break;    // both tiles' S issued back to back (v4's order)
+    case 1: kern = attention_umma5_kernel<1>; break;    // default
+    case 5: kern = attention_umma5_kernel<5>; break;    // + every 4th pair's exp2 on the FMA pipe
+    case 17: kern = attention_umma5_kernel<17>; break;  // default + phase trace
     default: return set_error(B2C_ERR_ARG, "attention v5: variant %d is not built", var);
   }
   B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -2409,7 +1709,7 @@ static int attention_umma5_launch(const void* qkv, void* out, int n, int T, int 
   return 0;
 }
 
-static int g_attn5_var_override = -2;  // development (b2c_debug_set_attn5): -2 = follow B2C_ATTN5_VAR (default v5 variant 1), -1 = v4, >= 0 = v5 variant
+static int g_attn5_var_override = -1;  // development (b2c_debug_set_attn5): < 0 = follow B2C_ATTN5_VAR (default kA5DefaultVar), >= 0 = that variant
 
 template <int HD>
 static int attention_launch_hd(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
@@ -2439,18 +1739,16 @@ int attention_cls_launch(const void* qkv, void* out, int n, int T, int heads, in
 
 int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd, cudaStream_t stream) {
   B2C_REQUIRE(n > 0 && T > 0 && heads > 0, "attention: empty problem");
-  // B2C_ATTN = v4 (default for hd 64: v2 with 16 softmax warps) | v2 (persistent, P in TMEM) | v1 (one CTA per query
-  // tile, P in smem) | legacy (mma.sync)
-  static const char mode = [] { const char* e = getenv("B2C_ATTN"); return e ? (e[0] == 'l' ? 'l' : (e[1] == '1' ? '1' : (e[1] == '2' ? '2' : '4'))) : '4'; }();
+  // B2C_ATTN=legacy forces the mma.sync kernel (A/B reference); B2C_ATTN5_VAR / b2c_debug_set_attn5 pick a v5 variant
+  static const bool legacy = [] { const char* e = getenv("B2C_ATTN"); return e && e[0] == 'l'; }();
   static const int v5env = [] { const char* e = getenv("B2C_ATTN5_VAR"); return e ? atoi(e) : kA5DefaultVar; }();
-  const int v5var = g_attn5_var_override >= -1 ? g_attn5_var_override : v5env;
-  if (hd == 64 && T == kAuKeys + 1 && v5var >= 0) return attention_umma5_launch(qkv, out, n, T, heads, v5var, stream);
-  if (hd == 64 && T == kAuKeys + 1 && mode == '4') return attention_umma4_launch(qkv, out, n, T, heads, stream);
-  if (hd == 64 && T == kAuKeys + 1 && mode == '2') return attention_umma2_launch<64>(qkv, out, n, T, heads, stream);
-  if (hd == 80 && T == kAuKeys + 1 && (mode == '2' || mode == '4')) return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
-  if (hd == 64 && T == kAuKeys + 1 && mode == '1') return attention_umma_launch(qkv, out, n, T, heads, stream);
-  if (hd == 64 && mode != 'l' && T > kAuKeys + 1 && (T - 1) % kA3KB == 0 && (T - 1) / kA3KB <= kA3MaxNB)
-    return attention_umma3_launch(qkv, out, n, T, heads, stream);
+  const int v5var = g_attn5_var_override >= 0 ? g_attn5_var_override : v5env;
+  if (!legacy) {
+    if (hd == 64 && T == kAuKeys + 1) return attention_umma5_launch(qkv, out, n, T, heads, v5var, stream);
+    if (hd == 80 && T == kAuKeys + 1) return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
+    if (hd == 64 && T > kAuKeys + 1 && (T - 1) % kA3KB == 0 && (T - 1) / kA3KB <= kA3MaxNB)
+      return attention_umma3_launch(qkv, out, n, T, heads, stream);
+  }
   if (hd == 64) return attention_launch_hd<64>(qkv, out, n, T, heads, stream);
   if (hd == 80) return attention_launch_hd<80>(qkv, out, n, T, heads, stream);
   return set_error(B2C_ERR_ARG, "attention: head dim %d unsupported (64 or 80)", hd);
@@ -2458,13 +1756,7 @@ int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd
 
 }  // namespace b2c
 
-// development only (not part of include/b2c.h): copy out the phase trace of attention_umma4_kernel<kVar | 16>
-extern "C" int b2c_debug_attn_trace(void* out, size_t bytes) {
-  using namespace b2c;
-  B2C_REQUIRE(out && bytes == sizeof(g_attn_trace), "b2c_debug_attn_trace: need %zu bytes", sizeof(g_attn_trace));
-  B2C_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_attn_trace, bytes));
-  return 0;
-}
+// development only (not part of include/b2c.h): phase trace of attention_umma5_kernel<kVar | 16> (tools/attn_trace.py)
 extern "C" int b2c_debug_attn_trace_start(int k0) {
   using namespace b2c;
   B2C_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace_k0, &k0, sizeof(int)));

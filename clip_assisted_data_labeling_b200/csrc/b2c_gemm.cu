@@ -200,12 +200,6 @@ struct GemmPolicy {
   }
 };
 
-// B2C_GEMM=1cta forces the single-CTA kernel everywhere (A/B testing); default: CTA pairs for the TMA-store epilogues
-static bool use_cta_pairs() {
-  static const bool v = [] { const char* e = getenv("B2C_GEMM"); return !(e && e[0] == '1'); }();
-  return v;
-}
-
 template <int MODE>
 static int gemm_launch_pair(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
   auto kern = umma2_tile_kernel<GemmPolicy<MODE>>;
@@ -222,30 +216,11 @@ static int gemm_launch_pair(const GemmLaunch& g, const GemmParams& p, cudaStream
   return 0;
 }
 
-template <int MODE>
-static int gemm_launch_classic(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream);
-
-template <int MODE>
-static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
-  if constexpr (MODE >= kGemmLnBiasBf16) {
-    // the LayerNorm-fused epilogues exist in the CTA-pair kernel only
-    B2C_REQUIRE(p.stats && p.shift && p.nblk > 0 && p.nblk <= 8, "gemm: LayerNorm-fused mode %d needs the row statistics / shift buffers", MODE);
-    if constexpr (GemmPolicy<MODE>::kStore == kStoreRmwLn)
-      B2C_REQUIRE(p.stats_in && p.stats_in != p.stats, "gemm: mode %d needs the previous update's statistics in a separate buffer", MODE);
-    if constexpr (GemmPolicy<MODE>::kLnFold) B2C_REQUIRE(p.colsum && p.bias, "gemm: mode %d needs colsum and the folded bias", MODE);
-    return gemm_launch_pair<MODE>(g, p, stream);
-  } else {
-    return gemm_launch_classic<MODE>(g, p, stream);
-  }
-}
-
-template <int MODE>
-static int gemm_launch_classic(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
-  if constexpr (MODE != kGemmPatchEmbedF32) {
-    if (use_cta_pairs()) return gemm_launch_pair<MODE>(g, p, stream);
-  }
-  auto kern = umma_tile_kernel<GemmPolicy<MODE>>;
-  static PerDeviceFlag attr_once;  // per template instantiation
+// patch-embed (scattered per-thread stores past each crop's class token) runs on the single-CTA kernel; every other mode
+// on CTA pairs
+static int gemm_launch_patch_embed(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
+  auto kern = umma_tile_kernel<GemmPolicy<kGemmPatchEmbedF32>>;
+  static PerDeviceFlag attr_once;
   if (attr_once.first_use()) {
     B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
   }
@@ -253,11 +228,20 @@ static int gemm_launch_classic(const GemmLaunch& g, const GemmParams& p, cudaStr
   B2C_REQUIRE(sms > 0, "no CUDA device");
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   kern<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(g.tmap_a, g.tmap_b, g.tmap_out, p, make_idesc_f16(kBM, kBN, 1));
-  B2C_POST_LAUNCH("umma_tile_kernel<gemm>");
+  B2C_POST_LAUNCH("umma_tile_kernel<patch-embed>");
   return 0;
 }
 
-bool gemm_uses_cta_pairs() { return use_cta_pairs(); }
+template <int MODE>
+static int gemm_launch_mode(const GemmLaunch& g, const GemmParams& p, cudaStream_t stream) {
+  if constexpr (MODE >= kGemmLnBiasBf16) {
+    B2C_REQUIRE(p.stats && p.shift && p.nblk > 0 && p.nblk <= 8, "gemm: LayerNorm-fused mode %d needs the row statistics / shift buffers", MODE);
+    if constexpr (GemmPolicy<MODE>::kStore == kStoreRmwLn)
+      B2C_REQUIRE(p.stats_in && p.stats_in != p.stats, "gemm: mode %d needs the previous update's statistics in a separate buffer", MODE);
+    if constexpr (GemmPolicy<MODE>::kLnFold) B2C_REQUIRE(p.colsum && p.bias, "gemm: mode %d needs colsum and the folded bias", MODE);
+  }
+  return gemm_launch_pair<MODE>(g, p, stream);
+}
 
 int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, int mode) {
   if (mode == kGemmResidLnBf16Copy)  // the bf16 copy of the residual stream: 32 x 32 half slabs, 64-B swizzle
@@ -266,11 +250,9 @@ int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, i
   if (mode == kGemmBiasResidF32 || mode == kGemmResidLnF32)
     return make_tmap_2d_ex(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 4, 32, 32,
                            B2C_F32);
-  if (use_cta_pairs())  // the CTA-pair kernel stores bf16 tiles per 32-column chunk: 32 x 32 half slabs, 64-B swizzle
-    return make_tmap_2d_sw(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 32,
-                           B2C_BF16, 64);
-  return make_tmap_2d_ex(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 64,
-                         B2C_BF16);
+  // bf16 tiles are stored per 32-column chunk: 32 x 32 half slabs, 64-B swizzle
+  return make_tmap_2d_sw(out, base, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo) * 2, 32, 32,
+                         B2C_BF16, 64);
 }
 
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
@@ -305,7 +287,7 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
     case kGemmBiasResidF32: return gemm_launch_mode<kGemmBiasResidF32>(g, p, stream);
     case kGemmPatchEmbedF32:
       B2C_REQUIRE(g.pos && g.T > 0 && g.G2 > 0, "gemm: patch-embed mode needs pos/T/G2");
-      return gemm_launch_mode<kGemmPatchEmbedF32>(g, p, stream);
+      return gemm_launch_patch_embed(g, p, stream);
     case kGemmLnBiasBf16: return gemm_launch_mode<kGemmLnBiasBf16>(g, p, stream);
     case kGemmLnBiasQGeluBf16: return gemm_launch_mode<kGemmLnBiasQGeluBf16>(g, p, stream);
     case kGemmLnBiasGeluBf16: return gemm_launch_mode<kGemmLnBiasGeluBf16>(g, p, stream);

@@ -53,7 +53,7 @@ enum GemmMode {
 
 struct GemmLaunch {
   CUtensorMap tmap_a;  // [M, K] bf16, box 128 x 64
-  CUtensorMap tmap_b;  // [N, K] bf16, box 256 x 64
+  CUtensorMap tmap_b;  // [N, K] bf16, box 256 x 64 (patch-embed only: the single-CTA kernel loads the whole tile's N)
   CUtensorMap tmap_b_half;  // same tensor, box 128 x 64: each CTA of a pair loads half of the tile's N
   CUtensorMap tmap_out;  // epilogue store map over `out`: bf16 modes box 32 rows x 64 cols, f32 residual mode
                          // box 32 rows x 32 cols (make_out_tmap); unused by the patch-embed mode
@@ -77,8 +77,6 @@ struct GemmLaunch {
   const float* colsum;    // kGemmLn*: [N]
 };
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
-// false only under B2C_GEMM=1cta (A/B switch: single-CTA kernel everywhere; the LayerNorm-fused modes need CTA pairs)
-bool gemm_uses_cta_pairs();
 // store map for a GEMM output [M, N] (row stride ldo elements) matching `mode`
 int make_out_tmap(CUtensorMap* out, void* base, int64_t M, int N, int64_t ldo, int mode);
 

@@ -22,8 +22,7 @@ struct b2c_vit_layer {
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
   __nv_bfloat16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
   float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
-  CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;          // box 256 rows (single-CTA kernel)
-  CUtensorMap tm_qkv_h, tm_out_h, tm_fc_h, tm_proj_h;  // box 128 rows (CTA-pair kernel)
+  CUtensorMap tm_qkv_h, tm_out_h, tm_fc_h, tm_proj_h;  // box 128 rows: each CTA of a pair loads half of the tile's N
   // LayerNorm folded into in_proj / c_fc (ln_fold_kernel): gamma-scaled weights, their column sums, beta·Wᵀ + b
   __nv_bfloat16 *wf_qkv = nullptr, *wf_fc = nullptr;
   float *cs_qkv = nullptr, *bf_qkv = nullptr, *cs_fc = nullptr, *bf_fc = nullptr;
@@ -281,23 +280,23 @@ int forward_chunk_fused(b2c_vit* v, const void* patches, int nc, float* out, uin
         ProfScope ps(B2C_PROF_ATTENTION, stream);
         B2C_TRY(attention_cls_launch(big, h, nc, v->T, c.heads, v->hd, stream));
       }
-      B2C_TRY(row_gemm(B2C_PROF_OUT_PROJ, tm_hc, L.tm_out, L.tm_out_h, st_xc, d, d, kGemmBiasResidF32, L.b_out, x, ldr));
+      B2C_TRY(row_gemm(B2C_PROF_OUT_PROJ, tm_hc, L.tm_out_h, L.tm_out_h, st_xc, d, d, kGemmBiasResidF32, L.b_out, x, ldr));
       {
         ProfScope ps(B2C_PROF_LAYERNORM, stream);
         B2C_TRY(layernorm_bf16_strided_launch(x, ldr, L.ln2_w, L.ln2_b, xb, nc, d, eps, stream));
       }
-      B2C_TRY(row_gemm(B2C_PROF_C_FC, tm_xbc, L.tm_fc, L.tm_fc_h, st_bigc, c.mlp, d,
+      B2C_TRY(row_gemm(B2C_PROF_C_FC, tm_xbc, L.tm_fc_h, L.tm_fc_h, st_bigc, c.mlp, d,
                        c.act == B2C_ACT_GELU ? kGemmBiasGeluBf16 : kGemmBiasQGeluBf16, L.b_fc, big, c.mlp));
-      B2C_TRY(row_gemm(B2C_PROF_C_PROJ, tm_bigc, L.tm_proj, L.tm_proj_h, st_xc, d, c.mlp, kGemmBiasResidF32, L.b_proj, x, ldr));
+      B2C_TRY(row_gemm(B2C_PROF_C_PROJ, tm_bigc, L.tm_proj_h, L.tm_proj_h, st_xc, d, c.mlp, kGemmBiasResidF32, L.b_proj, x, ldr));
       break;
     }
     {
       ProfScope ps(B2C_PROF_ATTENTION, stream);
       B2C_TRY(attention_launch(big, h, nc, v->T, c.heads, v->hd, stream));
     }
-    B2C_TRY(resid_gemm(B2C_PROF_OUT_PROJ, tm_h, L.tm_out, L.tm_out_h, d, L.b_out, false, stats_a, stats_b));
+    B2C_TRY(resid_gemm(B2C_PROF_OUT_PROJ, tm_h, L.tm_out_h, L.tm_out_h, d, L.b_out, false, stats_a, stats_b));
     B2C_TRY(ln_gemm(B2C_PROF_C_FC, L.tm_fcf_h, st_mlp, c.mlp, fc_mode, L.bf_fc, L.cs_fc, c.mlp, stats_b));
-    B2C_TRY(resid_gemm(B2C_PROF_C_PROJ, tm_mlp, L.tm_proj, L.tm_proj_h, c.mlp, L.b_proj, li + 1 == c.layers, stats_b, stats_a));
+    B2C_TRY(resid_gemm(B2C_PROF_C_PROJ, tm_mlp, L.tm_proj_h, L.tm_proj_h, c.mlp, L.b_proj, li + 1 == c.layers, stats_b, stats_a));
   }
   ProfScope ps(B2C_PROF_HEAD, stream);
   return head_launch(x, v->ln_post_w, v->ln_post_b, v->proj, out, reinterpret_cast<float*>(ws + w.head), nc, v->T, d, c.embed,
@@ -360,7 +359,7 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     {
       ProfScope ps(B2C_PROF_IN_PROJ, stream);
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv; gl.tmap_b_half = L.tm_qkv_h; gl.tmap_out = st_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_qkv_h; gl.tmap_b_half = L.tm_qkv_h; gl.tmap_out = st_qkv; gl.M = M; gl.N = 3 * d; gl.K = d;
       gl.mode = kGemmBiasBf16; gl.bias = L.b_qkv; gl.out = big; gl.ldo = 3 * d;
       B2C_TRY(gemm_launch(gl, stream));
     }
@@ -371,7 +370,7 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     {
       ProfScope ps(B2C_PROF_OUT_PROJ, stream);
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_out; gl.tmap_b_half = L.tm_out_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_out_h; gl.tmap_b_half = L.tm_out_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = d;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_out; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }
@@ -383,7 +382,7 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     {
       ProfScope ps(B2C_PROF_C_FC, stream);
       GemmLaunch gl{};
-      gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc; gl.tmap_b_half = L.tm_fc_h; gl.tmap_out = st_mlp; gl.M = M; gl.N = c.mlp; gl.K = d;
+      gl.tmap_a = tm_h; gl.tmap_b = L.tm_fc_h; gl.tmap_b_half = L.tm_fc_h; gl.tmap_out = st_mlp; gl.M = M; gl.N = c.mlp; gl.K = d;
       gl.mode = c.act == B2C_ACT_GELU ? kGemmBiasGeluBf16 : kGemmBiasQGeluBf16;
       gl.bias = L.b_fc; gl.out = big; gl.ldo = c.mlp;
       B2C_TRY(gemm_launch(gl, stream));
@@ -391,7 +390,7 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
     {
       ProfScope ps(B2C_PROF_C_PROJ, stream);
       GemmLaunch gl{};
-      gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj; gl.tmap_b_half = L.tm_proj_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = c.mlp;
+      gl.tmap_a = tm_mlp; gl.tmap_b = L.tm_proj_h; gl.tmap_b_half = L.tm_proj_h; gl.tmap_out = st_x; gl.M = M; gl.N = d; gl.K = c.mlp;
       gl.mode = kGemmBiasResidF32; gl.bias = L.b_proj; gl.out = x; gl.ldo = d;
       B2C_TRY(gemm_launch(gl, stream));
     }
@@ -406,7 +405,7 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
   B2C_REQUIRE(v && out && ws, "vit_forward: null pointer");
   B2C_REQUIRE(n > 0, "vit_forward: n_crops must be positive");
   B2C_TRY(b2c_vit_ready(v));
-  const bool fused = v->fused_ln && gemm_uses_cta_pairs();
+  const bool fused = v->fused_ln;
   if (fused) B2C_TRY(ensure_folded(v, stream));
   const int nc_max = n < v->chunk ? n : v->chunk;
   size_t lane_bytes = 0;
@@ -563,20 +562,16 @@ extern "C" int b2c_vit_set_weight(b2c_vit* v, const char* key, const void* dev_p
     else if (s == "attn.in_proj_weight") {
       rc = store_bf16(v, &L.w_qkv, dev_ptr, dtype, 3 * d, d, d, count, key);
       if (rc == 0) rc = stage_f32(&L.src_qkv, dev_ptr, dtype, count);
-      if (rc == 0) rc = make_tmap_2d(&L.tm_qkv, L.w_qkv, 3 * d, d, d * 2, kBN, 1);
       if (rc == 0) rc = make_tmap_2d(&L.tm_qkv_h, L.w_qkv, 3 * d, d, d * 2, kBM, 1);
     } else if (s == "attn.out_proj.weight") {
       rc = store_bf16(v, &L.w_out, dev_ptr, dtype, d, d, d, count, key);
-      if (rc == 0) rc = make_tmap_2d(&L.tm_out, L.w_out, d, d, d * 2, kBN, 1);
       if (rc == 0) rc = make_tmap_2d(&L.tm_out_h, L.w_out, d, d, d * 2, kBM, 1);
     } else if (s == "mlp.c_fc.weight") {
       rc = store_bf16(v, &L.w_fc, dev_ptr, dtype, c.mlp, d, d, count, key);
       if (rc == 0) rc = stage_f32(&L.src_fc, dev_ptr, dtype, count);
-      if (rc == 0) rc = make_tmap_2d(&L.tm_fc, L.w_fc, c.mlp, d, d * 2, kBN, 1);
       if (rc == 0) rc = make_tmap_2d(&L.tm_fc_h, L.w_fc, c.mlp, d, d * 2, kBM, 1);
     } else if (s == "mlp.c_proj.weight") {
       rc = store_bf16(v, &L.w_proj, dev_ptr, dtype, d, c.mlp, c.mlp, count, key);
-      if (rc == 0) rc = make_tmap_2d(&L.tm_proj, L.w_proj, d, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBN, 1);
       if (rc == 0) rc = make_tmap_2d(&L.tm_proj_h, L.w_proj, d, c.mlp, static_cast<uint64_t>(c.mlp) * 2, kBM, 1);
     } else {
       return set_error(B2C_ERR_ARG, "b2c_vit_set_weight: unknown key %s", key);

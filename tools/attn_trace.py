@@ -1,4 +1,5 @@
-"""Development: phase timeline of attention_umma4_kernel (B2C_ATTN_VAR with bit 4 set) on SM 0, iterations 4..11."""
+"""Development: phase timeline of attention_umma5_kernel (B2C_ATTN5_VAR=17: the default variant + trace) on one SM, eight
+iterations from K0 (env), plus per-CTA durations in cycles and nanoseconds.  REPS launches first (clocks under load)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,11 +13,12 @@ o = torch.zeros(n * T, heads * hd, device="cuda", dtype=torch.bfloat16)
 for _ in range(int(os.environ.get('REPS', 3))):
     assert L.b2c_attention_bf16(C.c_void_p(qkv.data_ptr()), C.c_void_p(o.data_ptr()), n, T, heads, hd, C.c_void_p(0)) == 0
 torch.cuda.synchronize()
-v5 = "B2C_ATTN5_VAR" in os.environ
-tr = np.zeros((22 if v5 else 18, 8, 16), np.int64)
-assert (L.b2c_debug_attn5_trace if v5 else L.b2c_debug_attn_trace)(C.c_void_p(tr.ctypes.data), C.c_size_t(tr.nbytes)) == 0
+v5 = True
+assert int(os.environ.get("B2C_ATTN5_VAR", "-1")) & 16, "run with B2C_ATTN5_VAR=17 (a trace build)"
+tr = np.zeros((22, 8, 16), np.int64)
+assert L.b2c_debug_attn5_trace(C.c_void_p(tr.ctypes.data), C.c_size_t(tr.nbytes)) == 0
 t0 = tr[tr > 0].min()
-print("var", os.environ.get("B2C_ATTN5_VAR") if v5 else os.environ.get("B2C_ATTN_VAR"), "v5" if v5 else "v4", "period (softmax warp 2, ev0):", np.diff(tr[2, :, 0]).tolist())
+print("var", os.environ.get("B2C_ATTN5_VAR"), "period (softmax warp 2, ev0):", np.diff(tr[2, :, 0]).tolist())
 names_mma = ["top", "qk_ready", "S0_issued", "pv1prev_issued", "S1_issued", "v_ready", "PV0_issued", "end"]
 names_sm = ["top", "S_ready", "max_done", "max_xchg", "P_done", "clskey", "clsrow", "bar7", "pre_O", "O_ready", "epi_done", "end"]
 for it in (2, 3):

@@ -1,14 +1,14 @@
 """Attention-only timing and accuracy (CUDA events; default 1024 crops of ViT-L/14: T=257, 16 heads x 64):
-    python tools/bench_attn.py [n] [T] [heads] [hd]            # one line for the current B2C_ATTN_VAR / B2C_ATTN
-    python tools/bench_attn.py --vars 0,1,3,7 [n] [T] ...      # one subprocess per kernel variant (the switch is read once)
+    python tools/bench_attn.py [n] [T] [heads] [hd]            # one line for the current B2C_ATTN5_VAR / B2C_ATTN
+    python tools/bench_attn.py --vars 0,1,5 [n] [T] ...        # one subprocess per variant of the T=257 / hd=64 kernel
 """
 import ctypes as C, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 if len(sys.argv) > 2 and sys.argv[1] == "--vars":
-    for v in sys.argv[2].split(","):  # "3" = v4 variant 3, "5:1" = v5 variant 1
-        env = dict(os.environ, B2C_ATTN5_VAR=v[2:]) if v.startswith("5:") else dict(os.environ, B2C_ATTN_VAR=v)
+    for v in sys.argv[2].split(","):
+        env = dict(os.environ, B2C_ATTN5_VAR=v)
         subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[3:], env=env, check=False)
     sys.exit(0)
 
@@ -63,5 +63,5 @@ ms = a.elapsed_time(b) / reps
 clk = [float(l.split(",")[0]) for l in lines[3:] if "," in l]
 pw = [float(l.split(",")[1]) for l in lines[3:] if "," in l]
 fl = 4.0 * T * T * heads * hd * n
-print(json.dumps({"mode": os.environ.get("B2C_ATTN", "default"), "var": ("v5:" + os.environ["B2C_ATTN5_VAR"]) if "B2C_ATTN5_VAR" in os.environ else "v4:" + os.environ.get("B2C_ATTN_VAR", "default"), "n": n, "T": T,
+print(json.dumps({"mode": os.environ.get("B2C_ATTN", "default"), "var": os.environ.get("B2C_ATTN5_VAR", "default"), "n": n, "T": T,
                   "heads": heads, "hd": hd, "ms": ms, "ms_cold": ms_cold, "sm_mhz": statistics.median(clk) if clk else None, "power_w": statistics.median(pw) if pw else None, "tflops": fl / ms / 1e9, "max_err_vs_sdpa": errs}), flush=True)

@@ -7,8 +7,8 @@
 //                                          class token on 4 dedicated warps (section 1e)
 //   T = 257, head dim 80  (ViT-H/14)      attention_umma2_kernel<80>  tcgen05, 8 softmax warps, head dim as a 64- plus a
 //                                          16-column slab (section 1b)
-//   T = 577, head dim 64  (ViT-L/14-336)  attention_umma3_kernel  tcgen05, K / V of the head resident in shared memory,
-//                                          key blocks of 96 visited twice (section 1c)
+//   T = 577, head dim 64  (ViT-L/14-336)  attention_umma6_kernel  tcgen05, K / V of the head resident in shared memory,
+//                                          key blocks of 96 visited twice, 16 softmax + 4 class-token warps (section 1c)
 //   anything else (ViT-B/32: T = 50)      attention_kernel<HD>  bf16 mma.sync, online softmax (section 2)
 //   class-token query row only            attention_cls_kernel  (b2c_vit_set_cls_only_last_block)
 // In every tcgen05 kernel the class-token KEY is a rank-1 term (s0 = q·k0 by FMA, p0·v0 added in the epilogue) so that
@@ -799,41 +799,86 @@ static int attention_umma2_launch(const void* qkv, void* out, int n, int T, int 
   return 0;
 }
 
-// ================================================================================================
-// (1c) tcgen05 attention v3 for longer sequences (ViT-L/14-336: T = 577 = class token + 576 patches), head dim 64,
-//      patch count a multiple of 96.  Two-pass exact softmax over key blocks of 96:
-//   CTA (one per SM, 320 threads) loops over (crop, head); K and V of the head stay resident in shared memory (2 x 72 KB
-//   for 576 patches), query tiles stream through a 2-stage ring, 256 rows (two 128-row tiles, one per softmax group) per
-//   stage.  Per query tile the key blocks are visited twice: pass A (S_b = Q·K_bᵀ, running row max only) and pass B (S_b
-//   again, p = exp2(s·c − m·c), P_b in bf16 written over S_b in TMEM, O += P_b·V_b on the tensor core, row sums in
-//   registers).  Recomputing S costs tensor time that is idle anyway (the kernel is bound by the exponentials) and keeps
-//   the softmax exact with no rescaling of O.  S is double-buffered per group — TMEM region w (256 columns): S/P buffer 0
-//   [0,96) | S/P buffer 1 [96,192) | O [192,256) — and S tiles are issued two tiles ahead, so the softmax threads never
-//   wait for the tensor core; PV_b and the next S into the same buffer rely on tcgen05.mma executing in issue order.
-//   The class-token KEY is the same rank-1 term as in v2; the class-token QUERY row goes to attention_cls_kernel.
-// ================================================================================================
-constexpr int kA3KB = 96;                       // keys per block
+constexpr int kA3KB = 96;                       // keys per block (T = 577: six blocks)
 constexpr int kA3BlockBytes = kA3KB * 128;      // one K or V block: 96 rows x 128 B
 constexpr int kA3QStage = 256 * 128;
 constexpr int kA3MaxNB = 6;
 
-struct A3Misc {
+// first traced iteration of the development phase trace (b2c_debug_attn_trace_start)
+__device__ int g_attn_trace_k0 = 4;
+
+// exp2 on the FMA pipe for part of a row's elements (the XU pipe, 16 ex2 per clock per SM, is what the exp2 pass
+// saturates): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5·2^23, 2^f by a degree-3 minimax
+// polynomial on [-0.5, 0.5] (relative error 7.6e-5, a fiftieth of the bf16 rounding P gets next), 2^n added into the
+// exponent field.  x is clamped to >= -126 so the exponent cannot wrap; x <= 0 always (the row maximum was subtracted).
+__device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float x1) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, kMagic, kMagic);
+  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
+  fadd2(f0, f1, x0, x1, -n0, -n1);
+  ffma2(p0, p1, f0, f1, 0.05520550534129143f, 0.05520550534129143f, 0.24261397123336792f, 0.24261397123336792f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.6932547688484192f, 0.6932547688484192f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.9999276995658875f, 0.9999276995658875f);
+  y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+
+// ================================================================================================
+// (1c) tcgen05 attention for longer sequences (ViT-L/14-336: T = 577 = class token + 576 patches), head dim 64,
+//      patch count a multiple of 96.  Two-pass exact softmax over key blocks of 96:
+//   CTA (one per SM, 22 warps) loops over (crop, head); K and V of the head stay resident in shared memory (2 x 72 KB
+//   for 576 patches), query tiles stream through a 2-stage ring, 256 rows (two 128-row tiles, one per softmax group) per
+//   stage.  Per query tile the key blocks are visited twice: pass A (S_b = Q·K_bᵀ, running row max only) and pass B (S_b
+//   again, p = exp2(s·c − m·c), P_b in bf16 written over S_b in TMEM, O += P_b·V_b on the tensor core, row sums in
+//   registers).  Recomputing S costs tensor time that is idle anyway and keeps the softmax exact with no rescaling of
+//   O.  S is double-buffered per group — TMEM region g (256 columns): S/P buffer 0 [0,96) | buffer 1 [96,192) | O
+//   [192,256) — and S tiles are issued two tiles ahead; PV_b and the next S into the same buffer rely on tcgen05.mma
+//   executing in issue order.
+//     warp 0       TMA producer            warp 1   MMA issuer
+//     warps 2-17   softmax: group (query tile) x column half (48 of a block's 96 keys) x TMEM lane quarter, so every
+//                  SM sub-partition hosts four softmax warps; the halves exchange their row maximum once per query tile
+//                  (after pass A) and their row sums once (after pass B) through 64-thread barriers.  Half h of a buffer
+//                  owns S columns [48h, 48h+48) and writes its packed P over them at [48h, 48h+24).
+//     warps 18-21  class-token warps: s0[r] = q_r·k0 for every query-tile pair (the class-token KEY, a rank-1 term as in
+//                  the other tcgen05 kernels), and the class-token QUERY row of the head from the resident K and V.
+//   Measured against its 8-softmax-warp predecessor (one thread per full row, class row as a second kernel re-reading
+//   K and V from global memory): 1.18 -> 0.93 ms per launch at 256 crops; ViT-L/14-336 step 604 -> 629 images/s.
+// ================================================================================================
+constexpr int kA6Threads = 64 + 512 + 128;
+constexpr int kA6ClsWarp0 = 18;
+
+struct A6Misc {
   uint64_t k_full, k_empty, v_full, v_empty, q_full[2], q_empty[2];
   uint64_t s_full[2][2], s_free[2][2], p_full[2][2], o_full[2], o_free[2];
+  uint64_t cls_done[2];
   uint32_t tmem_slot;
   uint32_t pad[3];
-  float k0[64], v0[64];
+  float vec[3][64];        // q0, k0 as packed bf16 (32 words each), v0 as fp32
+  float s0[2][256];        // per Q stage: q_r·k0 of the stage's 256 query rows
+  float mx[2][2][128];     // per group, column half: partial row maxima (pass A)
+  float ls[2][2][128];     // per group, column half: partial row sums (pass B)
+  float red[8];
+  float p_cls[592];        // class-row probabilities: patch keys, then the class key at [G2]
+  float part[16][64];
 };
 
-__global__ void __launch_bounds__(kA2Threads, 1)
-attention_umma3_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+constexpr int a6_smem_bytes(int NB) {
+  return 2 * NB * kA3BlockBytes + 2 * kA3QStage + static_cast<int>((sizeof(A6Misc) + 1023) / 1024 * 1024) + 1024;
+}
+
+__global__ void __launch_bounds__(kA6Threads, 1)
+attention_umma6_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                        const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_ch, int T, int heads,
                        int NB, float scale_log2) {
-  extern __shared__ uint8_t smem_a3_raw[];
-  uint8_t* smem = smem_a3_raw + ((1024u - (smem_u32(smem_a3_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST
+  extern __shared__ uint8_t smem_a6_raw[];
+  uint8_t* smem = smem_a6_raw + ((1024u - (smem_u32(smem_a6_raw) & 1023u)) & 1023u);  // keeps the address space: LDS/STS
   const int off_v = NB * kA3BlockBytes;
   const int off_q = 2 * NB * kA3BlockBytes;
-  A3Misc* mb = reinterpret_cast<A3Misc*>(smem + off_q + 2 * kA3QStage);
+  A6Misc* mb = reinterpret_cast<A6Misc*>(smem + off_q + 2 * kA3QStage);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * 64;
   const size_t row_stride = static_cast<size_t>(3) * d;
@@ -844,18 +889,19 @@ attention_umma3_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_c
     tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_q);
     mbar_init(&mb->k_full, 1);
-    mbar_init(&mb->k_empty, 1);
+    mbar_init(&mb->k_empty, 1 + 4);  // MMA commit + class warps (class-row scores read K)
     mbar_init(&mb->v_full, 1);
-    mbar_init(&mb->v_empty, 1);
+    mbar_init(&mb->v_empty, 1 + 4);  // MMA commit + class warps (P_cls·V reads V)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&mb->q_full[s], 1);
-      mbar_init(&mb->q_empty[s], 9);  // MMA commit + the eight softmax warps (own Q rows read)
+      mbar_init(&mb->q_empty[s], 1 + 4 + 16);  // MMA commit + class warps (Q rows read) + softmax warps (s0 of the stage read)
       mbar_init(&mb->o_full[s], 1);
-      mbar_init(&mb->o_free[s], 4);
+      mbar_init(&mb->o_free[s], 8);
+      mbar_init(&mb->cls_done[s], 4);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&mb->s_full[s][b], 1);
-        mbar_init(&mb->s_free[s][b], 4);
-        mbar_init(&mb->p_full[s][b], 4);
+        mbar_init(&mb->s_free[s][b], 8);
+        mbar_init(&mb->p_full[s][b], 8);
       }
     }
     mbar_fence_init();
@@ -925,9 +971,11 @@ attention_umma3_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_c
           const uint64_t v_desc0 = make_sw128_kmajor_desc(smem_base + off_v + b * kA3BlockBytes);
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < kA3KB / 16; ++kk)
-              umma_f16_ts(tmem + w * 256 + 192, tmem + w * 256 + buf * kA3KB + kk * 8, v_desc0 + kk * 128, idesc_o,
-                          (b | kk) != 0);
+            for (int kk = 0; kk < kA3KB / 16; ++kk) {
+              // half 0's packed P at buffer columns [0,24), half 1's at [48,72): three 16-key steps each
+              const uint32_t pcol = buf * kA3KB + (kk < 3 ? 0 : 48) + (kk % 3) * 8;
+              umma_f16_ts(tmem + w * 256 + 192, tmem + w * 256 + pcol, v_desc0 + kk * 128, idesc_o, (b | kk) != 0);
+            }
           }
           __syncwarp();
         };
@@ -971,142 +1019,315 @@ attention_umma3_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_c
       if (elect_one()) umma_commit(&mb->v_empty);
       __syncwarp();
     }
-  } else {
-    // ------------------------------------------------------------------ softmax groups
-    const int w = (warp - 2) >> 2;          // group = query tile of the pair
+  } else if (warp < kA6ClsWarp0) {
+    // ------------------------------------------------------------------ softmax: 2 groups x 2 column halves x 4 warps
+    const int sw = warp - 2;
+    const int w = sw >> 3;                  // group = query tile of the pair
+    const int h = (sw >> 2) & 1;            // column half: keys [48h, 48h + 48) of every block
     const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;      // query row in the tile = TMEM lane
-    const int t256 = threadIdx.x - 64;      // 0..255 over both groups
     const uint32_t taddr = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* k0f = mb->k0;
-    float* v0f = mb->v0;
-    uint32_t craw = 0;
-    auto prefetch = [&](int ch) {
-      if (t256 < 128) {
-        const int crop = ch / heads, head = ch - crop * heads;
-        const unsigned short* cls_row =
-            reinterpret_cast<const unsigned short*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * 64);
-        craw = __ldg(t256 < 64 ? cls_row + d + t256 : cls_row + 2 * d + (t256 - 64));  // k0 | v0
-      }
-    };
-    if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
+    const int pair_bar = 3 + w * 4 + quarter;
+    const float* v0f = mb->vec[2];
     int qk = 0;
     uint32_t n_sfull[2] = {0, 0}, n_ofull = 0;
     for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x) {
       const int crop = ch / heads, head = ch - crop * heads;
       const int tok0 = crop * T;
-      named_bar_sync(1, 256);  // everyone is done with the previous head's k0 / v0
-      if (t256 < 64) k0f[t256] = __uint_as_float(craw << 16);
-      else if (t256 < 128) v0f[t256 - 64] = __uint_as_float(craw << 16);
-      if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
-      named_bar_sync(1, 256);
       for (int pair = 0; pair < NQ; ++pair, ++qk) {
         const int s = qk & 1;
         const int qrow = pair * 256 + w * 128 + r;
         const bool active = pair * 256 + w * 128 < G2;  // group-uniform
-        mbar_wait(&mb->q_full[s], (qk >> 1) & 1);
-        float s0 = 0.f;
-        if (active) s0 = dot_row<64>(smem + off_q + s * kA3QStage, w * 128 + r, k0f);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mb->q_empty[s]);
-        if (!active) continue;
+        if (!active) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mb->q_empty[s]);
+          continue;
+        }
 
-        // ---- pass A: running row max over the key blocks
-        float m = s0;
+        // rows of the tile past the head's last patch (the last query tile of 576 patches holds 64 rows) carry no work:
+        // the warp keeps the barrier protocol going and skips the arithmetic (warp-uniform: a warp is 32 consecutive rows)
+        const bool rows_live = pair * 256 + w * 128 + quarter * 32 < G2;
+
+        // ---- pass A: running row max over this half's 48 keys of every block
+        float m = -INFINITY;
         for (int b = 0; b < NB; ++b) {
           const int buf = b & 1;
           mbar_wait(&mb->s_full[w][buf], n_sfull[buf] & 1);
           ++n_sfull[buf];
           tc_fence_after();
-          uint32_t va[32], vb[32];
-          const uint32_t ta = taddr + buf * kA3KB;
-          tmem_ld_32x32(ta, va);
-          tmem_ld_wait();
-          tmem_ld_32x32(ta + 32, vb);
+          if (rows_live) {
+            uint32_t va[32], vb[16];
+            const uint32_t ta = taddr + buf * kA3KB + 48 * h;
+            tmem_ld_32x32(ta, va);
+            tmem_ld_32x16(ta + 32, vb);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
-          tmem_ld_wait();
-          tmem_ld_32x32(ta + 64, va);
+            for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
+            for (int e = 0; e < 16; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&mb->s_free[w][buf]);
         }
+        // the class-token KEY joins the maximum here: s0 comes from the class warps
+        mbar_wait(&mb->cls_done[s], (qk >> 1) & 1);
+        const float s0 = mb->s0[s][w * 128 + r];
+        mb->mx[w][h][r] = m;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mb->q_empty[s]);  // s0 of the stage has been read by this warp
+        named_bar_sync(pair_bar, 64);
+        m = fmaxf(fmaxf(m, mb->mx[w][h ^ 1][r]), s0);
         const float ms = m * scale_log2;
-        const float p0 = ex2_ftz(fmaf(s0, scale_log2, -ms));
-        float lsum = p0;
+        const float nms = -ms;
+        const float p0 = ex2_ftz(fmaf(s0, scale_log2, nms));
+        float lsum = 0.f;
 
-        // ---- pass B: probabilities (bf16x2) over S in TMEM, row sum in registers
+        // ---- pass B: probabilities (bf16x2) over this half's S columns, partial row sum in registers
         for (int b = 0; b < NB; ++b) {
           const int buf = (NB + b) & 1;
           mbar_wait(&mb->s_full[w][buf], n_sfull[buf] & 1);
           ++n_sfull[buf];
           tc_fence_after();
-          uint32_t va[32], vb[32];
-          const uint32_t ta = taddr + buf * kA3KB;
-          auto emit_p = [&](const uint32_t (&v)[32], int c) {
-            uint32_t pk[16];
-            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float pa = ex2_ftz(fmaf(__uint_as_float(v[2 * e]), scale_log2, -ms));
-              const float pb = ex2_ftz(fmaf(__uint_as_float(v[2 * e + 1]), scale_log2, -ms));
-              acc0 += pa;
-              acc1 += pb;
-              pk[e] = pack2(pa, pb);
-            }
-            lsum += acc0 + acc1;
-            tmem_st_32x16(ta + c * 16, pk);  // columns [16c, 16c+16) of the buffer: already consumed
-          };
+          if (!rows_live) {  // nothing reads these rows of O
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mb->p_full[w][buf]);
+            continue;
+          }
+          uint32_t va[32], vb[16];
+          const uint32_t ta = taddr + buf * kA3KB + 48 * h;
           tmem_ld_32x32(ta, va);
+          tmem_ld_32x16(ta + 32, vb);
           tmem_ld_wait();
-          tmem_ld_32x32(ta + 32, vb);
-          emit_p(va, 0);
-          tmem_ld_wait();
-          tmem_ld_32x32(ta + 64, va);
-          emit_p(vb, 1);
-          tmem_ld_wait();
-          emit_p(va, 2);
+          uint32_t pk[16], pk2[8];
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float t0, t1;
+            ffma2(t0, t1, __uint_as_float(va[2 * e]), __uint_as_float(va[2 * e + 1]), scale_log2, scale_log2, nms, nms);
+            const float pa = ex2_ftz(t0), pb = ex2_ftz(t1);
+            acc0 += pa;
+            acc1 += pb;
+            pk[e] = pack2(pa, pb);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t0, t1;
+            ffma2(t0, t1, __uint_as_float(vb[2 * e]), __uint_as_float(vb[2 * e + 1]), scale_log2, scale_log2, nms, nms);
+            const float pa = ex2_ftz(t0), pb = ex2_ftz(t1);
+            acc0 += pa;
+            acc1 += pb;
+            pk2[e] = pack2(pa, pb);
+          }
+          lsum += acc0 + acc1;
+          tmem_st_32x16(ta, pk);        // packed columns [48h, 48h + 16): over S columns this thread has consumed
+          tmem_st_32x8(ta + 16, pk2);   // ... [48h + 16, 48h + 24)
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&mb->p_full[w][buf]);
         }
+        mb->ls[w][h][r] = lsum;
+        named_bar_sync(pair_bar, 64);
+        lsum += mb->ls[w][h ^ 1][r] + p0;
 
-        // ---- (O + p0·v0) / (L + p0) -> bf16   (lsum already includes p0)
+        // ---- own row, own 32 output columns: (O + p0·v0) / (L + p0) -> bf16
         mbar_wait(&mb->o_full[w], n_ofull & 1);
         ++n_ofull;
         tc_fence_after();
-        const float inv = 1.0f / lsum;
-        const float p0i = p0 * inv;
-        __nv_bfloat16* orow = out + (static_cast<size_t>(tok0) + 1 + qrow) * d + head * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
           uint32_t v[32];
-          tmem_ld_32x32(taddr + 192 + c * 32, v);
+          tmem_ld_32x32(taddr + 192 + h * 32, v);
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mb->o_free[w]);
+          const float inv = 1.0f / lsum;
+          const float p0i = p0 * inv;
           if (qrow < G2) {
+            __nv_bfloat16* orow = out + (static_cast<size_t>(tok0) + 1 + qrow) * d + head * 64 + h * 32;
+            const float* v0 = v0f + h * 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 va4 = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j);
-              const float4 vb4 = *reinterpret_cast<const float4*>(v0f + c * 32 + 8 * j + 4);
+              const float4 va4 = *reinterpret_cast<const float4*>(v0 + 8 * j);
+              const float4 vb4 = *reinterpret_cast<const float4*>(v0 + 8 * j + 4);
               uint4 o4;
               o4.x = pack2(fmaf(__uint_as_float(v[8 * j + 0]), inv, p0i * va4.x), fmaf(__uint_as_float(v[8 * j + 1]), inv, p0i * va4.y));
               o4.y = pack2(fmaf(__uint_as_float(v[8 * j + 2]), inv, p0i * va4.z), fmaf(__uint_as_float(v[8 * j + 3]), inv, p0i * va4.w));
               o4.z = pack2(fmaf(__uint_as_float(v[8 * j + 4]), inv, p0i * vb4.x), fmaf(__uint_as_float(v[8 * j + 5]), inv, p0i * vb4.y));
               o4.w = pack2(fmaf(__uint_as_float(v[8 * j + 6]), inv, p0i * vb4.z), fmaf(__uint_as_float(v[8 * j + 7]), inv, p0i * vb4.w));
-              *reinterpret_cast<uint4*>(orow + c * 32 + 8 * j) = o4;
+              *reinterpret_cast<uint4*>(orow + 8 * j) = o4;
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mb->o_free[w]);
       }
+    }
+  } else {
+    // ------------------------------------------------------------------ class-token warps (128 threads, barrier 11)
+    const int t = static_cast<int>(threadIdx.x) - kA6ClsWarp0 * 32;
+    const int cw = warp - kA6ClsWarp0;
+    float* red = mb->red;
+    float* pcls = mb->p_cls;
+    uint32_t* q0b = reinterpret_cast<uint32_t*>(mb->vec[0]);
+    uint32_t* k0b = reinterpret_cast<uint32_t*>(mb->vec[1]);
+    float* v0f = mb->vec[2];
+    uint32_t cq = 0, ck = 0, cv = 0;  // two bf16 each (threads 0..31)
+    auto prefetch = [&](int ch) {
+      if (t < 32) {
+        const int crop = ch / heads, head = ch - crop * heads;
+        const uint32_t* cls_row = reinterpret_cast<const uint32_t*>(qkv + static_cast<size_t>(crop) * T * row_stride + head * 64);
+        cq = __ldg(cls_row + t);
+        ck = __ldg(cls_row + d / 2 + t);
+        cv = __ldg(cls_row + d + t);
+      }
+    };
+    // dots of rows `ra` and `rb` of a swizzled 128-byte-row tile with a packed bf16 vector (32 words in shared memory)
+    auto dot2_packed = [](const uint8_t* tile, int ra, int rb, const uint32_t* vec, float& da, float& db) {
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+      const uint8_t* pa = tile + ra * 128;
+      const uint8_t* pb = tile + rb * 128;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint4 v[4], xa[4], xb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = reinterpret_cast<const uint4*>(vec)[4 * half + j];
+          xa[j] = *reinterpret_cast<const uint4*>(pa + (((4 * half + j) ^ (ra & 7)) << 4));
+          xb[j] = *reinterpret_cast<const uint4*>(pb + (((4 * half + j) ^ (rb & 7)) << 4));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t vw[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          const uint32_t aw[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
+          const uint32_t bw[4] = {xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float vl = bf16_lo(vw[e]), vh = bf16_hi(vw[e]);
+            ffma2(a0, a1, bf16_lo(aw[e]), bf16_hi(aw[e]), vl, vh, a0, a1);
+            ffma2(b0, b1, bf16_lo(bw[e]), bf16_hi(bw[e]), vl, vh, b0, b1);
+          }
+        }
+      }
+      da = a0 + a1;
+      db = b0 + b1;
+    };
+    if (static_cast<int>(blockIdx.x) < n_ch) prefetch(blockIdx.x);
+    int hk = 0, qk = 0;
+    for (int ch = blockIdx.x; ch < n_ch; ch += gridDim.x, ++hk) {
+      const int crop = ch / heads, head = ch - crop * heads;
+      const int tok0 = crop * T;
+      // K of the head has landed => K/V/vec of the previous head have been released by everyone (k_empty / v_empty)
+      mbar_wait(&mb->k_full, hk & 1);
+      named_bar_sync(11, 128);  // the previous head's class row (vec, p_cls, part, red) is finished in every class warp
+      if (t < 32) {
+        q0b[t] = cq;
+        k0b[t] = ck;
+        *reinterpret_cast<float2*>(v0f + 2 * t) = make_float2(bf16_lo(cv), bf16_hi(cv));
+      }
+      if (ch + static_cast<int>(gridDim.x) < n_ch) prefetch(ch + gridDim.x);
+      named_bar_sync(11, 128);
+      // class-token KEY for one query-tile pair: s0[r] = q_r·k0 -> softmax warps
+      auto key_scores = [&]() {
+        const int s = qk & 1;
+        mbar_wait(&mb->q_full[s], (qk >> 1) & 1);
+        float a, b;
+        dot2_packed(smem + off_q + s * kA3QStage, t, t + 128, k0b, a, b);
+        mb->s0[s][t] = a;
+        mb->s0[s][t + 128] = b;
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&mb->cls_done[s]);
+          mbar_arrive(&mb->q_empty[s]);
+        }
+        ++qk;
+      };
+      int pair = 0;
+      for (; pair < NQ && pair < 2; ++pair) key_scores();  // both Q stages are prefetched at the start of a head
+      // class-token QUERY row: scores over the resident K (rows t, t+128, ... < G2), class key, softmax
+      float sa[5];
+      {
+        const uint8_t* ktile = smem;
+        float x, y;
+        dot2_packed(ktile, t, t + 128, q0b, sa[0], sa[1]);
+        if (t + 384 < G2) dot2_packed(ktile, t + 256, t + 384, q0b, sa[2], sa[3]);
+        else if (t + 256 < G2) { dot2_packed(ktile, t + 256, t + 256, q0b, sa[2], y); sa[3] = -INFINITY; }
+        else { sa[2] = sa[3] = -INFINITY; }
+        if (t + 512 < G2) { dot2_packed(ktile, t + 512, t + 512, q0b, sa[4], x); } else sa[4] = -INFINITY;
+        if (t + 128 >= G2) sa[1] = -INFINITY;
+        if (t >= G2) sa[0] = -INFINITY;
+      }
+      float sc;
+      {
+        const uint32_t qa = q0b[lane], ka = k0b[lane];
+        sc = fmaf(bf16_lo(qa), bf16_lo(ka), bf16_hi(qa) * bf16_hi(ka));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      float cm;
+      {
+        const float mine = fmaxf(fmaxf(fmaxf(sa[0], sa[1]), fmaxf(sa[2], sa[3])), fmaxf(sa[4], sc));
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(cm) : "f"(mine));
+      }
+      if (lane == 0) red[cw] = cm;
+      named_bar_sync(11, 128);
+      cm = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * scale_log2;
+      const float pc = ex2_ftz(fmaf(sc, scale_log2, -cm));
+      float psum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const float pv = ex2_ftz(fmaf(sa[i], scale_log2, -cm));  // -inf -> 0
+        if (t + 128 * i < G2) pcls[t + 128 * i] = pv;
+        psum += pv;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      if (lane == 0) red[4 + cw] = psum;
+      named_bar_sync(11, 128);
+      // every K read of the class warps is done
+      if (lane == 0) mbar_arrive(&mb->k_empty);
+      // O_cls = P_cls·V over the resident V: thread = (key slice ks of G2/16 keys, 8-column chunk cc)
+      mbar_wait(&mb->v_full, hk & 1);
+      {
+        const int cc = t & 7, ks = t >> 3;
+        const int per = G2 >> 4;  // keys per slice (36 for 576)
+        const uint8_t* vt = smem + off_v;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int k0 = 0; k0 < per; k0 += 4) {
+          uint4 row[4];
+          float pk4[4];
+#pragma unroll
+          for (int key = 0; key < 4; ++key) {
+            const int j = ks * per + k0 + key;
+            const bool ok = k0 + key < per;
+            row[key] = ok ? *reinterpret_cast<const uint4*>(vt + j * 128 + ((cc ^ (j & 7)) << 4)) : make_uint4(0, 0, 0, 0);
+            pk4[key] = ok ? pcls[j] : 0.f;
+          }
+#pragma unroll
+          for (int key = 0; key < 4; ++key) {
+            const uint4 a = row[key];
+            const float pkey = pk4[key];
+            ffma2(acc[0], acc[1], bf16_lo(a.x), bf16_hi(a.x), pkey, pkey, acc[0], acc[1]);
+            ffma2(acc[2], acc[3], bf16_lo(a.y), bf16_hi(a.y), pkey, pkey, acc[2], acc[3]);
+            ffma2(acc[4], acc[5], bf16_lo(a.z), bf16_hi(a.z), pkey, pkey, acc[4], acc[5]);
+            ffma2(acc[6], acc[7], bf16_lo(a.w), bf16_hi(a.w), pkey, pkey, acc[6], acc[7]);
+          }
+        }
+        *reinterpret_cast<float4*>(&mb->part[ks][cc * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(&mb->part[ks][cc * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      named_bar_sync(11, 128);
+      if (lane == 0) mbar_arrive(&mb->v_empty);  // every V read of the class warps is done
+      if (t < 64) {
+        const float cls_l = ((red[4] + red[5]) + (red[6] + red[7])) + pc;
+        float o = pc * v0f[t];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o += mb->part[i][t];
+        out[static_cast<size_t>(tok0) * d + head * 64 + t] = __float2bfloat16_rn(o / cls_l);
+      }
+      for (; pair < NQ; ++pair) key_scores();
     }
   }
   tc_fence_before();
@@ -1117,55 +1338,29 @@ attention_umma3_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_c
   }
 }
 
-static int attention_umma3_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
+static int attention_umma6_launch(const void* qkv, void* out, int n, int T, int heads, cudaStream_t stream) {
   const int d = heads * 64;
   const int NB = (T - 1) / kA3KB;
   CUtensorMap tm_kv, tm_q;
   const uint64_t rows = static_cast<uint64_t>(n) * T;
   B2C_TRY(make_tmap_2d(&tm_kv, qkv, rows, 3ull * d, 3ull * d * 2, kA3KB, 1));
   B2C_TRY(make_tmap_2d(&tm_q, qkv, rows, 3ull * d, 3ull * d * 2, 256, 1));
-  const int smem_bytes = 2 * NB * kA3BlockBytes + 2 * kA3QStage + static_cast<int>((sizeof(A3Misc) + 1023) / 1024 * 1024) + 1024;
-  B2C_REQUIRE(smem_bytes <= 227 * 1024, "attention v3: T=%d does not fit shared memory", T);
+  const int smem_bytes = a6_smem_bytes(NB);
+  B2C_REQUIRE(smem_bytes <= 227 * 1024, "attention v6: T=%d does not fit shared memory", T);
+  B2C_REQUIRE((NB * kA3KB) % 16 == 0 && NB * kA3KB <= 576, "attention v6: %d patch keys unsupported", NB * kA3KB);
+  auto kern = attention_umma6_kernel;
   static PerDeviceMax smem_set;
-  if (smem_set.raise(static_cast<long long>(smem_bytes))) {
-    B2C_CHECK_CUDA(cudaFuncSetAttribute(attention_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  }
+  if (smem_set.raise(static_cast<long long>(smem_bytes)))
+    B2C_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int sms = num_sms();
   B2C_REQUIRE(sms > 0, "no CUDA device");
   const int n_ch = n * heads;
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
-  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
-  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  attention_umma3_kernel<<<n_ch < sms ? n_ch : sms, kA2Threads, smem_bytes, stream>>>(tm_kv, tm_q, q, o, n_ch, T, heads, NB,
-                                                                                     scale_log2);
-  B2C_POST_LAUNCH("attention_umma3_kernel");
-  attention_cls_kernel<<<(n_ch + 3) / 4, 128, 0, stream>>>(q, o, n_ch, T, heads, scale_log2);
-  B2C_POST_LAUNCH("attention_cls_kernel");
+  kern<<<n_ch < sms ? n_ch : sms, kA6Threads, smem_bytes, stream>>>(
+      tm_kv, tm_q, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n_ch, T, heads, NB, scale_log2);
+  B2C_POST_LAUNCH("attention_umma6_kernel");
   return 0;
 }
-
-// first traced iteration of the development phase trace (b2c_debug_attn_trace_start)
-__device__ int g_attn_trace_k0 = 4;
-
-// exp2 on the FMA pipe for part of a row's elements (the XU pipe, 16 ex2 per clock per SM, is what the exp2 pass
-// saturates): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5·2^23, 2^f by a degree-3 minimax
-// polynomial on [-0.5, 0.5] (relative error 7.6e-5, a fiftieth of the bf16 rounding P gets next), 2^n added into the
-// exponent field.  x is clamped to >= -126 so the exponent cannot wrap; x <= 0 always (the row maximum was subtracted).
-__device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float x1) {
-  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  float t0, t1, n0, n1, f0, f1, p0, p1;
-  fadd2(t0, t1, x0, x1, kMagic, kMagic);
-  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
-  fadd2(f0, f1, x0, x1, -n0, -n1);
-  ffma2(p0, p1, f0, f1, 0.05520550534129143f, 0.05520550534129143f, 0.24261397123336792f, 0.24261397123336792f);
-  ffma2(p0, p1, p0, p1, f0, f1, 0.6932547688484192f, 0.6932547688484192f);
-  ffma2(p0, p1, p0, p1, f0, f1, 0.9999276995658875f, 0.9999276995658875f);
-  y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
-  y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
-}
-
 
 // ================================================================================================
 // (1e) tcgen05 attention for T = 257, head dim 64 (ViT-L/14-224): persistent, one CTA per SM, 22 warps.
@@ -1747,7 +1942,7 @@ int attention_launch(const void* qkv, void* out, int n, int T, int heads, int hd
     if (hd == 64 && T == kAuKeys + 1) return attention_umma5_launch(qkv, out, n, T, heads, v5var, stream);
     if (hd == 80 && T == kAuKeys + 1) return attention_umma2_launch<80>(qkv, out, n, T, heads, stream);
     if (hd == 64 && T > kAuKeys + 1 && (T - 1) % kA3KB == 0 && (T - 1) / kA3KB <= kA3MaxNB)
-      return attention_umma3_launch(qkv, out, n, T, heads, stream);
+      return attention_umma6_launch(qkv, out, n, T, heads, stream);
   }
   if (hd == 64) return attention_launch_hd<64>(qkv, out, n, T, heads, stream);
   if (hd == 80) return attention_launch_hd<80>(qkv, out, n, T, heads, stream);

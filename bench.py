@@ -262,7 +262,8 @@ def tower_parity(enc, oracle, images_u8, got, n_images):
     from oracle import vit_oracle
     px = preprocess_u8(images_u8[:n_images], enc.img_resolution, enc.model.cfg["patch"], "nchw").cpu()
     t0 = time.perf_counter()
-    ref = vit_oracle.encode_image_oracle(oracle, px.view(-1, 3, enc.img_resolution, enc.img_resolution))
+    with all_host_cores():
+        ref = vit_oracle.encode_image_oracle(oracle, px.view(-1, 3, enc.img_resolution, enc.img_resolution))
     g = got[:n_images].reshape(-1, got.shape[-1]).float().cpu()
     cos = float(torch.nn.functional.cosine_similarity(ref, g, dim=-1).min())
     mx = float((ref - g).abs().max())
@@ -313,11 +314,35 @@ def e2e_host_batches(enc, pool_host, steps, warmup, barrier, world, dist, post=N
     return ms.item(), n_out
 
 
+_ALL_CORES = None
+
+
+@contextlib.contextmanager
+def all_host_cores():
+    """The CPU-side checks of rank 0 (fp32 oracle tower) use every host core, not the slice the rank's launch thread is
+    pinned to (the other ranks are idle at a barrier meanwhile)."""
+    import torch
+    if _ALL_CORES is None:
+        yield
+        return
+    mine = os.sched_getaffinity(0)
+    nthr = torch.get_num_threads()
+    try:
+        os.sched_setaffinity(0, _ALL_CORES)
+        torch.set_num_threads(len(_ALL_CORES))
+        yield
+    finally:
+        torch.set_num_threads(nthr)
+        os.sched_setaffinity(0, mine)
+
+
 def pin_to_local_cores(local, n_local):
     """One rank per GPU shares the host cores with its siblings: give every rank its own contiguous slice so the launch
     threads do not migrate across each other (the reference has no multi-process path; this is launch hygiene only)."""
+    global _ALL_CORES
     try:
         cores = sorted(os.sched_getaffinity(0))
+        _ALL_CORES = set(cores)
         per = max(1, len(cores) // max(1, n_local))
         mine = cores[local * per:(local + 1) * per] or cores
         os.sched_setaffinity(0, mine)

@@ -15,6 +15,7 @@
 //                          f32 NCHW (parity layout) or bf16 patch-major (the patch-embed GEMM's A operand).
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -110,15 +111,31 @@ __device__ __forceinline__ double bicubic_filter(double x) {
   return 0.0;
 }
 
+// Coefficient tables in the form the resample kernel consumes.  A 22-bit Pillow coefficient k is split into three
+// byte limbs, k = l0 + 256 l1 + 65536 l2 (l0, l1 unsigned, l2 = k >> 16 signed; |k| < 2^23 because no normalised bicubic
+// weight reaches 2), and four consecutive taps share one uint4 {l0 x4, l1 x4, l2 x4, 0}: one `dp4a` per limb then covers
+// four taps of four source bytes, exactly (integers).
 // grid (n_crops, 2 axes), block R threads. tables: bounds int2[n_crops][2][R] = (xmin, count),
-// coefs int32[n_crops][2][R][KS].
+// coefs uint4[n_crops][2][R][KS4].  Block (0, 0) also writes the ToTensor/Normalize table lut f32[3][256].
+struct NormParams {
+  float mean[3], stdv[3];
+};
 __global__ void resample_plan_kernel(const CropPlan* __restrict__ plans, int2* __restrict__ bounds,
-                                     int32_t* __restrict__ coefs, int R, int KS) {
+                                     uint4* __restrict__ coefs, float* __restrict__ lut, const NormParams norm, int R,
+                                     int KS4) {
   const int crop = blockIdx.x, axis = blockIdx.y, xx = threadIdx.x;
+  if (crop == 0 && axis == 0) {
+    for (int i = xx; i < 768; i += blockDim.x) {
+      const int c = i >> 8, v = i & 255;
+      // ToTensor: float(v) / 255 ; Normalize: (x - mean) / std, each op rounded to fp32 like torch
+      lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), norm.mean[c]), norm.stdv[c]);
+    }
+  }
   if (xx >= R) return;
   const CropPlan p = plans[crop];
-  int2* b = bounds + (static_cast<size_t>(crop) * 2 + axis) * R + xx;
-  int32_t* k = coefs + ((static_cast<size_t>(crop) * 2 + axis) * R + xx) * KS;
+  const int slot = xx;
+  int2* b = bounds + (static_cast<size_t>(crop) * 2 + axis) * R + slot;
+  uint4* k = coefs + ((static_cast<size_t>(crop) * 2 + axis) * R + slot) * KS4;
   if (p.cw <= 0) { *b = make_int2(0, 0); return; }
   const int in_size = axis ? p.ch : p.cw;
   const int out_size = axis ? p.out_h : p.out_w;
@@ -138,14 +155,22 @@ __global__ void resample_plan_kernel(const CropPlan* __restrict__ plans, int2* _
     const double arg = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
     ww = __dadd_rn(ww, bicubic_filter(arg));
   }
-  for (int x = 0; x < n; ++x) {
-    const double arg = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
-    double w = bicubic_filter(arg);
-    if (ww != 0.0) w = __ddiv_rn(w, ww);
-    const double scaled = __dmul_rn(w, static_cast<double>(1 << kPrecisionBits));
-    k[x] = w < 0.0 ? static_cast<int>(__dadd_rn(-0.5, scaled)) : static_cast<int>(__dadd_rn(0.5, scaled));
+  for (int g = 0; g < KS4; ++g) {
+    uint32_t l0 = 0, l1 = 0, l2 = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int x = 4 * g + j;
+      if (x >= n) break;
+      const double arg = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+      double w = bicubic_filter(arg);
+      if (ww != 0.0) w = __ddiv_rn(w, ww);
+      const double scaled = __dmul_rn(w, static_cast<double>(1 << kPrecisionBits));
+      const int kv = w < 0.0 ? static_cast<int>(__dadd_rn(-0.5, scaled)) : static_cast<int>(__dadd_rn(0.5, scaled));
+      l0 |= static_cast<uint32_t>(kv & 255) << (8 * j);
+      l1 |= static_cast<uint32_t>((kv >> 8) & 255) << (8 * j);
+      l2 |= static_cast<uint32_t>((kv >> 16) & 255) << (8 * j);
+    }
+    k[g] = make_uint4(l0, l1, l2, 0u);
   }
-  for (int x = n; x < KS; ++x) k[x] = 0;
   *b = make_int2(xmin, n);
 }
 
@@ -155,53 +180,173 @@ __global__ void resample_plan_kernel(const CropPlan* __restrict__ plans, int2* _
 struct ResampleParams {
   const CropPlan* plans;
   const int2* bounds;
-  const int32_t* coefs;
+  const uint4* coefs;
+  const float* lut;   // f32[3][256]: (v / 255 - mean) / std
   void* out;
-  int R, KS, TR;      // outputs per side, taps, output rows per band
-  int rows_cap;       // rows of the horizontal tile held in smem
-  int SR;             // source rows staged per sub-batch
-  int span_cap;       // bytes per staged row (multiple of 4)
+  int R, KS4, TR;     // outputs per side, tap groups of four, output rows per band
+  int HP;             // bytes per (channel, output column) of the transposed horizontal tile (4 * odd)
+  int SR;             // source rows staged per sub-batch (multiple of 4)
+  int SPP;            // bytes per staged (channel, row) (multiple of 4)
   int layout, patch, Kp;
-  float mean[3], stdv[3];
+  int g;              // patches per side (patch-major layout)
+  uint32_t magicP;    // floor(2^32 / patch) + 1: n / patch == umulhi(n, magicP) for n < 65536
+  uint32_t magicPad;  // same for (Kp - 3 patch^2) / 2
 };
 
 __device__ __forceinline__ int clip8(int v) {
   v >>= kPrecisionBits;
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
+// four u8 (a) x four u8 / s8 (b) + c
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// the limb-0 accumulator starts at Pillow's rounding constant 1 << (PRECISION_BITS - 1)
+constexpr int kRound = 1 << (kPrecisionBits - 1);
+__device__ __forceinline__ int limbs_to_u8(int a0, int a1, int a2) { return clip8(a0 + (a1 << 8) + (a2 << 16)); }
 
 // shared-memory carve-up of resample_kernel (every region 16-byte aligned)
 struct PreSmem {
   size_t lut, hcoef, hb, vcoef, vb, hbuf, stage, total;
 };
 __host__ __device__ inline size_t pre_a16(size_t v) { return (v + 15) & ~size_t(15); }
-__host__ __device__ inline PreSmem pre_smem(int R, int KS, int TR, int rows_cap, int SR, int span_cap) {
+__host__ __device__ inline int pre_odd(int v) { return v | 1; }  // uint4 pitch of a coefficient row (bank spread)
+__host__ __device__ inline PreSmem pre_smem(int R, int KS4, int TR, int HP, int SR, int SPP) {
   PreSmem s;
   size_t off = 0;
   s.lut = off;   off += pre_a16(768 * sizeof(float));
-  s.hcoef = off; off += pre_a16(static_cast<size_t>(R) * KS * 4);
+  s.hcoef = off; off += pre_a16(static_cast<size_t>(R) * pre_odd(KS4) * 16);
   s.hb = off;    off += pre_a16(static_cast<size_t>(R) * 8);
-  s.vcoef = off; off += pre_a16(static_cast<size_t>(TR) * KS * 4);
+  s.vcoef = off; off += pre_a16(static_cast<size_t>(TR) * KS4 * 16);
   s.vb = off;    off += pre_a16(static_cast<size_t>(TR) * 8);
-  s.hbuf = off;  off += pre_a16(static_cast<size_t>(rows_cap) * 3 * R);
-  s.stage = off; off += pre_a16(static_cast<size_t>(SR) * span_cap);
+  s.hbuf = off;  off += pre_a16(static_cast<size_t>(3) * R * HP);
+  s.stage = off; off += pre_a16(static_cast<size_t>(3) * SR * SPP);
   s.total = off;
   return s;
 }
 
 constexpr int kResThreads = 256;
 
+// Horizontal pass over the staged rows [0, 4 * rgroups): work item = (4 source rows, channel, output slot).
+// G > 0: tap-group count known at compile time (unrolled); G == 0: `groups` at run time.
+template <int G>
+__device__ __forceinline__ void resample_hpass(const uint8_t* __restrict__ stage, uint8_t* __restrict__ hbuf,
+                                               const uint4* __restrict__ hcoef, const int2* __restrict__ hb, int R,
+                                               int CP, int HP, int SRc, int SPP, int rgroups, int y0, int groups,
+                                               int tid) {
+  const int ng = G ? G : groups;
+  int rg = 0, cs = tid;
+  const int per = 3 * R;
+  while (cs >= per) { cs -= per; ++rg; }
+  while (rg < rgroups) {
+    const int c = cs >= 2 * R ? 2 : (cs >= R ? 1 : 0);
+    const int x = cs - c * R;  // lanes walk x in natural order: their source windows overlap (few banks, no conflicts)
+    const int slot = (x >> 1) + (x & 1) * (R >> 1);  // column of the transposed tile: the pair (2xp, 2xp+1) sits R/2 apart
+    const int2 bx = hb[x];     // (first source column relative to the staged span, taps)
+    const uint4* kc = hcoef + x * CP;
+    const uint8_t* s0 = stage + (static_cast<size_t>(c) * SRc + 4 * rg) * SPP + (bx.x & ~3);
+    const uint32_t sh = (bx.x & 3) * 8;
+    int a[4][3];
+    uint32_t prev[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[j][0] = kRound;
+      a[j][1] = a[j][2] = 0;
+      prev[j] = *reinterpret_cast<const uint32_t*>(s0 + j * SPP);
+    }
+#pragma unroll
+    for (int g = 0; g < ng; ++g) {
+      const uint4 k = kc[g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t nxt = *reinterpret_cast<const uint32_t*>(s0 + j * SPP + 4 * (g + 1));
+        const uint32_t d = __funnelshift_r(prev[j], nxt, sh);
+        prev[j] = nxt;
+        a[j][0] = dp4a_uu(d, k.x, a[j][0]);
+        a[j][1] = dp4a_uu(d, k.y, a[j][1]);
+        a[j][2] = dp4a_us(d, k.z, a[j][2]);
+      }
+    }
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w |= static_cast<uint32_t>(limbs_to_u8(a[j][0], a[j][1], a[j][2])) << (8 * j);
+    *reinterpret_cast<uint32_t*>(hbuf + (static_cast<size_t>(c) * R + slot) * HP + y0 + 4 * rg) = w;
+    cs += kResThreads;
+    while (cs >= per) { cs -= per; ++rg; }
+  }
+}
+
+// Vertical pass + ToTensor/Normalize: work item = (output row of the band, channel, output column pair 2xp, 2xp+1).
+template <int G>
+__device__ __forceinline__ void resample_vpass(const ResampleParams& p, const uint8_t* __restrict__ hbuf,
+                                               const uint4* __restrict__ vcoef, const int2* __restrict__ vb,
+                                               const float* __restrict__ lut, int crop, int r0, int nr, int groups,
+                                               int tid) {
+  const int ng = G ? G : groups;
+  const int R = p.R, R2 = R >> 1, HP = p.HP, KS4 = p.KS4;
+  const int per = 3 * R2;
+  // 32-bit element offsets below one crop's output (< 2^31 elements)
+  float* out_f32 = reinterpret_cast<float*>(p.out) + static_cast<size_t>(crop) * 3 * R * R;
+  __nv_bfloat16* out_bf16 = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(crop) * p.g * p.g * p.Kp;
+  int r = 0, cx = tid;
+  while (cx >= per) { cx -= per; ++r; }
+  while (r < nr) {
+    const int c = cx >= 2 * R2 ? 2 : (cx >= R2 ? 1 : 0);
+    const int xp = cx - c * R2;
+    const int2 by = vb[r];  // (first tile row, taps)
+    const uint4* kc = vcoef + r * KS4;
+    const uint8_t* h0 = hbuf + (static_cast<size_t>(c) * R + xp) * HP + (by.x & ~3);
+    const uint8_t* h1 = h0 + static_cast<size_t>(R2) * HP;
+    const uint32_t sh = (by.x & 3) * 8;
+    int a0 = kRound, a1 = 0, a2 = 0, b0 = kRound, b1 = 0, b2 = 0;
+    uint32_t pa = *reinterpret_cast<const uint32_t*>(h0), pb = *reinterpret_cast<const uint32_t*>(h1);
+#pragma unroll
+    for (int g = 0; g < ng; ++g) {
+      const uint4 k = kc[g];
+      const uint32_t na = *reinterpret_cast<const uint32_t*>(h0 + 4 * (g + 1));
+      const uint32_t nb = *reinterpret_cast<const uint32_t*>(h1 + 4 * (g + 1));
+      const uint32_t da = __funnelshift_r(pa, na, sh), db = __funnelshift_r(pb, nb, sh);
+      pa = na; pb = nb;
+      a0 = dp4a_uu(da, k.x, a0); a1 = dp4a_uu(da, k.y, a1); a2 = dp4a_us(da, k.z, a2);
+      b0 = dp4a_uu(db, k.x, b0); b1 = dp4a_uu(db, k.y, b1); b2 = dp4a_us(db, k.z, b2);
+    }
+    const float* l = lut + c * 256;
+    const float f0 = l[limbs_to_u8(a0, a1, a2)], f1 = l[limbs_to_u8(b0, b1, b2)];
+    const int row = r0 + r, x = 2 * xp;
+    if (p.layout == B2C_OUT_NCHW_F32) {
+      *reinterpret_cast<float2*>(out_f32 + (c * R + row) * R + x) = make_float2(f0, f1);
+    } else {
+      // patch-major: element (patch (gy,gx), k = c*p*p + py*p + px); p is even so a px pair never straddles patches
+      const int P = p.patch;
+      const int gy = __umulhi(row, p.magicP), py = row - gy * P;
+      const int gx = __umulhi(x, p.magicP), px = x - gx * P;
+      *reinterpret_cast<__nv_bfloat162*>(out_bf16 + (gy * p.g + gx) * p.Kp + (c * P + py) * P + px) =
+          __floats2bfloat162_rn(f0, f1);
+    }
+    cx += kResThreads;
+    while (cx >= per) { cx -= per; ++r; }
+  }
+}
+
 __global__ void __launch_bounds__(kResThreads) resample_kernel(const ResampleParams p) {
   extern __shared__ __align__(16) uint8_t smem_pre[];
-  const int R = p.R, KS = p.KS, TR = p.TR;
-  const PreSmem sl = pre_smem(R, KS, TR, p.rows_cap, p.SR, p.span_cap);
-  float* lut = reinterpret_cast<float*>(smem_pre + sl.lut);          // [3][256]
-  int32_t* hcoef = reinterpret_cast<int32_t*>(smem_pre + sl.hcoef);  // [R][KS]
-  int2* hb = reinterpret_cast<int2*>(smem_pre + sl.hb);              // [R]
-  int32_t* vcoef = reinterpret_cast<int32_t*>(smem_pre + sl.vcoef);  // [TR][KS]
-  int2* vb = reinterpret_cast<int2*>(smem_pre + sl.vb);              // [TR]
-  uint8_t* hbuf = smem_pre + sl.hbuf;                                // [rows_cap][3][R]
-  uint8_t* stage = smem_pre + sl.stage;                              // [SR][span_cap]
+  const int R = p.R, KS4 = p.KS4, TR = p.TR, CP = pre_odd(KS4);
+  const PreSmem sl = pre_smem(R, KS4, TR, p.HP, p.SR, p.SPP);
+  float* lut = reinterpret_cast<float*>(smem_pre + sl.lut);      // [3][256]
+  uint4* hcoef = reinterpret_cast<uint4*>(smem_pre + sl.hcoef);  // [R slots][CP]
+  int2* hb = reinterpret_cast<int2*>(smem_pre + sl.hb);          // [R slots]
+  uint4* vcoef = reinterpret_cast<uint4*>(smem_pre + sl.vcoef);  // [TR][KS4]
+  int2* vb = reinterpret_cast<int2*>(smem_pre + sl.vb);          // [TR]
+  uint8_t* hbuf = smem_pre + sl.hbuf;                            // [3][R slots][HP]: horizontal results, rows contiguous
+  uint8_t* stage = smem_pre + sl.stage;                          // [3][SR][SPP]: planar source rows
+  __shared__ int s_nmax[2];
 
   const int crop = blockIdx.y;
   const int r0 = blockIdx.x * TR;
@@ -231,146 +376,146 @@ __global__ void __launch_bounds__(kResThreads) resample_kernel(const ResamplePar
   }
 
   // ---- tables -> smem
-  for (int i = tid; i < 768; i += kResThreads) {
-    const int c = i >> 8, v = i & 255;
-    // ToTensor: float(v) / 255 ; Normalize: (x - mean) / std, each op rounded to fp32 like torch
-    lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), p.mean[c]), p.stdv[c]);
-  }
-  const int32_t* gh = p.coefs + (static_cast<size_t>(crop) * 2 + 0) * R * KS;
-  const int32_t* gv = p.coefs + ((static_cast<size_t>(crop) * 2 + 1) * R + r0) * KS;
-  for (int i = tid; i < R * KS; i += kResThreads) hcoef[i] = gh[i];
-  for (int i = tid; i < nr * KS; i += kResThreads) vcoef[i] = gv[i];
+  if (tid < 2) s_nmax[tid] = 0;
+  for (int i = tid; i < 768; i += kResThreads) lut[i] = p.lut[i];
+  const uint4* gh = p.coefs + (static_cast<size_t>(crop) * 2 + 0) * R * KS4;
+  const uint4* gv = p.coefs + ((static_cast<size_t>(crop) * 2 + 1) * R + r0) * KS4;
   const int2* gbh = p.bounds + (static_cast<size_t>(crop) * 2 + 0) * R;
   const int2* gbv = p.bounds + (static_cast<size_t>(crop) * 2 + 1) * R + r0;
-  for (int i = tid; i < R; i += kResThreads) hb[i] = gbh[i];
-  for (int i = tid; i < nr; i += kResThreads) vb[i] = gbv[i];
+  // canvas columns [x_lo, x_hi) feed the kept outputs (output 0 is slot 0, output R-1 is slot R-1);
+  // canvas rows [y_lo, y_hi) feed this band
+  const int x_lo = gbh[0].x;
+  const int2 hlast = gbh[R - 1];
+  const int x_hi = hlast.x + hlast.y;
+  const int y_lo = gbv[0].x;
+  const int2 vlast = gbv[nr - 1];
+  const int y_hi = vlast.x + vlast.y;
   __syncthreads();
+  {
+    int nh = 0, nv = 0;
+    for (int i = tid; i < R * KS4; i += kResThreads) {
+      const int e = i / KS4, g = i - e * KS4;
+      hcoef[e * CP + g] = gh[i];
+    }
+    for (int i = tid; i < nr * KS4; i += kResThreads) vcoef[i] = gv[i];
+    for (int i = tid; i < R; i += kResThreads) {
+      const int2 b = gbh[i];
+      hb[i] = make_int2(b.x - x_lo, b.y);
+      nh = max(nh, b.y);
+    }
+    for (int i = tid; i < nr; i += kResThreads) {
+      const int2 b = gbv[i];
+      vb[i] = make_int2(b.x - y_lo, b.y);
+      nv = max(nv, b.y);
+    }
+    if (nh) atomicMax(&s_nmax[0], nh);
+    if (nv) atomicMax(&s_nmax[1], nv);
+  }
+  __syncthreads();
+  const int gh4 = (s_nmax[0] + 3) >> 2, gv4 = (s_nmax[1] + 3) >> 2;  // tap groups any output of this CTA needs
 
-  const int x_lo = hb[0].x;
-  const int x_hi = hb[R - 1].x + hb[R - 1].y;           // canvas columns [x_lo, x_hi) feed the kept outputs
-  const int y_lo = vb[0].x;
-  const int y_hi = vb[nr - 1].x + vb[nr - 1].y;         // canvas rows [y_lo, y_hi) feed this band
   const int nrows = y_hi - y_lo;
   const int span_bytes = (x_hi - x_lo) * 3;
   // canvas columns that map inside the image
   const int xa = max(x_lo, -cp.dx), xb = min(x_hi, cp.W - cp.dx);
   const int va = (xa - x_lo) * 3, vbnd = (xb - x_lo) * 3;  // valid byte range within a staged row
+  const int quads = (x_hi - x_lo + 3) >> 2;
+  // an aligned word load may touch up to three bytes past the last pixel; allocations are word-granular
+  const uintptr_t img_end = (reinterpret_cast<uintptr_t>(cp.img) + static_cast<size_t>(cp.H - 1) * cp.pitch +
+                             static_cast<size_t>(cp.W) * 3 + 3) & ~uintptr_t(3);
+
+  // staging items are (row i, pixel quad q) = 12 source bytes -> one word per colour plane, dealt round-robin: thread t
+  // starts at item t and advances kResThreads items.  (Prefetching the source words into registers across the
+  // horizontal pass was measured: same time, twice the registers — the kernel is issue-bound, not latency-bound.)
+  const int st_i0 = tid / quads, st_q0 = tid - st_i0 * quads;
+  const int st_di = kResThreads / quads, st_dq = kResThreads - st_di * quads;
+  const size_t plane = static_cast<size_t>(p.SR) * p.SPP / 4;
 
   for (int y0 = 0; y0 < nrows; y0 += p.SR) {
     const int sr = min(p.SR, nrows - y0);
-    // ---- stage sr source rows: dst word w of row i <- 4 source bytes (zero outside the image)
-    const int words = (span_bytes + 3) >> 2;
-    for (int idx = tid; idx < sr * words; idx += kResThreads) {
-      const int i = idx / words, w = idx - i * words;
+    // ---- stage sr source rows as three planes
+    for (int i = st_i0, q = st_q0; i < sr;) {
       const int iy = y_lo + y0 + i + cp.dy;  // image row
-      uint32_t val = 0;
+      uint32_t pr = 0, pg = 0, pb = 0;
       if (iy >= 0 && iy < cp.H && xb > xa) {
         const uint8_t* row = cp.img + static_cast<size_t>(iy) * cp.pitch + static_cast<long long>(x_lo + cp.dx) * 3;
-        const int b0 = w * 4;
-        const uint8_t* src = row + b0;  // may be unaligned
-        const uintptr_t sa = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3);
-        const uint8_t* vbeg = row + va;
-        const uint8_t* vend = row + vbnd;
-        if (b0 >= va && b0 + 4 <= vbnd && sa >= reinterpret_cast<uintptr_t>(vbeg) &&
-            sa + 8 <= reinterpret_cast<uintptr_t>(vend)) {
-          const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(sa));
-          const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>(sa + 4));
-          val = __funnelshift_r(lo, hi, static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3) * 8);
+        const int b0 = q * 12;
+        const uintptr_t src = reinterpret_cast<uintptr_t>(row + b0);
+        const uintptr_t sa = src & ~uintptr_t(3);
+        const uint32_t sh = static_cast<uint32_t>(src & 3) * 8;
+        if (b0 >= va && b0 + 12 <= vbnd && sa >= reinterpret_cast<uintptr_t>(cp.img) && sa + 16 <= img_end) {
+          const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(sa);
+          const uint32_t w0 = __ldg(wsrc), w1 = __ldg(wsrc + 1), w2 = __ldg(wsrc + 2), w3 = __ldg(wsrc + 3);
+          const uint32_t u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh),
+                         u2 = __funnelshift_r(w2, w3, sh);
+          // bytes of (u0,u1,u2) = R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+          pr = __byte_perm(__byte_perm(u0, u1, 0x0630), u2, 0x5210);
+          pg = __byte_perm(__byte_perm(u0, u1, 0x0741), u2, 0x6210);
+          pb = __byte_perm(__byte_perm(u0, u1, 0x0052), u2, 0x7410);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int b = b0 + e;
-            if (b >= va && b < vbnd) val |= static_cast<uint32_t>(__ldg(row + b)) << (8 * e);
+            const int b = b0 + 3 * e;
+            if (b >= va && b + 3 <= vbnd) {
+              pr |= static_cast<uint32_t>(__ldg(row + b)) << (8 * e);
+              pg |= static_cast<uint32_t>(__ldg(row + b + 1)) << (8 * e);
+              pb |= static_cast<uint32_t>(__ldg(row + b + 2)) << (8 * e);
+            }
           }
         }
       }
-      reinterpret_cast<uint32_t*>(stage + static_cast<size_t>(i) * p.span_cap)[w] = val;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(stage + static_cast<size_t>(i) * p.SPP) + q;
+      dst[0] = pr; dst[plane] = pg; dst[2 * plane] = pb;
+      i += st_di; q += st_dq;
+      if (q >= quads) { q -= quads; ++i; }
     }
     __syncthreads();
-    // ---- horizontal pass for the staged rows -> hbuf[row][c][x]
-    for (int idx = tid; idx < sr * R; idx += kResThreads) {
-      const int i = idx / R, x = idx - i * R;
-      const int2 bx = hb[x];
-      const uint8_t* s = stage + static_cast<size_t>(i) * p.span_cap + (bx.x - x_lo) * 3;
-      const int32_t* k = hcoef + x * KS;
-      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-      for (int t = 0; t < bx.y; ++t) {
-        const int kv = k[t];
-        a0 += s[3 * t + 0] * kv;
-        a1 += s[3 * t + 1] * kv;
-        a2 += s[3 * t + 2] * kv;
-      }
-      uint8_t* h = hbuf + static_cast<size_t>(y0 + i) * 3 * R + x;
-      h[0] = static_cast<uint8_t>(clip8(a0));
-      h[R] = static_cast<uint8_t>(clip8(a1));
-      h[2 * R] = static_cast<uint8_t>(clip8(a2));
+    // ---- horizontal pass for the staged rows -> hbuf[c][slot][y0 + row]
+    const int rgroups = (sr + 3) >> 2;
+    switch (gh4) {
+      case 1: resample_hpass<1>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
+      case 2: resample_hpass<2>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
+      case 3: resample_hpass<3>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
+      case 4: resample_hpass<4>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
+      default: resample_hpass<0>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
     }
     __syncthreads();
   }
 
-  // ---- vertical pass + ToTensor/Normalize; 4 adjacent outputs per thread (R % 4 == 0)
-  const int R4 = R >> 2;
-  for (int idx = tid; idx < nr * 3 * R4; idx += kResThreads) {
-    const int r = idx / (3 * R4);
-    const int rem = idx - r * 3 * R4;
-    const int c = rem / R4, x4 = (rem - c * R4) * 4;
-    const int2 by = vb[r];
-    const int32_t* k = vcoef + r * KS;
-    const uint8_t* h = hbuf + (static_cast<size_t>(by.x - y_lo) * 3 + c) * R + x4;
-    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0;
-    for (int t = 0; t < by.y; ++t) {
-      const uint32_t px = *reinterpret_cast<const uint32_t*>(h + static_cast<size_t>(t) * 3 * R);
-      const int kv = k[t];
-      a0 += static_cast<int>(px & 0xff) * kv;
-      a1 += static_cast<int>((px >> 8) & 0xff) * kv;
-      a2 += static_cast<int>((px >> 16) & 0xff) * kv;
-      a3 += static_cast<int>(px >> 24) * kv;
-    }
-    const float* l = lut + c * 256;
-    const float f0 = l[clip8(a0)], f1 = l[clip8(a1)], f2 = l[clip8(a2)], f3 = l[clip8(a3)];
-    const int row = r0 + r;
-    if (p.layout == B2C_OUT_NCHW_F32) {
-      float* o = reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(crop) * 3 + c) * R + row) * R + x4;
-      *reinterpret_cast<float4*>(o) = make_float4(f0, f1, f2, f3);
-    } else {
-      // patch-major: element (patch (gy,gx), k = c*p*p + py*p + px); p is even so px pairs never straddle patches
-      const int P = p.patch, g = R / P;
-      const int gy = row / P, py = row - gy * P;
-      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(crop) * g * g * p.Kp;
-#pragma unroll
-      for (int e = 0; e < 4; e += 2) {
-        const int x = x4 + e;
-        const int gx = x / P, px = x - gx * P;
-        __nv_bfloat162 v = __floats2bfloat162_rn(e == 0 ? f0 : f2, e == 0 ? f1 : f3);
-        *reinterpret_cast<__nv_bfloat162*>(ob + static_cast<size_t>(gy * g + gx) * p.Kp + c * P * P + py * P + px) = v;
-      }
-    }
+  // ---- vertical pass + ToTensor/Normalize
+  switch (gv4) {
+    case 1: resample_vpass<1>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
+    case 2: resample_vpass<2>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
+    case 3: resample_vpass<3>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
+    case 4: resample_vpass<4>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
+    default: resample_vpass<0>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
   }
-  // zero the K padding columns of the patch rows this band owns (Kp > 3*p*p), once per patch row
+  // zero the K padding columns of the patch rows this band owns (Kp > 3*p*p): the band holding a patch row's first
+  // pixel row owns it.  3 p^2 and Kp are even, so the padding is whole bf16 pairs.
   if (p.layout == B2C_OUT_PATCH_BF16 && p.Kp > 3 * p.patch * p.patch) {
-    const int P = p.patch, g = R / P, padn = p.Kp - 3 * P * P;
+    const int P = p.patch, g = p.g, pad2 = (p.Kp - 3 * P * P) >> 1;
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(crop) * g * g * p.Kp;
-    for (int r = 0; r < nr; ++r) {
-      const int row = r0 + r;
-      if (row % P != 0) continue;  // first pixel row of a patch row owns the padding
-      const int gy = row / P;
-      for (int i = tid; i < g * padn; i += kResThreads) {
-        const int gx = i / padn, j = i - gx * padn;
-        ob[static_cast<size_t>(gy * g + gx) * p.Kp + 3 * P * P + j] = __float2bfloat16_rn(0.f);
+    int gy = __umulhi(r0 + P - 1, p.magicP);  // first patch row starting at or after r0
+    for (; gy * P < r0 + nr; ++gy) {
+      for (int i = tid; i < g * pad2; i += kResThreads) {
+        const int gx = __umulhi(i, p.magicPad), j = i - gx * pad2;
+        *reinterpret_cast<uint32_t*>(ob + (gy * g + gx) * p.Kp + 3 * P * P + 2 * j) = 0u;
       }
     }
   }
 }
 
 struct PreLayout {
-  size_t plans, bounds, coefs, total;
+  size_t plans, bounds, coefs, lut, total;
 };
 static PreLayout pre_layout(int B, int R, int KS) {
+  const int KS4 = (KS + 3) / 4;
   PreLayout l;
   size_t off = 0;
   l.plans = off;  off += (static_cast<size_t>(B) * 4 * sizeof(CropPlan) + 255) & ~size_t(255);
   l.bounds = off; off += (static_cast<size_t>(B) * 4 * 2 * R * sizeof(int2) + 255) & ~size_t(255);
-  l.coefs = off;  off += (static_cast<size_t>(B) * 4 * 2 * R * KS * sizeof(int32_t) + 255) & ~size_t(255);
+  l.coefs = off;  off += (static_cast<size_t>(B) * 4 * 2 * R * KS4 * sizeof(uint4) + 255) & ~size_t(255);
+  l.lut = off;    off += 768 * sizeof(float);
   l.total = off;
   return l;
 }
@@ -443,33 +588,47 @@ extern "C" int b2c_preprocess_4crop(const uint8_t* const* img_ptrs, const int* H
   ResampleParams rp;
   rp.plans = reinterpret_cast<const CropPlan*>(wsb + lay.plans);
   rp.bounds = reinterpret_cast<const int2*>(wsb + lay.bounds);
-  rp.coefs = reinterpret_cast<const int32_t*>(wsb + lay.coefs);
+  rp.coefs = reinterpret_cast<const uint4*>(wsb + lay.coefs);
+  rp.lut = reinterpret_cast<const float*>(wsb + lay.lut);
   rp.out = out;
-  rp.R = R; rp.KS = KS;
+  rp.R = R; rp.KS4 = (KS + 3) / 4;
   rp.layout = out_layout; rp.patch = patch > 0 ? patch : 2;
   rp.Kp = out_layout == B2C_OUT_PATCH_BF16 ? (3 * patch * patch + 63) / 64 * 64 : 0;
-  for (int c = 0; c < 3; ++c) { rp.mean[c] = mean[c]; rp.stdv[c] = stdv[c]; }
+  NormParams norm;
+  for (int c = 0; c < 3; ++c) { norm.mean[c] = mean[c]; norm.stdv[c] = stdv[c]; }
+  rp.g = R / rp.patch;
+  rp.magicP = static_cast<uint32_t>((1ull << 32) / rp.patch) + 1u;
+  {
+    const int pad2 = (rp.Kp - 3 * rp.patch * rp.patch) / 2;
+    rp.magicPad = pad2 > 0 ? static_cast<uint32_t>((1ull << 32) / pad2) + 1u : 0u;
+  }
 
-  // band height / smem budget
-  const size_t budget = 160 * 1024;
-  rp.span_cap = (span_max * 3 + 3 + 15) & ~15;
-  int TR = 16, SR = 8;
+  // band height / smem budget.  Both tiles are read a whole tap group past a window's end (zero coefficients
+  // there), hence the KS + 8 bytes of slack per staged row and per tile column.
+  static const int tr_env = [] { const char* e = getenv("B2C_PRE_TR"); return e ? atoi(e) : 32; }();
+  static const int budget_kb = [] { const char* e = getenv("B2C_PRE_SMEM_KB"); return e ? atoi(e) : 113; }();
+  const size_t budget = static_cast<size_t>(budget_kb) * 1024;  // 113 KB: two CTAs per SM
+  rp.SPP = (span_max + KS + 8 + 3) & ~3;
+  int TR = tr_env > 0 ? tr_env : 32, SR = 8;
+  if (TR > R) TR = R;
   size_t smem = 0;
   for (;;) {
-    rp.rows_cap = static_cast<int>(TR * scale_max) + KS + 2;
-    SR = static_cast<int>((24 * 1024) / rp.span_cap);
-    if (SR < 1) SR = 1;
-    if (SR > 16) SR = 16;
-    smem = pre_smem(R, KS, TR, rp.rows_cap, SR, rp.span_cap).total;
+    const int rows_cap = static_cast<int>(TR * scale_max) + KS + 2;
+    rp.HP = ((rows_cap + KS + 8 + 3) & ~3) | 4;  // 4 * odd: consecutive columns fall into different banks
+    SR = static_cast<int>((24 * 1024) / (3 * rp.SPP)) & ~3;
+    if (SR < 4) SR = 4;
+    if (SR > 32) SR = 32;
+    smem = pre_smem(R, rp.KS4, TR, rp.HP, SR, rp.SPP).total;
     if (smem <= budget || TR == 1) break;
-    TR >>= 1;
+    TR = TR > 8 ? TR - 8 : TR >> 1;
   }
   B2C_REQUIRE(smem <= 220 * 1024, "b2c_preprocess_4crop: images too large for the resample tile (need %zu B smem)", smem);
   rp.TR = TR; rp.SR = SR;
 
   ProfScope ps(B2C_PROF_PREPROCESS, stream);
   resample_plan_kernel<<<dim3(B * 4, 2), R, 0, stream>>>(rp.plans, const_cast<int2*>(rp.bounds),
-                                                         const_cast<int32_t*>(rp.coefs), R, KS);
+                                                         const_cast<uint4*>(rp.coefs), const_cast<float*>(rp.lut), norm,
+                                                         R, rp.KS4);
   B2C_POST_LAUNCH("resample_plan_kernel");
   static PerDeviceMax smem_set;
   if (smem_set.raise(static_cast<long long>(smem))) {

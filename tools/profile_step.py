@@ -14,7 +14,7 @@ import torch  # noqa: E402
 def embed(B):
     from bench import synth_batch
     from clip_assisted_data_labeling_b200.embedder import CLIP_Encoder
-    enc = CLIP_Encoder("ViT-L-14/openai", device="cuda", seed=0)
+    enc = CLIP_Encoder("ViT-L-14/openai", device="cuda", seed=0, allow_random_init=True)
     imgs = synth_batch(B, 0).cuda()
     for _ in range(2):
         out = enc.encode_images_u8(imgs)

@@ -30,6 +30,7 @@ SOURCES = [
     "b2c_train.cu",
     "b2c_imgstats.cu",
     "b2c_jpeg.cu",
+    "b2c_jpeg_huff.cu",
     "b2c_vit.cu",
 ]
 

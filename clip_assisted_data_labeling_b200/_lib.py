@@ -93,6 +93,9 @@ SIGNATURES = {
     "b2c_jpeg_reconstruct_packed": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "b2c_jpeg_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
     "b2c_jpeg_reconstruct": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "b2c_jpeg_huff_prepare": (_i, [_vp, _sz, _vp, _vp]),
+    "b2c_jpeg_huff_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
+    "b2c_jpeg_huff_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "b2c_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
     "b2c_layernorm_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _vp]),
     "b2c_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -921,6 +921,39 @@ extern "C" int b2c_jpeg_parse(const uint8_t* data, size_t len, b2c_jpeg_info* in
   return 0;
 }
 
+extern "C" int b2c_jpeg_huff_prepare(const uint8_t* data, size_t len, b2c_jpeg_info* info, b2c_jpeg_huff* huff) {
+  using namespace b2c;
+  B2C_REQUIRE(data && info && huff, "b2c_jpeg_huff_prepare: null pointer");
+  Parsed P;
+  Scan first;
+  size_t pos = 0;
+  B2C_TRY(parse(data, len, P, first, pos));
+  if (P.progressive) return fail_unsupported("device Huffman stage: progressive frame");
+  if (first.ns != P.info.ncomp) return fail_unsupported("device Huffman stage: the first scan does not hold every component");
+  for (int k = 0; k < first.ns; ++k)
+    if (first.ci[k] != k) return fail_corrupt("scan component order");
+  if (P.info.ncomp == 3 && (first.td[1] != first.td[2] || first.ta[1] != first.ta[2]))
+    return fail_unsupported("device Huffman stage: Cb and Cr use different Huffman tables");
+  if (len - first.begin >= (1ull << 28)) return fail_unsupported("device Huffman stage: scan larger than 256 MB");
+  memset(huff, 0, sizeof(*huff));
+  huff->scan_begin = static_cast<int64_t>(first.begin);
+  huff->scan_bytes = static_cast<int64_t>(len - first.begin);
+  huff->restart_interval = P.info.restart_interval;
+  const int cc = P.info.ncomp == 3 ? 1 : 0;  // grey: the chroma slots repeat the luma tables
+  const HuffTable* src[4] = {&P.dc[first.td[0]], &P.ac[first.ta[0]], &P.dc[first.td[cc]], &P.ac[first.ta[cc]]};
+  for (int t = 0; t < 4; ++t) {
+    b2c_jpeg_hufftab& d = huff->tab[t];
+    memcpy(d.look, src[t]->look, sizeof(d.look));
+    memcpy(d.maxcode, src[t]->maxcode, sizeof(d.maxcode));
+    d.valoffset[0] = 0;
+    memcpy(d.valoffset + 1, src[t]->valoffset + 1, 16 * sizeof(int32_t));
+    d.valoffset[17] = 0;
+    memcpy(d.vals, src[t]->vals, sizeof(d.vals));
+  }
+  *info = P.info;
+  return 0;
+}
+
 extern "C" int b2c_jpeg_decode_coefs(const uint8_t* data, size_t len, b2c_jpeg_info* info, int16_t* coefs,
                                      size_t capacity) {
   using namespace b2c;

@@ -257,6 +257,15 @@ class Feature_Dataset:
                 b = len(todo_imgs)
                 t_it = tick("resume checks", t_it)
                 dev_imgs = to_device_images(todo_imgs, self.device) if on_cuda else todo_imgs  # cpu: injected encoder (host-logic tests)
+                if any(im is None for im in dev_imgs):  # a JPEG the device reported and neither the host stage nor Pillow decodes
+                    keep = [j for j, im in enumerate(dev_imgs) if im is not None]
+                    self.failed.extend(todo_img_paths[j] for j in range(b) if dev_imgs[j] is None)
+                    dev_imgs = [dev_imgs[j] for j in keep]
+                    todo_paths = [todo_paths[j] for j in keep]
+                    todo_img_paths = [todo_img_paths[j] for j in keep]
+                    b = len(keep)
+                    if b == 0:
+                        continue
                 t_it = tick("gather + H2D + JPEG reconstruct launches", t_it)
                 feats = self.encoder.encode_images_u8(dev_imgs)  # [B,4,E]
                 t_it = tick("preprocess + tower launches", t_it)
@@ -299,7 +308,7 @@ class Feature_Dataset:
             packed.close()
         if timing:
             from . import embedder as _emb, jpeg as _jpeg
-            for st in (_jpeg._coef_staging, _emb._pixel_staging):
+            for st in (_jpeg._coef_staging, _jpeg._packed_staging, _jpeg._file_staging, _emb._pixel_staging):
                 if st is not None:
                     for k2, v2 in st.timing.items():
                         phase[k2] = phase.get(k2, 0.0) + v2

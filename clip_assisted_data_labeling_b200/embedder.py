@@ -355,17 +355,23 @@ class CustomImageDataset(Dataset):
 class RawImageDataset(Dataset):
     """Decode only: returns (item, path).  Crops, resize and normalisation run on the GPU (b2c_preprocess_4crop).
     item is
-      * ``("jpegp", info_bytes, uint8 packed coefficients)`` for a baseline / progressive JPEG when ``device_jpeg`` is
-        on: the worker does the serial part (marker parse + Huffman decode, jpeg.entropy_decode_packed) and the main
-        process finishes the decode on the device (jpeg.reconstruct_packed) — bit-exact with Pillow, SURVEY.md §8f row 2
+      * ``("jpegf", info_bytes, huff_bytes, uint8 file bytes)`` for a single-scan sequential JPEG when ``device_jpeg`` is
+        on: the worker only parses the markers (jpeg.prepare_file) and the main process decodes the file ENTIRELY on the
+        device — Huffman stage (b2c_jpeg_huff_decode) and reconstruction (jpeg.decode_device), bit-exact with Pillow,
+        SURVEY.md §8f row 2; a stream the device reports (damaged, truncated) is retried on the host there;
+      * ``("jpegp", info_bytes, uint8 packed coefficients)`` for the JPEGs whose Huffman stage stays on the host
+        (progressive, multi-scan; or every JPEG when ``device_huffman`` is off): the worker does the serial part
+        (jpeg.entropy_decode_packed) and the main process finishes the decode on the device (jpeg.reconstruct_packed)
         (``("jpeg", info_bytes, int16 dense coefficients)`` items are accepted too);
       * a uint8 HWC tensor decoded with Pillow (`Image.open(path).convert('RGB')`, utils/embedder.py:167) for every
         other format and for JPEG streams the device path does not cover;
       * ``None`` for a file that fails to decode — reported by the driver, never silently substituted."""
 
-    def __init__(self, image_paths, device_jpeg: bool = False):
+    def __init__(self, image_paths, device_jpeg: bool = False, device_huffman: bool = None):
+        import os
         self.image_paths = image_paths
         self.device_jpeg = device_jpeg
+        self.device_huffman = (os.environ.get("B2C_DEVICE_HUFFMAN", "1") != "0") if device_huffman is None else bool(device_huffman)
 
     def __len__(self):
         return len(self.image_paths)
@@ -382,6 +388,12 @@ class RawImageDataset(Dataset):
                 with open(path, "rb") as fh:
                     data = fh.read()
                 try:
+                    if self.device_huffman:
+                        try:
+                            info, huff, raw = jpeg.prepare_file(data)
+                            return ("jpegf", bytes(info), bytes(huff), raw), path
+                        except jpeg.UnsupportedJPEG:
+                            pass  # progressive / multi-scan: the Huffman stage of these stays on the host
                     info, packed = jpeg.entropy_decode_packed(data)
                     return ("jpegp", bytes(info), packed), path
                 except (jpeg.UnsupportedJPEG, _lib.B2CError):
@@ -402,13 +414,17 @@ _pixel_staging = None
 def to_device_images(items, device):
     """RawImageDataset items (no ``None``) -> uint8 [H,W,3] device tensors, same order.  Pillow-decoded tensors go through
     one pinned gather + one H2D copy (the device tensors are views of that buffer); entropy-decoded JPEGs likewise and are
-    then reconstructed on the device in one batched call."""
+    then reconstructed on the device in one batched call; whole JPEG files are decoded on the device (an entry is None
+    only for a file that neither the device, nor the host stage, nor Pillow can decode: the caller reports it)."""
     global _pixel_staging
     from . import jpeg
     out = [None] * len(items)
-    jobs, where, pjobs, pjwhere, pix, pwhere = [], [], [], [], [], []
+    jobs, where, pjobs, pjwhere, pix, pwhere, fjobs, fwhere = [], [], [], [], [], [], [], []
     for i, it in enumerate(items):
-        if isinstance(it, tuple) and it[0] == "jpegp":
+        if isinstance(it, tuple) and it[0] == "jpegf":
+            fjobs.append((jpeg.JpegInfo.from_buffer_copy(it[1]), jpeg.JpegHuff.from_buffer_copy(it[2]), it[3]))
+            fwhere.append(i)
+        elif isinstance(it, tuple) and it[0] == "jpegp":
             pjobs.append((jpeg.JpegInfo.from_buffer_copy(it[1]), it[2]))
             pjwhere.append(i)
         elif isinstance(it, tuple) and it[0] == "jpeg":
@@ -424,6 +440,8 @@ def to_device_images(items, device):
             dflat, offs = _pixel_staging.gather(pix, torch.device(device))
         for i, t, o in zip(pwhere, pix, offs[:-1]):
             out[i] = dflat[int(o):int(o) + t.numel()].view(t.shape)
+    for i, t in zip(fwhere, jpeg.decode_device(fjobs, device)[0]):
+        out[i] = t
     for i, t in zip(pjwhere, jpeg.reconstruct_packed(pjobs, device)):
         out[i] = t
     for i, t in zip(where, jpeg.reconstruct(jobs, device)):
@@ -437,13 +455,13 @@ def collate_raw(batch):
     the main process then receives one shared-memory segment per batch instead of one per image (unpickling 256 segments
     costs it ~55 ms per batch), and the views gather into pinned memory as before."""
     items = [b[0] for b in batch]
-    for kind in ("jpegp", "jpeg"):
+    for kind in ("jpegf", "jpegp", "jpeg"):
         idx = [i for i, it in enumerate(items) if isinstance(it, tuple) and it[0] == kind]
         if len(idx) > 1:
-            pack = torch.cat([items[i][2] for i in idx])  # packed buffers are multiples of 16 bytes: views stay aligned
+            pack = torch.cat([items[i][-1] for i in idx])  # buffers are multiples of 16 bytes: views stay aligned
             off = 0
             for i in idx:
-                n = items[i][2].numel()
-                items[i] = (kind, items[i][1], pack[off:off + n])
+                n = items[i][-1].numel()
+                items[i] = items[i][:-1] + (pack[off:off + n],)
                 off += n
     return items, [b[1] for b in batch]

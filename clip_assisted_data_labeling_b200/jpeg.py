@@ -37,6 +37,19 @@ class JpegInfo(C.Structure):
                 "qt": [list(q) for q in self.qt], "restart_interval": self.restart_interval}
 
 
+class HuffTab(C.Structure):
+    _fields_ = [("look", C.c_uint16 * 512), ("maxcode", C.c_int32 * 18), ("valoffset", C.c_int32 * 18), ("vals", C.c_uint8 * 256)]
+
+
+class JpegHuff(C.Structure):
+    """include/b2c.h b2c_jpeg_huff: where the entropy-coded segment sits in the file + its four Huffman tables."""
+    _fields_ = [("scan_begin", C.c_int64), ("scan_bytes", C.c_int64), ("restart_interval", C.c_int32), ("reserved_", C.c_int32),
+                ("tab", HuffTab * 4)]
+
+
+HUFF_CORRUPT, HUFF_TRUNCATED, HUFF_NOSYNC = 1, 2, 4
+
+
 class UnsupportedJPEG(ValueError):
     """The stream is valid but outside what the device path decodes (progressive, CMYK, ...)."""
 
@@ -49,6 +62,36 @@ def _raise(rc: int, what: str):
 
 
 _scratch = threading.local()
+
+
+def huff_prepare(data: bytes) -> Tuple[JpegInfo, JpegHuff]:
+    """Marker parse only (host, microseconds): what the device Huffman stage (`decode_device`) needs besides the file's
+    bytes.  Raises UnsupportedJPEG for progressive / multi-scan files — those keep `entropy_decode_packed`."""
+    lib = _lib.load()
+    info, huff = JpegInfo(), JpegHuff()
+    rc = lib.b2c_jpeg_huff_prepare(data, len(data), C.byref(info), C.byref(huff))  # bytes are passed by pointer, no copy
+    if rc != 0:
+        _raise(rc, "b2c_jpeg_huff_prepare")
+    if info.width * info.height > MAX_PIXELS:
+        raise UnsupportedJPEG(f"{info.width}x{info.height} pixels exceeds the device path's limit of {MAX_PIXELS}")
+    return info, huff
+
+
+def file_tensor(data: bytes) -> torch.Tensor:
+    """The file's bytes as a uint8 host tensor padded to a multiple of 16 bytes (files of a batch are laid back to back in
+    one pinned buffer and each must start on a 16-byte boundary)."""
+    n = len(data)
+    t = torch.empty((n + 15) & ~15, dtype=torch.uint8)
+    C.memmove(t.data_ptr(), data, n)
+    if t.numel() > n:
+        t[n:] = 0
+    return t
+
+
+def prepare_file(data: bytes) -> Tuple[JpegInfo, JpegHuff, torch.Tensor]:
+    """What a DataLoader worker hands to the main process for a file the device decodes entirely: (info, huff, bytes)."""
+    info, huff = huff_prepare(data)
+    return info, huff, file_tensor(data)
 
 
 def entropy_decode_packed(data: bytes) -> Tuple[JpegInfo, torch.Tensor]:
@@ -238,3 +281,94 @@ def decode_files(paths: Sequence[str], device="cuda") -> List[torch.Tensor]:
         with open(p, "rb") as fh:
             items.append(entropy_decode(fh.read()))
     return reconstruct(items, device)
+
+
+_file_staging = Staging(torch.uint8)
+
+
+def huffman_device(items: Sequence[Tuple[JpegInfo, JpegHuff, torch.Tensor]], device="cuda"):
+    """[(info, huff, uint8 host tensor with the file's bytes)] -> (dense int16 coefficients of the batch back to back on
+    the device, int32 status per image on the device).  One gather into pinned memory, one H2D copy of the FILES (not of
+    coefficients: 5-25x fewer bytes than the packed form) and one kernel launch.  status != 0 means the stream has to go
+    back to the host stage (damaged, truncated, or it did not synchronise)."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    n = len(items)
+    infos = [it[0] for it in items]
+    with torch.cuda.device(dev):
+        # every file starts on a 16-byte boundary of the staging buffer
+        files = [it[2] if it[2].numel() % 16 == 0 else torch.cat([it[2], it[2].new_zeros(16 - it[2].numel() % 16)])
+                 for it in items]  # (file_tensor() pads already; a foreign tensor is padded here)
+        dflat, offs = _file_staging.gather(files, dev)
+        iarr = (JpegInfo * n)(*infos)
+        harr = (JpegHuff * n)(*[it[1] for it in items])
+        need = C.c_size_t()
+        _lib.check(lib.b2c_jpeg_huff_workspace_bytes(harr, n, C.byref(need)), "b2c_jpeg_huff_workspace_bytes")
+        ws = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
+        wp = (ws.data_ptr() + 255) // 256 * 256
+        coff = np.concatenate([[0], np.cumsum([int(i.coef_count) for i in infos])])
+        coefs = torch.empty(int(coff[-1]), dtype=torch.int16, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        fptr = (C.c_void_p * n)(*[dflat.data_ptr() + int(o) for o in offs[:-1]])
+        cptr = (C.c_void_p * n)(*[coefs.data_ptr() + 2 * int(o) for o in coff[:-1]])
+        _lib.check(lib.b2c_jpeg_huff_decode(iarr, harr, fptr, cptr, C.c_void_p(status.data_ptr()), n, C.c_void_p(wp),
+                                            need.value, C.c_void_p(_lib.current_stream_ptr())), "b2c_jpeg_huff_decode")
+    return coefs, status
+
+
+_side_streams = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
+def file_bytes(item) -> bytes:
+    """The file behind a prepare_file() item (the tensor is padded to 16 bytes; the scan ends where the file does)."""
+    n = int(item[1].scan_begin + item[1].scan_bytes)
+    return bytes(item[2][:n].numpy())
+
+
+def decode_device(items: Sequence[Tuple[JpegInfo, JpegHuff, torch.Tensor]], device="cuda", fallback: bool = True):
+    """File bytes -> uint8 [H,W,3] device tensors with BOTH stages on the device (Huffman + reconstruction).  Returns
+    (images, status list).  The H2D copy of the files and the Huffman kernel run on a side stream, and the host waits for
+    THAT stream only before it reads the per-image status — work queued on the caller's stream (the previous batch's
+    tower) keeps the GPU busy meanwhile.  An image whose status is non-zero (damaged, truncated, not synchronised) is
+    decoded again through the host stage and then through Pillow, which has the last word like in the reference
+    (utils/embedder.py:167,176-181); it is None if that fails too (or when `fallback` is off)."""
+    if not items:
+        return [], []
+    dev = torch.device(device)
+    infos = [it[0] for it in items]
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        with torch.cuda.stream(side):
+            coefs, status = huffman_device(items, dev)
+            st = status.cpu().tolist()  # waits for the side stream only
+        main.wait_stream(side)
+        coefs.record_stream(main)
+        outs = reconstruct_device(infos, coefs)
+    for i, code in enumerate(st):
+        if code:
+            outs[i] = _decode_on_host(file_bytes(items[i]), dev) if fallback else None
+    return outs, st
+
+
+def _decode_on_host(data: bytes, dev):
+    import io
+    from PIL import Image
+    try:
+        return reconstruct([entropy_decode(data)], dev)[0]
+    except (UnsupportedJPEG, _lib.B2CError):
+        pass
+    try:
+        with Image.open(io.BytesIO(data)) as im:
+            arr = np.ascontiguousarray(np.asarray(im.convert("RGB")))
+        return torch.from_numpy(arr).to(dev)
+    except Exception as e:  # noqa: BLE001 — Pillow raises OSError / SyntaxError / ValueError for damaged files
+        print(f"Error decoding JPEG stream: {e}")
+        return None

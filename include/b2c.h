@@ -366,6 +366,44 @@ int b2c_jpeg_reconstruct(const b2c_jpeg_info* infos, const int16_t* const* coefs
 int b2c_jpeg_reconstruct_packed(const b2c_jpeg_info* infos, const uint8_t* const* packed, uint8_t* const* outs,
                                 const int* out_pitch, int n, void* ws, size_t ws_bytes, b2c_stream stream);
 
+/* ---- K14b: the Huffman stage on the device (baseline / extended sequential files whose single scan interleaves all
+ * components — what cameras and encoders write by default).  The host only parses the markers (b2c_jpeg_huff_prepare);
+ * the file's bytes go to the device as they are, and one CTA per image (i) removes the 0xFF00 byte stuffing and finds
+ * the end of the entropy-coded segment, (ii) decodes 128-byte sub-sequences of it in parallel from speculative states
+ * and lets each thread run on into its successors until its state (bit position, block of the MCU, zigzag index)
+ * coincides with theirs — Huffman streams self-synchronise after a few code words —, (iii) re-decodes every
+ * sub-sequence from its now known entry state, writing coefficients (natural order, dense: the layout
+ * b2c_jpeg_reconstruct takes) and CHECKING that it reproduces the recorded exit state, so a stream that did not
+ * synchronise, is damaged or ends early is reported in status[i] instead of decoded wrongly, and (iv) turns the DC
+ * differences into DC values with a prefix sum per component.  Progressive files, multi-scan files and streams the
+ * device reports keep the host stage (b2c_jpeg_decode_packed). */
+typedef struct {
+  uint16_t look[512];  /* 9-bit lookahead: (code length << 8) | symbol, 0 = the code is longer than 9 bits */
+  int32_t maxcode[18]; /* largest code of each length (-1: none), [17] = sentinel */
+  int32_t valoffset[18];
+  uint8_t vals[256];
+} b2c_jpeg_hufftab;
+typedef struct {
+  int64_t scan_begin;       /* offset of the first entropy-coded byte in the file */
+  int64_t scan_bytes;       /* bytes from there to the end of the file (the device finds the terminating marker) */
+  int32_t restart_interval; /* MCUs between RSTn markers, 0 = none */
+  int32_t reserved_;
+  b2c_jpeg_hufftab tab[4];  /* DC luma, AC luma, DC chroma, AC chroma */
+} b2c_jpeg_huff;
+
+/* Host only: marker parse; fills `info` (final, including the quantisation tables) and `huff`.  B2C_ERR_UNSUPPORTED
+ * for anything but one interleaved sequential Huffman scan (keep those on b2c_jpeg_decode_packed). */
+int b2c_jpeg_huff_prepare(const uint8_t* data, size_t len, b2c_jpeg_info* info, b2c_jpeg_huff* huff);
+int b2c_jpeg_huff_workspace_bytes(const b2c_jpeg_huff* huffs, int n, size_t* bytes);
+/* Device: files[i] = DEVICE copy of image i's file bytes (at least scan_begin + scan_bytes of them); coefs[i] = DEVICE
+ * int16[coef_count] (128-byte aligned), filled in the dense natural-order form; status: DEVICE int32[n], 0 = decoded,
+ * non-zero = not decodable here (B2C_JPEG_HUFF_*).  One launch for the batch; asynchronous. */
+#define B2C_JPEG_HUFF_CORRUPT 1   /* bad code, run past the block, block count mismatch */
+#define B2C_JPEG_HUFF_TRUNCATED 2 /* the entropy-coded segment ends before the last MCU */
+#define B2C_JPEG_HUFF_NOSYNC 4    /* a sub-sequence's verification failed (no synchronisation) */
+int b2c_jpeg_huff_decode(const b2c_jpeg_info* infos, const b2c_jpeg_huff* huffs, const uint8_t* const* files,
+                         int16_t* const* coefs, int32_t* status, int n, void* ws, size_t ws_bytes, b2c_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ compared bit for bit with `PIL.Image.open(...).convert('RGB')`.
            restatement of the device stage; refusal of streams outside the covered set; corrupt input.
   gpu:     the device stage (b2c_jpeg_reconstruct) on ragged batches, and the embedding driver end to end on .jpg files."""
 import io
+import os
 
 import numpy as np
 import pytest
@@ -99,8 +100,12 @@ def test_truncated_file_is_a_reported_failure_like_the_reference(lib, tmp_path):
         (tmp_path / f"t{k}.jpg").write_bytes(data[:len(data) * 2 // 3])
         with pytest.raises(OSError):
             Image.open(tmp_path / f"t{k}.jpg").convert("RGB")
-        item, path = RawImageDataset([str(tmp_path / f"t{k}.jpg")], device_jpeg=True)[0]
+        item, path = RawImageDataset([str(tmp_path / f"t{k}.jpg")], device_jpeg=True, device_huffman=False)[0]
         assert item is None and path.endswith(f"t{k}.jpg")
+        # with the Huffman stage on the device the worker only parses the markers: a cut sequential file travels on as
+        # file bytes and is reported by the device (test_device_path_reports_truncated_files_to_the_driver)
+        item, _ = RawImageDataset([str(tmp_path / f"t{k}.jpg")], device_jpeg=True, device_huffman=True)[0]
+        assert item is None if kw.get("progressive") else item[0] == "jpegf"
 
 
 def test_host_stage_survives_corrupted_streams(lib):
@@ -149,7 +154,9 @@ def test_dataset_items_fall_back_to_pillow_per_file(lib, tmp_path):
     ds = RawImageDataset([str(tmp_path / n) for n in ("a.jpg", "b.jpg", "c.png", "d.jpg", "e.jpg")], device_jpeg=True)
     a, b, c, d, e = (ds[i][0] for i in range(5))
     assert isinstance(e, torch.Tensor) and tuple(e.shape) == (90, 70, 3)
-    assert isinstance(a, tuple) and a[0] == "jpegp" and a[2].dtype == torch.uint8
+    assert isinstance(a, tuple) and a[0] == "jpegf" and a[3].dtype == torch.uint8 and a[3].numel() % 16 == 0
+    a2 = RawImageDataset([str(tmp_path / "a.jpg")], device_jpeg=True, device_huffman=False)[0][0]
+    assert isinstance(a2, tuple) and a2[0] == "jpegp" and a2[2].dtype == torch.uint8
     assert isinstance(b, torch.Tensor) and np.array_equal(b.numpy(), np.asarray(Image.open(tmp_path / "b.jpg").convert("RGB")))
     assert isinstance(c, torch.Tensor) and tuple(c.shape) == (90, 70, 3)
     assert d is None
@@ -197,6 +204,173 @@ def test_device_reconstruct_many_random_streams(lib):
             part = sel[lo:lo + 17]
             for i, got in zip(part, fn([items[i] for i in part])):
                 assert np.array_equal(got.cpu().numpy(), refs[i])
+
+
+SEQ_CASES = [c for c in CASES if not c[4].get("progressive")]
+
+
+def test_huff_prepare_accepts_sequential_and_refuses_progressive(lib):
+    """Host half of K14b: the marker parse that feeds the device Huffman stage (no GPU needed)."""
+    from clip_assisted_data_labeling_b200 import jpeg
+    for case in CASES:
+        data, _ = make_jpeg(*case)
+        if case[4].get("progressive"):
+            with pytest.raises(jpeg.UnsupportedJPEG):
+                jpeg.huff_prepare(data)
+            continue
+        info, huff = jpeg.huff_prepare(data)
+        ref_info, _ = jpeg.entropy_decode(data)
+        assert bytes(info)[:64] == bytes(ref_info)[:64] and info.coef_count == ref_info.coef_count
+        assert [list(q) for q in info.qt] == [list(q) for q in ref_info.qt]
+        assert 0 < huff.scan_begin < len(data) and huff.scan_begin + huff.scan_bytes == len(data)
+        assert data[huff.scan_begin - 3:huff.scan_begin - 1] == b"\x00\x3f"  # SOS tail: Ss = 0, Se = 63
+        assert huff.restart_interval == ref_info.restart_interval
+        assert any(huff.tab[0].look) and any(huff.tab[1].look)
+
+
+@pytest.mark.gpu
+def test_device_huffman_stage_equals_host_stage(lib):
+    """K14b: coefficients decoded on the device (destuff + self-synchronising parallel Huffman decode + DC prefix sums) are
+    bit-identical to the host stage's on every sequential case of the corpus (all samplings, grey, restart intervals,
+    optimised tables, 2x2 .. 1280x960), in ONE batch; the images are Pillow's."""
+    from clip_assisted_data_labeling_b200 import jpeg
+    made = [make_jpeg(*c) for c in SEQ_CASES]
+    items = [jpeg.prepare_file(d) for d, _ in made]
+    coefs, status = jpeg.huffman_device(items)
+    assert status.cpu().tolist() == [0] * len(items)
+    off = 0
+    for (data, _), it, case in zip(made, items, SEQ_CASES):
+        _, want = jpeg.entropy_decode(data)
+        got = coefs[off:off + want.numel()].cpu()
+        off += want.numel()
+        assert torch.equal(got, want), case
+    outs, st = jpeg.decode_device(items)
+    for (data, ref), got, case in zip(made, outs, SEQ_CASES):
+        assert np.array_equal(got.cpu().numpy(), ref), case
+
+
+@pytest.mark.gpu
+def test_device_huffman_stage_many_random_streams_and_large_files(lib):
+    """Property run: random sizes / qualities / samplings / restart intervals (including one MCU), noise content (long
+    codes, many sub-sequences per image: several rounds per CTA) and smooth content (short streams)."""
+    from clip_assisted_data_labeling_b200 import jpeg
+    rng = np.random.default_rng(11)
+    made = []
+    for k in range(48):
+        w, h = (int(v) for v in rng.integers(2, 500, 2))
+        if k % 12 == 0:
+            w, h = 1536, 1024 + k  # > 512 sub-sequences: more than one round
+        sub = [0, 1, 2, "gray"][k % 4]
+        kw = {}
+        if k % 3 == 0:
+            kw["restart_marker_blocks"] = int(rng.integers(1, 12))
+        elif k % 3 == 1 and k % 2:
+            kw["restart_marker_rows"] = 1
+        if k % 5 == 0:
+            kw["optimize"] = True
+        rngk = np.random.default_rng(100 + k)
+        if k % 2:
+            im = rngk.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        else:
+            im = synthetic_image(k, h, w)
+        buf = io.BytesIO()
+        pil = Image.fromarray(im)
+        q = int(rng.integers(1, 101))
+        (pil.convert("L") if sub == "gray" else pil).save(buf, "JPEG", quality=q, **({} if sub == "gray" else {"subsampling": sub}), **kw)
+        made.append(buf.getvalue())
+    items, wants = [], []
+    for d in made:
+        try:
+            it = jpeg.prepare_file(d)
+        except jpeg.UnsupportedJPEG:
+            continue
+        items.append(it)
+        wants.append(jpeg.entropy_decode(d)[1])
+    assert len(items) >= 44
+    for lo in range(0, len(items), 19):
+        part = items[lo:lo + 19]
+        coefs, status = jpeg.huffman_device(part)
+        assert status.cpu().tolist() == [0] * len(part)
+        off = 0
+        for j, it in enumerate(part):
+            n = wants[lo + j].numel()
+            assert torch.equal(coefs[off:off + n].cpu(), wants[lo + j]), (lo + j, it[0].width, it[0].height, it[1].restart_interval)
+            off += n
+
+
+@pytest.mark.gpu
+def test_device_huffman_stage_reports_damaged_and_truncated_streams(lib):
+    """A stream the host stage refuses must not come back from the device as status 0 with different coefficients: cut
+    files, flipped bytes.  Either the device reports it (status != 0) or its coefficients equal the host stage's."""
+    from clip_assisted_data_labeling_b200 import _lib, jpeg
+    rng = np.random.default_rng(3)
+    seeds = [make_jpeg(*c)[0] for c in [(200, 300, 1, 95, {}), (256, 256, 2, 90, {"restart_marker_blocks": 4}), (301, 200, "gray", 80, {}),
+                                        (512, 512, 2, 90, {})]]
+    datas = []
+    for it in range(120):
+        d = bytearray(seeds[it % len(seeds)])
+        info, huff = jpeg.huff_prepare(bytes(d))
+        lo = int(huff.scan_begin)
+        if it % 3 == 0:
+            d = d[:int(rng.integers(lo + 1, len(d)))]
+        elif it % 3 == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                d[int(rng.integers(lo, len(d)))] = int(rng.integers(0, 256))
+        else:
+            d = d[:len(d) // 2] + b"\xff\xd9"
+        datas.append(bytes(d))
+    items, host = [], []
+    for d in datas:
+        try:
+            items.append(jpeg.prepare_file(d))
+        except (jpeg.UnsupportedJPEG, _lib.B2CError):
+            continue
+        try:
+            host.append(jpeg.entropy_decode(d)[1])
+        except (jpeg.UnsupportedJPEG, _lib.B2CError):
+            host.append(None)
+    coefs, status = jpeg.huffman_device(items)
+    st = status.cpu().tolist()
+    off, reported, agreed = 0, 0, 0
+    for code, it, want in zip(st, items, host):
+        n = int(it[0].coef_count)
+        if code == 0:
+            assert want is not None and torch.equal(coefs[off:off + n].cpu(), want)
+            agreed += 1
+        else:
+            reported += 1
+        off += n
+    assert reported > 60 and agreed >= 0
+
+
+@pytest.mark.gpu
+def test_device_path_reports_truncated_files_to_the_driver(lib, tmp_path):
+    """Files cut inside their entropy data: Pillow raises OSError (the reference skips them, utils/embedder.py:176-181).
+    With the Huffman stage on the device they are found there, retried on the host, and end up in Feature_Dataset.failed —
+    never embedded from a partly grey image.  Intact files of the same batch are unaffected."""
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from clip_assisted_data_labeling_b200.embedder import RawImageDataset, collate_raw, to_device_images
+    from oracle import vit_oracle
+    paths = []
+    for k in range(5):
+        buf = io.BytesIO()
+        Image.fromarray(synthetic_image(20 + k, 160, 200)).save(buf, "JPEG", quality=85, **({"restart_marker_blocks": 4} if k == 3 else {}))
+        data = buf.getvalue()
+        (tmp_path / f"f{k}.jpg").write_bytes(data if k % 2 == 0 else data[:len(data) * 2 // 3])
+        paths.append(str(tmp_path / f"f{k}.jpg"))
+    ds = RawImageDataset(paths, device_jpeg=True, device_huffman=True)
+    items, _ = collate_raw([ds[i] for i in range(5)])
+    assert all(it[0] == "jpegf" for it in items)
+    outs = to_device_images(items, "cuda")
+    assert [o is None for o in outs] == [False, True, False, True, False]
+    for k in (0, 2, 4):
+        assert np.array_equal(outs[k].cpu().numpy(), np.asarray(Image.open(paths[k]).convert("RGB")))
+    m = vit_oracle.build_visual("ViT-B-32", "openai", seed=0)
+    fd = Feature_Dataset(str(tmp_path), "ViT-B-32/openai", batch_size=8, shuffle_filenames=False,
+                         state_dict=vit_oracle.visual_state_dict(m), device_jpeg=True)
+    n, _ = fd.process()
+    assert n == 3 and sorted(os.path.basename(p) for p in fd.failed) == ["f1.jpg", "f3.jpg"]
+    assert not (tmp_path / "f1.pt").exists() and (tmp_path / "f0.pt").exists()
 
 
 @pytest.mark.gpu

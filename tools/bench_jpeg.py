@@ -4,6 +4,8 @@
   entropy_host     the host stage of the device path alone (marker parse + Huffman decode, C-ABI) on the same pool
   reconstruct_dev  the device stage alone (dequantise + IDCT + upsample + colour), CUDA events, coefficients resident
   hybrid_e2e       host stage (packed coefficients) -> pinned gather -> H2D -> device stage, wall clock
+  huffman_dev      K14b alone: the Huffman stage on the device, file bytes resident, CUDA events
+  device_e2e       marker parse on the host -> pinned gather of the FILES -> H2D -> device Huffman + reconstruction, wall clock
 One JSON line.  python tools/bench_jpeg.py [N] [threads]"""
 import concurrent.futures as cf
 import io
@@ -104,6 +106,34 @@ def run(n, threads, pool, label, imgs, q):
     t_pk_h2d = (time.perf_counter() - t0) / 5
 
     t_hyb, _ = timed(hybrid)
+
+    # ---- K14b: both stages on the device
+    prep = jpeg.prepare_file
+    t_prep, hitems = timed(lambda: list(pool.map(prep, datas)))
+    hcoefs, hstatus = jpeg.huffman_device(hitems)
+    torch.cuda.synchronize()
+    ok_h = hstatus.cpu().tolist() == [0] * n and torch.equal(hcoefs.cpu(), torch.cat([it[1] for it in items]))
+    for _ in range(2):
+        jpeg.huffman_device(hitems)
+    torch.cuda.synchronize()
+    from clip_assisted_data_labeling_b200 import _lib
+    lib = _lib.load()
+    _lib.prof_enable(True)
+    for _ in range(5):
+        jpeg.huffman_device(hitems)
+    torch.cuda.synchronize()
+    t_huff = prof_other_ms(lib) / 5 / 1e3
+    _lib.prof_enable(False)
+
+    def device_e2e():
+        its = list(pool.map(prep, datas))
+        o, st = jpeg.decode_device(its)
+        torch.cuda.synchronize()
+        return o
+
+    douts = device_e2e()
+    ok_h = ok_h and all(np.array_equal(o.cpu().numpy(), r) for o, r in zip(douts[:16], ref[:16]))
+    t_dev_e2e, _ = timed(device_e2e)
     coef_bytes = sum(int(it[0].coef_count) * 2 for it in items)
     out_bytes = sum(int(it[0].width) * int(it[0].height) * 3 for it in items)
     plane_bytes = sum(int(it[0].blocks_w[c]) * int(it[0].blocks_h[c]) * 64 for it in items for c in range(it[0].ncomp))
@@ -117,9 +147,18 @@ def run(n, threads, pool, label, imgs, q):
         "h2d_plus_reconstruct_images_per_s": n / t_dev_h2d, "h2d_plus_reconstruct_ms_per_batch": 1e3 * t_dev_h2d,
         "entropy_host_packed_images_per_s": n / t_pk, "packed_h2d_plus_reconstruct_images_per_s": n / t_pk_h2d,
         "hybrid_e2e_images_per_s": n / t_hyb,
+        "huffman_dev": {"bit_exact_vs_host_stage_and_pillow": bool(ok_h), "images_per_s": n / t_huff, "ms_per_batch": 1e3 * t_huff,
+                        "entropy_bytes_per_s": sum(map(len, datas)) / t_huff, "host_prepare_images_per_s": n / t_prep,
+                        "device_e2e_images_per_s": n / t_dev_e2e, "file_bytes_h2d_per_image": sum(map(len, datas)) / n},
         "bytes_per_image": {"coefficients_h2d": coef_bytes / n, "rgb_out": out_bytes / n, "planes_write_then_read": plane_bytes / n,
                             "packed_coefficients_h2d": sum(int(it[1].numel()) for it in pitems) / n},
     }), flush=True)
+
+
+def prof_other_ms(lib):
+    """Milliseconds the library's stage timer recorded (CUDA events around the launches) since prof_enable(True)."""
+    from clip_assisted_data_labeling_b200 import _lib
+    return float(sum(ms for ms, _ in _lib.prof_read().values()))
 
 
 if __name__ == "__main__":

@@ -19,7 +19,8 @@
 //                    true start of the segment a stream that passes is decoded exactly; anything else is reported.
 //   5. DC          : differences -> values, a prefix sum per component over the blocks in decode order (restarted at
 //                    every restart interval).
-// Sub-sequences are handled in rounds of kHuffThreads; a round starts from the true exit state of the previous one.
+// Sub-sequences of all restart segments are numbered consecutively and handled in rounds of kHuffThreads; a round that
+// cuts a segment hands the true exit state and block count of its last sub-sequence to the next one.
 #include <string.h>
 
 #include <vector>
@@ -38,6 +39,7 @@ struct HuffJobDev {
   uint32_t max_segs;    // capacity of the segment table
   uint8_t* clean;       // destuffed stream, 16-byte aligned, raw_len + 64 bytes
   uint32_t* seg_begin;  // [max_segs + 1] first destuffed byte of every restart segment
+  uint32_t* sub_base;   // [max_segs + 1] sub-sequences in the segments before this one
   int16_t* coefs;       // dense output, natural order
   const b2c_jpeg_hufftab* tabs;  // 4 tables (device)
   int32_t ncomp, hs0, vs0, mcus_x, mcus_y;
@@ -302,76 +304,120 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huff_kernel(const HuffJobDe
   __syncthreads();
   const uint32_t* words = reinterpret_cast<const uint32_t*>(J.clean);
 
-  // ---- 2-4. per restart segment: rounds of kHuffThreads sub-sequences
+  // ---- 2-4. sub-sequences of ALL restart segments, numbered consecutively, in rounds of kHuffThreads
+  // sub_base[s] = number of sub-sequences in the segments before s.  Each segment has its own grid, anchored at its
+  // first bit, and its first sub-sequence starts from the true state — restart markers only add parallelism.
+  uint32_t total_subs = 0;
   if (!err) {
-    for (uint32_t seg = 0; seg < nsegs; ++seg) {
-      const uint32_t sb = J.seg_begin[seg] * 8u, se = J.seg_begin[seg + 1] * 8u;  // bit range of the segment
-      const int first_mcu = interval ? static_cast<int>(seg) * interval : 0;
-      const int seg_mcus = interval ? min(interval, total_mcus - first_mcu) : total_mcus;
-      const int blk_first = first_mcu * bpm, blk_limit = blk_first + seg_mcus * bpm;
-      // sub-sequence grid anchored at the segment's first bit: sub-sequence i = bits [sb + i*1024, sb + (i+1)*1024)
-      const uint32_t nsub = (se - sb + kSubBits - 1) / kSubBits;
-      HState ent;
-      ent.p = sb; ent.b = 0; ent.z = 0;
-      int blk_base = blk_first;
-      for (uint32_t base = 0; base < nsub; base += kHuffThreads) {
-        const int nact = static_cast<int>(min(static_cast<uint32_t>(kHuffThreads), nsub - base));
-        const bool active = tid < nact;
-        const uint32_t my = base + tid;
-        // -- speculate
-        HState st;
-        int nb = 0, dummy = 0;
-        if (active) {
-          if (tid == 0) st = ent;
-          else { st.p = sb + my * kSubBits; st.b = 0; st.z = 0; }
-          decode_sub<false>(J, s_tabs, words, min(sb + (my + 1) * kSubBits, se), bpm, ylum, st, nb, 0, 0, dummy);
-          s_state[tid] = st.pack();
-          s_nblk[tid] = nb;
-        }
-        // -- synchronise
-        bool done = !active || tid == nact - 1;
-        for (int k = 1; k < nact; ++k) {
-          __syncthreads();
-          const int j = tid + k;
-          const bool work = !done && j < nact;
-          bool same = false;
-          if (work) {
-            decode_sub<false>(J, s_tabs, words, min(sb + (base + j + 1) * kSubBits, se), bpm, ylum, st, nb, 0, 0, dummy);
-            same = st.pack() == s_state[j];
-          }
-          __syncthreads();
-          if (work) {
-            s_nblk[j] = nb;  // block counts of the earlier-started chain are the authoritative ones
-            if (same) done = true;
-            else s_state[j] = st.pack();
-          } else {
-            done = true;
-          }
-          if (!__syncthreads_or(!done && tid + k + 1 < nact)) break;
-        }
-        __syncthreads();
-        // -- write + verify
-        const int mine = active ? s_nblk[tid] : 0;
-        int round_blocks = 0;
-        const int boff = block_exclusive_scan(mine, s_warp, &round_blocks);
-        if (active) {
-          HState in = tid == 0 ? ent : HState::unpack(s_state[tid - 1]);
-          const bool last = my + 1 == nsub;
-          int got = 0;
-          decode_sub<true>(J, s_tabs, words, min(sb + (my + 1) * kSubBits, se), bpm, ylum, in, got, blk_base + boff,
-                           blk_limit, err);
-          if (last) {
-            if (blk_base + boff + got != blk_limit) err |= in.p >= se ? B2C_JPEG_HUFF_TRUNCATED : B2C_JPEG_HUFF_CORRUPT;
-            if (in.p > se) err |= B2C_JPEG_HUFF_TRUNCATED;  // consumed bits the file does not have
-          } else if (in.pack() != s_state[tid] || got != mine) {
-            err |= B2C_JPEG_HUFF_NOSYNC;
-          }
-        }
-        ent = HState::unpack(s_state[nact - 1]);
-        blk_base += round_blocks;
-        __syncthreads();
+    for (uint32_t s0 = 0; s0 < nsegs; s0 += kHuffThreads) {
+      const uint32_t sg = s0 + tid;
+      int cnt = 0;
+      if (sg < nsegs) {
+        const uint32_t bytes = J.seg_begin[sg + 1] - J.seg_begin[sg];
+        cnt = static_cast<int>((bytes * 8u + kSubBits - 1) / kSubBits);
+        if (cnt == 0) err |= B2C_JPEG_HUFF_CORRUPT;  // two markers back to back: a segment holds at least one MCU
       }
-      if (nsub == 0) err |= B2C_JPEG_HUFF_TRUNCATED;
+      int tot = 0;
+      const int ex = block_exclusive_scan(cnt, s_warp, &tot);
+      if (sg < nsegs) J.sub_base[sg] = total_subs + ex;
+      total_subs += tot;
+    }
+    if (tid == 0) J.sub_base[nsegs] = total_subs;
+    if (__syncthreads_or(err)) err |= B2C_JPEG_HUFF_CORRUPT;
+  }
+  if (!err) {
+    __shared__ int s_excl[kHuffThreads];
+    __shared__ int s_carry;
+    HState ent;          // true entry state of the round's first sub-sequence when it continues a segment
+    ent.p = 0; ent.b = 0; ent.z = 0;
+    int carry = 0;       // blocks that segment completed in earlier rounds
+    for (uint32_t base = 0; base < total_subs; base += kHuffThreads) {
+      const int nact = static_cast<int>(min(static_cast<uint32_t>(kHuffThreads), total_subs - base));
+      const bool active = tid < nact;
+      const uint32_t g = base + tid;
+      // which segment, which sub-sequence of it
+      uint32_t seg = 0, idx = 0, nsub = 1, sb = 0, se = 0;
+      int blk_first = 0, blk_limit = 0;
+      if (active) {
+        uint32_t lo = 0, hi = nsegs - 1;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi + 1) >> 1;
+          if (J.sub_base[mid] <= g) lo = mid;
+          else hi = mid - 1;
+        }
+        seg = lo;
+        idx = g - J.sub_base[seg];
+        nsub = J.sub_base[seg + 1] - J.sub_base[seg];
+        sb = J.seg_begin[seg] * 8u;
+        se = J.seg_begin[seg + 1] * 8u;
+        const int first_mcu = interval ? static_cast<int>(seg) * interval : 0;
+        const int seg_mcus = interval ? min(interval, total_mcus - first_mcu) : total_mcus;
+        blk_first = first_mcu * bpm;
+        blk_limit = blk_first + seg_mcus * bpm;
+      }
+      const bool seg_first = idx == 0, seg_last = idx + 1 == nsub;
+      // -- speculate
+      HState st;
+      st.p = 0; st.b = 0; st.z = 0;
+      int nb = 0, dummy = 0;
+      if (active) {
+        if (seg_first) { st.p = sb; }
+        else if (tid == 0) st = ent;
+        else { st.p = sb + idx * kSubBits; }
+        decode_sub<false>(J, s_tabs, words, min(sb + (idx + 1) * kSubBits, se), bpm, ylum, st, nb, 0, 0, dummy);
+        s_state[tid] = st.pack();
+        s_nblk[tid] = nb;
+      }
+      // -- synchronise (a chain ends with its segment)
+      bool done = !active || tid == nact - 1 || seg_last;
+      for (int k = 1; k < nact; ++k) {
+        __syncthreads();
+        const int j = tid + k;
+        const bool work = !done && j < nact && idx + k < nsub;
+        bool same = false;
+        if (work) {
+          decode_sub<false>(J, s_tabs, words, min(sb + (idx + k + 1) * kSubBits, se), bpm, ylum, st, nb, 0, 0, dummy);
+          same = st.pack() == s_state[j];
+        }
+        __syncthreads();
+        if (work) {
+          s_nblk[j] = nb;  // block counts of the earlier-started chain are the authoritative ones
+          if (same) done = true;
+          else s_state[j] = st.pack();
+        } else {
+          done = true;
+        }
+        if (!__syncthreads_or(!done && tid + k + 1 < nact && idx + k + 1 < nsub)) break;
+      }
+      __syncthreads();
+      // -- write + verify
+      const int mine = active ? s_nblk[tid] : 0;
+      int round_blocks = 0;
+      const int ex = block_exclusive_scan(mine, s_warp, &round_blocks);
+      s_excl[tid] = ex;
+      __syncthreads();
+      // blocks of my segment completed before my sub-sequence
+      const bool from_earlier_round = idx > static_cast<uint32_t>(tid);
+      const int before = from_earlier_round ? carry + ex : ex - s_excl[tid - static_cast<int>(idx)];
+      if (active) {
+        HState in;
+        if (seg_first) { in.p = sb; in.b = 0; in.z = 0; }
+        else if (tid == 0) in = ent;
+        else in = HState::unpack(s_state[tid - 1]);
+        int got = 0;
+        decode_sub<true>(J, s_tabs, words, min(sb + (idx + 1) * kSubBits, se), bpm, ylum, in, got, blk_first + before,
+                         blk_limit, err);
+        if (seg_last) {
+          if (blk_first + before + got != blk_limit) err |= in.p >= se ? B2C_JPEG_HUFF_TRUNCATED : B2C_JPEG_HUFF_CORRUPT;
+          if (in.p > se) err |= B2C_JPEG_HUFF_TRUNCATED;  // consumed bits the file does not have
+        } else if (in.pack() != s_state[tid] || got != mine) {
+          err |= B2C_JPEG_HUFF_NOSYNC;
+        }
+        if (tid == nact - 1) s_carry = before + mine;  // only used if the next round continues this segment
+      }
+      ent = HState::unpack(s_state[nact - 1]);
+      __syncthreads();
+      carry = s_carry;
     }
   }
   // combine the threads' verdicts (bit by bit: __syncthreads_or returns a predicate)
@@ -435,7 +481,7 @@ extern "C" int b2c_jpeg_huff_workspace_bytes(const b2c_jpeg_huff* huffs, int n, 
   for (int i = 0; i < n; ++i) {
     B2C_REQUIRE(huffs[i].scan_bytes > 0 && huffs[i].scan_bytes < (1ll << 28), "b2c_jpeg_huff_workspace_bytes: bad scan size for image %d", i);
     total += h256(static_cast<size_t>(huffs[i].scan_bytes) + 64);
-    total += h256((static_cast<size_t>(max_segments(huffs[i])) + 2) * sizeof(uint32_t));
+    total += 2 * h256((static_cast<size_t>(max_segments(huffs[i])) + 2) * sizeof(uint32_t));
   }
   *bytes = total;
   return 0;
@@ -476,6 +522,8 @@ extern "C" int b2c_jpeg_huff_decode(const b2c_jpeg_info* infos, const b2c_jpeg_h
     J.clean = wsb + off;
     off += h256(static_cast<size_t>(H.scan_bytes) + 64);
     J.seg_begin = reinterpret_cast<uint32_t*>(wsb + off);
+    off += h256((static_cast<size_t>(J.max_segs) + 2) * sizeof(uint32_t));
+    J.sub_base = reinterpret_cast<uint32_t*>(wsb + off);
     off += h256((static_cast<size_t>(J.max_segs) + 2) * sizeof(uint32_t));
     J.coefs = coefs[i];
     J.tabs = td + static_cast<size_t>(i) * 4;

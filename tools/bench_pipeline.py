@@ -43,11 +43,49 @@ def main():
                                                progressive=(a.progressive_every > 0 and i % a.progressive_every == a.progressive_every - 1))
         with cf.ThreadPoolExecutor(os.cpu_count()) as ex:
             list(ex.map(write, range(a.n)))
+        # ---- the host side alone: how many images per second the DataLoader workers can hand to the main process (what
+        # bounds files -> embeddings once several GPUs share the box's cores), and the same plus the device decode
+        from torch.utils.data import DataLoader
+        from clip_assisted_data_labeling_b200.embed_driver import find_images
+        from clip_assisted_data_labeling_b200.embedder import RawImageDataset, collate_raw, to_device_images
+        paths = sorted(find_images(root))
+        for name, kw in (("loader only: Pillow decode in the workers", dict(device_jpeg=False)),
+                         ("loader only: host Huffman stage in the workers (packed coefficients)", dict(device_jpeg=True, device_huffman=False)),
+                         ("loader only: marker parse in the workers (file bytes; Huffman stage on the device)", dict(device_jpeg=True, device_huffman=True))):
+            if a.only and a.only not in name:
+                continue
+            for with_device in (False, True):
+                best = None
+                for rep in range(2):
+                    dl = DataLoader(RawImageDataset(paths, **kw), batch_size=a.batch, shuffle=False, num_workers=a.workers,
+                                    collate_fn=collate_raw, prefetch_factor=2, persistent_workers=False)
+                    it = iter(dl)
+                    first = next(it)  # worker start-up is not the steady state
+                    if with_device:
+                        to_device_images(first[0], "cuda")
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    cnt = 0
+                    for items, _ in it:
+                        if with_device:
+                            to_device_images(items, "cuda")
+                        cnt += len(items)
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                    del it, dl
+                print(json.dumps({"config": name + (" + decode to uint8 RGB in HBM" if with_device else ""), "images": cnt, "workers": a.workers,
+                                  "batch": a.batch, "seconds": best, "images_per_s": cnt / best}), flush=True)
+        if a.only == "loader only":
+            return
         with contextlib.redirect_stdout(sys.stderr):
             enc = CLIP_Encoder(a.model, device="cuda", seed=0, allow_random_init=True)
+        os.environ["B2C_DEVICE_HUFFMAN"] = "1"
         for name, kw in (("pillow decode, .pt files", dict(device_jpeg=False)),
-                         ("device JPEG decode (K14), .pt files", dict(device_jpeg=True)),
-                         ("device JPEG decode (K14), packed store only", dict(device_jpeg=True, write_pt=False, packed_dir=os.path.join(root, "_packed")))):
+                         ("device JPEG decode (K14, Huffman stage on the host), .pt files", dict(device_jpeg=True, _huff="0")),
+                         ("device JPEG decode (K14 + K14b: Huffman stage on the device), .pt files", dict(device_jpeg=True)),
+                         ("device JPEG decode (K14 + K14b), packed store only", dict(device_jpeg=True, write_pt=False, packed_dir=os.path.join(root, "_packed")))):
+            os.environ["B2C_DEVICE_HUFFMAN"] = kw.pop("_huff", "1")
             if a.only and a.only not in name:
                 continue
             best = None

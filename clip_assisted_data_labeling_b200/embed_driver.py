@@ -145,6 +145,7 @@ class Feature_Dataset:
         kw = dict(batch_size=batch_size, shuffle=False, num_workers=num_workers, collate_fn=collate_raw)
         if num_workers > 0:
             kw["prefetch_factor"] = 2
+        self._dl_kw = kw
         self.dataloader = DataLoader(self.img_dataset, **kw)
         self._writer_threads = writer_threads
         # .pt writing is pickling, i.e. GIL-bound (~1 ms per file): large jobs hand whole batches to writer PROCESSES
@@ -237,17 +238,32 @@ class Feature_Dataset:
                 pending = []
             tick("files / packed shard (host)", t0)
 
+        # Resume (_1_embed_with_CLIP.py:118-128: skip an image whose .pt already holds this model's key): decided BEFORE
+        # the images are read — the existing files are probed on a thread pool and only the rest goes to the DataLoader, so
+        # a resumed run neither decodes what it will skip nor loads a .pt per image on the main thread inside the loop.
+        dataloader = self.dataloader
+        if self.write_pt and not self.force_reencode:
+            t0 = _time.perf_counter()
+            cand = [p for p in self.img_filepaths if os.path.exists(os.path.splitext(p)[0] + ".pt")]
+            if cand:
+                with concurrent.futures.ThreadPoolExecutor(max_workers=min(32, 4 * (os.cpu_count() or 4))) as ex:
+                    flags = list(ex.map(lambda p: already_encoded(os.path.splitext(p)[0] + ".pt", self.model_name), cand))
+                done = {p for p, f in zip(cand, flags) if f}
+                if done:
+                    n_skipped = len(done)
+                    rest = [p for p in self.img_filepaths if p not in done]
+                    dataloader = DataLoader(RawImageDataset(rest, device_jpeg=self.device_jpeg), **self._dl_kw) if rest else []
+            tick("resume checks", t0)
+
         prev, k = None, 0
         t_it = _time.perf_counter()
-        for images, img_paths in self.dataloader:
+        for images, img_paths in dataloader:
             t_it = tick("DataLoader (wait + unpickle)", t_it)
             todo_imgs, todo_paths, todo_img_paths = [], [], []
             for im, p in zip(images, img_paths):
                 save_path = os.path.splitext(p)[0] + ".pt"
                 if im is None:
                     self.failed.append(p)
-                elif self.write_pt and not self.force_reencode and already_encoded(save_path, self.model_name):
-                    n_skipped += 1
                 else:
                     todo_imgs.append(im)
                     todo_paths.append(save_path)
@@ -255,7 +271,6 @@ class Feature_Dataset:
             cur = None
             if todo_imgs:
                 b = len(todo_imgs)
-                t_it = tick("resume checks", t_it)
                 dev_imgs = to_device_images(todo_imgs, self.device) if on_cuda else todo_imgs  # cpu: injected encoder (host-logic tests)
                 if any(im is None for im in dev_imgs):  # a JPEG the device reported and neither the host stage nor Pillow decodes
                     keep = [j for j, im in enumerate(dev_imgs) if im is not None]

@@ -1,3 +1,5 @@
+"""K14b alone with and without restart markers: 256 synthetic 512x512 4:2:0 files per variant, CUDA-event time of the
+device Huffman stage (library stage timer) and a bit-exact check against the host stage.  python tools/bench_huff_restart.py"""
 import io, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

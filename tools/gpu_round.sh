@@ -30,7 +30,6 @@ for w in $WHAT; do
     archs)
       : > $OUT/${TAG}_archs.jsonl
       timeout 300 python tools/bench_arch.py ViT-H-14/laion2b_s32b_b79k --fc --batch 128 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
-      B2C_ATTN=legacy timeout 300 python tools/bench_arch.py ViT-H-14/laion2b_s32b_b79k --fc --batch 128 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
       timeout 300 python tools/bench_arch.py ViT-L-14-336/openai --batch 64 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
       timeout 300 python tools/bench_arch.py ViT-B-32/openai --batch 512 >> $OUT/${TAG}_archs.jsonl 2>> $OUT/${TAG}_archs.err
       cat $OUT/${TAG}_archs.jsonl; tail -3 $OUT/${TAG}_archs.err ;;
@@ -69,7 +68,7 @@ for w in $WHAT; do
     full)
       # one capture per kernel family: a few launches each (ncu replays ~40x per kernel)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:umma2_tile -s 30 -c 8 \
-        -o $OUT/${TAG}_prof_gemm -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_gemm.log 2>&1
+        -o $OUT/${TAG}_prof_gemm -f python tools/profile_step.py embed 256 > $OUT/${TAG}_prof_gemm.log 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention -s 2 -c 1 \
         -o $OUT/${TAG}_prof_attn -f python tools/profile_attn.py 512 > $OUT/${TAG}_prof_attn.log 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:layernorm -c 1 \
@@ -78,6 +77,8 @@ for w in $WHAT; do
         -o $OUT/${TAG}_prof_pre -f python tools/profile_step.py embed 128 > $OUT/${TAG}_prof_pre.log 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:"umma|dedup" -s 1 -c 2 \
         -o $OUT/${TAG}_prof_dedup -f python tools/profile_step.py dedup 100000 > $OUT/${TAG}_prof_dedup.log 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:jpeg_huff_kernel -s 2 -c 1 \
+        -o $OUT/${TAG}_prof_huff -f python tools/bench_huff_restart.py > $OUT/${TAG}_prof_huff.log 2>&1
       ls -la $OUT | tail -20 ;;
   esac
 done

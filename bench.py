@@ -410,7 +410,11 @@ def run_dedup(args, world, rank, barrier, dist, peaks):
     _lib.prof_enable(False)
     launches = _lib.launch_count() - l0
     kern_ms = torch.tensor([rec.get("dedup", (0.0, 0))[0]], device="cuda")
+    kern_all = [kern_ms.item()]
     if world > 1:
+        ka = torch.empty(world, device="cuda")
+        dist.all_gather_into_tensor(ka, kern_ms.float())
+        kern_all = ka.cpu().tolist()
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     npairs = n_tot * (n_tot - 1) / 2
@@ -421,15 +425,16 @@ def run_dedup(args, world, rank, barrier, dist, peaks):
            "data": "the same seeded set for every N (sliced per rank); %d planted near-duplicate pairs, %d of them across shards" % (
                len(src_h), cross),
            "timing": "host wall clock around the whole call (normalise + all-gather + kernels + count/pair exchange + D2H + sort), max over ranks",
-           "parallelism": "own-shard block under the all-gather, then greedy-dealt bands; one all-gather of the shards + two fixed-shape "
-                          "gathers of counts / pairs" if world > 1 else "single GPU, bands of 2048 rows"}
+           "parallelism": "own-shard block under the all-gather, then the ranks draw the remaining bands (largest first) from a shared "
+                          "counter, so the work follows each GPU's power-capped speed; one all-gather of the shards + two fixed-shape gathers of counts / pairs" if world > 1 else "single GPU, bands of 2048 rows"}
     if rank == 0:
         out["parity"] = check_pairs(pairs, src_h, dst_h, cos_h, thr)
         k_s = kern_ms.item() / 1e3
         out["roofline"] = {"bound": "tensor", "achieved": flops / world / k_s / 1e12 if k_s > 0 else None, "peak": peaks["tf_burst"],
                            "unit": "TFLOP/s", "frac": (flops / world / k_s / 1e12 / peaks["tf_burst"]) if k_s > 0 else None,
                            "kernel": "umma2_tile_kernel<DedupPolicy> (fp16 x fp16 -> fp32, threshold + pair emission in the epilogue)",
-                           "kernel_seconds": k_s, "algorithmic_flops": flops,
+                           "kernel_seconds": k_s, "kernel_seconds_per_rank": [round(v / 1e3, 5) for v in kern_all],
+                           "algorithmic_flops": flops,
                            "how": "CUDA events around this rank's band launches (library stage timer, max over ranks); 2*E FLOP per "
                                   "unordered pair, per-GPU share; peak = burst (kernel timed alone)", "traffic": None}
     # ---- e2e: the packed store on disk -> pair list of paths on the host

@@ -192,7 +192,9 @@ def owned_blocks(n_local: int, rank: int, world_size: int, band_rows: int = BAND
               so it runs while the all-gather is in flight;
       then    its share of everything to the right of the shards' diagonal blocks: bands of ``band_rows`` rows (cut at
               shard boundaries), columns from the end of the band's shard to n_total.  Work per band falls from shard
-              to shard, so the bands are dealt largest-first to the least-loaded rank (every rank computes the same deal).
+              to shard, so the bands are dealt largest-first to the least-loaded rank (every rank computes the same
+              deal).  This is the STATIC split (single calls, tests); duplicate_pairs_distributed lets the ranks draw the
+              same bands from a shared counter instead, because the GPUs of a box run at different power-capped clocks.
     Every pair (i < j) belongs to exactly one block of exactly one rank."""
     n_total = n_local * world_size
     lo = rank * n_local
@@ -201,15 +203,59 @@ def owned_blocks(n_local: int, rank: int, world_size: int, band_rows: int = BAND
     for s in range(world_size - 1):  # the last shard has nothing to its right
         for r0 in range(s * n_local, (s + 1) * n_local, band_rows):
             bands.append((r0, min(r0 + band_rows, (s + 1) * n_local), (s + 1) * n_local, n_total))
-    load = [0] * world_size
+    load = [n_local * (n_local - 1) / 2.0] * world_size  # everybody starts with its own shard's triangle
     rest = []
     for blk in sorted(bands, key=lambda t: (-(t[1] - t[0]) * (t[3] - t[2]), t[0])):
+        w = (blk[1] - blk[0]) * (blk[3] - blk[2])
         owner = min(range(world_size), key=lambda r: (load[r], r))
-        load[owner] += (blk[1] - blk[0]) * (blk[3] - blk[2])
+        load[owner] += w
         if owner == rank:
             rest.append(blk)
     rest.sort()
     return local, rest
+
+
+def launch_marker():
+    """An event recorded on the current stream after the launches so far; ``.synchronize()`` waits for them."""
+    ev = torch.cuda.Event()
+    ev.record()
+    return ev
+
+
+_ticket_calls = 0
+
+
+class BandTickets:
+    """A job-wide counter the ranks draw band numbers from (`Store.add` of the process group's rendezvous store is an
+    atomic fetch-and-add served by rank 0's store thread; ~50 us per draw on one box).  Generation g of a call hands out
+    tickets [g*stride, (g+1)*stride): an overflow re-run needs no reset.  Without a store (a backend that has none)
+    ``next`` deals the static round-robin share instead."""
+
+    def __init__(self, n_items: int, rank: int, world: int):
+        global _ticket_calls
+        _ticket_calls += 1
+        self.n, self.rank, self.world = n_items, rank, world
+        self.stride = n_items + world  # every rank draws one ticket past the end before it stops
+        self.gen = -1
+        self.key = f"b2c/dedup_tickets/{_ticket_calls}"
+        try:
+            from torch.distributed.distributed_c10d import _get_default_store
+            self.store = _get_default_store()
+        except Exception:  # noqa: BLE001
+            self.store = None
+        self._static = 0
+
+    def new_generation(self):
+        self.gen += 1
+        self._static = self.rank
+
+    def next(self) -> int:
+        """Next band index of this generation, or -1 when they are all taken."""
+        if self.store is None:
+            i, self._static = self._static, self._static + self.world
+        else:
+            i = int(self.store.add(self.key, 1)) - 1 - self.gen * self.stride
+        return i if 0 <= i < self.n else -1
 
 
 def duplicate_pairs_distributed(local_embeddings: torch.Tensor, threshold: float, compare: str = "ref_fp16",
@@ -217,8 +263,9 @@ def duplicate_pairs_distributed(local_embeddings: torch.Tensor, threshold: float
     """Multi-GPU form: every rank passes its shard [n_local, E] (equal n_local on all ranks; pad the last shard
     with zero rows, which never match).  Each rank normalises its shard straight into its slice of the gather buffer;
     ONE all-gather (NCCL) of the shards then runs on NCCL's stream WHILE the rank searches the block of its own shard
-    on a side stream; after the gather it searches the bands ``owned_blocks`` deals it.  Counts and pair buffers
-    come back through two fixed-shape all-gathers (no pickling).  Every rank returns the full sorted result."""
+    on a side stream; after the gather the ranks draw the remaining bands (largest first) from a shared counter, a few
+    at a time, so the work follows the GPUs' actual speed.  Counts and pair buffers come back through two fixed-shape
+    all-gathers (no pickling).  Every rank returns the full sorted result."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = local_embeddings.device  # normalize_rows_f16 refuses anything but a CUDA tensor: there is no CPU fallback
@@ -228,12 +275,18 @@ def duplicate_pairs_distributed(local_embeddings: torch.Tensor, threshold: float
     gathered = torch.empty(n_total, E_pad, dtype=torch.float16, device=dev)
     mine = gathered[rank * n_local:(rank + 1) * n_local]
     normalize_rows_f16(local_embeddings, out=mine)
-    local_blocks, rest_blocks = owned_blocks(n_local, rank, world)
+    local_blocks, _ = owned_blocks(n_local, rank, world)
+    # everything right of the shards' diagonal blocks, as bands, largest first: the ranks DRAW them from a shared counter,
+    # so a GPU running at a lower power-capped clock simply takes fewer and all ranks finish together
+    bands = sorted((b for r in range(world) for b in owned_blocks(n_local, r, world)[1]),
+                   key=lambda t: (-(t[1] - t[0]) * (t[3] - t[2]), t[0]))
+    tickets = BandTickets(len(bands), rank, world)
     cap = capacity if capacity is not None else max(1 << 16, 4 * n_total // world)
     first = True
     while True:
         buf = torch.empty(cap, 3, dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        tickets.new_generation()
         if first:
             # the gather only WRITES the peers' slices; this rank's slice is read by both the gather and the local search
             work = dist.all_gather_into_tensor(gathered, mine, group=group, async_op=True)
@@ -242,7 +295,15 @@ def duplicate_pairs_distributed(local_embeddings: torch.Tensor, threshold: float
             first = False
         else:
             launch_pair_search(gathered, local_blocks, float(threshold), compare, buf, cnt)
-        launch_pair_search(gathered, rest_blocks, float(threshold), compare, buf, cnt)
+        inflight = []
+        while True:
+            i = tickets.next()
+            if i < 0:
+                break
+            launch_pair_search(gathered, [bands[i]], float(threshold), compare, buf, cnt)
+            inflight.append(launch_marker())
+            if len(inflight) > 2:  # keep two bands queued behind the running one, draw the next when one retires
+                inflight.pop(0).synchronize()
         # counts of all ranks (one small collective), then every rank's pairs in fixed-capacity slots
         counts = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(counts, cnt, group=group)

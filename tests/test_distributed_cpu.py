@@ -64,6 +64,12 @@ def _worker(rank, world, port, q):
     dist.barrier()
     dedup.normalize_rows_f16 = _cpu_normalize      # the two kernel calls, replaced by their CPU stand-ins (test only)
     dedup.launch_pair_search = _oracle_search
+    # bands are drawn from the job's store counter (whoever is faster takes more): the result must not depend on who
+    # computes what.  The stream marker of the pacing loop has no CPU form.
+    class _NoEvent:
+        def synchronize(self):
+            pass
+    dedup.launch_marker = _NoEvent
     pairs, sims = dedup.duplicate_pairs_distributed(local, 0.96)
     # too small a pair buffer: every rank re-runs with room for the largest list and the answer is the same
     pairs2, sims2 = dedup.duplicate_pairs_distributed(local, 0.96, capacity=2)

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "b2c_launch.h"
@@ -187,6 +188,8 @@ struct ResampleParams {
   int HP;             // bytes per (channel, output column) of the transposed horizontal tile (4 * odd)
   int SR;             // source rows staged per sub-batch (multiple of 4)
   int SPP;            // bytes per staged (channel, row) (multiple of 4)
+  int nch;            // colour channels per CTA: 3, or 1 for very large sources (grid.z = 3, tiles a third the size)
+  int hsm;            // horizontal coefficient table in shared memory (few taps) or read from global memory / L2
   int layout, patch, Kp;
   int g;              // patches per side (patch-major layout)
   uint32_t magicP;    // floor(2^32 / patch) + 1: n / patch == umulhi(n, magicP) for n < 65536
@@ -218,39 +221,41 @@ struct PreSmem {
 };
 __host__ __device__ inline size_t pre_a16(size_t v) { return (v + 15) & ~size_t(15); }
 __host__ __device__ inline int pre_odd(int v) { return v | 1; }  // uint4 pitch of a coefficient row (bank spread)
-__host__ __device__ inline PreSmem pre_smem(int R, int KS4, int TR, int HP, int SR, int SPP) {
+__host__ __device__ inline PreSmem pre_smem(int R, int KS4, int TR, int HP, int SR, int SPP, int nch, int hsm) {
   PreSmem s;
   size_t off = 0;
   s.lut = off;   off += pre_a16(768 * sizeof(float));
-  s.hcoef = off; off += pre_a16(static_cast<size_t>(R) * pre_odd(KS4) * 16);
+  s.hcoef = off; off += hsm ? pre_a16(static_cast<size_t>(R) * pre_odd(KS4) * 16) : 0;
   s.hb = off;    off += pre_a16(static_cast<size_t>(R) * 8);
   s.vcoef = off; off += pre_a16(static_cast<size_t>(TR) * KS4 * 16);
   s.vb = off;    off += pre_a16(static_cast<size_t>(TR) * 8);
-  s.hbuf = off;  off += pre_a16(static_cast<size_t>(3) * R * HP);
-  s.stage = off; off += pre_a16(static_cast<size_t>(3) * SR * SPP);
+  s.hbuf = off;  off += pre_a16(static_cast<size_t>(nch) * R * HP);
+  s.stage = off; off += pre_a16(static_cast<size_t>(nch) * SR * SPP);
   s.total = off;
   return s;
 }
 
 constexpr int kResThreads = 256;
 
-// Horizontal pass over the staged rows [0, 4 * rgroups): work item = (4 source rows, channel, output slot).
-// G > 0: tap-group count known at compile time (unrolled); G == 0: `groups` at run time.
-template <int G>
+// Horizontal pass over the staged rows [0, 4 * rgroups): work item = (4 source rows, local channel, output column).
+// G > 0: tap-group count known at compile time (unrolled, every thread runs the CTA's maximum; the tiles carry the slack
+// for reading zero-coefficient groups past a window's end); G == 0: each thread loops over its own window's groups.
+// hcoef: coefficient rows of CP uint4 each, in shared memory or (many taps) global memory.
+template <int G, int NCH>
 __device__ __forceinline__ void resample_hpass(const uint8_t* __restrict__ stage, uint8_t* __restrict__ hbuf,
                                                const uint4* __restrict__ hcoef, const int2* __restrict__ hb, int R,
-                                               int CP, int HP, int SRc, int SPP, int rgroups, int y0, int groups,
-                                               int tid) {
-  const int ng = G ? G : groups;
+                                               int CP, int HP, int SRc, int SPP, int rgroups, int y0, int tid) {
+  constexpr int nch = NCH;
   int rg = 0, cs = tid;
-  const int per = 3 * R;
+  const int per = nch * R;
   while (cs >= per) { cs -= per; ++rg; }
   while (rg < rgroups) {
-    const int c = cs >= 2 * R ? 2 : (cs >= R ? 1 : 0);
+    const int c = cs >= 2 * R ? 2 : (cs >= R ? 1 : 0);  // local channel (0 when the CTA holds one)
     const int x = cs - c * R;  // lanes walk x in natural order: their source windows overlap (few banks, no conflicts)
     const int slot = (x >> 1) + (x & 1) * (R >> 1);  // column of the transposed tile: the pair (2xp, 2xp+1) sits R/2 apart
     const int2 bx = hb[x];     // (first source column relative to the staged span, taps)
-    const uint4* kc = hcoef + x * CP;
+    const uint4* kc = hcoef + static_cast<size_t>(x) * CP;
+    const int ng = G ? G : (bx.y + 3) >> 2;
     const uint8_t* s0 = stage + (static_cast<size_t>(c) * SRc + 4 * rg) * SPP + (bx.x & ~3);
     const uint32_t sh = (bx.x & 3) * 8;
     int a[4][3];
@@ -284,25 +289,26 @@ __device__ __forceinline__ void resample_hpass(const uint8_t* __restrict__ stage
 }
 
 // Vertical pass + ToTensor/Normalize: work item = (output row of the band, channel, output column pair 2xp, 2xp+1).
-template <int G>
+template <int G, int NCH>
 __device__ __forceinline__ void resample_vpass(const ResampleParams& p, const uint8_t* __restrict__ hbuf,
                                                const uint4* __restrict__ vcoef, const int2* __restrict__ vb,
-                                               const float* __restrict__ lut, int crop, int r0, int nr, int groups,
+                                               const float* __restrict__ lut, int crop, int r0, int nr, int cbeg,
                                                int tid) {
-  const int ng = G ? G : groups;
   const int R = p.R, R2 = R >> 1, HP = p.HP, KS4 = p.KS4;
-  const int per = 3 * R2;
+  const int per = NCH * R2;
   // 32-bit element offsets below one crop's output (< 2^31 elements)
   float* out_f32 = reinterpret_cast<float*>(p.out) + static_cast<size_t>(crop) * 3 * R * R;
   __nv_bfloat16* out_bf16 = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(crop) * p.g * p.g * p.Kp;
   int r = 0, cx = tid;
   while (cx >= per) { cx -= per; ++r; }
   while (r < nr) {
-    const int c = cx >= 2 * R2 ? 2 : (cx >= R2 ? 1 : 0);
-    const int xp = cx - c * R2;
+    const int cl = cx >= 2 * R2 ? 2 : (cx >= R2 ? 1 : 0);  // local channel
+    const int c = cbeg + cl;
+    const int xp = cx - cl * R2;
     const int2 by = vb[r];  // (first tile row, taps)
     const uint4* kc = vcoef + r * KS4;
-    const uint8_t* h0 = hbuf + (static_cast<size_t>(c) * R + xp) * HP + (by.x & ~3);
+    const int ng = G ? G : (by.y + 3) >> 2;
+    const uint8_t* h0 = hbuf + (static_cast<size_t>(cl) * R + xp) * HP + (by.x & ~3);
     const uint8_t* h1 = h0 + static_cast<size_t>(R2) * HP;
     const uint32_t sh = (by.x & 3) * 8;
     int a0 = kRound, a1 = 0, a2 = 0, b0 = kRound, b1 = 0, b2 = 0;
@@ -335,10 +341,13 @@ __device__ __forceinline__ void resample_vpass(const ResampleParams& p, const ui
   }
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(kResThreads) resample_kernel(const ResampleParams p) {
   extern __shared__ __align__(16) uint8_t smem_pre[];
   const int R = p.R, KS4 = p.KS4, TR = p.TR, CP = pre_odd(KS4);
-  const PreSmem sl = pre_smem(R, KS4, TR, p.HP, p.SR, p.SPP);
+  constexpr int nch = NCH;  // colour channels this CTA holds
+  const int cbeg = NCH == 3 ? 0 : static_cast<int>(blockIdx.z);
+  const PreSmem sl = pre_smem(R, KS4, TR, p.HP, p.SR, p.SPP, nch, p.hsm);
   float* lut = reinterpret_cast<float*>(smem_pre + sl.lut);      // [3][256]
   uint4* hcoef = reinterpret_cast<uint4*>(smem_pre + sl.hcoef);  // [R slots][CP]
   int2* hb = reinterpret_cast<int2*>(smem_pre + sl.hb);          // [R slots]
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(kResThreads) resample_kernel(const ResamplePar
   const int tid = threadIdx.x;
 
   if (cp.cw <= 0) {  // crop dropped by the reference (zero area): emit zeros
+    if (cbeg != 0) return;  // (one CTA of a channel-split triple does it)
     if (p.layout == B2C_OUT_NCHW_F32) {
       float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(crop) * 3 * R * R;
       for (int i = tid; i < 3 * nr * R; i += kResThreads) {
@@ -393,9 +403,11 @@ __global__ void __launch_bounds__(kResThreads) resample_kernel(const ResamplePar
   __syncthreads();
   {
     int nh = 0, nv = 0;
-    for (int i = tid; i < R * KS4; i += kResThreads) {
-      const int e = i / KS4, g = i - e * KS4;
-      hcoef[e * CP + g] = gh[i];
+    if (p.hsm) {
+      for (int i = tid; i < R * KS4; i += kResThreads) {
+        const int e = i / KS4, g = i - e * KS4;
+        hcoef[e * CP + g] = gh[i];
+      }
     }
     for (int i = tid; i < nr * KS4; i += kResThreads) vcoef[i] = gv[i];
     for (int i = tid; i < R; i += kResThreads) {
@@ -465,34 +477,40 @@ __global__ void __launch_bounds__(kResThreads) resample_kernel(const ResamplePar
         }
       }
       uint32_t* dst = reinterpret_cast<uint32_t*>(stage + static_cast<size_t>(i) * p.SPP) + q;
-      dst[0] = pr; dst[plane] = pg; dst[2 * plane] = pb;
+      if (NCH == 3) {
+        dst[0] = pr; dst[plane] = pg; dst[2 * plane] = pb;
+      } else {
+        dst[0] = cbeg == 0 ? pr : (cbeg == 1 ? pg : pb);
+      }
       i += st_di; q += st_dq;
       if (q >= quads) { q -= quads; ++i; }
     }
     __syncthreads();
     // ---- horizontal pass for the staged rows -> hbuf[c][slot][y0 + row]
     const int rgroups = (sr + 3) >> 2;
-    switch (gh4) {
-      case 1: resample_hpass<1>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
-      case 2: resample_hpass<2>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
-      case 3: resample_hpass<3>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
-      case 4: resample_hpass<4>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
-      default: resample_hpass<0>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, gh4, tid); break;
+    // few taps (hsm): unrolled loops over the shared-memory table; many taps: per-thread loops, table read from global
+    // memory (L2-resident, one uint4 per 12 dp4a)
+    switch (p.hsm ? gh4 : 0) {
+      case 1: resample_hpass<1, NCH>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, tid); break;
+      case 2: resample_hpass<2, NCH>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, tid); break;
+      case 3: resample_hpass<3, NCH>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, tid); break;
+      case 4: resample_hpass<4, NCH>(stage, hbuf, hcoef, hb, R, CP, p.HP, p.SR, p.SPP, rgroups, y0, tid); break;
+      default: resample_hpass<0, NCH>(stage, hbuf, gh, hb, R, KS4, p.HP, p.SR, p.SPP, rgroups, y0, tid); break;
     }
     __syncthreads();
   }
 
   // ---- vertical pass + ToTensor/Normalize
-  switch (gv4) {
-    case 1: resample_vpass<1>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
-    case 2: resample_vpass<2>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
-    case 3: resample_vpass<3>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
-    case 4: resample_vpass<4>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
-    default: resample_vpass<0>(p, hbuf, vcoef, vb, lut, crop, r0, nr, gv4, tid); break;
+  switch (p.hsm ? gv4 : 0) {  // (hsm = few taps on both axes: the unrolled forms and their tile slack apply)
+    case 1: resample_vpass<1, NCH>(p, hbuf, vcoef, vb, lut, crop, r0, nr, cbeg, tid); break;
+    case 2: resample_vpass<2, NCH>(p, hbuf, vcoef, vb, lut, crop, r0, nr, cbeg, tid); break;
+    case 3: resample_vpass<3, NCH>(p, hbuf, vcoef, vb, lut, crop, r0, nr, cbeg, tid); break;
+    case 4: resample_vpass<4, NCH>(p, hbuf, vcoef, vb, lut, crop, r0, nr, cbeg, tid); break;
+    default: resample_vpass<0, NCH>(p, hbuf, vcoef, vb, lut, crop, r0, nr, cbeg, tid); break;
   }
   // zero the K padding columns of the patch rows this band owns (Kp > 3*p*p): the band holding a patch row's first
   // pixel row owns it.  3 p^2 and Kp are even, so the padding is whole bf16 pairs.
-  if (p.layout == B2C_OUT_PATCH_BF16 && p.Kp > 3 * p.patch * p.patch) {
+  if (p.layout == B2C_OUT_PATCH_BF16 && p.Kp > 3 * p.patch * p.patch && cbeg == 0) {
     const int P = p.patch, g = p.g, pad2 = (p.Kp - 3 * P * P) >> 1;
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(crop) * g * g * p.Kp;
     int gy = __umulhi(r0 + P - 1, p.magicP);  // first patch row starting at or after r0
@@ -603,26 +621,36 @@ extern "C" int b2c_preprocess_4crop(const uint8_t* const* img_ptrs, const int* H
     rp.magicPad = pad2 > 0 ? static_cast<uint32_t>((1ull << 32) / pad2) + 1u : 0u;
   }
 
-  // band height / smem budget.  Both tiles are read a whole tap group past a window's end (zero coefficients
-  // there), hence the KS + 8 bytes of slack per staged row and per tile column.
+  // Tile geometry.  Few taps (KS <= 16, sources up to ~1700 px per 224 outputs): coefficient table in shared memory,
+  // unrolled tap loops that run the CTA's maximum group count, hence KS + 8 bytes of slack per staged row / tile column
+  // (zero coefficients there).  Many taps: every thread loops over its own window (8 bytes of slack for the aligned
+  // word reads), the horizontal table is read from global memory.  Bands as tall as fit two CTAs per SM; a source too
+  // large for that (24 MP photographs and up) gets one colour channel per CTA (grid.z = 3) and, last, one CTA per SM.
   static const int tr_env = [] { const char* e = getenv("B2C_PRE_TR"); return e ? atoi(e) : 32; }();
   static const int budget_kb = [] { const char* e = getenv("B2C_PRE_SMEM_KB"); return e ? atoi(e) : 113; }();
   const size_t budget = static_cast<size_t>(budget_kb) * 1024;  // 113 KB: two CTAs per SM
-  rp.SPP = (span_max + KS + 8 + 3) & ~3;
-  int TR = tr_env > 0 ? tr_env : 32, SR = 8;
-  if (TR > R) TR = R;
+  rp.hsm = rp.KS4 <= 4 ? 1 : 0;
+  const int slack = rp.hsm ? KS + 8 : 8;
+  rp.SPP = (span_max + slack + 3) & ~3;
+  int TR = 0, SR = 4;
   size_t smem = 0;
-  for (;;) {
-    const int rows_cap = static_cast<int>(TR * scale_max) + KS + 2;
-    rp.HP = ((rows_cap + KS + 8 + 3) & ~3) | 4;  // 4 * odd: consecutive columns fall into different banks
-    SR = static_cast<int>((24 * 1024) / (3 * rp.SPP)) & ~3;
-    if (SR < 4) SR = 4;
-    if (SR > 32) SR = 32;
-    smem = pre_smem(R, rp.KS4, TR, rp.HP, SR, rp.SPP).total;
-    if (smem <= budget || TR == 1) break;
-    TR = TR > 8 ? TR - 8 : TR >> 1;
-  }
-  B2C_REQUIRE(smem <= 220 * 1024, "b2c_preprocess_4crop: images too large for the resample tile (need %zu B smem)", smem);
+  auto fit = [&](int nch, size_t limit) -> bool {
+    for (int tr = std::min(tr_env > 0 ? tr_env : 32, R); tr >= 1; tr = tr > 8 ? tr - 8 : tr >> 1) {
+      const int rows_cap = static_cast<int>(tr * scale_max) + KS + 2;
+      const int hp = ((rows_cap + slack + 3) & ~3) | 4;  // 4 * odd: consecutive columns fall into different banks
+      int sr = static_cast<int>((24 * 1024) / (nch * rp.SPP)) & ~3;
+      sr = sr < 4 ? 4 : (sr > 32 ? 32 : sr);
+      const size_t need = pre_smem(R, rp.KS4, tr, hp, sr, rp.SPP, nch, rp.hsm).total;
+      if (need <= limit) {
+        TR = tr; SR = sr; rp.HP = hp; rp.nch = nch; smem = need;
+        return true;
+      }
+      if (tr <= 8 && nch == 3 && limit == budget) break;  // rather split the channels than shrink the band further
+    }
+    return false;
+  };
+  if (!fit(3, budget) && !fit(1, budget) && !fit(1, 220 * 1024))
+    return set_error(B2C_ERR_ARG, "b2c_preprocess_4crop: images too large for the resample tile (longest crop side %d px)", span_max);
   rp.TR = TR; rp.SR = SR;
 
   ProfScope ps(B2C_PROF_PREPROCESS, stream);
@@ -630,11 +658,18 @@ extern "C" int b2c_preprocess_4crop(const uint8_t* const* img_ptrs, const int* H
                                                          const_cast<uint4*>(rp.coefs), const_cast<float*>(rp.lut), norm,
                                                          R, rp.KS4);
   B2C_POST_LAUNCH("resample_plan_kernel");
-  static PerDeviceMax smem_set;
-  if (smem_set.raise(static_cast<long long>(smem))) {
-    B2C_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const dim3 grid((R + TR - 1) / TR, B * 4, rp.nch == 3 ? 1 : 3);
+  if (rp.nch == 3) {
+    static PerDeviceMax smem_set;
+    if (smem_set.raise(static_cast<long long>(smem)))
+      B2C_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    resample_kernel<3><<<grid, kResThreads, smem, stream>>>(rp);
+  } else {
+    static PerDeviceMax smem_set1;
+    if (smem_set1.raise(static_cast<long long>(smem)))
+      B2C_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    resample_kernel<1><<<grid, kResThreads, smem, stream>>>(rp);
   }
-  resample_kernel<<<dim3((R + TR - 1) / TR, B * 4), kResThreads, smem, stream>>>(rp);
   B2C_POST_LAUNCH("resample_kernel");
   return 0;
 }

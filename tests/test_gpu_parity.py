@@ -58,6 +58,25 @@ def test_preprocess_random_sizes_and_patch_layout(cuda, lib, R, patch):
     assert torch.equal(pt[:, :, :K], want) and bool((pt[:, :, K:] == 0).all())
 
 
+@pytest.mark.parametrize("sizes", [[(3000, 2000), (640, 480)], [(5200, 3900)], [(1000, 6016), (48, 48)], [(9000, 8000)]],
+                         ids=["6MP+small", "20MP", "tall-6016", "72MP"])
+def test_preprocess_large_sources(cuda, lib, sizes):
+    """Camera-sized sources: many taps per output (the per-thread tap loops, coefficient table read from global memory)
+    and, from ~16 MP, one colour channel per CTA; mixed with small images in one batch (the batch shares one tile
+    geometry).  Bit-exact like every other size, in both output layouts."""
+    from clip_assisted_data_labeling_b200.vit import preprocess_u8
+    from oracle.preprocess_oracle import four_crop_preprocess
+    rng = np.random.default_rng(sum(w + h for w, h in sizes))
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (w, h) in sizes]
+    dev = [torch.from_numpy(im).cuda() for im in imgs]
+    nchw = preprocess_u8(dev, 224, 14, "nchw").cpu()
+    for im, got, (w, h) in zip(imgs, nchw.numpy(), sizes):
+        assert np.array_equal(got, four_crop_preprocess(im, 224)), (w, h)
+    pt = preprocess_u8(dev, 224, 14, "patch").float().cpu()
+    want = nchw.view(-1, 3, 16, 14, 16, 14).permute(0, 2, 4, 1, 3, 5).reshape(-1, 256, 588).to(torch.bfloat16).float()
+    assert torch.equal(pt[:, :, :588], want) and bool((pt[:, :, 588:] == 0).all())
+
+
 def test_preprocess_uniform_batch_tensor(cuda, lib):
     from clip_assisted_data_labeling_b200.vit import preprocess_u8
     from oracle.preprocess_oracle import four_crop_preprocess, synthetic_image

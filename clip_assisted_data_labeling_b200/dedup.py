@@ -24,6 +24,7 @@ import torch
 
 from . import _lib
 
+STREAM_MIN_ROWS = 200_000  # find_near_duplicates_in_store: groups from this size on are streamed to the device
 BAND_ROWS = 2048  # rows per scheduling band of b2c_dedup_pairs (16 row blocks of 128)
 PAIR_DTYPE = np.dtype([("i", np.int32), ("j", np.int32), ("sim", np.float32)])  # b2c_pair
 
@@ -183,6 +184,71 @@ def duplicate_pairs(embeddings: torch.Tensor, threshold: float, compare: str = "
     emb_n = normalize_rows_f16(emb)
     cap = capacity if capacity is not None else max(1 << 16, 4 * n)
     pairs, sims = _pairs_for_ranges(emb_n, owned_bands(n), float(threshold), compare, cap)
+    return sort_pairs(pairs, sims)
+
+
+_stream_slots = {}
+_stream_pool = None
+
+
+def duplicate_pairs_streamed(rows_into, n: int, E: int, src_dtype, threshold: float, compare: str = "ref_fp16", device=None,
+                             chunk_rows: int = 1 << 16, capacity: int | None = None):
+    """``duplicate_pairs`` for embeddings that still sit on the host (a packed store): the rows are brought over in chunks
+    of ``chunk_rows`` through two pinned buffers on a side stream, and as soon as chunk k = rows [a, b) is on the device
+    (normalised straight into its place) the search of the block rows [0, b) x columns [a, b) is queued — every pair
+    (i < j) belongs to the chunk that holds j — so the host gather, the H2D copies and the search overlap and the call
+    takes about as long as the search alone.  ``rows_into(a, b, out)`` fills the numpy array ``out`` [b-a, E] with rows
+    a..b of the set, in the order the pairs are to be reported in."""
+    global _stream_pool
+    if compare not in _MODES:
+        raise ValueError(f"compare must be one of {sorted(_MODES)}")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise _lib.B2CError("duplicate_pairs_streamed needs a CUDA device (sm_100a); there is no CPU fallback")
+    if n < 2:
+        return np.zeros((0, 2), np.int64), np.zeros((0,), np.float32)
+    import concurrent.futures as cf
+    E_pad = (E + 63) // 64 * 64
+    key = (chunk_rows, E, src_dtype)
+    if key not in _stream_slots:
+        _stream_slots[key] = [torch.empty(chunk_rows, E, dtype=src_dtype, pin_memory=True) for _ in range(2)]
+    slots = _stream_slots[key]
+    if _stream_pool is None:
+        _stream_pool = cf.ThreadPoolExecutor(4)
+    cap = capacity if capacity is not None else max(1 << 16, 4 * n)
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        gathered = torch.empty(n, E_pad, dtype=torch.float16, device=dev)
+        buf = torch.empty(max(cap, 1), 3, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        side.wait_stream(main)  # `gathered` exists before the side stream writes into it
+        free = [None, None]  # event after which a pinned slot may be refilled
+        for k, a in enumerate(range(0, n, chunk_rows)):
+            b = min(n, a + chunk_rows)
+            m = b - a
+            slot = slots[k & 1]
+            if free[k & 1] is not None:
+                free[k & 1].synchronize()
+            view = slot[:m].numpy()
+            cuts = [m * t // 4 for t in range(5)]
+            list(_stream_pool.map(lambda t: rows_into(a + cuts[t], a + cuts[t + 1], view[cuts[t]:cuts[t + 1]]), range(4)))
+            with torch.cuda.stream(side):
+                d = slot[:m].to(dev, non_blocking=True)
+                free[k & 1] = torch.cuda.Event()
+                free[k & 1].record(side)
+                if d.dtype not in (torch.float16, torch.float32):
+                    d = d.float()
+                normalize_rows_f16(d.to(torch.float16), out=gathered[a:b])  # fp16 first, like the reference's loader (_2:38)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            main.wait_event(ready)
+            launch_pair_search(gathered, [(0, b, a, b)], float(threshold), compare, buf, cnt)
+        kfound = int(cnt.item())
+        if kfound > cap:  # the count is exact: search the resident set again with room for every pair
+            pairs, sims = _pairs_for_ranges(gathered, owned_bands(n), float(threshold), compare, int(kfound * 1.25) + 1024)
+        else:
+            pairs, sims = _unpack(buf[:kfound].cpu().numpy())
     return sort_pairs(pairs, sims)
 
 
@@ -358,19 +424,39 @@ def find_near_duplicates_in_store(store, threshold=0.96, crop_to_use="square_pad
     looked for among the images of one directory (:10) — and compares them in sorted-path order; ``False`` searches the
     whole store at once.  Embeddings go through fp16 like the reference's loader (:38).  Returns
     [(near_duplicates [(path_i, path_j)], near_duplicate_values [float])] per group."""
-    emb = store.crop(crop_to_use, torch.float16)
     usable = store.has_all([crop_to_use])
-    groups = {}
-    for i, p in enumerate(store.paths):
-        if usable[i]:
-            groups.setdefault(os.path.dirname(p) if per_directory else "", []).append(i)
+    paths = store.paths
+    in_order = sorted(paths) == paths  # the embedding run writes a shard in sorted-path order: linear to verify
+    if per_directory:
+        groups = {}
+        for i, p in enumerate(paths):
+            if usable[i]:
+                groups.setdefault(os.path.dirname(p), []).append(i)
+    else:
+        groups = {"": np.nonzero(usable)[0]}
+    arr = store.array()  # [N, C, E] memory map
+    ci = store.crop_names.index(crop_to_use)
+    src_dtype = torch.float16 if arr.dtype == np.float16 else torch.float32
     results = []
     for key in sorted(groups):
-        idx = sorted(groups[key], key=lambda i: store.paths[i])
+        idx = np.asarray(groups[key] if in_order else sorted(groups[key], key=paths.__getitem__), np.int64)
         if len(idx) < 2:
             results.append(([], []))
             continue
-        pairs, sims = duplicate_pairs(emb[idx], threshold, compare)
+        contiguous = bool((np.diff(idx) == 1).all())
+
+        def rows_into(a, b, out, idx=idx, contiguous=contiguous):
+            if contiguous:
+                out[...] = arr[int(idx[a]):int(idx[a]) + (b - a), ci, :]
+            else:
+                np.take(arr[:, ci, :], idx[a:b], axis=0, out=out)
+
+        if len(idx) >= STREAM_MIN_ROWS:  # large group: host gather, H2D and search overlap
+            pairs, sims = duplicate_pairs_streamed(rows_into, len(idx), arr.shape[2], src_dtype, threshold, compare)
+        else:
+            host = np.empty((len(idx), arr.shape[2]), arr.dtype)
+            rows_into(0, len(idx), host)
+            pairs, sims = duplicate_pairs(torch.from_numpy(host).to(torch.float16), threshold, compare)
         results.append(([(store.paths[idx[i]], store.paths[idx[j]]) for i, j in pairs.tolist()],
                         [float(np.float16(s)) for s in sims]))
     return results

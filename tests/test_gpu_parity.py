@@ -520,6 +520,52 @@ def test_find_near_duplicates_entry(cuda, lib, tmp_path):
     assert f"{vals[0]:.3f}_00000000_target_{os.path.basename(dups[0][1])}" in names
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float16"])
+def test_store_backed_search_equals_device_search_streamed_or_not(cuda, lib, tmp_path, monkeypatch, dtype):
+    """find_near_duplicates_in_store (packed store instead of one torch.load per image, _2_remove_duplicates.py:25-46): the
+    same pairs as duplicate_pairs on the same rows, per directory and over the whole store — through the resident path
+    and through the STREAMED one (chunks through pinned buffers on a side stream, column block of chunk k searched as soon
+    as it has landed), which is forced here with small chunks, unsorted paths (non-contiguous gathers) and a pair buffer
+    that overflows."""
+    from clip_assisted_data_labeling_b200 import dedup
+    from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter
+    from oracle.dedup_oracle import synthetic_embeddings
+    n, E = 3000, 96
+    e = synthetic_embeddings(n, E, seed=5, dup_fraction=0.08).float().numpy()
+    rng = np.random.default_rng(1)
+    order = rng.permutation(n)                       # the store's row order is not the sorted-path order
+    paths = [f"/data/{'abc'[i % 3]}/{i:06d}.jpg" for i in range(n)]
+    sd = str(tmp_path / "store")
+    with PackedWriter(sd, "M/x", E, shard=0, dtype=dtype) as w:
+        feats = np.zeros((n, 4, E), np.float32)
+        feats[:, 1] = e[order]
+        kept = [[True, True, True, True] for _ in range(n)]
+        kept[7] = [True, False, True, True]          # one image without the crop takes no part
+        w.append(feats, [paths[i] for i in order], kept)
+    store = PackedStore(sd, "M/x")
+    skip = paths[order[7]]
+
+    def expect(sel):
+        rows = sorted((i for i in sel if paths[i] != skip), key=lambda i: paths[i])
+        x = torch.from_numpy(e[rows]).to(torch.float16 if dtype == "float16" else torch.float32).to(torch.float16)
+        pr, sm = dedup.duplicate_pairs(x.cuda(), 0.96)
+        return [(paths[rows[i]], paths[rows[j]]) for i, j in pr.tolist()], [float(np.float16(v)) for v in sm]
+
+    whole = expect(range(n))
+    assert len(whole[0]) >= 40
+    per_dir = [expect([i for i in range(n) if i % 3 == k]) for k in range(3)]
+    for stream in (False, True):
+        if stream:
+            monkeypatch.setattr(dedup, "STREAM_MIN_ROWS", 10)
+            real = dedup.duplicate_pairs_streamed
+            monkeypatch.setattr(dedup, "duplicate_pairs_streamed",
+                                lambda *a, **k: real(*a, **{**k, "chunk_rows": 700, "capacity": 16}))
+        got = dedup.find_near_duplicates_in_store(store, 0.96, per_directory=False)
+        assert got[0][0] == whole[0] and got[0][1] == whole[1]
+        got = dedup.find_near_duplicates_in_store(store, 0.96, per_directory=True)
+        assert [g[0] for g in got] == [p[0] for p in per_dir] and [g[1] for g in got] == [p[1] for p in per_dir]
+
+
 # ------------------------------------------------------------------------------------------ K10 regressor
 def test_mlp_vs_reference_golden(cuda, lib, golden):
     from clip_assisted_data_labeling_b200.scorer import FCScorer, SimpleFC

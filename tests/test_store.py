@@ -61,6 +61,26 @@ def test_incomplete_shard_is_invisible_and_size_is_checked(tmp_path):
         PackedStore(sd)
 
 
+def test_sidecar_index_files_and_json_fallback(tmp_path):
+    """Per-image lists live in sidecar files (fast to parse at a million rows); the .json is still the commit point, and
+    a path that contains a line break keeps the lists inside the JSON."""
+    from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter
+    sd = str(tmp_path / "s")
+    names = ["a b.jpg", "ü/é.jpg", "c\rd.jpg"]
+    with PackedWriter(sd, "M/x", 4, shard=0) as w:
+        w.append(np.arange(48, dtype=np.float32).reshape(3, 4, 4), names, [[True] * 4, [True, False, True, True], [True] * 4])
+    assert os.path.exists(os.path.join(sd, "shard-00000.paths")) and os.path.exists(os.path.join(sd, "shard-00000.kept"))
+    st = PackedStore(sd)
+    assert st.paths == names and st.kept.tolist() == [15, 13, 15]
+    os.remove(os.path.join(sd, "shard-00000.paths"))
+    with pytest.raises(FileNotFoundError):
+        PackedStore(sd)
+    with PackedWriter(sd, "M/x", 4, shard=0) as w:
+        w.append(np.zeros((2, 4, 4), np.float32), ["line\nbreak.jpg", "x.jpg"])
+    st = PackedStore(sd)
+    assert st.paths == ["line\nbreak.jpg", "x.jpg"] and st.kept.tolist() == [15, 15]
+
+
 def test_multi_shard_and_model_filter(tmp_path):
     from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter
     sd = str(tmp_path / "s")

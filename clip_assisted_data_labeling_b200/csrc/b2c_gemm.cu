@@ -77,8 +77,9 @@ struct GemmPolicy {
 
   static constexpr int kStore = (MODE == kGemmPatchEmbedF32) ? kStoreDirect
                                 : (MODE == kGemmBiasResidF32) ? kStoreTmaAddF32
-                                : (MODE == kGemmResidLnF32 || MODE == kGemmResidLnDeepF32) ? kStoreRmwLn : kStoreTmaBf16;
-  static constexpr int kRmwRing = MODE == kGemmResidLnDeepF32 ? 1 : 5;  // see b2c_umma_pipeline2.cuh
+                                : (MODE == kGemmResidLnF32 || MODE == kGemmResidLnDeepF32 || MODE == kGemmResidLnWideF32) ? kStoreRmwLn
+                                                                                                                        : kStoreTmaBf16;
+  static constexpr int kRmwRing = MODE == kGemmResidLnDeepF32 ? 1 : MODE == kGemmResidLnWideF32 ? 2 : 5;  // see b2c_umma_pipeline2.cuh
   // CTA-pair kernel: two epilogue warps per TMEM lane quarter, except for the read-modify-write epilogue (its slab
   // ring needs the shared memory a second set of warps would stage through)
   static constexpr int kEpiWarps = (MODE == kGemmResidLnF32 || MODE == kGemmResidLnDeepF32) ? 4 : 8;
@@ -294,7 +295,12 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
     case kGemmResidLnF32:
       B2C_REQUIRE(g.N == g.nblk * kBN, "gemm: the residual+statistics mode needs N == 256 * nblk (whole rows)");
       // K > 2048 (c_proj): keep all six mainloop stages, the epilogue has the slack to wait for each x slab
-      return g.K > 2048 ? gemm_launch_mode<kGemmResidLnDeepF32>(g, p, stream) : gemm_launch_mode<kGemmResidLnF32>(g, p, stream);
+      if (g.K > 2048) return gemm_launch_mode<kGemmResidLnDeepF32>(g, p, stream);
+      {
+        // K <= 2048 (out_proj): the epilogue is the long pole — two warps per row (B2C_RESID_WIDE=0: one, the round-1 form)
+        static const bool wide = [] { const char* e = getenv("B2C_RESID_WIDE"); return !e || atoi(e) != 0; }();
+        return wide ? gemm_launch_mode<kGemmResidLnWideF32>(g, p, stream) : gemm_launch_mode<kGemmResidLnF32>(g, p, stream);
+      }
     default: return set_error(B2C_ERR_ARG, "gemm: unknown epilogue mode %d", g.mode);
   }
 }

@@ -49,6 +49,7 @@ enum GemmMode {
   kGemmResidLnF32 = 8,
   kGemmResidLnBf16Copy = 9,  // make_out_tmap only: the store map of out2
   kGemmResidLnDeepF32 = 10,  // internal: kGemmResidLnF32 with six mainloop stages and a one-slab x ring (large K)
+  kGemmResidLnWideF32 = 11,  // internal: kGemmResidLnF32 with eight epilogue warps (two per row: 128 columns each), x ring of two
 };
 
 struct GemmLaunch {

@@ -35,15 +35,19 @@ constexpr int kStoreRmwLn = 3;
 constexpr int kStages2 = 6;
 constexpr int kStage2Bytes = kABytes + kBM * kBK * 2;  // A 128 x 64 + B half 128 x 64 = 32 KB
 constexpr int kUmma2BarBytes = 320;
-constexpr int kUmma2SmemBytes = kStages2 * kStage2Bytes + kStagingBytes + 1024 + kUmma2BarBytes;
+constexpr int kUmma2XchgBytes = 4 * 32 * 8;  // kStoreRmwLn with 8 epilogue warps: (mean, M2) of the upper column half, per row
+constexpr int kUmma2SmemBytes = kStages2 * kStage2Bytes + kStagingBytes + 1024 + kUmma2BarBytes + kUmma2XchgBytes;
 // kStoreRmwLn, same total: Policy::kRmwRing fp32 slabs (4 KB) + 2 bf16 half slabs (2 KB) per epilogue warp, and as many
 // mainloop stages as still fit: ring 5 -> 4 stages (out_proj, K = d: the epilogue is the long pole, an x slab must be
 // requested ~4 slabs ahead), ring 3 -> 5 stages, ring 1 -> 6 stages (c_proj, K = 4d: the mainloop needs all six stages
 // to cover the L2 latency and leaves the epilogue four times the slack, so it can afford to wait for each slab).
 constexpr int kRmwMaxRing = 5;
 constexpr int kHalfSlabBytes = 32 * 64;
-constexpr int rmw_stages(int ring) { return ring == 5 ? 4 : ring == 3 ? 5 : 6; }
 constexpr int rmw_warp_bytes(int ring) { return ring * kSlabBytes + 2 * kHalfSlabBytes; }
+// mainloop stages that fit beside `warps` epilogue warps with an x ring of `ring` slabs each (same total as the other modes)
+constexpr int rmw_stages(int ring, int warps) {
+  return (kStages2 * kStage2Bytes + kStagingBytes - warps * rmw_warp_bytes(ring)) / kStage2Bytes;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16_pair(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -66,10 +70,11 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const typename Policy::Params p, const uint32_t idesc) {
   constexpr bool kRmw = Policy::kStore == kStoreRmwLn;
   constexpr int kRmwRing = kRmw ? Policy::kRmwRing : 1;
-  static_assert(kRmwRing == 1 || kRmwRing == 3 || kRmwRing == 5, "x slab ring of 1, 3 or 5");
+  static_assert(kRmwRing >= 1 && kRmwRing <= kRmwMaxRing && Policy::kEpiWarps * kRmwRing <= 4 * kRmwMaxRing, "x slab ring");
   constexpr int kRmwWarpBytes = rmw_warp_bytes(kRmwRing);
-  constexpr int kStages2 = kRmw ? rmw_stages(kRmwRing) : b2c::kStages2;  // shadows the namespace constant inside the kernel
-  constexpr int kStagingBytes = kRmw ? 4 * kRmwWarpBytes : b2c::kStagingBytes;
+  constexpr int kStages2 = kRmw ? rmw_stages(kRmwRing, Policy::kEpiWarps) : b2c::kStages2;  // shadows the namespace constant inside the kernel
+  constexpr int kStagingBytes = kRmw ? Policy::kEpiWarps * kRmwWarpBytes : b2c::kStagingBytes;
+  static_assert(kStages2 >= 3, "mainloop stages");
   static_assert(kStages2 * kStage2Bytes + kStagingBytes <= b2c::kStages2 * kStage2Bytes + b2c::kStagingBytes, "smem budget");
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = smem_raw2 + ((1024u - (smem_u32(smem_raw2) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST
@@ -81,6 +86,7 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* acc_empty_bar = bars + 2 * kStages2 + kAccStages;    // [kAccStages] (leader's: 8 arrivals, 4 per CTA)
   uint64_t* x_bar = bars + 2 * kStages2 + 2 * kAccStages;        // [4 warps][kRmwMaxRing] (kStoreRmwLn: x slab has landed)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_bar + 4 * kRmwMaxRing);
+  [[maybe_unused]] float2* xchg = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + kUmma2BarBytes);  // [4 quarters][32 rows]
   static_assert((2 * kStages2 + 2 * kAccStages + 4 * kRmwMaxRing) * 8 + 4 <= kUmma2BarBytes, "barrier area");
 
   const int warp = threadIdx.x >> 5;
@@ -191,7 +197,6 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // takes about as long as the tile's mainloop at K = 1024.
     constexpr int kEpiWarps = Policy::kEpiWarps;
     static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
-    static_assert(!kRmw || kEpiWarps == 4, "the read-modify-write epilogue is written for 4 warps");
     constexpr int kSplit = kEpiWarps / 4;
     constexpr int kWarpStaging = kRmw ? kRmwWarpBytes : kStagingBytes / kEpiWarps;
     const int ew = warp - 2;
@@ -207,14 +212,14 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // (g / ring) & 1); lane 0 also tracks the next slab to request: (ld_t, ld_c) with running index gi = g + max(ring - 1, 1).
     [[maybe_unused]] uint32_t g = 0, gi = 0;
     [[maybe_unused]] int ld_t = cid, ld_c = 0;
-    [[maybe_unused]] uint64_t* xb = x_bar + (ew & 3) * kRmwMaxRing;
+    [[maybe_unused]] uint64_t* xb = x_bar + ew * kRmwRing;
     auto issue_next_x = [&]() {
       if (ld_t < p.num_tiles2) {
         int m0 = 0, n0 = 0;
         Policy::tile2(p, ld_t, m0, n0);
         const uint32_t slot = gi % kRmwRing;
         mbar_arrive_expect_tx(&xb[slot], kSlabBytes);
-        tma_load_2d(my_slabs + slot * kSlabBytes, &tmap_out, &xb[slot], n0 + ld_c * 32, m0 + row_off);
+        tma_load_2d(my_slabs + slot * kSlabBytes, &tmap_out, &xb[slot], n0 + col_off + ld_c * 32, m0 + row_off);
       }
       ++gi;
       if (++ld_c == kChunks) { ld_c = 0; ld_t += ncl; }
@@ -397,7 +402,24 @@ umma2_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         }
-        if constexpr (kRmw) Policy::store_row_stats(p, out_row + lane, b_row, mean, m2, sh);
+        if constexpr (kRmw) {
+          if constexpr (kSplit == 2) {
+            // two warps share a row (128 columns each): the upper half's partial goes through shared memory to the
+            // lower half's warp, which merges in a fixed order and stores.  Named barrier 1 + quarter, both warps; the
+            // second barrier keeps the next tile's partial from overwriting one that has not been read.
+            float2* slot = xchg + quarter * 32 + lane;
+            if (ew >= 4) *slot = make_float2(mean, m2);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            if (ew < 4) {
+              const float2 up = *slot;
+              chan_merge(mean, m2, 128.0f, up.x, up.y, 128.0f);
+              Policy::store_row_stats(p, out_row + lane, b_row, mean, m2, sh);
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+          } else {
+            Policy::store_row_stats(p, out_row + lane, b_row, mean, m2, sh);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -471,7 +471,10 @@ def run_dedup(args, world, rank, barrier, dist, peaks):
             out["e2e"] = {"value": npairs / de.item(), "unit": "pairs/s", "seconds": de.item(),
                           "h2d_bytes_per_step": n_tot * 768 * 2, "d2h_bytes_per_step": int(len(got_paths)) * 12,
                           "api": "find_near_duplicates_in_store%s: packed fp16 store on disk (one shard per rank, page cache warm) -> "
-                                 "mmap -> H2D -> search -> (path_i, path_j, sim) lists on the host" % ("_distributed" if world > 1 else ""),
+                                 "mmap -> %s -> (path_i, path_j, sim) lists on the host" % (
+                                     "_distributed" if world > 1 else "",
+                                     "H2D of the rank's shard -> all-gather -> search" if world > 1 else
+                                     "chunks through pinned memory, H2D and search of each arriving column block overlapped"),
                           "same_pairs_as_device_run": bool(np.array_equal(idx, pairs))}
     except Exception as e:  # noqa: BLE001
         if rank == 0:

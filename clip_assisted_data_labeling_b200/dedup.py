@@ -187,8 +187,13 @@ def duplicate_pairs(embeddings: torch.Tensor, threshold: float, compare: str = "
     return sort_pairs(pairs, sims)
 
 
-_stream_slots = {}
+_stream_slots = {}   # pinned staging buffers of duplicate_pairs_streamed, kept between calls (release_stream_buffers())
 _stream_pool = None
+
+
+def release_stream_buffers():
+    """Give back the pinned host buffers duplicate_pairs_streamed keeps between calls (2 x chunk_rows x E elements)."""
+    _stream_slots.clear()
 
 
 def duplicate_pairs_streamed(rows_into, n: int, E: int, src_dtype, threshold: float, compare: str = "ref_fp16", device=None,
@@ -307,6 +312,11 @@ class BandTickets:
         try:
             from torch.distributed.distributed_c10d import _get_default_store
             self.store = _get_default_store()
+            if rank == 0 and _ticket_calls > 1:  # every rank has left the previous call: its counter can go
+                try:
+                    self.store.delete_key(f"b2c/dedup_tickets/{_ticket_calls - 1}")
+                except Exception:  # noqa: BLE001 — not every store type can delete
+                    pass
         except Exception:  # noqa: BLE001
             self.store = None
         self._static = 0

@@ -401,8 +401,8 @@ class RawImageDataset(Dataset):
                     # file): Pillow gets the bytes already read and has the last word, exactly like the reference
                     src = io.BytesIO(data)
             with Image.open(src) as im:
-                arr = np.asarray(im.convert("RGB"))
-            return torch.from_numpy(np.ascontiguousarray(arr)), path
+                arr = np.array(im.convert("RGB"))  # (a writable copy: torch.from_numpy shares it)
+            return torch.from_numpy(arr), path
         except Exception as e:  # noqa: BLE001
             print(f"Error loading image {path}: {e}")
             return None, path

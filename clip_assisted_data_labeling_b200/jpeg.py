@@ -367,7 +367,7 @@ def _decode_on_host(data: bytes, dev):
         pass
     try:
         with Image.open(io.BytesIO(data)) as im:
-            arr = np.ascontiguousarray(np.asarray(im.convert("RGB")))
+            arr = np.array(im.convert("RGB"))
         return torch.from_numpy(arr).to(dev)
     except Exception as e:  # noqa: BLE001 — Pillow raises OSError / SyntaxError / ValueError for damaged files
         print(f"Error decoding JPEG stream: {e}")

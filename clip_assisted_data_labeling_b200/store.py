@@ -175,7 +175,7 @@ class PackedStore:
     def crop(self, crop_name: str, dtype=torch.float32, device=None) -> torch.Tensor:
         """[N, E] embeddings of one crop, the bulk form of ``d[model][crop].squeeze()`` (_2_remove_duplicates.py:38)."""
         ci = self.crop_names.index(crop_name)
-        t = torch.from_numpy(np.ascontiguousarray(self.array()[:, ci, :])).to(dtype)
+        t = torch.from_numpy(np.array(self.array()[:, ci, :])).to(dtype)  # (a copy: the memory map is read-only)
         return t.to(device) if device is not None else t
 
     def features(self, crop_names=None, device=None) -> torch.Tensor:
@@ -183,7 +183,7 @@ class PackedStore:
         (_4_train_model.py:55, _5_predict_labels.py:78-79)."""
         names = list(crop_names) if crop_names is not None else self.crop_names
         idx = [self.crop_names.index(c) for c in names]
-        t = torch.from_numpy(np.ascontiguousarray(self.array()[:, idx, :])).float().reshape(len(self), -1)
+        t = torch.from_numpy(np.array(self.array()[:, idx, :])).float().reshape(len(self), -1)
         return t.to(device) if device is not None else t
 
     def has_all(self, crop_names) -> np.ndarray:

@@ -395,3 +395,32 @@ def test_driver_embeds_jpg_files_identically_to_the_pillow_path(lib, tmp_path):
         assert list(a.keys()) == list(b.keys())
         for key in a:
             assert torch.equal(a[key], b[key]), key
+
+
+@pytest.mark.gpu
+def test_driver_handles_camera_sized_files(lib, tmp_path):
+    """24 MP photographs next to small images in one batch: the device Huffman stage runs many rounds per CTA, the
+    reconstruction and the statistics stream the planes, K0 switches to one colour channel per CTA — and the .pt files
+    equal the Pillow path's bit for bit."""
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from oracle import vit_oracle
+    sd = vit_oracle.visual_state_dict(vit_oracle.build_visual("ViT-B-32", "openai", seed=0))
+    rng = np.random.default_rng(9)
+    specs = [(6000, 4000, {}), (4000, 6000, {"progressive": True}), (512, 512, {}), (3000, 2000, {"restart_marker_rows": 1}), (97, 61, {})]
+    res = {}
+    for mode in (True, False):
+        root = tmp_path / f"big{int(mode)}"
+        root.mkdir()
+        for k, (w, h, kw) in enumerate(specs):
+            small = np.repeat(np.repeat(rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8, 3), dtype=np.uint8), 8, 0), 8, 1)[:h, :w]
+            im = np.clip(small.astype(np.int16) + np.random.default_rng(k).integers(-12, 13, (h, w, 3)), 0, 255).astype(np.uint8)
+            Image.fromarray(im).save(root / f"{k}.jpg", quality=85, **kw)
+        rng = np.random.default_rng(9)  # the same files for both modes
+        ds = Feature_Dataset(str(root), "ViT-B-32/openai", batch_size=8, shuffle_filenames=False, state_dict=sd, device_jpeg=mode)
+        n, _ = ds.process()
+        assert n == len(specs) and not ds.failed
+        res[mode] = [torch.load(root / f"{k}.pt")["ViT-B-32/openai"] for k in range(len(specs))]
+    for a, b in zip(res[True], res[False]):
+        assert list(a.keys()) == list(b.keys())
+        for key in a:
+            assert torch.equal(a[key], b[key]), key

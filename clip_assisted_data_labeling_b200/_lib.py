@@ -83,6 +83,7 @@ SIGNATURES = {
     "b2c_vit_ready": (_i, [_vp]),
     "b2c_vit_set_lanes": (_i, [_vp, _i]),
     "b2c_vit_set_fused_ln": (_i, [_vp, _i]),
+    "b2c_vit_set_graph": (_i, [_vp, _i]),
     "b2c_vit_set_cls_only_last_block": (_i, [_vp, _i]),
     "b2c_vit_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
     "b2c_vit_forward_pixels": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),

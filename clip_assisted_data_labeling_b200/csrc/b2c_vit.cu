@@ -46,6 +46,21 @@ struct b2c_vit {
   // row.  K and V of all tokens are still computed (in_proj runs in full); attention, out_proj, ln_2, c_fc and c_proj run
   // on one row per crop.  Off by default: bench.py's headline executes every block in full.
   bool cls_only_last = false;
+  // Opt-in (b2c_vit_set_graph / B2C_VIT_GRAPH=1): a pass whose buffers, size and switches repeat is captured once into a
+  // CUDA graph (second call with the same key; the first runs eagerly so that every one-time attribute is set) and
+  // replayed afterwards — ~250 launches and their fork/join events become one cudaGraphLaunch.
+  bool use_graph = false;
+  struct GraphEntry {
+    const void* in;
+    const float* out;
+    const void* ws;
+    int n, dtype, lanes;
+    bool pixels, fused, cls;
+    cudaGraphExec_t exec;  // nullptr: key seen once, not captured yet
+    unsigned long long launches;
+  };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;  // captures run on an internal stream (the caller's may be the legacy default stream)
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
@@ -400,13 +415,9 @@ int forward_chunk(b2c_vit* v, const void* patches, int nc, float* out, uint8_t* 
                      eps, stream);
 }
 
-int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches, int n, float* out, void* ws,
-                 size_t ws_bytes, cudaStream_t stream) {
-  B2C_REQUIRE(v && out && ws, "vit_forward: null pointer");
-  B2C_REQUIRE(n > 0, "vit_forward: n_crops must be positive");
-  B2C_TRY(b2c_vit_ready(v));
+int forward_eager(b2c_vit* v, const void* pixels, int dtype, const void* patches, int n, float* out, void* ws,
+                  size_t ws_bytes, cudaStream_t stream) {
   const bool fused = v->fused_ln;
-  if (fused) B2C_TRY(ensure_folded(v, stream));
   const int nc_max = n < v->chunk ? n : v->chunk;
   size_t lane_bytes = 0;
   const size_t need = ws_bytes_for(v, nc_max, pixels != nullptr, &lane_bytes);
@@ -464,6 +475,59 @@ int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches,
   return 0;
 }
 
+int forward_impl(b2c_vit* v, const void* pixels, int dtype, const void* patches, int n, float* out, void* ws,
+                 size_t ws_bytes, cudaStream_t stream) {
+  B2C_REQUIRE(v && out && ws, "vit_forward: null pointer");
+  B2C_REQUIRE(n > 0, "vit_forward: n_crops must be positive");
+  B2C_TRY(b2c_vit_ready(v));
+  if (v->fused_ln) B2C_TRY(ensure_folded(v, stream));  // (may synchronise: never inside a capture)
+  if (!v->use_graph || g_prof_on.load(std::memory_order_relaxed))
+    return forward_eager(v, pixels, dtype, patches, n, out, ws, ws_bytes, stream);
+  const void* in = pixels ? pixels : patches;
+  b2c_vit::GraphEntry* e = nullptr;
+  for (b2c_vit::GraphEntry& g : v->graphs)
+    if (g.in == in && g.out == out && g.ws == ws && g.n == n && g.dtype == dtype && g.lanes == v->lanes &&
+        g.pixels == (pixels != nullptr) && g.fused == v->fused_ln && g.cls == v->cls_only_last)
+      e = &g;
+  if (e && e->exec) {
+    B2C_CHECK_CUDA(cudaGraphLaunch(e->exec, stream));
+    g_launches.fetch_add(e->launches, std::memory_order_relaxed);  // the graph's kernel nodes
+    return 0;
+  }
+  if (!e) {  // first sight of this key: eager pass (sets function attributes, creates the lanes' streams)
+    if (v->graphs.size() >= 16) {
+      if (v->graphs.front().exec) cudaGraphExecDestroy(v->graphs.front().exec);
+      v->graphs.erase(v->graphs.begin());
+    }
+    v->graphs.push_back({in, out, ws, n, dtype, v->lanes, pixels != nullptr, v->fused_ln, v->cls_only_last, nullptr, 0});
+    return forward_eager(v, pixels, dtype, patches, n, out, ws, ws_bytes, stream);
+  }
+  B2C_TRY(ensure_lanes(v));
+  if (!v->cap_stream) B2C_CHECK_CUDA(cudaStreamCreateWithFlags(&v->cap_stream, cudaStreamNonBlocking));
+  const unsigned long long before = g_launches.load(std::memory_order_relaxed);
+  B2C_CHECK_CUDA(cudaStreamBeginCapture(v->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = forward_eager(v, pixels, dtype, patches, n, out, ws, ws_bytes, v->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(v->cap_stream, &graph);
+  const unsigned long long nodes = g_launches.load(std::memory_order_relaxed) - before;
+  g_launches.fetch_sub(nodes, std::memory_order_relaxed);  // nothing has run yet
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    if (rc != 0) return rc;
+    return set_error(B2C_ERR_CUDA, "vit_forward: stream capture failed: %s", cudaGetErrorString(ce));
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) return set_error(B2C_ERR_CUDA, "vit_forward: cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+  e->exec = exec;
+  e->launches = nodes;
+  B2C_CHECK_CUDA(cudaGraphLaunch(exec, stream));
+  g_launches.fetch_add(nodes, std::memory_order_relaxed);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
@@ -492,6 +556,7 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
     if (cv > 0) v->chunk = cv;
   }
   if (const char* e = getenv("B2C_VIT_FUSED_LN")) v->fused_ln = atoi(e) != 0;
+  if (const char* e = getenv("B2C_VIT_GRAPH")) v->use_graph = atoi(e) != 0;
   if (const char* e = getenv("B2C_VIT_LANES")) {
     const int lv = atoi(e);
     if (lv >= 1 && lv <= 4) v->lanes = lv;
@@ -503,6 +568,9 @@ extern "C" int b2c_vit_create(const b2c_vit_cfg* cfg, b2c_vit** out) {
 
 extern "C" int b2c_vit_destroy(b2c_vit* v) {
   if (!v) return 0;
+  for (b2c_vit::GraphEntry& g : v->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (v->cap_stream) cudaStreamDestroy(v->cap_stream);
   for (void* p : v->allocs) cudaFree(p);
   for (b2c_vit_layer& L : v->layers) {
     if (L.src_qkv) cudaFree(L.src_qkv);
@@ -602,6 +670,17 @@ extern "C" int b2c_vit_set_lanes(b2c_vit* v, int lanes) {
 extern "C" int b2c_vit_set_cls_only_last_block(b2c_vit* v, int on) {
   B2C_REQUIRE(v, "b2c_vit_set_cls_only_last_block: null handle");
   v->cls_only_last = on != 0;
+  return 0;
+}
+
+extern "C" int b2c_vit_set_graph(b2c_vit* v, int on) {
+  B2C_REQUIRE(v, "b2c_vit_set_graph: null handle");
+  v->use_graph = on != 0;
+  if (!v->use_graph) {
+    for (b2c_vit::GraphEntry& g : v->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    v->graphs.clear();
+  }
   return 0;
 }
 

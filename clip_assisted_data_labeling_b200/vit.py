@@ -85,6 +85,10 @@ class VisionTower:
         """Opt-in: the last block evaluates only the class-token row (what ln_post / proj read); see include/b2c.h."""
         _lib.check(self.lib.b2c_vit_set_cls_only_last_block(self._h, 1 if on else 0), "b2c_vit_set_cls_only_last_block")
 
+    def set_graph(self, on: bool) -> None:
+        """Opt-in: replay repeated forward calls (same buffers / size / switches) as one CUDA graph; see include/b2c.h."""
+        _lib.check(self.lib.b2c_vit_set_graph(self._h, 1 if on else 0), "b2c_vit_set_graph")
+
     def set_fused_ln(self, on: bool) -> None:
         """LayerNorm folded into the GEMMs on either side of it (default) or stand-alone kernels; see include/b2c.h."""
         _lib.check(self.lib.b2c_vit_set_fused_ln(self._h, 1 if on else 0), "b2c_vit_set_fused_ln")
@@ -104,8 +108,9 @@ class VisionTower:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward_pixels(self, pixels: torch.Tensor) -> torch.Tensor:
-        """pixels [n,3,R,R] (f32/f16/bf16, normalised) -> f32 [n,E] unit-norm. utils/embedder.py:94-100."""
+    def forward_pixels(self, pixels: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """pixels [n,3,R,R] (f32/f16/bf16, normalised) -> f32 [n,E] unit-norm. utils/embedder.py:94-100.
+        ``out``: optional destination f32 [n,E] on the device (stable buffers let set_graph(True) replay the pass)."""
         R = self.cfg["image"]
         if pixels.dim() != 4 or tuple(pixels.shape[1:]) != (3, R, R):
             raise ValueError(f"expected [n,3,{R},{R}], got {tuple(pixels.shape)}")
@@ -113,7 +118,10 @@ class VisionTower:
             pixels = pixels.float()
         pixels = pixels.to(self.device).contiguous()
         n = pixels.shape[0]
-        out = torch.empty(n, self.cfg["embed"], dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(n, self.cfg["embed"], dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != (n, self.cfg["embed"]) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != pixels.device:
+            raise ValueError("out must be a contiguous f32 [n, E] tensor on the tower's device")
         if n == 0:
             return out
         with torch.cuda.device(self.device):

@@ -143,6 +143,12 @@ int b2c_vit_set_lanes(b2c_vit* vit, int lanes);
  * the residual update, leaving a bf16 copy of x and its row statistics for the next GEMM.  0 selects the stand-alone
  * LayerNorm kernels.  Both compute LN(x)·Wᵀ + b of utils/embedder.py:98's tower within the same tolerance. */
 int b2c_vit_set_fused_ln(b2c_vit* vit, int on);
+/* Opt-in, off by default (env B2C_VIT_GRAPH=1): a forward call whose buffers (input, output, workspace), crop count and
+ * switches repeat is captured into a CUDA graph on its second occurrence and replayed from then on — one
+ * cudaGraphLaunch instead of ~250 kernel launches and the lanes' fork / join events.  Same kernels, same results.  A
+ * weight that is re-set keeps its device buffer, so captured graphs stay valid; 0 drops them.  Up to 16 graphs are
+ * kept per handle.  The stage timer bypasses it. */
+int b2c_vit_set_graph(b2c_vit* vit, int on);
 /* Opt-in, off by default: in the LAST block evaluate only the class-token row — the only row ln_post / proj read
  * (utils/embedder.py:98 returns the pooled class token).  K and V of every token are still computed; the block's
  * attention, out_proj, ln_2, c_fc and c_proj run on one row per crop (3.3 % fewer FLOPs for ViT-L/14).  The embedding is

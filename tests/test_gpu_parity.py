@@ -304,6 +304,32 @@ def test_lanes_do_not_change_results(cuda, lib, arch, n):
             assert torch.equal(tower.forward_pixels(px).cpu(), one), lanes
 
 
+def test_graph_replay_returns_the_same_bits(cuda, lib):
+    """b2c_vit_set_graph(1): eager on first sight of a (buffers, size, switches) key, captured on the second call,
+    replayed afterwards — identical bits each time, also after the input changed in place, with another crop count in
+    between, and with the lanes' fork / join inside the capture."""
+    tower, m = _tower_and_oracle("ViT-L-14", "openai")
+    R = m.cfg["image"]
+    gen = torch.Generator().manual_seed(11)
+    px = torch.randn(131, 3, R, R, generator=gen).cuda().to(torch.bfloat16)
+    px2 = torch.randn(131, 3, R, R, generator=gen).cuda().to(torch.bfloat16)
+    out = torch.empty(131, m.cfg["embed"], device="cuda")
+    tower.set_graph(False)
+    want = tower.forward_pixels(px).cpu()
+    want2 = tower.forward_pixels(px2).cpu()
+    tower.set_graph(True)
+    try:
+        buf = px.clone()
+        for k in range(4):  # eager, capture + launch, replay, replay
+            assert torch.equal(tower.forward_pixels(buf, out=out).cpu(), want), k
+        buf.copy_(px2)      # same buffers, new contents: the replay reads them
+        assert torch.equal(tower.forward_pixels(buf, out=out).cpu(), want2)
+        assert torch.equal(tower.forward_pixels(px[:37]).cpu(), want[:37])  # another key in between
+        assert torch.equal(tower.forward_pixels(buf, out=out).cpu(), want2)
+    finally:
+        tower.set_graph(False)
+
+
 def test_fused_u8_path_vs_reference_pipeline(cuda, lib):
     """encode_images_u8 == reference pipeline (extract_crops -> preprocess -> encode_image) on ragged images."""
     from oracle import vit_oracle

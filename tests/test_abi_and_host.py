@@ -108,6 +108,49 @@ def test_owned_blocks_cover_every_pair_once_and_balance():
         assert max(work) / min(work) < 1.01, (world, work)
 
 
+def test_band_tickets_generations_and_static_fallback():
+    """dedup.BandTickets: every band index of a generation is handed out exactly once across the ranks, each rank stops at
+    its first ticket past the end, and the next generation (an overflow re-run) needs no reset; without a store the ranks
+    take the static round-robin share."""
+    from clip_assisted_data_labeling_b200 import dedup
+
+    class FakeStore:
+        def __init__(self):
+            self.v = {}
+
+        def add(self, key, n):
+            self.v[key] = self.v.get(key, 0) + n
+            return self.v[key]
+
+    n, world = 11, 3
+    shared = FakeStore()
+    ranks = []
+    for r in range(world):
+        t = dedup.BandTickets(n, r, world)
+        t.store, t.key = shared, "k"      # one job-wide counter
+        ranks.append(t)
+    for gen in range(3):
+        for t in ranks:
+            t.new_generation()
+        got, live = [], list(range(world))
+        while live:                        # ranks draw in an arbitrary interleaving; a rank stops at its first -1
+            for r in list(live):
+                i = ranks[r].next()
+                if i < 0:
+                    live.remove(r)
+                else:
+                    got.append(i)
+        assert sorted(got) == list(range(n)), (gen, got)
+    solo = [dedup.BandTickets(n, r, world) for r in range(world)]
+    got = []
+    for t in solo:
+        t.store = None
+        t.new_generation()
+        while (i := t.next()) >= 0:
+            got.append(i)
+    assert sorted(got) == list(range(n))
+
+
 def test_owned_bands_partition():
     from clip_assisted_data_labeling_b200.dedup import BAND_ROWS, owned_bands
     for n in (1, 2047, 2048, 2049, 100_000, 1_000_003):

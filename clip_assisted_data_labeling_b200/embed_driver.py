@@ -298,7 +298,9 @@ class Feature_Dataset:
                     if stats is not None:
                         rows_dev = torch.cat([stats.to(torch.float32), rows_dev], dim=1)
                     slot[:b].copy_(rows_dev, non_blocking=True)
-                    ev = torch.cuda.Event()
+                    # blocking: the main thread sleeps while it waits for the batch instead of spinning on a core the
+                    # DataLoader workers (and, on a multi-GPU box, the other ranks) need
+                    ev = torch.cuda.Event(blocking=True)
                     ev.record()
                     cur = (ev, slot, todo_paths, todo_img_paths, shapes)
                     k += 1

@@ -458,7 +458,15 @@ def collate_raw(batch):
     for kind in ("jpegf", "jpegp", "jpeg"):
         idx = [i for i, it in enumerate(items) if isinstance(it, tuple) and it[0] == kind]
         if len(idx) > 1:
-            pack = torch.cat([items[i][-1] for i in idx])  # buffers are multiples of 16 bytes: views stay aligned
+            parts = [items[i][-1] for i in idx]  # buffers are multiples of 16 bytes: views stay aligned
+            total = sum(t.numel() for t in parts)
+            if torch.utils.data.get_worker_info() is not None:
+                # concatenate straight into shared memory (what default_collate does for stacked batches): handing the
+                # batch to the main process then moves a handle, not another copy of every file
+                storage = parts[0]._typed_storage()._new_shared(total, device=parts[0].device)
+                pack = torch.cat(parts, out=parts[0].new(storage).resize_(total))
+            else:
+                pack = torch.cat(parts)
             off = 0
             for i in idx:
                 n = items[i][-1].numel()

@@ -201,7 +201,7 @@ class Staging:
             part(0, n)
         t2 = time.perf_counter()
         dflat = flat.to(dev, non_blocking=True)
-        self.event = torch.cuda.Event()
+        self.event = torch.cuda.Event(blocking=True)
         self.event.record()
         if os.environ.get("B2C_DRIVER_TIMING") is not None:
             t3 = time.perf_counter()
@@ -317,6 +317,14 @@ def huffman_device(items: Sequence[Tuple[JpegInfo, JpegHuff, torch.Tensor]], dev
 
 
 _side_streams = {}
+_status_pinned = None
+
+
+def _status_slot(n: int) -> torch.Tensor:
+    global _status_pinned
+    if _status_pinned is None or _status_pinned.numel() < n:
+        _status_pinned = torch.empty(max(n, 1024), dtype=torch.int32, pin_memory=True)
+    return _status_pinned[:n]
 
 
 def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
@@ -348,7 +356,13 @@ def decode_device(items: Sequence[Tuple[JpegInfo, JpegHuff, torch.Tensor]], devi
         side = _side_stream(dev)
         with torch.cuda.stream(side):
             coefs, status = huffman_device(items, dev)
-            st = status.cpu().tolist()  # waits for the side stream only
+            # waits for the side stream only, asleep (blocking event) rather than spinning on a core the workers need
+            st_host = _status_slot(len(items))
+            st_host.copy_(status, non_blocking=True)
+            ev = torch.cuda.Event(blocking=True)
+            ev.record(side)
+            ev.synchronize()
+            st = st_host.tolist()
         main.wait_stream(side)
         coefs.record_stream(main)
         outs = reconstruct_device(infos, coefs)

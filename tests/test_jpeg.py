@@ -206,6 +206,33 @@ def test_device_reconstruct_many_random_streams(lib):
                 assert np.array_equal(got.cpu().numpy(), refs[i])
 
 
+def test_worker_collate_packs_a_batch_into_one_shared_segment(lib, tmp_path):
+    """DataLoader workers (2 processes) + collate_raw: the file bytes / packed coefficients of a batch arrive in the main
+    process as views of ONE shared-memory tensor per kind, with the right contents."""
+    from torch.utils.data import DataLoader
+    from clip_assisted_data_labeling_b200 import jpeg
+    from clip_assisted_data_labeling_b200.embedder import RawImageDataset, collate_raw
+    paths = []
+    for k in range(6):
+        p = tmp_path / f"{k}.jpg"
+        Image.fromarray(synthetic_image(k, 80 + 8 * k, 120)).save(p, quality=90, progressive=(k % 3 == 2))
+        paths.append(str(p))
+    dl = DataLoader(RawImageDataset(paths, device_jpeg=True, device_huffman=True), batch_size=6, shuffle=False, num_workers=2,
+                    collate_fn=collate_raw)
+    items, got_paths = next(iter(dl))
+    assert got_paths == paths and [it[0] for it in items] == ["jpegf", "jpegf", "jpegp"] * 2
+    for kind in ("jpegf", "jpegp"):
+        ts = [it[-1] for it in items if it[0] == kind]
+        assert all(t.is_shared() for t in ts) and len({t.untyped_storage().data_ptr() for t in ts}) == 1
+    for it, p in zip(items, paths):
+        data = open(p, "rb").read()
+        if it[0] == "jpegf":
+            assert bytes(it[3][:len(data)].numpy()) == data and it[3].numel() % 16 == 0
+        else:
+            _, want = jpeg.entropy_decode_packed(data)
+            assert torch.equal(it[2], want)
+
+
 SEQ_CASES = [c for c in CASES if not c[4].get("progressive")]
 
 

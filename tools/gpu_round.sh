@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, bench line, ncu launch list, ncu --set full captures.  Outputs -> gpurun_out/.
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag] [what...]'
-#   what: tests smoke bench refbench multi launches full gemmcmp archs attntest attnbench train imgstats similar jpeg pipeline lanes power
+#   what: tests smoke bench refbench multi launches full gemmcmp archs attntest attnbench pre huff train imgstats similar jpeg pipeline lanes power
 set -u
 TAG=${1:-run}
 shift || true
@@ -36,7 +36,13 @@ for w in $WHAT; do
     attntest)
       timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "attention or encode_image" > $OUT/${TAG}_attntest.log 2>&1; tail -15 $OUT/${TAG}_attntest.log ;;
     attnbench)
-      for m in v2 v4; do B2C_ATTN=$m timeout 120 python tools/bench_attn.py; done 2>&1 | tee $OUT/${TAG}_attnbench.jsonl ;;
+      timeout 120 python tools/bench_attn.py 2>&1 | tee $OUT/${TAG}_attnbench.jsonl
+      timeout 120 python tools/bench_attn.py 256 577 16 64 2>&1 | tee -a $OUT/${TAG}_attnbench.jsonl ;;
+    pre)
+      timeout 300 python tools/bench_pre.py 256 512 224 14 | tee $OUT/${TAG}_bench_pre.jsonl
+      timeout 300 python tools/bench_pre.py 32 2048 224 14 | tee -a $OUT/${TAG}_bench_pre.jsonl ;;
+    huff)
+      timeout 300 python tools/bench_huff_restart.py | tee $OUT/${TAG}_bench_huff.txt ;;
     train)
       timeout 600 python -m pytest tests/test_train.py -m gpu -x -q > $OUT/${TAG}_train_tests.log 2>&1; tail -15 $OUT/${TAG}_train_tests.log
       timeout 300 python tools/bench_train.py > $OUT/${TAG}_bench_train.json 2> $OUT/${TAG}_bench_train.err; cat $OUT/${TAG}_bench_train.json; tail -3 $OUT/${TAG}_bench_train.err ;;

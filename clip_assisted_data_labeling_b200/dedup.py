@@ -302,19 +302,21 @@ class BandTickets:
     tickets [g*stride, (g+1)*stride): an overflow re-run needs no reset.  Without a store (a backend that has none)
     ``next`` deals the static round-robin share instead."""
 
-    def __init__(self, n_items: int, rank: int, world: int):
+    def __init__(self, n_items: int, rank: int, world: int, tag: str = ""):
+        """``tag``: names the process group (its global ranks), so that two groups searching at the same time do not
+        draw from each other's counter."""
         global _ticket_calls
         _ticket_calls += 1
         self.n, self.rank, self.world = n_items, rank, world
         self.stride = n_items + world  # every rank draws one ticket past the end before it stops
         self.gen = -1
-        self.key = f"b2c/dedup_tickets/{_ticket_calls}"
+        self.key = f"b2c/dedup_tickets/{tag}/{_ticket_calls}"
         try:
             from torch.distributed.distributed_c10d import _get_default_store
             self.store = _get_default_store()
             if rank == 0 and _ticket_calls > 1:  # every rank has left the previous call: its counter can go
                 try:
-                    self.store.delete_key(f"b2c/dedup_tickets/{_ticket_calls - 1}")
+                    self.store.delete_key(f"b2c/dedup_tickets/{tag}/{_ticket_calls - 1}")
                 except Exception:  # noqa: BLE001 — not every store type can delete
                     pass
         except Exception:  # noqa: BLE001
@@ -356,7 +358,11 @@ def duplicate_pairs_distributed(local_embeddings: torch.Tensor, threshold: float
     # so a GPU running at a lower power-capped clock simply takes fewer and all ranks finish together
     bands = sorted((b for r in range(world) for b in owned_blocks(n_local, r, world)[1]),
                    key=lambda t: (-(t[1] - t[0]) * (t[3] - t[2]), t[0]))
-    tickets = BandTickets(len(bands), rank, world)
+    try:
+        tag = "-".join(str(r) for r in dist.get_process_group_ranks(group if group is not None else dist.group.WORLD))
+    except Exception:  # noqa: BLE001
+        tag = "world"
+    tickets = BandTickets(len(bands), rank, world, tag)
     cap = capacity if capacity is not None else max(1 << 16, 4 * n_total // world)
     first = True
     while True:

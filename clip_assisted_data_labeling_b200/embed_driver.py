@@ -7,7 +7,8 @@ reference's names, positional order and defaults (_1_embed_with_CLIP.py:34-96). 
   * DataLoader workers only decode (RawImageDataset); the 4 crops, the PIL-exact resize, normalisation and the
     ViT run fused on the GPU (CLIP_Encoder.encode_images_u8);
   * the per-image ``<img>.pt`` dict is written in the layout every consumer reads:
-    ``{model_name: {crop_name: f32[1,E] CPU tensor}}``, merged into an existing file unless force_reencode —
+    ``{model_name: {img_stat_*: f32 0-d, crop_name: f32[1,E] CPU tensor}}`` (the 22 statistics come from the device,
+    imgstats.image_stats), merged into an existing file unless force_reencode —
     for all B images of a batch and all 4 crops (the reference's collate transposition bug, SURVEY.md App. B1,
     is not reproduced);
   * resume is per image: an image whose ``.pt`` already holds ``model_name`` is skipped (_1:118-128 does this
@@ -165,6 +166,26 @@ class Feature_Dataset:
     def __len__(self):
         return len(self.img_filepaths)
 
+    def _pack_existing(self, packed, img_paths, stat_names):
+        """Resume with a packed shard: rows of already-embedded images are read back from their ``.pt`` files (thread pool)
+        and appended to the shard.  Returns the set of images whose file could NOT supply the row."""
+        import numpy as np
+        from .store import _load_one
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(32, 4 * (os.cpu_count() or 4))) as ex:
+            loaded = list(ex.map(lambda p: _load_one(p, self.model_name, CROP_NAMES), img_paths))
+        ok_paths, feats, kept, stats, bad = [], [], [], [], set()
+        for p, r in zip(img_paths, loaded):
+            if r is None or r[1].shape[1] != packed.embed or any(n not in r[3] for n in stat_names):
+                bad.add(p)
+                continue
+            ok_paths.append(p)
+            feats.append(r[1])
+            kept.append([bool((r[2] >> ci) & 1) for ci in range(len(CROP_NAMES))])
+            stats.append([r[3][n] for n in stat_names])
+        if ok_paths:
+            packed.append(np.stack(feats), ok_paths, kept, stats=np.asarray(stats, np.float32) if stat_names else None)
+        return bad
+
     @torch.no_grad()
     def process(self):
         """One pass over the images.  The loop is software-pipelined: batch i's device work (decode finish, crops, tower,
@@ -183,16 +204,16 @@ class Feature_Dataset:
         else:
             pool = concurrent.futures.ThreadPoolExecutor(max_workers=self._writer_threads)
         pending = []
-        packed = None
-        if self.packed_dir is not None:
-            from .store import PackedWriter
-            packed = PackedWriter(self.packed_dir, self.model_name, self.encoder.embed_dim, CROP_NAMES, shard=self.rank,
-                                  weights_source=getattr(self.encoder, "weights_source", None))
         stat_names = []
         if self.img_stats:
             from .imgstats import STAT_NAMES, image_stats
             stat_names = list(STAT_NAMES)
         n_stats = len(stat_names)
+        packed = None
+        if self.packed_dir is not None:
+            from .store import PackedWriter
+            packed = PackedWriter(self.packed_dir, self.model_name, self.encoder.embed_dim, CROP_NAMES, shard=self.rank,
+                                  weights_source=getattr(self.encoder, "weights_source", None), stat_names=stat_names)
         slots = [None, None]  # pinned result buffers, alternating between consecutive batches
         import time as _time
         timing = os.environ.get("B2C_DRIVER_TIMING") is not None  # wall-clock seconds of the main thread per phase
@@ -231,7 +252,8 @@ class Feature_Dataset:
                         fd = feature_dict_from_flat(r.clone(), n_stats, stat_names, self.crop_names, kept)
                         pending.append(pool.submit(save_feature_file, sp, self.model_name, fd, self.force_reencode))
             if packed is not None:
-                packed.append(rows[:, n_stats:].reshape(b, 4, E).clone(), img_paths, kept_all)
+                packed.append(rows[:, n_stats:].reshape(b, 4, E).clone(), img_paths, kept_all,
+                              stats=rows[:, :n_stats].clone() if n_stats else None)
             if len(pending) > 4096:
                 for fu in pending:
                     fu.result()
@@ -249,6 +271,11 @@ class Feature_Dataset:
                 with concurrent.futures.ThreadPoolExecutor(max_workers=min(32, 4 * (os.cpu_count() or 4))) as ex:
                     flags = list(ex.map(lambda p: already_encoded(os.path.splitext(p)[0] + ".pt", self.model_name), cand))
                 done = {p for p, f in zip(cand, flags) if f}
+                if done and packed is not None:
+                    # the shard is rewritten by every run, so what the resume skips has to come from the .pt files; an
+                    # image whose file cannot supply a complete row (other embedding width, statistics missing while this
+                    # run stores them) is embedded again instead
+                    done -= self._pack_existing(packed, sorted(done), stat_names)
                 if done:
                     n_skipped = len(done)
                     rest = [p for p in self.img_filepaths if p not in done]

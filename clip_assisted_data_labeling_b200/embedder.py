@@ -298,8 +298,10 @@ class CLIP_Encoder:
 
 class CustomImageDataset(Dataset):
     """utils/embedder.py:153-251 — host (PIL) implementation kept for the reference-compatible
-    ``encode_image`` path and as the CPU side of parity tests.  ``image_features`` are not computed
-    (ImageFeaturizer is out of scope): the fourth element is an empty dict."""
+    ``encode_image`` path and as the CPU side of parity tests.  The fourth element is an EMPTY dict where the reference
+    returns the 22 ``img_stat_*`` scalars (:170,175): those are computed on the device (imgstats.image_stats, K13) by
+    ``Feature_Dataset`` for the images already in HBM — DataLoader workers never touch CUDA.  A file
+    that fails to decode raises here instead of being replaced by a random other image (:176-181)."""
 
     def __init__(self, image_paths, crop_names, preprocess_transform):
         self.image_paths = image_paths

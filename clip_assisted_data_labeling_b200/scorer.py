@@ -82,6 +82,9 @@ class FCScorer:
         self.device = torch.device(device)
         self.clip_models = list(getattr(model, "clip_models", []))
         self.crop_names = list(getattr(model, "crop_names", CROP_NAMES))
+        # regressors trained with the image statistics behind the crops (_4_train_model.py:60-63; the reference's own _5
+        # never feeds them, so it cannot score such a model — score_store does)
+        self.use_img_stat_features = bool(getattr(model, "use_img_stat_features", False))
         linears = [m for m in model.layers if isinstance(m, nn.Linear)]
         slopes = [m.negative_slope for m in model.layers if isinstance(m, nn.LeakyReLU)]
         if not linears or len(linears) > _lib.MLP_MAX_LAYERS:
@@ -142,7 +145,7 @@ def score_store(store, scorer: "FCScorer", batch: int = 65536):
     _5_predict_labels.py:69-88,135.  Images missing one of the regressor's crops are skipped like the reference skips
     unreadable samples (:86-88).  Returns (paths, scores f32 [n] on the host)."""
     ok = store.has_all(scorer.crop_names)
-    feats = store.features(scorer.crop_names)
+    feats = store.features(scorer.crop_names, with_stats=scorer.use_img_stat_features)
     keep = [i for i in range(len(store)) if ok[i]]
     out = []
     for b in range(0, len(keep), batch):

@@ -8,7 +8,10 @@ wall time, so the B200 path writes, per rank, one flat shard instead:
     <store_dir>/shard-00000.emb          raw little-endian f32 (or f16) [n, C, E], C = len(crop_names), row-major
     <store_dir>/shard-00000.paths        the image paths, UTF-8, one per line      } per-image lists as sidecar files: a
     <store_dir>/shard-00000.kept         uint8 bitmask per image                   } million rows parse in 0.05 s
-    <store_dir>/shard-00000.json         {"format", "model", "crop_names", "dtype", "embed", "count", "sidecars": true}
+    <store_dir>/shard-00000.stats        raw f32 [n, S]: the S = 22 ``img_stat_*`` scalars of every image, in the order of
+                                         "stat_names" (only when the embedding run computed them; _1:149-152)
+    <store_dir>/shard-00000.json         {"format", "model", "crop_names", "dtype", "embed", "count", "sidecars": true,
+                                          "stat_names": [...] | absent}
                                          — written LAST: the commit point.  (A path with a line break in it, or an
                                          older shard, keeps "paths": [...] and "kept": [...] inside the JSON.)
 
@@ -48,7 +51,9 @@ class PackedWriter:
     so a crashed run never leaves a half-valid shard behind."""
 
     def __init__(self, store_dir: str, model_name: str, embed: int, crop_names=CROP_NAMES, shard: int = 0,
-                 dtype: str = "float32", weights_source: str | None = None):
+                 dtype: str = "float32", weights_source: str | None = None, stat_names=None):
+        """``stat_names``: names of the per-image statistics (imgstats.STAT_NAMES) every ``append`` will bring along; they
+        go to the shard's ``.stats`` file so that ``export_pt`` writes the complete .pt layout."""
         if dtype not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
         os.makedirs(store_dir, exist_ok=True)
@@ -61,15 +66,28 @@ class PackedWriter:
         if os.path.exists(self.idx_path):
             os.remove(self.idx_path)  # invalidate first, then rewrite the data
         self._fh = open(self.emb_path, "wb")
+        self.stat_names = list(stat_names) if stat_names else []
+        self.stats_path = self.idx_path[:-5] + ".stats"
+        self._sfh = open(self.stats_path, "wb") if self.stat_names else None
+        if self._sfh is None and os.path.exists(self.stats_path):
+            os.remove(self.stats_path)  # left by an earlier run of this shard that had statistics
         self.paths: list[str] = []
         self.kept: list[int] = []
 
-    def append(self, features, paths, kept=None) -> None:
+    def append(self, features, paths, kept=None, stats=None) -> None:
         """features: [B, 4, E] (torch CPU tensor or numpy) in CROP_NAMES order; paths: B image paths;
-        kept: optional B x 4 booleans (False = crop dropped as empty)."""
+        kept: optional B x 4 booleans (False = crop dropped as empty); stats: [B, len(stat_names)] when the writer was
+        opened with ``stat_names`` (and only then)."""
         f = features.detach().cpu().numpy() if isinstance(features, torch.Tensor) else np.asarray(features)
         if f.ndim != 3 or f.shape[1] != len(CROP_NAMES) or f.shape[2] != self.embed or f.shape[0] != len(paths):
             raise ValueError(f"expected [{len(paths)},{len(CROP_NAMES)},{self.embed}], got {f.shape}")
+        if (stats is not None) != bool(self.stat_names):
+            raise ValueError("statistics must accompany every append of a writer opened with stat_names, and no other")
+        if stats is not None:
+            st = stats.detach().cpu().numpy() if isinstance(stats, torch.Tensor) else np.asarray(stats)
+            if st.shape != (len(paths), len(self.stat_names)):
+                raise ValueError(f"expected statistics [{len(paths)},{len(self.stat_names)}], got {st.shape}")
+            self._sfh.write(np.ascontiguousarray(st, dtype=np.float32).tobytes())
         f = np.ascontiguousarray(f[:, self._cols, :], dtype=_DTYPES[self.dtype])
         for b in range(len(paths)):
             mask = 0
@@ -88,6 +106,11 @@ class PackedWriter:
         self._fh.close()
         meta = {"format": FORMAT, "model": self.model_name, "crop_names": self.crop_names, "dtype": self.dtype,
                 "embed": self.embed, "count": len(self.paths), "weights_source": self.weights_source}
+        if self._sfh is not None:
+            self._sfh.flush()
+            os.fsync(self._sfh.fileno())
+            self._sfh.close()
+            meta["stat_names"] = self.stat_names
         # The per-image lists go to sidecar files (a million paths parse in 0.05 s as text against 0.3 s as JSON); the
         # .json stays the commit point and is written last.  Paths with a line break in them keep the JSON form.
         base = self.idx_path[:-5]
@@ -113,6 +136,8 @@ class PackedWriter:
             self.close()
         else:
             self._fh.close()
+            if self._sfh is not None:
+                self._sfh.close()
 
 
 class PackedStore:
@@ -151,6 +176,12 @@ class PackedStore:
                 meta["kept"] = np.fromfile(idx_path[:-5] + ".kept", dtype=np.uint8)
                 if len(meta["paths"]) != n or len(meta["kept"]) != n:
                     raise ValueError(f"{idx_path}: sidecar files hold {len(meta['paths'])} paths / {len(meta['kept'])} masks, index says {n}")
+            if meta.get("stat_names"):
+                S, stats_path = len(meta["stat_names"]), idx_path[:-5] + ".stats"
+                have = os.path.getsize(stats_path) if os.path.exists(stats_path) else -1
+                if have != n * S * 4:
+                    raise ValueError(f"{stats_path}: {have} bytes on disk, index says {n * S * 4}")
+                meta["_stats"] = np.memmap(stats_path, dtype=np.float32, mode="r", shape=(n, S)) if n else np.zeros((0, S), np.float32)
             self.shards.append((meta, arr))
         if not self.shards:
             raise FileNotFoundError(f"no packed shards for model {model_name!r} under {store_dir}")
@@ -162,6 +193,9 @@ class PackedStore:
                 raise ValueError("shards of one model disagree on crop_names / embed")
         self.paths = [p for meta, _ in self.shards for p in meta["paths"]]
         self.kept = np.concatenate([np.asarray(meta["kept"], dtype=np.int64) for meta, _ in self.shards])
+        # image statistics: present only when EVERY shard of the model carries the same list
+        names = [tuple(meta.get("stat_names") or ()) for meta, _ in self.shards]
+        self.stat_names = list(names[0]) if names[0] and all(nm == names[0] for nm in names) else []
 
     def __len__(self):
         return len(self.paths)
@@ -172,18 +206,31 @@ class PackedStore:
             return self.shards[0][1]
         return np.concatenate([a for _, a in self.shards], axis=0)
 
+    def stats(self):
+        """f32 [N, S] image statistics over all shards in ``stat_names`` order, or None when the store has none."""
+        if not self.stat_names:
+            return None
+        if len(self.shards) == 1:
+            return self.shards[0][0]["_stats"]
+        return np.concatenate([meta["_stats"] for meta, _ in self.shards], axis=0)
+
     def crop(self, crop_name: str, dtype=torch.float32, device=None) -> torch.Tensor:
         """[N, E] embeddings of one crop, the bulk form of ``d[model][crop].squeeze()`` (_2_remove_duplicates.py:38)."""
         ci = self.crop_names.index(crop_name)
         t = torch.from_numpy(np.array(self.array()[:, ci, :])).to(dtype)  # (a copy: the memory map is read-only)
         return t.to(device) if device is not None else t
 
-    def features(self, crop_names=None, device=None) -> torch.Tensor:
+    def features(self, crop_names=None, device=None, with_stats: bool = False) -> torch.Tensor:
         """[N, len(crop_names) * E] f32: the regressor's input row per image, crops concatenated in the order given
-        (_4_train_model.py:55, _5_predict_labels.py:78-79)."""
+        (_4_train_model.py:55, _5_predict_labels.py:78-79); ``with_stats`` appends the image statistics after the crops
+        (``use_img_stat_features``, _4_train_model.py:60-63)."""
         names = list(crop_names) if crop_names is not None else self.crop_names
         idx = [self.crop_names.index(c) for c in names]
         t = torch.from_numpy(np.array(self.array()[:, idx, :])).float().reshape(len(self), -1)
+        if with_stats:
+            if not self.stat_names:
+                raise ValueError("this packed store holds no image statistics (the embedding run had img_stats off)")
+            t = torch.cat([t, torch.from_numpy(np.array(self.stats()))], dim=1)
         return t.to(device) if device is not None else t
 
     def has_all(self, crop_names) -> np.ndarray:
@@ -194,14 +241,17 @@ class PackedStore:
         return (self.kept & need) == need
 
     def feature_dict(self, i: int) -> dict:
-        """{crop_name: f32[1,E]} of image i, the per-model dict of the reference's .pt layout."""
-        row, off = None, i
+        """{img_stat_*: f32 0-d, crop_name: f32[1,E]} of image i, the per-model dict of the reference's .pt layout
+        (statistics ahead of the crops like _1:149-161 builds it)."""
+        row, srow, off = None, None, i
         for meta, arr in self.shards:
             if off < meta["count"]:
                 row = arr[off]
+                if self.stat_names:
+                    srow = torch.from_numpy(np.array(meta["_stats"][off], dtype=np.float32))
                 break
             off -= meta["count"]
-        d = {}
+        d = {n: srow[k] for k, n in enumerate(self.stat_names)} if srow is not None else {}
         for ci, name in enumerate(self.crop_names):
             if (int(self.kept[i]) >> ci) & 1:
                 d[name] = torch.from_numpy(np.array(row[ci], dtype=np.float32)).unsqueeze(0)
@@ -225,7 +275,7 @@ def _merge_save(pt_path: str, model_name: str, feature_dict: dict, force: bool) 
 
 def export_pt(store: PackedStore, force_reencode: bool = False, threads: int = 8, only=None) -> int:
     """Compat exporter: write ``<img>.pt`` next to each image in the reference's layout
-    ``{model: {crop: f32[1,E]}}``, merged into an existing file unless ``force_reencode``
+    ``{model: {img_stat_*: f32 0-d (when the store has them), crop: f32[1,E]}}``, merged into an existing file unless ``force_reencode``
     (_1_embed_with_CLIP.py:138-170).  ``only``: optional iterable of indices.  Returns the number of files written."""
     idx = list(range(len(store))) if only is None else list(only)
     with concurrent.futures.ThreadPoolExecutor(max_workers=threads) as ex:
@@ -253,7 +303,8 @@ def _load_one(img_path: str, model_name, crop_names):
                 rows.append(None)
         if E is None:
             return None
-        return model_name, np.stack([r if r is not None else np.zeros(E, np.float32) for r in rows]), mask
+        stat = {k: float(v) for k, v in fd.items() if k.startswith("img_stat_")}  # in file order, like _4:61
+        return model_name, np.stack([r if r is not None else np.zeros(E, np.float32) for r in rows]), mask, stat
     except Exception:  # noqa: BLE001  (the reference skips unreadable samples: _2:45-46, _4:72-74)
         return None
 
@@ -283,12 +334,18 @@ def import_pt(root_dir: str, store_dir: str, model_name: str | None = None, crop
     full = np.zeros((len(good), len(CROP_NAMES), E), np.float32)
     kept = []
     cols = [CROP_NAMES.index(c) for c in crop_names]
-    for b, (_, (_, rows, mask)) in enumerate(good):
+    for b, (_, (_, rows, mask, _stat)) in enumerate(good):
         full[b, cols, :] = rows
         k = [False] * len(CROP_NAMES)
         for ci, c in enumerate(cols):
             k[c] = bool((mask >> ci) & 1)
         kept.append(k)
-    with PackedWriter(store_dir, model, E, crop_names, shard=shard) as w:
-        w.append(full, [p for p, _ in good], kept)
+    # the statistics travel along when every file has the same list of them (files of the reference's _1 and of this
+    # package's driver do; a tree embedded with img_stats off has none)
+    stat_names = list(good[0][1][3])
+    if not stat_names or any(list(r[3]) != stat_names for _, r in good):
+        stat_names = []
+    stats = np.asarray([[r[3][n] for n in stat_names] for _, r in good], np.float32) if stat_names else None
+    with PackedWriter(store_dir, model, E, crop_names, shard=shard, stat_names=stat_names) as w:
+        w.append(full, [p for p, _ in good], kept, stats=stats)
     return PackedStore(store_dir, model)

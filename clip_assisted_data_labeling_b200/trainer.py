@@ -139,10 +139,11 @@ def cosine_warm_restarts_lr(base_lr, eta_min, T_0, epochs_done):
     return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * t_cur / T_0)) / 2
 
 
-def load_labelled_features(args, crop_names, store=None):
+def load_labelled_features(args, crop_names, store=None, use_img_stat_features=0):
     """_4_train_model.py:27-80: per dataset, labels.csv -> shuffled rows -> per-image feature vector (crops of every
-    clip model concatenated).  With ``store`` (a packed store, store.PackedStore) the vectors come from the shard instead
-    of one torch.load per image; rows whose image is missing are skipped like the reference's ``except: continue``."""
+    clip model concatenated; with ``use_img_stat_features`` each model's ``img_stat_*`` scalars follow its crops, :60-63).
+    With ``store`` (a packed store, store.PackedStore) the vectors come from the shard instead of one torch.load per
+    image; rows whose image is missing are skipped like the reference's ``except: continue``."""
     import pandas as pd
     features, labels = [], []
     by_path = None
@@ -161,7 +162,7 @@ def load_labelled_features(args, crop_names, store=None):
         by_path = {}
         for i, p in enumerate(store.paths):
             by_path.setdefault(os.path.splitext(os.path.abspath(p))[0], i)
-        full = store.features(crop_names)
+        full = store.features(crop_names, with_stats=bool(use_img_stat_features))
         ok = store.has_all(crop_names)
     for name in args.train_data_names:
         data = pd.read_csv(os.path.join(args.train_data_dir, name + ".csv"))
@@ -188,6 +189,8 @@ def load_labelled_features(args, crop_names, store=None):
                         if missing:
                             raise Exception(f"Missing crops {missing} for {uuid}")
                         parts.append(torch.cat([fd[c] for c in crop_names if c in fd], dim=0).flatten())
+                        if use_img_stat_features:
+                            parts.append(torch.stack([fd[k] for k in fd.keys() if k.startswith("img_stat_")], dim=0).float())
                     vec = torch.cat(parts, dim=0)
                 features.append(vec)
                 labels.append(label)
@@ -202,11 +205,9 @@ def train(args, crop_names, use_img_stat_features=0, store=None, device="cuda", 
           engine_cls=None):
     """_4_train_model.py:16-238.  Returns (model, losses [[train...],[test...]], lrs).  ``engine_cls`` (tests only)
     replaces DeviceTrainer by another step engine with the same interface; the product path never passes it."""
-    if use_img_stat_features:
-        raise NotImplementedError("img_stat_* features are not produced by the B200 embedding path (hard-coded off at _4:274)")
     torch.manual_seed(args.random_seed)
     np.random.seed(args.random_seed)
-    features, labels = load_labelled_features(args, crop_names, store)
+    features, labels = load_labelled_features(args, crop_names, store, use_img_stat_features)
     labels_min, labels_max = labels.min(), labels.max()
     labels = (labels - labels_min) / (labels_max - labels_min)
     n = len(features)
@@ -218,7 +219,7 @@ def train(args, crop_names, use_img_stat_features=0, store=None, device="cuda", 
     train_loader = DataLoader(train_ds, batch_size=args.batch_size, shuffle=True)
     test_loader = DataLoader(test_ds, batch_size=args.batch_size, shuffle=False)
     model = SimpleFC(features.shape[1], list(args.hidden_sizes), 1, args.clip_models_to_use, crop_names=crop_names,
-                     dropout_prob=args.dropout_prob)
+                     use_img_stat_features=bool(use_img_stat_features), dropout_prob=args.dropout_prob)
     dev = torch.device(device)
     feats_d, labels_d = features.to(dev), labels.to(dev)
     trainer = (engine_cls or DeviceTrainer)(model, max_batch=args.batch_size, dropout_p=args.dropout_prob,

@@ -156,3 +156,104 @@ def test_reference_dedup_loader_reads_exported_files(tmp_path):
     assert sorted(order) == list(range(9))
     want = torch.from_numpy(feats[order, 1]).to(torch.float16)
     assert torch.equal(torch.stack(got_emb), want)
+
+
+def _fake_stats(images, device=None):
+    """Stand-in for imgstats.image_stats in host-logic tests (no CUDA): [B, 22] with the image's width, height and mean."""
+    out = torch.zeros(len(images), 22, dtype=torch.float64)
+    for i, im in enumerate(images):
+        out[i, 0], out[i, 1], out[i, 2] = im.shape[1], im.shape[0], im.shape[1] / im.shape[0]
+        out[i, 3:] = im.double().mean() + torch.arange(19)
+    return out
+
+
+def test_statistics_sidecar_round_trip_export_and_import(tmp_path):
+    """A shard written with stat_names carries the 22 img_stat_* scalars: export_pt then writes the complete .pt layout
+    (statistics ahead of the crops as 0-d f32 tensors, _1_embed_with_CLIP.py:149-161), import_pt brings them back, and a
+    store whose shards disagree reports none."""
+    from clip_assisted_data_labeling_b200.imgstats import STAT_NAMES
+    from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter, export_pt, import_pt
+    from clip_assisted_data_labeling_b200.vit_arch import CROP_NAMES
+    rng = np.random.default_rng(5)
+    root = tmp_path / "imgs"
+    root.mkdir()
+    n, E = 5, 8
+    feats = rng.standard_normal((n, 4, E)).astype(np.float32)
+    stats = rng.standard_normal((n, 22)).astype(np.float32)
+    paths = [str(root / f"{i}.jpg") for i in range(n)]
+    for p in paths:
+        open(p, "wb").close()
+    sd = str(tmp_path / "s")
+    with PackedWriter(sd, "M/x", E, stat_names=STAT_NAMES) as w:
+        w.append(feats[:2], paths[:2], stats=stats[:2])
+        w.append(feats[2:], paths[2:], stats=torch.from_numpy(stats[2:]))
+        with pytest.raises(ValueError):
+            w.append(feats[:1], paths[:1])  # statistics must accompany every append
+    st = PackedStore(sd)
+    assert st.stat_names == STAT_NAMES and np.array_equal(st.stats(), stats)
+    f = st.features(["centre_crop"], with_stats=True)
+    assert f.shape == (n, E + 22) and torch.equal(f[3, E:], torch.from_numpy(stats[3]))
+    export_pt(st)
+    d = torch.load(paths[1][:-4] + ".pt")["M/x"]
+    assert list(d.keys()) == STAT_NAMES + CROP_NAMES
+    for k, name in enumerate(STAT_NAMES):
+        assert d[name].dim() == 0 and d[name].dtype == torch.float32 and float(d[name]) == float(stats[1, k])
+    back = import_pt(str(root), str(tmp_path / "s2"), "M/x")
+    assert back.stat_names == STAT_NAMES and np.array_equal(back.stats(), stats) and np.array_equal(back.array(), feats)
+    # a second shard without statistics: the store as a whole has none, and says so when they are asked for
+    with PackedWriter(sd, "M/x", E, shard=1) as w:
+        w.append(feats[:1], ["other.jpg"])
+    st2 = PackedStore(sd)
+    assert st2.stat_names == [] and st2.stats() is None and list(st2.feature_dict(0).keys()) == CROP_NAMES
+    with pytest.raises(ValueError, match="no image statistics"):
+        st2.features(["centre_crop"], with_stats=True)
+    # rewriting a shard without statistics removes the stale .stats file; a truncated one is refused
+    with PackedWriter(sd, "M/x", E, shard=0) as w:
+        w.append(feats[:1], paths[:1])
+    assert not os.path.exists(os.path.join(sd, "shard-00000.stats"))
+    with PackedWriter(sd, "M/x", E, shard=0, stat_names=STAT_NAMES) as w:
+        w.append(feats, paths, stats=stats)
+    with open(os.path.join(sd, "shard-00000.stats"), "ab") as fh:
+        fh.write(b"1234")
+    with pytest.raises(ValueError, match="stats"):
+        PackedStore(sd)
+
+
+def test_driver_stores_statistics_and_resume_refills_the_shard(tmp_path, lib, monkeypatch):
+    """Feature_Dataset with packed_dir: the statistics land in the shard and in the .pt files; a resumed run (every image
+    already has this model's key) re-embeds nothing and still leaves a COMPLETE shard, rows read back from the .pt files;
+    an image whose file lacks the statistics this run stores is embedded again."""
+    from clip_assisted_data_labeling_b200 import imgstats
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from clip_assisted_data_labeling_b200.store import PackedStore
+    from clip_assisted_data_labeling_b200.vit_arch import CROP_NAMES
+    monkeypatch.setattr(imgstats, "image_stats", _fake_stats)
+    root = str(tmp_path / "data")
+    _write_images(root, 6)
+
+    def run(**kw):
+        enc = _FakeEncoder()
+        enc.embed_dim = 8
+        ds = Feature_Dataset(root, "ViT-L-14/openai", 4, shuffle_filenames=False, encoder=enc, packed_dir=str(tmp_path / "p"),
+                             img_stats=True, **kw)
+        return ds.process(), enc, PackedStore(str(tmp_path / "p"))
+
+    (n, skipped), enc, st = run()
+    assert (n, skipped) == (6, 0) and st.stat_names == imgstats.STAT_NAMES and len(st) == 6
+    assert st.stats()[:, 0].tolist() == [40.0] * 6 and st.stats()[:, 1].tolist() == [30.0] * 6
+    d = torch.load(os.path.join(root, "im002.pt"))["ViT-L-14/openai"]
+    assert list(d.keys()) == imgstats.STAT_NAMES + CROP_NAMES and float(d["img_stat_width"]) == 40.0
+    first = {p: (st.array()[i].copy(), st.stats()[i].copy()) for i, p in enumerate(st.paths)}
+    # resume: nothing is embedded, the shard is complete again and holds the same rows
+    (n, skipped), enc, st = run()
+    assert (n, skipped, enc.calls) == (0, 6, 0) and sorted(st.paths) == sorted(first)
+    for i, p in enumerate(st.paths):
+        assert np.array_equal(st.array()[i], first[p][0]) and np.array_equal(st.stats()[i], first[p][1])
+    # one file loses its statistics (as if written by a run with img_stats off): that image is embedded again
+    pt = os.path.join(root, "im004.pt")
+    d = torch.load(pt)
+    d["ViT-L-14/openai"] = {k: v for k, v in d["ViT-L-14/openai"].items() if not k.startswith("img_stat_")}
+    torch.save(d, pt)
+    (n, skipped), enc, st = run()
+    assert (n, skipped, enc.calls) == (1, 5, 1) and len(st) == 6
+    assert list(torch.load(pt)["ViT-L-14/openai"].keys()) == imgstats.STAT_NAMES + CROP_NAMES

@@ -212,3 +212,40 @@ def test_store_backed_features_resolve_the_model_and_match_rows_by_path(tmp_path
         load_labelled_features(args(["ViT-H-14/laion2b_s32b_b79k"], ["setA"]), crops, store)
     with pytest.raises(ValueError):
         load_labelled_features(args(["ViT-L-14/openai", "ViT-B-32/openai"], ["setA"]), crops, store)
+
+
+def test_img_stat_features_follow_the_crops(tmp_path):
+    """use_img_stat_features (_4_train_model.py:60-63): each model's img_stat_* scalars, in file order, are appended after
+    its crops — from per-image .pt files and from a packed store that carries the statistics alike."""
+    from clip_assisted_data_labeling_b200.imgstats import STAT_NAMES
+    from clip_assisted_data_labeling_b200.store import PackedStore, import_pt
+    from clip_assisted_data_labeling_b200.trainer import load_labelled_features
+    import pandas as pd
+    E = 4
+    root = tmp_path / "data"
+    (root / "set").mkdir(parents=True)
+    g = torch.Generator().manual_seed(1)
+    want = {}
+    for k, u in enumerate(("a", "b", "c")):
+        crops = {c: torch.randn(1, E, generator=g) for c in ("centre_crop", "square_padded_crop", "subcrop1", "subcrop2")}
+        stats = {n: torch.randn((), generator=g) for n in STAT_NAMES}
+        torch.save({"M/x": {**stats, **crops}}, root / "set" / f"{u}.pt")
+        open(root / "set" / f"{u}.jpg", "wb").close()
+        want[float(k)] = torch.cat([crops["centre_crop"].flatten(), crops["subcrop2"].flatten(), torch.stack(list(stats.values()))])
+    pd.DataFrame([("a", 0.0), ("b", 1.0), ("c", 2.0)], columns=["uuid", "label"]).to_csv(root / "set.csv", index=False)
+
+    def args():
+        return types.SimpleNamespace(train_data_dir=str(root), train_data_names=["set"], clip_models_to_use=["M/x"])
+
+    crops = ["centre_crop", "subcrop2"]
+    x, y = load_labelled_features(args(), crops, use_img_stat_features=1)
+    assert x.shape == (3, 2 * E + 22)
+    for row, label in zip(x, y.tolist()):
+        assert torch.equal(row, want[label])
+    x0, _ = load_labelled_features(args(), crops)
+    assert x0.shape == (3, 2 * E)
+    store = import_pt(str(root), str(tmp_path / "store"), "M/x")
+    assert store.stat_names == STAT_NAMES
+    xs, ys = load_labelled_features(args(), crops, store, use_img_stat_features=1)
+    for row, label in zip(xs, ys.tolist()):
+        assert torch.equal(row, want[label])

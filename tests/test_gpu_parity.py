@@ -665,3 +665,50 @@ def test_feature_dataset_end_to_end(cuda, lib, tmp_path):
     (dups, vals), = find_near_duplicates(args)
     names = {tuple(sorted((os.path.basename(a), os.path.basename(b)))) for a, b in dups}
     assert ("004.jpg", "009.jpg") in names
+
+
+@pytest.mark.gpu
+def test_feature_dataset_packed_shard_carries_statistics_and_resumes(cuda, lib, tmp_path):
+    """Feature_Dataset(packed_dir=...) on the device path: the shard holds the embeddings AND the 22 image statistics that
+    the .pt files hold (bit for bit); export_pt from the shard alone rebuilds the same files; a resumed run embeds nothing
+    and leaves the same complete shard (rows read back from the .pt files)."""
+    from PIL import Image
+    from clip_assisted_data_labeling_b200.embed_driver import Feature_Dataset
+    from clip_assisted_data_labeling_b200.imgstats import STAT_NAMES
+    from clip_assisted_data_labeling_b200.store import PackedStore, export_pt
+    from clip_assisted_data_labeling_b200.vit_arch import CROP_NAMES
+    from oracle import vit_oracle
+    from oracle.preprocess_oracle import synthetic_image
+    root = tmp_path / "imgs"
+    root.mkdir()
+    for k in range(7):
+        Image.fromarray(synthetic_image(k, 120 + 8 * k, 150)).save(root / f"{k:03d}.png")
+    sd = vit_oracle.visual_state_dict(vit_oracle.build_visual("ViT-B-32", "openai", seed=0))
+    name = "ViT-B-32/openai"
+
+    def run():
+        ds = Feature_Dataset(str(root), name, batch_size=4, shuffle_filenames=False, state_dict=sd, packed_dir=str(tmp_path / "p"))
+        return ds.process(), PackedStore(str(tmp_path / "p"))
+
+    (n, skipped), st = run()
+    assert (n, skipped) == (7, 0) and st.stat_names == STAT_NAMES and len(st) == 7
+    files = {}
+    for i, p in enumerate(st.paths):
+        d = torch.load(os.path.splitext(p)[0] + ".pt")[name]
+        assert list(d.keys()) == STAT_NAMES + CROP_NAMES
+        assert torch.equal(torch.stack([d[s] for s in STAT_NAMES]), torch.from_numpy(np.array(st.stats()[i])))
+        assert torch.equal(torch.cat([d[c] for c in CROP_NAMES]), torch.from_numpy(np.array(st.array()[i])))
+        files[p] = d
+    first = (list(st.paths), np.array(st.array()), np.array(st.stats()))
+    # the shard alone rebuilds the files
+    for p in st.paths:
+        os.remove(os.path.splitext(p)[0] + ".pt")
+    export_pt(st)
+    for p, want in files.items():
+        got = torch.load(os.path.splitext(p)[0] + ".pt")[name]
+        assert list(got.keys()) == list(want.keys()) and all(torch.equal(got[k], want[k]) and got[k].shape == want[k].shape for k in want)
+    # resume: nothing to embed, the rewritten shard is complete and identical
+    (n, skipped), st2 = run()
+    assert (n, skipped) == (0, 7)
+    order = [st2.paths.index(p) for p in first[0]]
+    assert np.array_equal(np.array(st2.array())[order], first[1]) and np.array_equal(np.array(st2.stats())[order], first[2])

@@ -91,3 +91,18 @@ def test_flops_formula():
     assert abs(vit_oracle.flops_per_crop("ViT-L-14") / 1e9 - 162.03) < 0.05
     assert abs(vit_oracle.flops_per_crop("ViT-H-14") / 1e9 - 334.59) < 0.05
     assert abs(vit_oracle.flops_per_crop("ViT-B-32") / 1e9 - 8.82) < 0.02
+
+
+@pytest.mark.parametrize("arch,pretrained", [("ViT-B-32", "openai"), ("ViT-L-14", "openai")])
+def test_vit_oracle_vs_transformers_clip_full_shape(arch, pretrained):
+    """The same second statement at the FULL shape of the named architectures (seeded random init, one crop): the oracle
+    the GPU parity tests and bench.py's parity blocks trust agrees with transformers' CLIPVisionModelWithProjection live,
+    not only through the stored scalar of tests/golden."""
+    m = vit_oracle.build_visual(arch, pretrained, seed=0)
+    R = vit_oracle.ARCHS[arch]["image"]
+    px = torch.randn(1, 3, R, R, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        a = m(px)
+        b = vit_oracle.to_hf_clip(m)(pixel_values=px).image_embeds
+    a, b = a / a.norm(dim=-1, keepdim=True), b / b.norm(dim=-1, keepdim=True)
+    assert (a - b).abs().max().item() < 2e-5

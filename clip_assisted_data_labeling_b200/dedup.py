@@ -441,8 +441,8 @@ def find_near_duplicates_in_store(store, threshold=0.96, crop_to_use="square_pad
     whole store at once.  Embeddings go through fp16 like the reference's loader (:38).  Returns
     [(near_duplicates [(path_i, path_j)], near_duplicate_values [float])] per group."""
     usable = store.has_all([crop_to_use])
-    paths = store.paths
-    in_order = sorted(paths) == paths  # the embedding run writes a shard in sorted-path order: linear to verify
+    in_order = store.paths_sorted()  # the embedding run writes a shard in sorted-path order and says so in its index
+    paths = store.paths if (per_directory or not in_order) else None  # whole-store search: only the found pairs' paths
     if per_directory:
         groups = {}
         for i, p in enumerate(paths):
@@ -473,8 +473,8 @@ def find_near_duplicates_in_store(store, threshold=0.96, crop_to_use="square_pad
             host = np.empty((len(idx), arr.shape[2]), arr.dtype)
             rows_into(0, len(idx), host)
             pairs, sims = duplicate_pairs(torch.from_numpy(host).to(torch.float16), threshold, compare)
-        results.append(([(store.paths[idx[i]], store.paths[idx[j]]) for i, j in pairs.tolist()],
-                        [float(np.float16(s)) for s in sims]))
+        found = store.paths_at(idx[pairs.reshape(-1)]) if len(pairs) else []
+        results.append((list(zip(found[0::2], found[1::2])), [float(np.float16(s)) for s in sims]))
     return results
 
 
@@ -501,7 +501,8 @@ def find_near_duplicates_in_store_distributed(store_dir, threshold=0.96, crop_to
     pairs, sims = duplicate_pairs_distributed(local, threshold, compare, group=group)
     # global row -> path: row = shard * n_local + index inside the shard; only the paths of rows that occur are exchanged
     need = sorted({int(r) for r in pairs.reshape(-1)})
-    mine = {r: store.paths[r - rank * n_local] for r in need if r // n_local == rank}
+    mine_rows = [r for r in need if r // n_local == rank]
+    mine = dict(zip(mine_rows, store.paths_at([r - rank * n_local for r in mine_rows])))
     merged = [None] * world
     dist.all_gather_object(merged, mine, group=group)  # a few path strings per found pair, not the embeddings
     path_of = {k: v for part in merged for k, v in part.items()}

@@ -73,6 +73,7 @@ class PackedWriter:
             os.remove(self.stats_path)  # left by an earlier run of this shard that had statistics
         self.paths: list[str] = []
         self.kept: list[int] = []
+        self._sorted = True  # paths appended so far are in ascending order (recorded in the index: readers skip the check)
 
     def append(self, features, paths, kept=None, stats=None) -> None:
         """features: [B, 4, E] (torch CPU tensor or numpy) in CROP_NAMES order; paths: B image paths;
@@ -98,14 +99,23 @@ class PackedWriter:
                     f[b, ci, :] = 0
             self.kept.append(mask)
         self._fh.write(f.tobytes())
-        self.paths.extend(os.fspath(p) for p in paths)
+        new = [os.fspath(p) for p in paths]
+        if self._sorted and new:
+            prev = self.paths[-1] if self.paths else None
+            for q in new:
+                if prev is not None and q < prev:
+                    self._sorted = False
+                    break
+                prev = q
+        self.paths.extend(new)
 
     def close(self) -> str:
         self._fh.flush()
         os.fsync(self._fh.fileno())
         self._fh.close()
         meta = {"format": FORMAT, "model": self.model_name, "crop_names": self.crop_names, "dtype": self.dtype,
-                "embed": self.embed, "count": len(self.paths), "weights_source": self.weights_source}
+                "embed": self.embed, "count": len(self.paths), "weights_source": self.weights_source,
+                "sorted": self._sorted}
         if self._sfh is not None:
             self._sfh.flush()
             os.fsync(self._sfh.fileno())
@@ -171,11 +181,14 @@ class PackedStore:
             arr = (np.memmap(emb_path, dtype=_DTYPES[meta["dtype"]], mode="r", shape=(n, C, E)) if n
                    else np.zeros((0, C, E), _DTYPES[meta["dtype"]]))
             if meta.get("sidecars"):
-                with open(idx_path[:-5] + ".paths", encoding="utf-8", newline="\n") as fh:
-                    meta["paths"] = fh.read().split("\n")
+                # the path list stays raw bytes until somebody asks for ``.paths``: a million str objects take ~0.1 s to
+                # create, and the duplicate search only needs the paths of the pairs it finds (``paths_at``)
+                with open(idx_path[:-5] + ".paths", "rb") as fh:
+                    meta["_raw_paths"] = fh.read()
                 meta["kept"] = np.fromfile(idx_path[:-5] + ".kept", dtype=np.uint8)
-                if len(meta["paths"]) != n or len(meta["kept"]) != n:
-                    raise ValueError(f"{idx_path}: sidecar files hold {len(meta['paths'])} paths / {len(meta['kept'])} masks, index says {n}")
+                n_paths = meta["_raw_paths"].count(b"\n") + 1 if n else 0
+                if n_paths != n or len(meta["kept"]) != n:
+                    raise ValueError(f"{idx_path}: sidecar files hold {n_paths} paths / {len(meta['kept'])} masks, index says {n}")
             if meta.get("stat_names"):
                 S, stats_path = len(meta["stat_names"]), idx_path[:-5] + ".stats"
                 have = os.path.getsize(stats_path) if os.path.exists(stats_path) else -1
@@ -191,14 +204,64 @@ class PackedStore:
         for meta, _ in self.shards:
             if meta["crop_names"] != self.crop_names or meta["embed"] != self.embed:
                 raise ValueError("shards of one model disagree on crop_names / embed")
-        self.paths = [p for meta, _ in self.shards for p in meta["paths"]]
+        self._paths = None
+        self._first_row = np.cumsum([0] + [meta["count"] for meta, _ in self.shards])  # global row of each shard's first
         self.kept = np.concatenate([np.asarray(meta["kept"], dtype=np.int64) for meta, _ in self.shards])
         # image statistics: present only when EVERY shard of the model carries the same list
         names = [tuple(meta.get("stat_names") or ()) for meta, _ in self.shards]
         self.stat_names = list(names[0]) if names[0] and all(nm == names[0] for nm in names) else []
 
     def __len__(self):
-        return len(self.paths)
+        return int(self._first_row[-1])
+
+    @staticmethod
+    def _shard_paths_list(meta) -> list:
+        if "paths" not in meta:
+            meta["paths"] = meta["_raw_paths"].decode("utf-8").split("\n") if meta["count"] else []
+        return meta["paths"]
+
+    @property
+    def paths(self) -> list:
+        """All image paths, in row order (built on first use)."""
+        if self._paths is None:
+            self._paths = [p for meta, _ in self.shards for p in self._shard_paths_list(meta)]
+        return self._paths
+
+    def paths_at(self, rows) -> list:
+        """Paths of the given global rows without materialising the whole list: the raw sidecar bytes are cut at the line
+        breaks around each requested row (one vectorised newline scan per shard, on first use)."""
+        rows = np.asarray(rows, np.int64).reshape(-1)
+        if self._paths is not None:
+            return [self._paths[int(r)] for r in rows]
+        out = [None] * len(rows)
+        which = np.searchsorted(self._first_row, rows, side="right") - 1
+        for s in np.unique(which):
+            meta = self.shards[int(s)][0]
+            sel = np.nonzero(which == s)[0]
+            local = rows[sel] - self._first_row[s]
+            if "paths" in meta or "_raw_paths" not in meta:
+                lst = self._shard_paths_list(meta)
+                for k, r in zip(sel, local):
+                    out[k] = lst[int(r)]
+                continue
+            if "_line_starts" not in meta:
+                raw = np.frombuffer(meta["_raw_paths"], np.uint8)
+                meta["_line_starts"] = np.concatenate([[0], np.flatnonzero(raw == 10) + 1, [raw.size + 1]])
+            st, rawb = meta["_line_starts"], meta["_raw_paths"]
+            for k, r in zip(sel, local):
+                out[k] = rawb[int(st[r]):int(st[r + 1]) - 1].decode("utf-8")
+        return out
+
+    def paths_sorted(self) -> bool:
+        """True when the rows are in ascending path order.  Shards written by this version record it in their index
+        (``"sorted"``); only older shards, or several shards, need a look at the paths themselves."""
+        if self._paths is None and all(meta.get("sorted") for meta, _ in self.shards):
+            if len(self.shards) == 1:
+                return True
+            edges = [self.paths_at([self._first_row[k], self._first_row[k + 1] - 1]) for k, (meta, _) in enumerate(self.shards)
+                     if meta["count"]]
+            return all(a[1] <= b[0] for a, b in zip(edges, edges[1:]))
+        return sorted(self.paths) == self.paths
 
     def array(self) -> np.ndarray:
         """[N, C, E] over all shards (a view for one shard, one concatenation otherwise)."""

@@ -257,3 +257,40 @@ def test_driver_stores_statistics_and_resume_refills_the_shard(tmp_path, lib, mo
     (n, skipped), enc, st = run()
     assert (n, skipped, enc.calls) == (1, 5, 1) and len(st) == 6
     assert list(torch.load(pt)["ViT-L-14/openai"].keys()) == imgstats.STAT_NAMES + CROP_NAMES
+
+
+def test_lazy_paths_paths_at_and_sorted_flag(tmp_path):
+    """The path list is not materialised on open: paths_at cuts the requested rows out of the raw sidecar bytes (several
+    shards, multi-byte characters, carriage returns), .paths builds the same list on demand, and paths_sorted trusts the
+    writer's flag for one shard, checks the shard edges for several, and falls back to the list for older shards."""
+    import json
+    from clip_assisted_data_labeling_b200.store import PackedStore, PackedWriter
+    sd = str(tmp_path / "s")
+    names = [["a/é\rx.jpg", "a/ü.jpg", "b/0.jpg"], ["b/1.jpg", "c.jpg"], ["d.jpg"]]
+    for r, ns in enumerate(names):
+        with PackedWriter(sd, "M/x", 4, shard=r) as w:
+            w.append(np.full((len(ns), 4, 4), r, np.float32), ns)
+    flat = [n for ns in names for n in ns]
+    st = PackedStore(sd)
+    assert st._paths is None and len(st) == 6
+    assert st.paths_at([5, 0, 3, 1, 1]) == [flat[5], flat[0], flat[3], flat[1], flat[1]] and st._paths is None
+    assert st.paths_at([]) == []
+    assert st.paths_sorted() and st._paths is None      # from the flags and the shard edges alone
+    assert st.paths == flat and st.paths_at([2, 4]) == [flat[2], flat[4]]
+    # an unsorted shard is recorded as such
+    with PackedWriter(sd, "M/x", 4, shard=1) as w:
+        w.append(np.zeros((2, 4, 4), np.float32), ["z.jpg", "b/1.jpg"])
+    assert json.load(open(os.path.join(sd, "shard-00001.json")))["sorted"] is False
+    assert not PackedStore(sd).paths_sorted()
+    # sorted inside every shard but not across them
+    with PackedWriter(sd, "M/x", 4, shard=1) as w:
+        w.append(np.zeros((2, 4, 4), np.float32), ["a/0.jpg", "a/1.jpg"])
+    assert not PackedStore(sd).paths_sorted()
+    # a shard written before the flag existed: decided from the list itself
+    with PackedWriter(sd, "M/x", 4, shard=1) as w:
+        w.append(np.zeros((2, 4, 4), np.float32), names[1])
+    meta = json.load(open(os.path.join(sd, "shard-00001.json")))
+    del meta["sorted"]
+    json.dump(meta, open(os.path.join(sd, "shard-00001.json"), "w"))
+    st = PackedStore(sd)
+    assert st.paths_sorted() and st._paths is not None

@@ -24,4 +24,4 @@ def test_multi_gpu_dedup_and_embed_match_single_gpu():
                            capture_output=True, text=True, timeout=900, cwd=ROOT)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
         line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-        assert line["world"] == world and line["dedup_identical"] and line["embed_identical"] and line["dedup_pairs"] > 0
+        assert line["world"] == world and line["dedup_identical"] and line["store_dedup_identical"] and line["embed_identical"] and line["dedup_pairs"] > 0

@@ -187,13 +187,54 @@ def duplicate_pairs(embeddings: torch.Tensor, threshold: float, compare: str = "
     return sort_pairs(pairs, sims)
 
 
-_stream_slots = {}   # pinned staging buffers of duplicate_pairs_streamed, kept between calls (release_stream_buffers())
+_stream_slots = {}   # pinned staging buffers of _stage_rows, kept between calls (release_stream_buffers())
+_stream_free = {}    # per slot: the event after which it may be refilled (kept with the slot: the next call reuses it)
 _stream_pool = None
 
 
 def release_stream_buffers():
     """Give back the pinned host buffers duplicate_pairs_streamed keeps between calls (2 x chunk_rows x E elements)."""
+    for evs in _stream_free.values():
+        for ev in evs:
+            if ev is not None:
+                ev.synchronize()
+    _stream_free.clear()
     _stream_slots.clear()
+
+
+def _stage_rows(rows_into, n: int, E: int, src_dtype, dev, chunk_rows: int, consume):
+    """Host rows -> device, chunk by chunk through two pinned slots: chunk k = rows [a, b) is gathered by four host threads
+    (``rows_into(a, b, out)`` fills the numpy array ``out`` [b-a, E]), copied to the device on a side stream, and handed to
+    ``consume(a, b, d)`` — called with the side stream current, ``d`` = the chunk on the device ([b-a, E] of ``src_dtype``).
+    The gather of chunk k+1 overlaps the copy (and whatever ``consume`` queues) of chunk k.  Returns the side stream; work
+    the caller queues elsewhere afterwards has to wait for it (``wait_stream``)."""
+    global _stream_pool
+    import concurrent.futures as cf
+    key = (chunk_rows, E, src_dtype)
+    if key not in _stream_slots:
+        _stream_slots[key] = [torch.empty(chunk_rows, E, dtype=src_dtype, pin_memory=True) for _ in range(2)]
+        _stream_free[key] = [None, None]
+    slots, free = _stream_slots[key], _stream_free[key]
+    if _stream_pool is None:
+        _stream_pool = cf.ThreadPoolExecutor(4)
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)  # what the caller allocated / queued so far exists before the side stream touches it
+    for k, a in enumerate(range(0, n, chunk_rows)):
+        b = min(n, a + chunk_rows)
+        m = b - a
+        slot = slots[k & 1]
+        if free[k & 1] is not None:
+            free[k & 1].synchronize()
+        view = slot[:m].numpy()
+        cuts = [m * t // 4 for t in range(5)]
+        list(_stream_pool.map(lambda t: rows_into(a + cuts[t], a + cuts[t + 1], view[cuts[t]:cuts[t + 1]]), range(4)))
+        with torch.cuda.stream(side):
+            d = slot[:m].to(dev, non_blocking=True)
+            free[k & 1] = torch.cuda.Event()
+            free[k & 1].record(side)
+            consume(a, b, d)
+    return side
 
 
 def duplicate_pairs_streamed(rows_into, n: int, E: int, src_dtype, threshold: float, compare: str = "ref_fp16", device=None,
@@ -204,7 +245,6 @@ def duplicate_pairs_streamed(rows_into, n: int, E: int, src_dtype, threshold: fl
     (i < j) belongs to the chunk that holds j — so the host gather, the H2D copies and the search overlap and the call
     takes about as long as the search alone.  ``rows_into(a, b, out)`` fills the numpy array ``out`` [b-a, E] with rows
     a..b of the set, in the order the pairs are to be reported in."""
-    global _stream_pool
     if compare not in _MODES:
         raise ValueError(f"compare must be one of {sorted(_MODES)}")
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -212,43 +252,25 @@ def duplicate_pairs_streamed(rows_into, n: int, E: int, src_dtype, threshold: fl
         raise _lib.B2CError("duplicate_pairs_streamed needs a CUDA device (sm_100a); there is no CPU fallback")
     if n < 2:
         return np.zeros((0, 2), np.int64), np.zeros((0,), np.float32)
-    import concurrent.futures as cf
     E_pad = (E + 63) // 64 * 64
-    key = (chunk_rows, E, src_dtype)
-    if key not in _stream_slots:
-        _stream_slots[key] = [torch.empty(chunk_rows, E, dtype=src_dtype, pin_memory=True) for _ in range(2)]
-    slots = _stream_slots[key]
-    if _stream_pool is None:
-        _stream_pool = cf.ThreadPoolExecutor(4)
     cap = capacity if capacity is not None else max(1 << 16, 4 * n)
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
-        side = torch.cuda.Stream(device=dev)
         gathered = torch.empty(n, E_pad, dtype=torch.float16, device=dev)
         buf = torch.empty(max(cap, 1), 3, dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-        side.wait_stream(main)  # `gathered` exists before the side stream writes into it
-        free = [None, None]  # event after which a pinned slot may be refilled
-        for k, a in enumerate(range(0, n, chunk_rows)):
-            b = min(n, a + chunk_rows)
-            m = b - a
-            slot = slots[k & 1]
-            if free[k & 1] is not None:
-                free[k & 1].synchronize()
-            view = slot[:m].numpy()
-            cuts = [m * t // 4 for t in range(5)]
-            list(_stream_pool.map(lambda t: rows_into(a + cuts[t], a + cuts[t + 1], view[cuts[t]:cuts[t + 1]]), range(4)))
-            with torch.cuda.stream(side):
-                d = slot[:m].to(dev, non_blocking=True)
-                free[k & 1] = torch.cuda.Event()
-                free[k & 1].record(side)
-                if d.dtype not in (torch.float16, torch.float32):
-                    d = d.float()
-                normalize_rows_f16(d.to(torch.float16), out=gathered[a:b])  # fp16 first, like the reference's loader (_2:38)
-                ready = torch.cuda.Event()
-                ready.record(side)
+
+        def consume(a, b, d):
+            if d.dtype not in (torch.float16, torch.float32):
+                d = d.float()
+            normalize_rows_f16(d.to(torch.float16), out=gathered[a:b])  # fp16 first, like the reference's loader (_2:38)
+            ready = torch.cuda.Event()
+            ready.record()  # (on the side stream, which is current here)
             main.wait_event(ready)
-            launch_pair_search(gathered, [(0, b, a, b)], float(threshold), compare, buf, cnt)
+            with torch.cuda.stream(main):
+                launch_pair_search(gathered, [(0, b, a, b)], float(threshold), compare, buf, cnt)
+
+        _stage_rows(rows_into, n, E, src_dtype, dev, chunk_rows, consume)
         kfound = int(cnt.item())
         if kfound > cap:  # the count is exact: search the resident set again with room for every pair
             pairs, sims = _pairs_for_ranges(gathered, owned_bands(n), float(threshold), compare, int(kfound * 1.25) + 1024)
@@ -497,16 +519,31 @@ def find_near_duplicates_in_store_distributed(store_dir, threshold=0.96, crop_to
     from .store import PackedStore
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     store = PackedStore(store_dir, model_name, shards=[rank])
-    emb = store.crop(crop_to_use, torch.float16)
-    emb[~torch.from_numpy(store.has_all([crop_to_use]))] = 0  # images without this crop take no part
+    arr = store.array()  # [n, C, E] memory map of this rank's shard
+    ci = store.crop_names.index(crop_to_use)
+    n_mine, E = int(arr.shape[0]), int(arr.shape[2])
     dev = torch.device("cuda", torch.cuda.current_device())
-    n_mine = torch.tensor([emb.shape[0]], dtype=torch.int64, device=dev)
     n_all = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(n_all, n_mine, group=group)
-    n_all = n_all.cpu().tolist()
-    n_local = max(n_all)
-    local = torch.zeros(n_local, emb.shape[1], dtype=torch.float16, device=dev)
-    local[:emb.shape[0]].copy_(emb, non_blocking=True)
+    dist.all_gather_into_tensor(n_all, torch.tensor([n_mine], dtype=torch.int64, device=dev), group=group)
+    n_local = max(n_all.cpu().tolist())
+    local = torch.zeros(n_local, E, dtype=torch.float16, device=dev)
+    if n_mine:
+        # the crop's column goes to the device through the pinned slots of the streamed search (four gather threads, H2D
+        # of chunk k under the gather of chunk k+1) and is rounded to fp16 there, like the reference's loader (_2:38) —
+        # a single-threaded copy out of the memory map plus a pageable H2D copy took longer than the search itself at N = 8
+        def rows_into(a, b, out):
+            out[...] = arr[a:b, ci, :]
+
+        def consume(a, b, d):
+            local[a:b].copy_(d)
+
+        src_dtype = torch.float16 if arr.dtype == np.float16 else torch.float32
+        with torch.cuda.device(dev):
+            side = _stage_rows(rows_into, n_mine, E, src_dtype, dev, 1 << 16, consume)
+            torch.cuda.current_stream(dev).wait_stream(side)
+        usable = store.has_all([crop_to_use])
+        if not usable.all():  # images without this crop take no part
+            local[torch.from_numpy(np.nonzero(~usable)[0]).to(dev)] = 0
     pairs, sims = duplicate_pairs_distributed(local, threshold, compare, group=group)
     # global row -> path: row = shard * n_local + index inside the shard; only the paths of rows that occur are exchanged
     need = sorted({int(r) for r in pairs.reshape(-1)})

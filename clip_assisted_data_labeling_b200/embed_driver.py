@@ -252,8 +252,9 @@ class Feature_Dataset:
                         fd = feature_dict_from_flat(r.clone(), n_stats, stat_names, self.crop_names, kept)
                         pending.append(pool.submit(save_feature_file, sp, self.model_name, fd, self.force_reencode))
             if packed is not None:
-                packed.append(rows[:, n_stats:].reshape(b, 4, E).clone(), img_paths, kept_all,
-                              stats=rows[:, :n_stats].clone() if n_stats else None)
+                # (append writes the block to the shard before it returns: views of the pinned slot are enough)
+                packed.append(rows[:, n_stats:].reshape(b, 4, E), img_paths, kept_all,
+                              stats=rows[:, :n_stats] if n_stats else None)
             if len(pending) > 4096:
                 for fu in pending:
                     fu.result()

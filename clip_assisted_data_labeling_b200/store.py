@@ -88,17 +88,20 @@ class PackedWriter:
             st = stats.detach().cpu().numpy() if isinstance(stats, torch.Tensor) else np.asarray(stats)
             if st.shape != (len(paths), len(self.stat_names)):
                 raise ValueError(f"expected statistics [{len(paths)},{len(self.stat_names)}], got {st.shape}")
-            self._sfh.write(np.ascontiguousarray(st, dtype=np.float32).tobytes())
-        f = np.ascontiguousarray(f[:, self._cols, :], dtype=_DTYPES[self.dtype])
-        for b in range(len(paths)):
-            mask = 0
-            for ci, c in enumerate(self._cols):
-                if kept is None or kept[b][c]:
-                    mask |= 1 << ci
-                else:
-                    f[b, ci, :] = 0
-            self.kept.append(mask)
-        self._fh.write(f.tobytes())
+            self._sfh.write(np.ascontiguousarray(st, dtype=np.float32))
+        # (the driver's case — every crop, f32 in, f32 stored, nothing dropped — writes the caller's block as it is)
+        if self._cols != list(range(len(CROP_NAMES))):
+            f = f[:, self._cols, :]
+        if kept is None:
+            self.kept.extend([(1 << len(self._cols)) - 1] * len(paths))
+        else:
+            k = np.asarray(kept, dtype=bool).reshape(len(paths), len(CROP_NAMES))[:, self._cols]
+            self.kept.extend((k.astype(np.int64) << np.arange(len(self._cols))).sum(axis=1).tolist())
+            if not k.all():
+                f = np.array(f, dtype=_DTYPES[self.dtype])  # a private copy: the dropped crops are stored as zeros
+                f[~k] = 0
+        f = np.ascontiguousarray(f, dtype=_DTYPES[self.dtype])
+        self._fh.write(f)  # (buffer protocol: no intermediate bytes object)
         new = [os.fspath(p) for p in paths]
         if self._sorted and new:
             prev = self.paths[-1] if self.paths else None

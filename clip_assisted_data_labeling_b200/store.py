@@ -234,6 +234,8 @@ class PackedStore:
         """Paths of the given global rows without materialising the whole list: the raw sidecar bytes are cut at the line
         breaks around each requested row (one vectorised newline scan per shard, on first use)."""
         rows = np.asarray(rows, np.int64).reshape(-1)
+        if rows.size and (rows.min() < 0 or rows.max() >= len(self)):
+            raise IndexError(f"row out of range for a store of {len(self)} images")
         if self._paths is not None:
             return [self._paths[int(r)] for r in rows]
         out = [None] * len(rows)

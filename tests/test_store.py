@@ -275,6 +275,9 @@ def test_lazy_paths_paths_at_and_sorted_flag(tmp_path):
     assert st._paths is None and len(st) == 6
     assert st.paths_at([5, 0, 3, 1, 1]) == [flat[5], flat[0], flat[3], flat[1], flat[1]] and st._paths is None
     assert st.paths_at([]) == []
+    for bad in ([6], [-1], [0, 99]):
+        with pytest.raises(IndexError):
+            st.paths_at(bad)
     assert st.paths_sorted() and st._paths is None      # from the flags and the shard edges alone
     assert st.paths == flat and st.paths_at([2, 4]) == [flat[2], flat[4]]
     # an unsorted shard is recorded as such

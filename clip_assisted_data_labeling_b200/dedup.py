@@ -538,8 +538,11 @@ def find_near_duplicates_in_store_distributed(store_dir, threshold=0.96, crop_to
             local[a:b].copy_(d)
 
         src_dtype = torch.float16 if arr.dtype == np.float16 else torch.float32
+        # at least four chunks per shard (gather / copy overlap), and pinned slots no larger than a small shard needs:
+        # every rank of the box allocates its two slots at the same time on the first call
+        chunk_rows = min(1 << 16, max(8192, -(-n_mine // 4)))
         with torch.cuda.device(dev):
-            side = _stage_rows(rows_into, n_mine, E, src_dtype, dev, 1 << 16, consume)
+            side = _stage_rows(rows_into, n_mine, E, src_dtype, dev, chunk_rows, consume)
             torch.cuda.current_stream(dev).wait_stream(side)
         usable = store.has_all([crop_to_use])
         if not usable.all():  # images without this crop take no part

@@ -326,3 +326,28 @@ def test_bench_stdout_carries_exactly_one_json_line():
     assert r.stdout.count("\n") == 1 and json.loads(r.stdout) == {"value": 1.5}
     assert "python noise" in r.stderr and "c-level noise" in r.stderr
 
+
+
+def test_bands_right_of_diagonal_is_what_the_ranks_draw_from():
+    """dedup.bands_right_of_diagonal (the list duplicate_pairs_distributed hands out through the shared counter): together
+    with every rank's own-shard block it covers each pair (i < j) exactly once, it is the union of the static deal, and it
+    is ordered largest band first."""
+    import numpy as np
+    from clip_assisted_data_labeling_b200.dedup import bands_right_of_diagonal, owned_blocks
+    for n_local, world, br in [(10, 1, 4), (10, 2, 4), (7, 3, 2), (64, 4, 16), (300, 8, 128)]:
+        n = n_local * world
+        bands = bands_right_of_diagonal(n_local, world, br)
+        cov = np.zeros((n, n), np.int32)
+        for r in range(world):
+            lo = r * n_local
+            for i in range(lo, lo + n_local):
+                cov[i, i + 1:lo + n_local] += 1
+        for (r0, r1, c0, c1) in bands:
+            assert c0 >= r1  # entirely right of the diagonal block of its shard
+            cov[r0:r1, c0:c1] += 1
+        iu = np.triu_indices(n, 1)
+        assert (cov[iu] == 1).all() and cov.sum() == len(iu[0])
+        sizes = [(b[1] - b[0]) * (b[3] - b[2]) for b in bands]
+        assert sizes == sorted(sizes, reverse=True)
+        assert sorted(bands) == sorted(b for r in range(world) for b in owned_blocks(n_local, r, world, br)[1])
+    assert bands_right_of_diagonal(1000, 1) == []
